@@ -1,0 +1,238 @@
+/*
+ * hcm.h -- C ABI of the B200 chunk mesher (libhcm.so).
+ *
+ * Drop-in boundary for HyperCraft's client mesh task.  A re-written
+ * `ChunkTaskRunner<ChunkTaskType::kMesh>::Run` (reference client/src/ChunkMeshTask.cpp:41-127) or a batched
+ * dispatcher draining many popped `ChunkTaskRunnerData<kMesh>` (client/include/client/ChunkMeshTask.inl:17-29)
+ * calls these entry points instead of BlockLightAlgo::PropagateLight + BlockMeshAlgo::Generate, and feeds the
+ * returned meshes to `WorldRenderer::PushChunkMesh` (client/include/client/WorldRenderer.hpp:69-87) unchanged.
+ *
+ * Plain pointers and sizes only: no C++ types, no torch types, no exceptions.  Every function returns
+ * HCM_OK (0) or a negative hcm_status; hcm_last_error() gives the text.  One hcm_ctx per GPU; calls on one
+ * ctx must be externally serialised (the dispatcher thread owns it) -- this replaces the reference's N worker
+ * threads each owning a runner (client/include/client/ChunkTaskPool.hpp:187-194).
+ *
+ * There is NO CPU fallback: hcm_create fails with HCM_ERR_CUDA when no sm_100 device is usable.
+ */
+#ifndef HCM_H
+#define HCM_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Constants fixed by the reference data model
+ * ---------------------------------------------------------------------------------------------------------- */
+#define HCM_CHUNK_SIZE 32            /* kChunkSize, common/include/common/Size.hpp:8 */
+#define HCM_CHUNK_VOXELS 32768       /* Block m_blocks[32^3], client/include/client/Chunk.hpp:95 */
+#define HCM_CHUNK_COLUMNS 1024       /* InnerPos1 m_sunlight_heights[32^2], Chunk.hpp:96 */
+#define HCM_MAX_MESH_FACES 16        /* block::kBlockMeshMaxFaceCount, block/include/block/BlockMesh.hpp:37 */
+#define HCM_MESH_MAX_VERTICES 65532u /* a BlockMesh is cut when cur_vertex + 4 > UINT16_MAX, BlockMeshAlgo.hpp:397-403 */
+
+typedef enum hcm_status {
+	HCM_OK = 0,
+	HCM_ERR_INVALID = -1,     /* bad argument / malformed registry */
+	HCM_ERR_CUDA = -2,        /* CUDA runtime/driver failure (text in hcm_last_error) */
+	HCM_ERR_UNSUPPORTED = -3, /* registry uses a feature the device path cannot mirror (unknown dynamic mesh, ...) */
+	HCM_ERR_NOT_RESIDENT = -4,/* a task's chunk or one of its 26 neighbours was never uploaded (reference: Pop returns
+	                             std::nullopt, ChunkMeshTask.cpp:29-31) */
+	HCM_ERR_OUT_OF_WINDOW = -5,/* chunk position outside the device-resident world window */
+	HCM_ERR_CAPACITY = -6,    /* more resident chunks / tasks than configured */
+	HCM_ERR_STATE = -7        /* call sequence error (fetch without batch, ...) */
+} hcm_status;
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Registry: flat mirror of the reference's compile-time tables
+ *   block::Block::kBlockDataProperties[65536]  (block/include/block/Block.hpp:35-41, block/generator/Block.cpp.in:19-30)
+ *   block::BlockProperty                        (block/include/block/BlockProperty.hpp:17-29)
+ *   block::BlockMesh / BlockMeshFace            (block/include/block/BlockMesh.hpp:15-49)
+ *   texture::BlockTexture flag tables           (texture/internal/generated/block_texture_transparency.inl:1-3)
+ * A function pointer (BlockMesh::p_dynamic_mesh_func) cannot cross the ABI; the exporter names the generator
+ * instead (dynamic_kind) and passes its template parameters.
+ * ---------------------------------------------------------------------------------------------------------- */
+#define HCM_TEX_TRANSPARENT 1u /* BlockTexture::IsTransparent, texture/include/texture/BlockTexture.hpp:33-36 */
+#define HCM_TEX_LIQUID 2u      /* BlockTexture::IsLiquid, :37-40 */
+#define HCM_TEX_TRANS_PASS 4u  /* BlockTexture::UseTransparentPass, :41-44 */
+
+#define HCM_DYNAMIC_NONE 0u
+#define HCM_DYNAMIC_LIQUID_FLOW 1u /* block::flow_mesh_gen<Config,Variant>, block/block/public/Liquid.hpp:171-282 */
+#define HCM_OBSTACLE_ID_NOT_AIR 0u /* WaterTrait::IsObstacle: id != kAir, block/block/public/Water.hpp:13 */
+
+#define HCM_LIQUID_NONE 0u
+#define HCM_LIQUID_SOURCE 1u /* block id == Config::kSourceID */
+#define HCM_LIQUID_FLOW 2u   /* block id == Config::kFlowID */
+
+typedef struct hcm_block_prop {
+	uint16_t tex[6];      /* BlockTexture::GetData() for faces Right,Left,Top,Bottom,Front,Back (BlockFace.hpp:10) */
+	uint8_t transparency; /* BlockTransparency: 0 opaque, 1 semi, 2 transparent (BlockProperty.hpp:15) */
+	uint8_t light_level;  /* LightLvl 0..15 */
+	uint8_t collision;    /* BlockCollision: 0 none, 1 solid, 2 water (BlockProperty.hpp:16) */
+	uint8_t custom_mesh;  /* 0 = regular cube, else index+1 into hcm_registry::meshes */
+	uint8_t liquid_role;  /* HCM_LIQUID_*: what flow_mesh_gen's get_nei_height sees for this block id (Liquid.hpp:179-184) */
+	uint8_t liquid_obstacle; /* Config::IsObstacle(block) (Water.hpp:13) */
+	uint8_t _pad[2];
+} hcm_block_prop; /* 20 bytes */
+
+typedef struct hcm_mesh_face {
+	uint8_t axis;        /* BlockMeshFace::axis */
+	uint8_t light_face;  /* BlockMeshFace::light_face */
+	uint8_t render_face; /* BlockMeshFace::render_face */
+	uint8_t _pad0;
+	uint16_t texture;    /* BlockTexture::GetData() */
+	uint16_t _pad1;
+	uint8_t verts[4][4]; /* x, y, z in 1/16 voxel, ao (4 = auto, BlockMesh.hpp:22) */
+} hcm_mesh_face; /* 24 bytes */
+
+typedef struct hcm_custom_mesh {
+	uint32_t face_count;   /* static faces (0 for dynamic meshes, Liquid.hpp:285-288) */
+	uint32_t dynamic_kind; /* HCM_DYNAMIC_* */
+	uint8_t liquid_source_id, liquid_flow_id; /* Config::kSourceID / kFlowID (informational) */
+	uint8_t liquid_height_unit;               /* 16 / Config::kFlowDistance (get_flow_height, Liquid.hpp:164-169) */
+	uint8_t liquid_variant;                   /* template parameter Variant of flow_mesh_gen */
+	uint16_t liquid_flow_tex;                 /* BlockTexture{Config::kFlowTex}.GetData() */
+	uint8_t liquid_obstacle_rule;             /* HCM_OBSTACLE_* (informational; the per-block bit is in hcm_block_prop) */
+	uint8_t _pad;
+	hcm_mesh_face faces[HCM_MAX_MESH_FACES];
+} hcm_custom_mesh; /* 400 bytes */
+
+typedef struct hcm_registry {
+	uint32_t n_props;    /* distinct property rows, <= 256 */
+	uint32_t n_meshes;   /* distinct custom meshes, <= 255 */
+	uint32_t n_textures; /* length of tex_flags (texture ids 0..n_textures-1; id 0 = kNone) */
+	uint32_t _pad;
+	const uint8_t *prop_index;     /* [65536]: Block::GetData() -> row of props (the flat table of Block.hpp:41) */
+	const hcm_block_prop *props;   /* [n_props] */
+	const hcm_custom_mesh *meshes; /* [n_meshes] */
+	const uint8_t *tex_flags;      /* [n_textures] HCM_TEX_* bits */
+} hcm_registry;
+
+/* Serialised registry ("blob"): header, prop_index[65536], props[], meshes[], tex_flags[]. */
+#define HCM_REGISTRY_MAGIC 0x4752434Du /* "MCRG" */
+#define HCM_REGISTRY_VERSION 1u
+typedef struct hcm_registry_blob_header {
+	uint32_t magic, version, n_props, n_meshes, n_textures, _pad[3];
+} hcm_registry_blob_header; /* 32 bytes */
+
+/* Point `out` into a blob held by the caller (no copy). */
+int hcm_registry_from_blob(const void *blob, size_t size, hcm_registry *out);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Context: one per GPU.  Holds the device-resident world window and the per-batch output arenas.
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct hcm_ctx hcm_ctx;
+
+typedef struct hcm_config {
+	int32_t device;           /* CUDA ordinal */
+	int16_t origin[3];        /* chunk position (ChunkPos3) of the window's minimum corner */
+	uint16_t extent[3];       /* window size in chunks per axis; positions in [origin, origin+extent) are addressable */
+	uint32_t max_chunks;      /* resident raw-chunk capacity (0 = extent product) */
+	uint32_t max_tasks;       /* max tasks per hcm_mesh_batch (0 = extent product) */
+	uint64_t vertex_capacity; /* initial output arena size in vertices (0 = default); grows on demand, never truncates */
+} hcm_config;
+
+int hcm_create(const hcm_registry *registry, const hcm_config *config, hcm_ctx **out);
+void hcm_destroy(hcm_ctx *ctx);
+const char *hcm_last_error(const hcm_ctx *ctx); /* ctx may be NULL: error of the last failed hcm_create */
+const char *hcm_status_string(int status);
+
+/* Pinned host memory for upload sources (so the host->device copies are truly asynchronous). */
+void *hcm_host_alloc(size_t bytes);
+void hcm_host_free(void *p);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Chunk residency.  Inputs are exactly what a reference Chunk exposes:
+ *   blocks : Chunk::GetBlockData(), 32768 x uint16 (Block::GetData(): id | meta << 8), index x + (y*32 + z)*32
+ *            (Chunk.hpp:50, common/include/common/Position.hpp:98-100)
+ *   heights: Chunk::GetSunlightHeight(idx), 1024 x int8, index x + z*32; sunlit(x,y,z) = y >= height (Chunk.hpp:65-76)
+ *   pos    : Chunk::GetPosition() (ChunkPos3 = i16vec3)
+ * The call enqueues the host->device copy and the derivation kernel on the ctx stream and returns; the host
+ * arrays must stay valid until hcm_sync / hcm_mesh_fetch.  Re-uploading a position replaces it (block edits).
+ * ---------------------------------------------------------------------------------------------------------- */
+int hcm_upload_chunks(hcm_ctx *ctx, uint32_t n, const int16_t *pos /* n x 3 */, const uint16_t *blocks /* n x 32768 */,
+                      const int8_t *heights /* n x 1024 */);
+int hcm_remove_chunks(hcm_ctx *ctx, uint32_t n, const int16_t *pos /* n x 3 */);
+int hcm_is_resident(const hcm_ctx *ctx, const int16_t pos[3]); /* 1 / 0 */
+int hcm_sync(hcm_ctx *ctx);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Meshing.  One task = one chunk position whose 26 neighbours are resident (the 27-array that
+ * ChunkTaskData<kMesh>::Pop captures, ChunkMeshTask.cpp:14-39).  hcm_mesh_batch launches asynchronously;
+ * hcm_mesh_fetch waits, copies the compacted output to pinned host memory owned by the ctx and returns views that
+ * stay valid until the next hcm_mesh_batch / hcm_destroy.
+ *
+ * Output contract (client/include/client/BlockVertex.hpp:8-25): per task, the list of BlockMesh in the order
+ * BlockMeshAlgo::Generate returns them (BlockMeshAlgo.hpp:494-521): meshes cut by the 16-bit index limit in
+ * overflow order, then the opaque remainder, then the transparent remainder, empty ones skipped.  Zero meshes is a
+ * valid result and must still be pushed (WorldRenderer.hpp:81-86).
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct hcm_mesh_desc {
+	uint32_t task;         /* index into the batch */
+	uint32_t transparent;  /* BlockMesh::transparent */
+	uint64_t vertex_offset;/* first vertex in hcm_batch_view::vertices */
+	uint64_t index_offset; /* first index in hcm_batch_view::indices */
+	uint32_t vertex_count; /* BlockMesh::vertices.size() */
+	uint32_t index_count;  /* BlockMesh::indices.size() */
+	uint32_t aabb_min[3];  /* BlockMesh::aabb (AABB<uint32_t>, 1/16 voxel units; default min=UINT32_MAX,max=0 dep/AABB.hpp:11) */
+	uint32_t aabb_max[3];
+} hcm_mesh_desc; /* 56 bytes */
+
+typedef struct hcm_task_result {
+	uint32_t first_mesh; /* index into hcm_batch_view::meshes */
+	uint32_t n_meshes;
+} hcm_task_result;
+
+typedef struct hcm_batch_view {
+	uint32_t n_tasks;
+	uint32_t n_meshes;
+	uint64_t n_vertices;
+	uint64_t n_indices;
+	const hcm_task_result *tasks; /* [n_tasks] */
+	const hcm_mesh_desc *meshes;  /* [n_meshes] */
+	const uint64_t *vertices;     /* [n_vertices] packed BlockVertex {x10_y10_z10_axis2, tex10_trans3_face3_ao2_sl6_tl6} */
+	const uint16_t *indices;      /* [n_indices] */
+} hcm_batch_view;
+
+int hcm_mesh_batch(hcm_ctx *ctx, uint32_t n, const int16_t *pos /* n x 3 */);
+int hcm_mesh_fetch(hcm_ctx *ctx, hcm_batch_view *out);
+
+/* Device-side completion only (no output copy): waits for the last batch and reports its totals. */
+typedef struct hcm_batch_counts {
+	uint32_t n_tasks, n_meshes;
+	uint64_t n_vertices, n_indices;
+	uint32_t n_worked; /* tasks that went through the full light+mesh kernel (not classified trivial) */
+	uint32_t _pad;
+} hcm_batch_counts;
+int hcm_mesh_wait(hcm_ctx *ctx, hcm_batch_counts *out);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Measurement and debugging
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct hcm_stats {
+	/* CUDA-event times of the most recent call of each kind, on the ctx stream, milliseconds */
+	float upload_copy_ms;  /* host->device copy of the last hcm_upload_chunks */
+	float derive_ms;       /* derive kernel of the last hcm_upload_chunks */
+	float classify_ms;     /* classify kernel of the last hcm_mesh_batch */
+	float mesh_ms;         /* mesh kernel of the last hcm_mesh_batch */
+	float fetch_copy_ms;   /* device->host copies of the last hcm_mesh_fetch */
+	uint32_t kernel_launches; /* kernels launched by this ctx since creation */
+	uint64_t h2d_bytes;    /* cumulative */
+	uint64_t d2h_bytes;    /* cumulative */
+	uint64_t device_bytes; /* device memory held by the ctx */
+} hcm_stats;
+int hcm_get_stats(hcm_ctx *ctx, hcm_stats *out);
+
+void *hcm_stream(hcm_ctx *ctx); /* the ctx's cudaStream_t, for external event timing */
+
+/* Light stage only, for stage-wise parity tests: the [-1,32]^3 light bytes the mesher reads
+ * (index (x+1) + ((z+1) + (y+1)*34)*34; value = block::Light data = torch << 4 | sun,
+ * block/include/block/Light.hpp:20-24) after the flood of ChunkMeshTask.cpp:48-111. */
+int hcm_debug_light(hcm_ctx *ctx, const int16_t pos[3], uint8_t *out /* 39304 */);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HCM_H */

@@ -1,0 +1,224 @@
+"""TEST INFRASTRUCTURE -- ctypes wrappers over the parity oracles.  Not part of the shipped product.
+
+* ``RefWorld``  : oracle/_ref/libhcref.so  -- the UNMODIFIED reference mesher / terrain / registry
+                  (built by ``make -C oracle ref`` from /root/reference; the prebuilt .so travels to the GPU box).
+* ``PortOracle``: oracle/libhcoracle.so    -- this repo's CPU restatement (oracle/hc_oracle.cpp).
+
+Only tests/, __graft_entry__.smoke() and bench.py (input generation, cpu_baseline, --impl reference) import this.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF_SO = os.path.join(HERE, "_ref", "libhcref.so")
+PORT_SO = os.path.join(HERE, "libhcoracle.so")
+
+_vp = ctypes.c_void_p
+
+
+def _ptr(a: np.ndarray):
+    return a.ctypes.data_as(_vp)
+
+
+def build(ref: bool = True, port: bool = True) -> None:
+    """Compile the oracles (reference only when /root/reference is present)."""
+    targets = []
+    if port:
+        targets.append("port")
+    if ref:
+        targets.append("ref")
+    subprocess.run(["make", "-C", HERE, "-j8"] + targets, check=True, stdout=subprocess.DEVNULL)
+
+
+def have_ref() -> bool:
+    return os.path.exists(REF_SO)
+
+
+def parse_meshes(buf: np.ndarray) -> list[dict]:
+    """Decode the serialised mesh list (layout documented in oracle/ref_shim.cpp)."""
+    n = int(buf[:4].view(np.uint32)[0])
+    hdr = buf[4:4 + 36 * n].view(np.uint32).reshape(n, 9)
+    off = 4 + 36 * n
+    out = []
+    for i in range(n):
+        nv, ni = int(hdr[i, 7]), int(hdr[i, 8])
+        v = buf[off:off + nv * 8].view(np.uint64).copy()
+        off += nv * 8
+        idx = buf[off:off + ni * 2].view(np.uint16).copy()
+        off += (ni * 2 + 3) & ~3
+        out.append(dict(transparent=int(hdr[i, 0]), aabb_min=hdr[i, 1:4].copy(), aabb_max=hdr[i, 4:7].copy(),
+                        vertices=v, indices=idx))
+    return out
+
+
+class RefWorld:
+    """A set of reference ``hc::client::Chunk`` objects + the reference mesher over them."""
+
+    def __init__(self):
+        if not have_ref():
+            raise RuntimeError("oracle/_ref/libhcref.so missing: run `make -C oracle ref` where /root/reference exists")
+        L = ctypes.CDLL(REF_SO)
+        L.hcref_world_create.restype = _vp
+        L.hcref_world_chunk_count.restype = ctypes.c_uint64
+        L.hcref_mesh.restype = ctypes.c_int64
+        L.hcref_result_copy.restype = ctypes.c_int64
+        L.hcref_registry_blob.restype = ctypes.c_int64
+        self.L = L
+        self.w = _vp(L.hcref_world_create())
+
+    def __del__(self):
+        try:
+            self.L.hcref_world_destroy(self.w)
+        except Exception:
+            pass
+
+    @staticmethod
+    def hardware_threads() -> int:
+        return os.cpu_count() or 1
+
+    def registry_blob(self) -> np.ndarray:
+        need = self.L.hcref_registry_blob(None, ctypes.c_uint64(0))
+        if need < 0:
+            raise RuntimeError(f"registry export failed: {need}")
+        blob = np.zeros(need, dtype=np.uint8)
+        self.L.hcref_registry_blob(_ptr(blob), ctypes.c_uint64(need))
+        return blob
+
+    def generate(self, positions: np.ndarray, seed: int = 12314524, threads: int = 0) -> None:
+        pos = np.ascontiguousarray(positions, dtype=np.int16).reshape(-1, 3)
+        self.L.hcref_world_generate(self.w, ctypes.c_uint32(seed), _ptr(pos), ctypes.c_uint64(len(pos)),
+                                    ctypes.c_int(threads or self.hardware_threads()))
+
+    def set_chunk(self, pos, blocks: np.ndarray, heights: np.ndarray) -> None:
+        p = np.asarray(pos, dtype=np.int16)
+        b = np.ascontiguousarray(blocks, dtype=np.uint16).reshape(-1)
+        h = np.ascontiguousarray(heights, dtype=np.int8).reshape(-1)
+        assert b.size == 32768 and h.size == 1024
+        self.L.hcref_world_set_chunk(self.w, _ptr(p), _ptr(b), _ptr(h))
+
+    def get_chunk(self, pos):
+        p = np.asarray(pos, dtype=np.int16)
+        b = np.empty(32768, dtype=np.uint16)
+        h = np.empty(1024, dtype=np.int8)
+        if self.L.hcref_world_get_chunk(self.w, _ptr(p), _ptr(b), _ptr(h)) != 0:
+            raise KeyError(tuple(int(x) for x in p))
+        return b, h
+
+    def get_chunks(self, positions: np.ndarray):
+        pos = np.ascontiguousarray(positions, dtype=np.int16).reshape(-1, 3)
+        b = np.empty((len(pos), 32768), dtype=np.uint16)
+        h = np.empty((len(pos), 1024), dtype=np.int8)
+        for i in range(len(pos)):
+            if self.L.hcref_world_get_chunk(self.w, _ptr(pos[i]), _ptr(b[i]), _ptr(h[i])) != 0:
+                raise KeyError(tuple(int(x) for x in pos[i]))
+        return b, h
+
+    def mesh(self, pos) -> np.ndarray:
+        """Unmodified ``ChunkTaskRunner<kMesh>::Run`` on one chunk; returns the serialised meshes."""
+        p = np.asarray(pos, dtype=np.int16)
+        n = self.L.hcref_mesh(self.w, _ptr(p))
+        if n < 0:
+            raise KeyError("a neighbour chunk is missing")
+        buf = np.zeros(n, dtype=np.uint8)
+        self.L.hcref_result_copy(self.w, _ptr(buf))
+        return buf
+
+    def mesh_batch(self, positions: np.ndarray, threads: int = 0, per_chunk: bool = False):
+        """Multithreaded reference mesher (one runner per thread). Returns (stats dict, per-chunk u64[n,4] or None)."""
+
+        class Stats(ctypes.Structure):
+            _fields_ = [("seconds", ctypes.c_double), ("chunks", ctypes.c_uint64), ("meshes", ctypes.c_uint64),
+                        ("vertices", ctypes.c_uint64), ("indices", ctypes.c_uint64), ("threads", ctypes.c_int32),
+                        ("missing", ctypes.c_int32)]
+
+        pos = np.ascontiguousarray(positions, dtype=np.int16).reshape(-1, 3)
+        pc = np.zeros((len(pos), 4), dtype=np.uint64) if per_chunk else None
+        st = Stats()
+        self.L.hcref_mesh_batch(self.w, _ptr(pos), ctypes.c_uint64(len(pos)), ctypes.c_int(threads or self.hardware_threads()),
+                                _ptr(pc) if per_chunk else None, ctypes.byref(st))
+        return {f[0]: getattr(st, f[0]) for f in Stats._fields_}, pc
+
+    def light34(self, pos) -> np.ndarray:
+        p = np.asarray(pos, dtype=np.int16)
+        out = np.zeros(34 * 34 * 34, dtype=np.uint8)
+        if self.L.hcref_light34(self.w, _ptr(p), _ptr(out)) != 0:
+            raise KeyError("a neighbour chunk is missing")
+        return out
+
+    def dynamic_mesh_eval(self, block: int, neighbours: np.ndarray):
+        nb = np.ascontiguousarray(neighbours, dtype=np.uint16)
+        faces = np.zeros(16 * 24, dtype=np.uint8)
+        tex = np.zeros(6, dtype=np.uint16)
+        dyn = ctypes.c_int(0)
+        n = self.L.hcref_dynamic_mesh_eval(ctypes.c_uint16(block), _ptr(nb), _ptr(faces), _ptr(tex), ctypes.byref(dyn))
+        return n, faces[:max(n, 0) * 24].copy(), tex, dyn.value
+
+
+# neighbour order of the 27-array: NeighbourIndex2CmpXYZ, common/include/common/Position.hpp:146-152
+def neighbour_offsets() -> np.ndarray:
+    rev = (1, -1, 0)
+    return np.array([[rev[i // 9], rev[(i // 3) % 3], rev[i % 3]] for i in range(27)], dtype=np.int16)
+
+
+class PortOracle:
+    """This repo's CPU restatement of the mesh task (oracle/hc_oracle.cpp)."""
+
+    def __init__(self, registry_blob: np.ndarray):
+        if not os.path.exists(PORT_SO):
+            build(ref=False, port=True)
+        L = ctypes.CDLL(PORT_SO)
+        L.hco_create.restype = _vp
+        L.hco_mesh.restype = ctypes.c_int64
+        self.L = L
+        self.blob = np.ascontiguousarray(registry_blob, dtype=np.uint8)
+        self.o = _vp(L.hco_create(_ptr(self.blob), ctypes.c_uint64(self.blob.size)))
+        if not self.o:
+            raise RuntimeError("bad registry blob")
+        self.offsets = neighbour_offsets()
+
+    def __del__(self):
+        try:
+            self.L.hco_destroy(self.o)
+        except Exception:
+            pass
+
+    def _arrays(self, chunks: dict, pos):
+        """chunks: {(x,y,z): (blocks u16[32768], heights i8[1024])}"""
+        bp = (_vp * 27)()
+        hp = (_vp * 27)()
+        keep = []
+        for i in range(27):
+            key = tuple(int(pos[k]) + int(self.offsets[i, k]) for k in range(3))
+            b, h = chunks[key]
+            b = np.ascontiguousarray(b, dtype=np.uint16).reshape(-1)
+            h = np.ascontiguousarray(h, dtype=np.int8).reshape(-1)
+            keep.append((b, h))
+            bp[i] = b.ctypes.data
+            hp[i] = h.ctypes.data
+        return bp, hp, keep
+
+    def mesh(self, chunks: dict, pos) -> np.ndarray:
+        bp, hp, keep = self._arrays(chunks, pos)
+        n = self.L.hco_mesh(self.o, bp, hp, None, ctypes.c_uint64(0))
+        buf = np.zeros(n, dtype=np.uint8)
+        self.L.hco_mesh(self.o, bp, hp, _ptr(buf), ctypes.c_uint64(n))
+        return buf
+
+    def light34(self, chunks: dict, pos) -> np.ndarray:
+        bp, hp, keep = self._arrays(chunks, pos)
+        out = np.zeros(34 * 34 * 34, dtype=np.uint8)
+        self.L.hco_light34(self.o, bp, hp, _ptr(out))
+        return out
+
+    def dynamic_mesh_eval(self, block: int, neighbours: np.ndarray):
+        nb = np.ascontiguousarray(neighbours, dtype=np.uint16)
+        faces = np.zeros(16 * 24, dtype=np.uint8)
+        tex = np.zeros(6, dtype=np.uint16)
+        dyn = ctypes.c_int(0)
+        n = self.L.hco_dynamic_mesh_eval(self.o, ctypes.c_uint16(block), _ptr(nb), _ptr(faces), _ptr(tex), ctypes.byref(dyn))
+        return n, faces[:max(n, 0) * 24].copy(), tex, dyn.value
