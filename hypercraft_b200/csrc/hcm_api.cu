@@ -1,0 +1,766 @@
+// C ABI of the B200 chunk mesher (include/hcm.h): context, residency, batching, output arenas.
+// All device work is enqueued on the ctx stream; there is no CPU fallback anywhere in this file.
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "hcm_device.cuh"
+
+namespace hcm {
+void launch_derive(const DevWorld &w, const UploadEntry *entries, uint32_t n, const uint8_t *prop_index, const DevTables *tables,
+                   const int8_t *raw_heights, cudaStream_t st);
+void launch_clear(const DevWorld &w, const UploadEntry *entries, uint32_t n, cudaStream_t st);
+void launch_classify(const DevWorld &w, const TaskIn *tasks, uint32_t n, uint32_t *worklist, BatchHeads *heads, hcm_task_result *task_out, int force_all,
+                     cudaStream_t st);
+cudaError_t mesh_kernel_prepare();
+int mesh_kernel_smem_bytes();
+void launch_mesh(const CUtensorMap &tmap, const MeshParams &p, int grid, cudaStream_t st);
+} // namespace hcm
+
+using namespace hcm;
+
+static thread_local std::string g_create_error;
+
+struct hcm_ctx {
+	int device = 0;
+	cudaStream_t stream = nullptr;
+	DevWorld w{};
+	size_t n_cells = 0; // window chunks
+	uint32_t max_chunks = 0, max_tasks = 0;
+
+	DevTables *d_tables = nullptr;
+	uint8_t *d_prop_index = nullptr;
+	hcm_custom_mesh *d_meshes = nullptr;
+	DevMeshInfo *d_mesh_info = nullptr;
+	uint16_t *d_raw = nullptr;
+	int8_t *d_rawh = nullptr;
+	UploadEntry *d_entries = nullptr;
+	CUtensorMap tmap{};
+
+	std::vector<int32_t> slot_of; // host mirror of DevWorld::slot
+	std::vector<int32_t> free_slots;
+
+	TaskIn *d_tasks = nullptr;
+	uint32_t *d_worklist = nullptr;
+	BatchHeads *d_heads = nullptr;
+	hcm_task_result *d_task_out = nullptr;
+	hcm_mesh_desc *d_mesh_out = nullptr;
+	uint64_t *d_vtx = nullptr;
+	uint16_t *d_idx = nullptr;
+	uint64_t vtx_cap = 0, idx_cap = 0;
+	uint32_t mesh_cap = 0;
+	DynRec *d_dyn = nullptr;
+	uint8_t *d_debug_light = nullptr;
+	int grid = 0;
+
+	BatchHeads *h_heads = nullptr; // pinned
+	hcm_task_result *h_task_out = nullptr;
+	hcm_mesh_desc *h_mesh_out = nullptr;
+	uint64_t *h_vtx = nullptr;
+	uint16_t *h_idx = nullptr;
+	uint64_t h_vtx_cap = 0, h_idx_cap = 0;
+	uint32_t h_mesh_cap = 0, h_task_cap = 0;
+
+	std::vector<TaskIn> tasks;
+	uint32_t batch_n = 0;
+	bool batch_pending = false, batch_done = false;
+	int force_all = 0;
+
+	cudaEvent_t ev[10]{};
+	bool ev_upload = false, ev_batch = false, ev_fetch = false;
+	hcm_stats stats{};
+	std::string err;
+};
+
+namespace {
+
+enum { EV_UP0, EV_UP1, EV_UP2, EV_B0, EV_B1, EV_B2, EV_F0, EV_F1, EV_COUNT };
+
+int fail(hcm_ctx *c, int status, const char *fmt, ...) {
+	char buf[512];
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(buf, sizeof(buf), fmt, ap);
+	va_end(ap);
+	if (c)
+		c->err = buf;
+	else
+		g_create_error = buf;
+	return status;
+}
+
+#define CU(call)                                                                                                       \
+	do {                                                                                                               \
+		cudaError_t e_ = (call);                                                                                       \
+		if (e_ != cudaSuccess)                                                                                         \
+			return fail(c, HCM_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+	} while (0)
+
+template <typename T> cudaError_t dev_alloc(hcm_ctx *c, T **p, size_t count) {
+	cudaError_t e = cudaMalloc((void **)p, count * sizeof(T));
+	if (e == cudaSuccess)
+		c->stats.device_bytes += count * sizeof(T);
+	return e;
+}
+
+bool in_window(const hcm_ctx *c, const int16_t *pos, int *cx, int *cy, int *cz) {
+	*cx = pos[0] - c->w.ox, *cy = pos[1] - c->w.oy, *cz = pos[2] - c->w.oz;
+	return *cx >= 0 && *cx < c->w.wx && *cy >= 0 && *cy < c->w.wy && *cz >= 0 && *cz < c->w.wz;
+}
+size_t cell(const hcm_ctx *c, int cx, int cy, int cz) { return ((size_t)cy * c->w.wz + cz) * c->w.wx + cx; }
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                    const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int build_tables(hcm_ctx *c, const hcm_registry *reg, DevTables &t, std::vector<DevMeshInfo> &minfo) {
+	memset(&t, 0, sizeof(t));
+	if (!reg || !reg->prop_index || !reg->props || !reg->tex_flags || (reg->n_meshes && !reg->meshes))
+		return fail(c, HCM_ERR_INVALID, "registry has null tables");
+	if (reg->n_props == 0 || reg->n_props > 256 || reg->n_meshes > 255)
+		return fail(c, HCM_ERR_INVALID, "registry sizes out of range (props %u, meshes %u)", reg->n_props, reg->n_meshes);
+	for (uint32_t i = 0; i < 65536; ++i)
+		if (reg->prop_index[i] >= reg->n_props)
+			return fail(c, HCM_ERR_INVALID, "prop_index[%u] = %u out of range", i, reg->prop_index[i]);
+	// texture codes: one per distinct BlockTexture value (equality on the whole u16, BlockTexture.hpp:78-79)
+	std::map<uint16_t, uint32_t> codes;
+	codes[0] = 0;
+	auto code_of = [&](uint16_t tex) -> int {
+		auto it = codes.find(tex);
+		if (it != codes.end())
+			return (int)it->second;
+		if (codes.size() >= 256)
+			return -1;
+		uint32_t k = (uint32_t)codes.size();
+		codes[tex] = k;
+		return (int)k;
+	};
+	auto tex_flags = [&](uint16_t tex, uint8_t *out) -> bool {
+		uint32_t id = tex & 0x1fffu;
+		if (id >= reg->n_textures)
+			return false;
+		*out = (uint8_t)((reg->tex_flags[id] & 7u) | (id == 0 ? TF_EMPTY : 0));
+		return true;
+	};
+	minfo.assign(reg->n_meshes, DevMeshInfo{});
+	for (uint32_t m = 0; m < reg->n_meshes; ++m) {
+		const hcm_custom_mesh &cm = reg->meshes[m];
+		DevMeshInfo &mi = minfo[m];
+		if (cm.face_count > HCM_MAX_MESH_FACES)
+			return fail(c, HCM_ERR_INVALID, "custom mesh %u has %u faces", m, cm.face_count);
+		if (cm.dynamic_kind != HCM_DYNAMIC_NONE && cm.dynamic_kind != HCM_DYNAMIC_LIQUID_FLOW)
+			return fail(c, HCM_ERR_UNSUPPORTED, "custom mesh %u uses unknown dynamic generator kind %u", m, cm.dynamic_kind);
+		mi.dynamic_kind = (uint8_t)cm.dynamic_kind;
+		for (uint32_t i = 0; i < cm.face_count; ++i) {
+			uint8_t fl;
+			if (!tex_flags(cm.faces[i].texture, &fl))
+				return fail(c, HCM_ERR_INVALID, "custom mesh %u face %u: texture id out of range", m, i);
+			if (cm.faces[i].axis > 2 || cm.faces[i].light_face > 5 || cm.faces[i].render_face > 5)
+				return fail(c, HCM_ERR_INVALID, "custom mesh %u face %u: bad axis/face", m, i);
+			if (fl & HCM_TEX_TRANS_PASS)
+				mi.n_trans++, mi.trans_mask |= (uint16_t)(1u << i);
+			else
+				mi.n_opaque++;
+		}
+		if (cm.dynamic_kind == HCM_DYNAMIC_LIQUID_FLOW) {
+			uint8_t fl;
+			int code = code_of(cm.liquid_flow_tex);
+			if (code < 0 || !tex_flags(cm.liquid_flow_tex, &fl))
+				return fail(c, HCM_ERR_UNSUPPORTED, "too many distinct textures / bad liquid texture");
+			mi.flow_code = (uint8_t)code;
+			mi.flow_trans = (fl & HCM_TEX_TRANS_PASS) ? 1 : 0;
+			mi.height_unit = cm.liquid_height_unit;
+			mi.variant = cm.liquid_variant;
+		}
+	}
+	std::vector<uint8_t> levels;
+	for (uint32_t i = 0; i < reg->n_props; ++i) {
+		const hcm_block_prop &p = reg->props[i];
+		if (p.transparency > 2 || p.collision > 2 || p.light_level > 15 || p.custom_mesh > reg->n_meshes)
+			return fail(c, HCM_ERR_INVALID, "property row %u out of range", i);
+		bool all_solid = true, all_empty = true;
+		for (int f = 0; f < 6; ++f) {
+			int code = code_of(p.tex[f]);
+			uint8_t fl;
+			if (code < 0)
+				return fail(c, HCM_ERR_UNSUPPORTED, "more than 255 distinct block textures");
+			if (!tex_flags(p.tex[f], &fl))
+				return fail(c, HCM_ERR_INVALID, "property row %u: texture id out of range", i);
+			t.ptex[i][f] = (uint8_t)code;
+			if (fl & TF_EMPTY)
+				all_solid = false;
+			else
+				all_empty = false;
+			if (fl & HCM_TEX_TRANSPARENT)
+				all_solid = false;
+		}
+		const bool dynamic = p.custom_mesh && reg->meshes[p.custom_mesh - 1].dynamic_kind != HCM_DYNAMIC_NONE;
+		uint8_t fl = 0;
+		if (p.transparency != 0)
+			fl |= PF_INDIRECT;
+		if (p.transparency == 2 || p.collision != 1)
+			fl |= PF_DIRECT;
+		if (all_solid && !p.custom_mesh)
+			fl |= PF_SOLID;
+		if (all_empty && !dynamic)
+			fl |= PF_EMPTY;
+		if (p.custom_mesh)
+			fl |= PF_CUSTOM;
+		if (dynamic)
+			fl |= PF_DYNAMIC;
+		if (p.liquid_role == HCM_LIQUID_SOURCE)
+			fl |= PF_LIQ_SOURCE;
+		if (p.liquid_role == HCM_LIQUID_FLOW)
+			fl |= PF_LIQ_FLOW;
+		t.pflags[i] = fl;
+		t.pmesh[i] = p.custom_mesh;
+		t.pmisc[i] = (uint8_t)((p.liquid_obstacle ? 1 : 0) | (p.light_level << 4));
+		if (p.light_level && std::find(levels.begin(), levels.end(), p.light_level) == levels.end())
+			levels.push_back(p.light_level);
+	}
+	for (const auto &kv : codes) {
+		t.tex16[kv.second] = kv.first;
+		uint8_t fl = 0;
+		tex_flags(kv.first, &fl);
+		t.texflags[kv.second] = fl;
+	}
+	if (levels.size() > (size_t)kMaxLightLevels)
+		return fail(c, HCM_ERR_UNSUPPORTED, "registry has %zu distinct light levels, at most %d supported", levels.size(), kMaxLightLevels);
+	std::sort(levels.begin(), levels.end(), [](uint8_t a, uint8_t b) { return a > b; });
+	c->w.n_levels = (int)levels.size();
+	for (size_t i = 0; i < levels.size(); ++i)
+		c->w.levels[i] = levels[i];
+	return HCM_OK;
+}
+
+int alloc_arenas(hcm_ctx *c, uint64_t vtx_cap, uint32_t mesh_cap) {
+	if (c->d_vtx) {
+		c->stats.device_bytes -= c->vtx_cap * 8 + c->idx_cap * 2;
+		cudaFree(c->d_vtx), cudaFree(c->d_idx);
+		c->d_vtx = nullptr, c->d_idx = nullptr;
+	}
+	if (c->d_mesh_out && mesh_cap != c->mesh_cap) {
+		c->stats.device_bytes -= (size_t)c->mesh_cap * sizeof(hcm_mesh_desc);
+		cudaFree(c->d_mesh_out);
+		c->d_mesh_out = nullptr;
+	}
+	vtx_cap = (vtx_cap + 3) & ~3ull;
+	c->vtx_cap = vtx_cap, c->idx_cap = vtx_cap / 4 * 6;
+	CU(dev_alloc(c, &c->d_vtx, c->vtx_cap));
+	CU(dev_alloc(c, &c->d_idx, c->idx_cap));
+	if (!c->d_mesh_out) {
+		c->mesh_cap = mesh_cap;
+		CU(dev_alloc(c, &c->d_mesh_out, c->mesh_cap));
+	}
+	return HCM_OK;
+}
+
+template <typename T> int host_reserve(hcm_ctx *c, T **p, uint64_t *cap, uint64_t need) {
+	if (need <= *cap)
+		return HCM_OK;
+	if (*p)
+		cudaFreeHost(*p);
+	*p = nullptr;
+	uint64_t ncap = std::max<uint64_t>(need + need / 4, 1024);
+	CU(cudaHostAlloc((void **)p, ncap * sizeof(T), cudaHostAllocDefault));
+	*cap = ncap;
+	return HCM_OK;
+}
+
+int launch_batch(hcm_ctx *c) {
+	cudaStream_t st = c->stream;
+	CU(cudaEventRecord(c->ev[EV_B0], st));
+	CU(cudaMemsetAsync(c->d_heads, 0, sizeof(BatchHeads), st));
+	launch_classify(c->w, c->d_tasks, c->batch_n, c->d_worklist, c->d_heads, c->d_task_out, c->force_all, st);
+	CU(cudaEventRecord(c->ev[EV_B1], st));
+	MeshParams p{};
+	p.w = c->w;
+	p.tables = c->d_tables, p.meshes = c->d_meshes, p.mesh_info = c->d_mesh_info;
+	p.tasks = c->d_tasks, p.worklist = c->d_worklist, p.heads = c->d_heads;
+	p.task_out = c->d_task_out, p.mesh_out = c->d_mesh_out, p.vtx = c->d_vtx, p.idx = c->d_idx;
+	p.vtx_cap = c->vtx_cap, p.idx_cap = c->idx_cap, p.mesh_cap = c->mesh_cap;
+	p.dyn_scratch = c->d_dyn, p.debug_light = c->d_debug_light;
+	launch_mesh(c->tmap, p, c->grid, st);
+	CU(cudaGetLastError());
+	CU(cudaEventRecord(c->ev[EV_B2], st));
+	c->stats.kernel_launches += 2;
+	c->ev_batch = true;
+	return HCM_OK;
+}
+
+// wait for the pending batch; re-run it with larger arenas if an allocation overflowed (never truncate)
+int wait_batch(hcm_ctx *c) {
+	if (!c->batch_pending && !c->batch_done)
+		return fail(c, HCM_ERR_STATE, "no batch submitted");
+	if (c->batch_done)
+		return HCM_OK;
+	for (int attempt = 0; attempt < 4; ++attempt) {
+		CU(cudaStreamSynchronize(c->stream));
+		CU(cudaMemcpy(c->h_heads, c->d_heads, sizeof(BatchHeads), cudaMemcpyDeviceToHost));
+		c->stats.d2h_bytes += sizeof(BatchHeads);
+		if (!c->h_heads->overflow) {
+			c->batch_pending = false, c->batch_done = true;
+			return HCM_OK;
+		}
+		const uint64_t need_v = std::max<uint64_t>(c->h_heads->vtx, c->h_heads->idx / 6 * 4);
+		const uint32_t need_m = c->h_heads->meshes;
+		int rc = alloc_arenas(c, std::max<uint64_t>(need_v + need_v / 8, c->vtx_cap), std::max<uint32_t>(need_m + need_m / 8 + 64, c->mesh_cap));
+		if (rc)
+			return rc;
+		rc = launch_batch(c);
+		if (rc)
+			return rc;
+	}
+	return fail(c, HCM_ERR_CAPACITY, "output arena kept overflowing");
+}
+
+} // namespace
+
+extern "C" {
+#pragma GCC visibility push(default)
+
+const char *hcm_status_string(int s) {
+	switch (s) {
+	case HCM_OK: return "ok";
+	case HCM_ERR_INVALID: return "invalid argument";
+	case HCM_ERR_CUDA: return "CUDA error";
+	case HCM_ERR_UNSUPPORTED: return "unsupported registry feature";
+	case HCM_ERR_NOT_RESIDENT: return "chunk or neighbour not resident";
+	case HCM_ERR_OUT_OF_WINDOW: return "position outside the world window";
+	case HCM_ERR_CAPACITY: return "capacity exceeded";
+	case HCM_ERR_STATE: return "call sequence error";
+	default: return "unknown status";
+	}
+}
+
+const char *hcm_last_error(const hcm_ctx *c) { return c ? c->err.c_str() : g_create_error.c_str(); }
+
+int hcm_registry_from_blob(const void *blob, size_t size, hcm_registry *out) {
+	if (!blob || !out || size < sizeof(hcm_registry_blob_header))
+		return HCM_ERR_INVALID;
+	const auto *h = (const hcm_registry_blob_header *)blob;
+	if (h->magic != HCM_REGISTRY_MAGIC || h->version != HCM_REGISTRY_VERSION)
+		return HCM_ERR_INVALID;
+	const size_t need = sizeof(*h) + 65536 + (size_t)h->n_props * sizeof(hcm_block_prop) + (size_t)h->n_meshes * sizeof(hcm_custom_mesh) + h->n_textures;
+	if (size < need)
+		return HCM_ERR_INVALID;
+	const uint8_t *p = (const uint8_t *)blob + sizeof(*h);
+	out->n_props = h->n_props, out->n_meshes = h->n_meshes, out->n_textures = h->n_textures, out->_pad = 0;
+	out->prop_index = p, p += 65536;
+	out->props = (const hcm_block_prop *)p, p += (size_t)h->n_props * sizeof(hcm_block_prop);
+	out->meshes = (const hcm_custom_mesh *)p, p += (size_t)h->n_meshes * sizeof(hcm_custom_mesh);
+	out->tex_flags = p;
+	return HCM_OK;
+}
+
+void *hcm_host_alloc(size_t bytes) {
+	void *p = nullptr;
+	if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess)
+		return nullptr;
+	return p;
+}
+void hcm_host_free(void *p) {
+	if (p)
+		cudaFreeHost(p);
+}
+
+void hcm_destroy(hcm_ctx *c) {
+	if (!c)
+		return;
+	cudaSetDevice(c->device);
+	if (c->stream)
+		cudaStreamSynchronize(c->stream);
+	void *dev[] = {c->w.prop8, c->w.pass, c->w.torch, c->w.height, c->w.cflags, c->w.slot, c->d_tables, c->d_prop_index, c->d_meshes, c->d_mesh_info, c->d_raw,
+	               c->d_rawh, c->d_entries, c->d_tasks, c->d_worklist, c->d_heads, c->d_task_out, c->d_mesh_out, c->d_vtx, c->d_idx, c->d_dyn, c->d_debug_light};
+	for (void *p : dev)
+		if (p)
+			cudaFree(p);
+	void *host[] = {c->h_heads, c->h_task_out, c->h_mesh_out, c->h_vtx, c->h_idx};
+	for (void *p : host)
+		if (p)
+			cudaFreeHost(p);
+	for (auto &e : c->ev)
+		if (e)
+			cudaEventDestroy(e);
+	if (c->stream)
+		cudaStreamDestroy(c->stream);
+	delete c;
+}
+
+int hcm_create(const hcm_registry *registry, const hcm_config *cfg, hcm_ctx **out) {
+	if (!out)
+		return HCM_ERR_INVALID;
+	*out = nullptr;
+	hcm_ctx *c = nullptr; // errors before the ctx exists go to the thread-local slot
+	if (!cfg || !registry)
+		return fail(c, HCM_ERR_INVALID, "null registry/config");
+	if (cfg->extent[0] < 3 || cfg->extent[1] < 3 || cfg->extent[2] < 3)
+		return fail(c, HCM_ERR_INVALID, "window extent must be at least 3 chunks per axis (a task needs its 26 neighbours)");
+	if ((uint64_t)cfg->extent[0] * 32 > 65535 || (uint64_t)cfg->extent[2] * 32 > 65535 || (uint64_t)cfg->extent[1] * 32 > 65535)
+		return fail(c, HCM_ERR_INVALID, "window extent too large");
+
+	int n_dev = 0;
+	cudaError_t ce = cudaGetDeviceCount(&n_dev);
+	if (ce != cudaSuccess || cfg->device < 0 || cfg->device >= n_dev)
+		return fail(c, HCM_ERR_CUDA, "no usable CUDA device %d (%s); this library has no CPU fallback", cfg->device,
+		            ce != cudaSuccess ? cudaGetErrorString(ce) : "ordinal out of range");
+	cudaDeviceProp prop;
+	if (cudaGetDeviceProperties(&prop, cfg->device) != cudaSuccess || prop.major != 10)
+		return fail(c, HCM_ERR_CUDA, "device %d is sm_%d%d; libhcm.so carries sm_100a code only", cfg->device, prop.major, prop.minor);
+
+	hcm_ctx *ctx = new hcm_ctx();
+	c = ctx;
+	auto bail = [&](int rc) {
+		g_create_error = c->err;
+		hcm_destroy(c);
+		return rc;
+	};
+	c->device = cfg->device;
+	DevTables tables;
+	std::vector<DevMeshInfo> minfo;
+	if (int rc = build_tables(c, registry, tables, minfo))
+		return bail(rc);
+
+#define CUB(call)                                                                                                      \
+	do {                                                                                                               \
+		cudaError_t e_ = (call);                                                                                       \
+		if (e_ != cudaSuccess) {                                                                                       \
+			fail(c, HCM_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__);        \
+			return bail(HCM_ERR_CUDA);                                                                                 \
+		}                                                                                                              \
+	} while (0)
+
+	CUB(cudaSetDevice(c->device));
+	CUB(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+	for (int i = 0; i < EV_COUNT; ++i)
+		CUB(cudaEventCreate(&c->ev[i]));
+
+	DevWorld &w = c->w;
+	w.ox = cfg->origin[0], w.oy = cfg->origin[1], w.oz = cfg->origin[2];
+	w.wx = cfg->extent[0], w.wy = cfg->extent[1], w.wz = cfg->extent[2];
+	w.X = 32 * w.wx, w.Z = 32 * w.wz;
+	c->n_cells = (size_t)w.wx * w.wy * w.wz;
+	c->max_chunks = cfg->max_chunks ? cfg->max_chunks : (uint32_t)c->n_cells;
+	c->max_tasks = cfg->max_tasks ? cfg->max_tasks : (uint32_t)c->n_cells;
+	const size_t n_cols = (size_t)w.wy * w.Z * w.X;
+
+	CUB(dev_alloc(c, &w.prop8, n_cols * 32));
+	CUB(dev_alloc(c, &w.pass, n_cols));
+	if (w.n_levels)
+		CUB(dev_alloc(c, &w.torch, n_cols * w.n_levels));
+	CUB(dev_alloc(c, &w.height, n_cols));
+	CUB(dev_alloc(c, &w.cflags, c->n_cells));
+	CUB(dev_alloc(c, &w.slot, c->n_cells));
+	CUB(cudaMemsetAsync(w.prop8, 0, n_cols * 32, c->stream));
+	CUB(cudaMemsetAsync(w.pass, 0, n_cols * 4, c->stream));
+	if (w.n_levels)
+		CUB(cudaMemsetAsync(w.torch, 0, n_cols * 4 * w.n_levels, c->stream));
+	CUB(cudaMemsetAsync(w.height, 0, n_cols, c->stream));
+	CUB(cudaMemsetAsync(w.cflags, 0, c->n_cells * 4, c->stream));
+	CUB(cudaMemsetAsync(w.slot, 0xff, c->n_cells * 4, c->stream));
+	CUB(dev_alloc(c, &c->d_raw, (size_t)c->max_chunks * HCM_CHUNK_VOXELS));
+	CUB(dev_alloc(c, &c->d_rawh, (size_t)c->max_chunks * HCM_CHUNK_COLUMNS));
+	CUB(dev_alloc(c, &c->d_entries, (size_t)c->max_chunks));
+	w.raw = c->d_raw;
+
+	CUB(dev_alloc(c, &c->d_tables, 1));
+	CUB(cudaMemcpyAsync(c->d_tables, &tables, sizeof(tables), cudaMemcpyHostToDevice, c->stream));
+	CUB(dev_alloc(c, &c->d_prop_index, 65536));
+	CUB(cudaMemcpyAsync(c->d_prop_index, registry->prop_index, 65536, cudaMemcpyHostToDevice, c->stream));
+	CUB(dev_alloc(c, &c->d_meshes, std::max<size_t>(registry->n_meshes, 1)));
+	CUB(dev_alloc(c, &c->d_mesh_info, std::max<size_t>(registry->n_meshes, 1)));
+	if (registry->n_meshes) {
+		CUB(cudaMemcpyAsync(c->d_meshes, registry->meshes, sizeof(hcm_custom_mesh) * registry->n_meshes, cudaMemcpyHostToDevice, c->stream));
+		CUB(cudaMemcpyAsync(c->d_mesh_info, minfo.data(), sizeof(DevMeshInfo) * registry->n_meshes, cudaMemcpyHostToDevice, c->stream));
+	}
+	CUB(cudaStreamSynchronize(c->stream)); // `tables`/`minfo` are stack/heap temporaries
+
+	c->slot_of.assign(c->n_cells, -1);
+	c->free_slots.resize(c->max_chunks);
+	for (uint32_t i = 0; i < c->max_chunks; ++i)
+		c->free_slots[i] = (int32_t)(c->max_chunks - 1 - i); // pop_back hands out 0,1,2,... -> contiguous uploads
+
+	CUB(dev_alloc(c, &c->d_tasks, c->max_tasks));
+	CUB(dev_alloc(c, &c->d_worklist, c->max_tasks));
+	CUB(dev_alloc(c, &c->d_heads, 1));
+	CUB(dev_alloc(c, &c->d_task_out, c->max_tasks));
+	CUB(cudaHostAlloc((void **)&c->h_heads, sizeof(BatchHeads), cudaHostAllocDefault));
+	const uint64_t v0 = cfg->vertex_capacity ? cfg->vertex_capacity : std::max<uint64_t>(4ull << 20, (uint64_t)c->max_tasks * 512);
+	if (int rc = alloc_arenas(c, v0, 2 * c->max_tasks + 64))
+		return bail(rc);
+
+	CUB(mesh_kernel_prepare());
+	c->grid = prop.multiProcessorCount; // one persistent CTA per SM (shared-memory bound)
+	CUB(dev_alloc(c, &c->d_dyn, (size_t)c->grid * kLightBytes));
+
+	// TMA descriptor over the dense property grid: dims (x, z, y), box 48 x 36 x 34, out-of-window reads give 0 (= air)
+	{
+		void *fn = nullptr;
+		cudaDriverEntryPointQueryResult qres;
+		CUB(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+		if (!fn || qres != cudaDriverEntryPointSuccess) {
+			fail(c, HCM_ERR_CUDA, "cuTensorMapEncodeTiled not available in this driver");
+			return bail(HCM_ERR_CUDA);
+		}
+		const cuuint64_t dims[3] = {(cuuint64_t)w.X, (cuuint64_t)w.Z, (cuuint64_t)w.wy * 32};
+		const cuuint64_t strides[2] = {(cuuint64_t)w.X, (cuuint64_t)w.X * w.Z};
+		const cuuint32_t box[3] = {(cuuint32_t)kVX, (cuuint32_t)kVZ, (cuuint32_t)kVY};
+		const cuuint32_t estr[3] = {1, 1, 1};
+		CUresult r = ((PFN_encodeTiled)fn)(&c->tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, w.prop8, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+		                                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+		if (r != CUDA_SUCCESS) {
+			fail(c, HCM_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+			return bail(HCM_ERR_CUDA);
+		}
+	}
+#undef CUB
+	*out = c;
+	return HCM_OK;
+}
+
+int hcm_is_resident(const hcm_ctx *c, const int16_t pos[3]) {
+	int cx, cy, cz;
+	if (!c || !pos || !in_window(c, pos, &cx, &cy, &cz))
+		return 0;
+	return c->slot_of[cell(c, cx, cy, cz)] >= 0 ? 1 : 0;
+}
+
+int hcm_upload_chunks(hcm_ctx *c, uint32_t n, const int16_t *pos, const uint16_t *blocks, const int8_t *heights) {
+	if (!c)
+		return HCM_ERR_INVALID;
+	if (n == 0)
+		return HCM_OK;
+	if (!pos || !blocks || !heights)
+		return fail(c, HCM_ERR_INVALID, "null upload arrays");
+	if (n > c->max_chunks)
+		return fail(c, HCM_ERR_CAPACITY, "upload of %u chunks exceeds max_chunks %u", n, c->max_chunks);
+	CU(cudaSetDevice(c->device));
+	std::vector<UploadEntry> entries(n);
+	std::vector<int32_t> fresh; // slots taken in this call (rolled back on error)
+	for (uint32_t i = 0; i < n; ++i) {
+		int cx, cy, cz;
+		int rc = HCM_OK;
+		if (!in_window(c, pos + 3 * i, &cx, &cy, &cz))
+			rc = fail(c, HCM_ERR_OUT_OF_WINDOW, "chunk (%d,%d,%d) is outside the window", pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]);
+		int32_t slot = -1;
+		if (!rc) {
+			slot = c->slot_of[cell(c, cx, cy, cz)];
+			if (slot < 0) {
+				if (c->free_slots.empty())
+					rc = fail(c, HCM_ERR_CAPACITY, "more than %u resident chunks", c->max_chunks);
+				else {
+					slot = c->free_slots.back();
+					c->free_slots.pop_back();
+					c->slot_of[cell(c, cx, cy, cz)] = slot;
+					fresh.push_back((int32_t)cell(c, cx, cy, cz));
+				}
+			}
+		}
+		if (rc) {
+			for (auto it = fresh.rbegin(); it != fresh.rend(); ++it) {
+				c->free_slots.push_back(c->slot_of[*it]);
+				c->slot_of[*it] = -1;
+			}
+			return rc;
+		}
+		entries[i] = UploadEntry{slot, (int16_t)cx, (int16_t)cy, (int16_t)cz, 0};
+	}
+	cudaStream_t st = c->stream;
+	CU(cudaEventRecord(c->ev[EV_UP0], st));
+	// host -> device, one copy per run of consecutive slots
+	for (uint32_t i = 0; i < n;) {
+		uint32_t j = i + 1;
+		while (j < n && entries[j].slot == entries[j - 1].slot + 1)
+			++j;
+		const size_t cnt = j - i;
+		CU(cudaMemcpyAsync(c->d_raw + (size_t)entries[i].slot * HCM_CHUNK_VOXELS, blocks + (size_t)i * HCM_CHUNK_VOXELS, cnt * HCM_CHUNK_VOXELS * 2,
+		                   cudaMemcpyHostToDevice, st));
+		CU(cudaMemcpyAsync(c->d_rawh + (size_t)entries[i].slot * HCM_CHUNK_COLUMNS, heights + (size_t)i * HCM_CHUNK_COLUMNS, cnt * HCM_CHUNK_COLUMNS,
+		                   cudaMemcpyHostToDevice, st));
+		i = j;
+	}
+	CU(cudaMemcpyAsync(c->d_entries, entries.data(), n * sizeof(UploadEntry), cudaMemcpyHostToDevice, st)); // pageable: staged before return
+	c->stats.h2d_bytes += (uint64_t)n * (HCM_CHUNK_VOXELS * 2 + HCM_CHUNK_COLUMNS + sizeof(UploadEntry));
+	CU(cudaEventRecord(c->ev[EV_UP1], st));
+	launch_derive(c->w, c->d_entries, n, c->d_prop_index, c->d_tables, c->d_rawh, st);
+	CU(cudaGetLastError());
+	CU(cudaEventRecord(c->ev[EV_UP2], st));
+	c->stats.kernel_launches += 1;
+	c->ev_upload = true;
+	return HCM_OK;
+}
+
+int hcm_remove_chunks(hcm_ctx *c, uint32_t n, const int16_t *pos) {
+	if (!c)
+		return HCM_ERR_INVALID;
+	if (n == 0)
+		return HCM_OK;
+	if (!pos)
+		return fail(c, HCM_ERR_INVALID, "null positions");
+	CU(cudaSetDevice(c->device));
+	std::vector<UploadEntry> entries;
+	for (uint32_t i = 0; i < n; ++i) {
+		int cx, cy, cz;
+		if (!in_window(c, pos + 3 * i, &cx, &cy, &cz))
+			continue;
+		int32_t &slot = c->slot_of[cell(c, cx, cy, cz)];
+		if (slot < 0)
+			continue;
+		entries.push_back(UploadEntry{slot, (int16_t)cx, (int16_t)cy, (int16_t)cz, 0});
+		c->free_slots.push_back(slot);
+		slot = -1;
+	}
+	if (entries.empty())
+		return HCM_OK;
+	CU(cudaMemcpyAsync(c->d_entries, entries.data(), entries.size() * sizeof(UploadEntry), cudaMemcpyHostToDevice, c->stream));
+	launch_clear(c->w, c->d_entries, (uint32_t)entries.size(), c->stream);
+	CU(cudaGetLastError());
+	c->stats.kernel_launches += 1;
+	return HCM_OK;
+}
+
+int hcm_sync(hcm_ctx *c) {
+	if (!c)
+		return HCM_ERR_INVALID;
+	CU(cudaSetDevice(c->device));
+	CU(cudaStreamSynchronize(c->stream));
+	return HCM_OK;
+}
+
+static int submit(hcm_ctx *c, uint32_t n, const int16_t *pos, int force_all) {
+	if (n > c->max_tasks)
+		return fail(c, HCM_ERR_CAPACITY, "batch of %u tasks exceeds max_tasks %u", n, c->max_tasks);
+	if (n && !pos)
+		return fail(c, HCM_ERR_INVALID, "null positions");
+	CU(cudaSetDevice(c->device));
+	c->tasks.resize(n);
+	for (uint32_t i = 0; i < n; ++i) {
+		int cx, cy, cz;
+		if (!in_window(c, pos + 3 * i, &cx, &cy, &cz))
+			return fail(c, HCM_ERR_OUT_OF_WINDOW, "task (%d,%d,%d) is outside the window", pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]);
+		// the 27-array of ChunkTaskData<kMesh>::Pop (ChunkMeshTask.cpp:18-34): every neighbour must exist
+		if (cx < 1 || cy < 1 || cz < 1 || cx > c->w.wx - 2 || cy > c->w.wy - 2 || cz > c->w.wz - 2)
+			return fail(c, HCM_ERR_NOT_RESIDENT, "task (%d,%d,%d) touches the window border: a neighbour cannot be resident", pos[3 * i], pos[3 * i + 1],
+			            pos[3 * i + 2]);
+		for (int dy = -1; dy <= 1; ++dy)
+			for (int dz = -1; dz <= 1; ++dz)
+				for (int dx = -1; dx <= 1; ++dx)
+					if (c->slot_of[cell(c, cx + dx, cy + dy, cz + dz)] < 0)
+						return fail(c, HCM_ERR_NOT_RESIDENT, "task (%d,%d,%d): neighbour (%d,%d,%d) is not resident", pos[3 * i], pos[3 * i + 1],
+						            pos[3 * i + 2], pos[3 * i] + dx, pos[3 * i + 1] + dy, pos[3 * i + 2] + dz);
+		c->tasks[i] = TaskIn{(int16_t)cx, (int16_t)cy, (int16_t)cz, 0};
+	}
+	c->batch_n = n;
+	c->batch_pending = true, c->batch_done = false;
+	c->force_all = force_all;
+	if (n)
+		CU(cudaMemcpyAsync(c->d_tasks, c->tasks.data(), n * sizeof(TaskIn), cudaMemcpyHostToDevice, c->stream));
+	c->stats.h2d_bytes += (uint64_t)n * sizeof(TaskIn);
+	return launch_batch(c);
+}
+
+int hcm_mesh_batch(hcm_ctx *c, uint32_t n, const int16_t *pos) {
+	if (!c)
+		return HCM_ERR_INVALID;
+	return submit(c, n, pos, 0);
+}
+
+int hcm_mesh_wait(hcm_ctx *c, hcm_batch_counts *out) {
+	if (!c)
+		return HCM_ERR_INVALID;
+	CU(cudaSetDevice(c->device));
+	if (int rc = wait_batch(c))
+		return rc;
+	if (out) {
+		out->n_tasks = c->batch_n, out->n_meshes = c->h_heads->meshes;
+		out->n_vertices = c->h_heads->vtx, out->n_indices = c->h_heads->idx;
+		out->n_worked = c->h_heads->n_work, out->_pad = 0;
+	}
+	return HCM_OK;
+}
+
+int hcm_mesh_fetch(hcm_ctx *c, hcm_batch_view *out) {
+	if (!c || !out)
+		return HCM_ERR_INVALID;
+	CU(cudaSetDevice(c->device));
+	if (int rc = wait_batch(c))
+		return rc;
+	const BatchHeads h = *c->h_heads;
+	uint64_t tcap = c->h_task_cap, mcap = c->h_mesh_cap;
+	if (int rc = host_reserve(c, &c->h_task_out, &tcap, c->batch_n))
+		return rc;
+	if (int rc = host_reserve(c, &c->h_mesh_out, &mcap, h.meshes))
+		return rc;
+	c->h_task_cap = (uint32_t)tcap, c->h_mesh_cap = (uint32_t)mcap;
+	if (int rc = host_reserve(c, &c->h_vtx, &c->h_vtx_cap, h.vtx))
+		return rc;
+	if (int rc = host_reserve(c, &c->h_idx, &c->h_idx_cap, h.idx))
+		return rc;
+	cudaStream_t st = c->stream;
+	CU(cudaEventRecord(c->ev[EV_F0], st));
+	if (c->batch_n)
+		CU(cudaMemcpyAsync(c->h_task_out, c->d_task_out, (size_t)c->batch_n * sizeof(hcm_task_result), cudaMemcpyDeviceToHost, st));
+	if (h.meshes)
+		CU(cudaMemcpyAsync(c->h_mesh_out, c->d_mesh_out, (size_t)h.meshes * sizeof(hcm_mesh_desc), cudaMemcpyDeviceToHost, st));
+	if (h.vtx)
+		CU(cudaMemcpyAsync(c->h_vtx, c->d_vtx, h.vtx * 8, cudaMemcpyDeviceToHost, st));
+	if (h.idx)
+		CU(cudaMemcpyAsync(c->h_idx, c->d_idx, h.idx * 2, cudaMemcpyDeviceToHost, st));
+	CU(cudaEventRecord(c->ev[EV_F1], st));
+	CU(cudaStreamSynchronize(st));
+	c->ev_fetch = true;
+	c->stats.d2h_bytes += (uint64_t)c->batch_n * sizeof(hcm_task_result) + (uint64_t)h.meshes * sizeof(hcm_mesh_desc) + h.vtx * 8 + h.idx * 2;
+	out->n_tasks = c->batch_n, out->n_meshes = h.meshes, out->n_vertices = h.vtx, out->n_indices = h.idx;
+	out->tasks = c->h_task_out, out->meshes = c->h_mesh_out, out->vertices = c->h_vtx, out->indices = c->h_idx;
+	return HCM_OK;
+}
+
+int hcm_get_stats(hcm_ctx *c, hcm_stats *out) {
+	if (!c || !out)
+		return HCM_ERR_INVALID;
+	CU(cudaSetDevice(c->device));
+	CU(cudaStreamSynchronize(c->stream));
+	if (c->ev_upload) {
+		CU(cudaEventElapsedTime(&c->stats.upload_copy_ms, c->ev[EV_UP0], c->ev[EV_UP1]));
+		CU(cudaEventElapsedTime(&c->stats.derive_ms, c->ev[EV_UP1], c->ev[EV_UP2]));
+	}
+	if (c->ev_batch) {
+		CU(cudaEventElapsedTime(&c->stats.classify_ms, c->ev[EV_B0], c->ev[EV_B1]));
+		CU(cudaEventElapsedTime(&c->stats.mesh_ms, c->ev[EV_B1], c->ev[EV_B2]));
+	}
+	if (c->ev_fetch)
+		CU(cudaEventElapsedTime(&c->stats.fetch_copy_ms, c->ev[EV_F0], c->ev[EV_F1]));
+	*out = c->stats;
+	return HCM_OK;
+}
+
+void *hcm_stream(hcm_ctx *c) { return c ? (void *)c->stream : nullptr; }
+
+int hcm_debug_light(hcm_ctx *c, const int16_t pos[3], uint8_t *out) {
+	if (!c || !pos || !out)
+		return HCM_ERR_INVALID;
+	CU(cudaSetDevice(c->device));
+	if (!c->d_debug_light)
+		CU(dev_alloc(c, &c->d_debug_light, (size_t)kLightBytes));
+	uint8_t *dl = c->d_debug_light;
+	int rc = submit(c, 1, pos, 1); // force the full path; task 0 -> debug slot 0
+	if (!rc)
+		rc = wait_batch(c);
+	if (!rc) {
+		cudaError_t e = cudaMemcpy(out, dl, kLightBytes, cudaMemcpyDeviceToHost);
+		if (e != cudaSuccess)
+			rc = fail(c, HCM_ERR_CUDA, "debug light copy failed: %s", cudaGetErrorString(e));
+	}
+	// leave debug mode
+	c->d_debug_light = nullptr;
+	cudaFree(dl);
+	c->stats.device_bytes -= kLightBytes;
+	c->batch_done = false, c->batch_pending = false;
+	return rc;
+}
+
+#pragma GCC visibility pop
+} // extern "C"

@@ -1,0 +1,153 @@
+// Device-side data model of the B200 chunk mesher.  See DESIGN.md for the HBM layout and the kernel pipeline.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/hcm.h"
+
+namespace hcm {
+
+// ---- launch geometry ------------------------------------------------------------------------------------------
+constexpr int kThreads = 512; // mesh kernel: 16 warps, one persistent CTA per SM (shared memory bound)
+constexpr int kWarps = kThreads / 32;
+
+// ---- shared-memory voxel volume (property index per voxel), filled by ONE 3-D TMA box -----------------------------
+// x,z in [-2,33] (the +-2 reach is only read by the liquid-flow generator), y in [-1,32].  The innermost box extent
+// must be a multiple of 16 bytes, hence 48.
+constexpr int kVX = 48, kVZ = 36, kVY = 34;
+constexpr int kVoxBytes = kVX * kVZ * kVY; // 58752
+__host__ __device__ constexpr int vox_index(int x, int y, int z) { return ((y + 1) * kVZ + (z + 2)) * kVX + (x + 2); }
+
+// ---- light volume on [-1,32]^3: byte = torch << 4 | sun (block/include/block/Light.hpp:20-24) --------------------
+constexpr int kLS = 34;
+constexpr int kLightBytes = kLS * kLS * kLS; // 39304
+__host__ __device__ constexpr int light_index(int x, int y, int z) { return (x + 1) + ((z + 1) + (y + 1) * kLS) * kLS; }
+
+// ---- face masks: one 32x32 bit mask per (axis, slice 0..32, direction) --------------------------------------------
+constexpr int kMasks = 3 * 33 * 2; // 198
+__host__ __device__ constexpr int mask_id(int axis, int xa, int dir) { return (axis * 33 + xa) * 2 + dir; }
+
+// ---- greedy-merge working set: faces of a group of consecutive masks ----------------------------------------------
+constexpr int kGroupCap = 6144; // faces per group (key 8 B + geometry 4 B each)
+
+// ---- flood domain: 62 x 62 columns (x,z in [-15,46]) of 62-bit words (bit = y + 15) -------------------------------
+constexpr int kFD = 62;
+constexpr int kFCols = kFD * kFD;       // 3844
+constexpr int kColsPerThread = 8;       // 8 * 512 >= 3844
+constexpr int kInner = 34;              // columns x,z in [-1,32] carry the result
+constexpr int kInnerCols = kInner * kInner;
+
+constexpr uint32_t kQuadsPerMesh = HCM_MESH_MAX_VERTICES / 4; // 16383 quads fill a BlockMesh (BlockMeshAlgo.hpp:397-403)
+constexpr int kMaxSplits = 40;                                 // >= ceil(622592 / 16383) meshes per stream
+
+// ---- per-property flags (DevTables::pflags) ------------------------------------------------------------------------
+constexpr uint8_t PF_INDIRECT = 1;  // Block::GetIndirectLightPass  (transparency != opaque), Block.hpp:70
+constexpr uint8_t PF_DIRECT = 2;    // GetVerticalLightPass || collision != solid, BlockMeshAlgo.hpp:119,124
+constexpr uint8_t PF_SOLID = 4;     // class O: six non-empty, non-transparent face textures, no dynamic mesh
+constexpr uint8_t PF_EMPTY = 8;     // class E: six empty face textures, no dynamic mesh
+constexpr uint8_t PF_CUSTOM = 16;   // has a custom mesh
+constexpr uint8_t PF_DYNAMIC = 32;  // custom mesh is dynamic (liquid flow)
+constexpr uint8_t PF_LIQ_SOURCE = 64;
+constexpr uint8_t PF_LIQ_FLOW = 128;
+
+// texture code flags (DevTables::texflags): HCM_TEX_* plus
+constexpr uint8_t TF_EMPTY = 8; // BlockTexture::Empty(): id == 0
+
+struct DevTables {
+	uint8_t ptex[256][8];  // property row -> texture code per face (codes index tex16/texflags; 0 = BlockTexture{} )
+	uint8_t pflags[256];   // PF_*
+	uint8_t pmesh[256];    // custom mesh index + 1, 0 = none
+	uint8_t pmisc[256];    // bit0: liquid obstacle, bits 4..7: light level
+	uint16_t tex16[256];   // code -> BlockTexture::GetData()
+	uint8_t texflags[256]; // code -> HCM_TEX_* | TF_EMPTY
+};
+static_assert(sizeof(DevTables) == 3584, "DevTables layout");
+
+// per custom mesh: static face counts per stream + liquid parameters, for the count pass
+struct DevMeshInfo {
+	uint8_t n_opaque, n_trans; // static faces per output stream
+	uint8_t dynamic_kind;
+	uint8_t flow_code;         // texture code of liquid_flow_tex
+	uint8_t flow_trans;        // liquid_flow_tex uses the transparent pass
+	uint8_t height_unit, variant, _pad;
+	uint16_t trans_mask;       // bit i: static face i goes to the transparent stream
+	uint16_t _pad2;
+};
+static_assert(sizeof(DevMeshInfo) == 12, "DevMeshInfo layout");
+
+// chunk summary flags (DevWorld::cflags), written by the derive kernel
+constexpr uint32_t CF_ALL_EMPTY = 1u << 0;   // every voxel class E
+constexpr uint32_t CF_ALL_SOLID = 1u << 1;   // every voxel class O
+constexpr uint32_t CF_HAS_CUSTOM = 1u << 2;
+constexpr uint32_t CF_HAS_DYNAMIC = 1u << 3;
+constexpr uint32_t CF_HAS_TORCH = 1u << 4;
+constexpr uint32_t CF_RESIDENT = 1u << 5;
+constexpr uint32_t CF_FACE_SOLID0 = 1u << 8; // + f: boundary layer on side f is all class O
+constexpr uint32_t CF_FACE_EMPTY0 = 1u << 16;
+
+constexpr int kMaxLightLevels = 4; // distinct non-zero BlockProperty::light_level values supported
+
+struct DevWorld {
+	int ox, oy, oz; // window origin (chunk coordinates)
+	int wx, wy, wz; // window extent (chunks)
+	int X, Z;       // voxel extents of the dense grids along x and z (32*wx, 32*wz)
+	uint8_t *prop8;       // [32*wy][Z][X]   property index per voxel (x fastest, then z, then y -- the chunk order)
+	uint32_t *pass;       // [wy][Z][X]      bit y_local: voxel lets indirect light pass
+	uint32_t *torch;      // [levels][wy][Z][X] bit y_local: voxel emits light level levels[l]
+	int8_t *height;       // [wy][Z][X]      sunlight height of the column within its chunk
+	uint32_t *cflags;     // [wy][wz][wx]
+	int32_t *slot;        // [wy][wz][wx]    raw slot or -1
+	const uint16_t *raw;  // [max_chunks][32768] uploaded Block data (needed for raw meta of flowing liquids)
+	int n_levels;
+	uint8_t levels[kMaxLightLevels]; // descending
+};
+
+struct UploadEntry {
+	int32_t slot;
+	int16_t cx, cy, cz; // window-relative chunk coordinates
+	int16_t _pad;
+};
+
+struct TaskIn {
+	int16_t cx, cy, cz; // window-relative chunk coordinates
+	int16_t _pad;
+};
+
+// dyn record of a liquid-flow voxel (global scratch, per CTA): heights, per-face texture mask, emitted side faces
+struct __align__(8) DynRec {
+	uint8_t h[4];     // h0..h3, Liquid.hpp:204-207
+	uint8_t texmask;  // bit f: face f carries the flow texture (else kNone), Liquid.hpp:211,287-292
+	uint8_t faces;    // bit0 top, bit1 left, bit2 right, bit3 back, bit4 front (emission order of flow_mesh_gen)
+	uint8_t flow_code;
+	uint8_t flow_trans;
+};
+
+struct BatchHeads {
+	unsigned long long vtx;   // vertices allocated
+	unsigned long long idx;   // indices allocated
+	unsigned int meshes;      // mesh descriptors allocated
+	unsigned int overflow;    // set when an allocation did not fit
+	unsigned int n_work;      // tasks appended to the work list by classify
+	unsigned int cursor;      // next work item
+};
+
+struct MeshParams {
+	DevWorld w;
+	const DevTables *tables;
+	const hcm_custom_mesh *meshes;
+	const DevMeshInfo *mesh_info;
+	const TaskIn *tasks;
+	const uint32_t *worklist;
+	BatchHeads *heads;
+	hcm_task_result *task_out;
+	hcm_mesh_desc *mesh_out;
+	uint64_t *vtx;
+	uint16_t *idx;
+	unsigned long long vtx_cap, idx_cap;
+	unsigned int mesh_cap;
+	DynRec *dyn_scratch;   // [gridDim.x][34^3]
+	uint8_t *debug_light;  // optional [n_tasks][39304]
+};
+
+} // namespace hcm

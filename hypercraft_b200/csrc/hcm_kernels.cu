@@ -1,0 +1,1275 @@
+// Hand-written sm_100a kernels of the B200 chunk mesher.
+//
+//   derive_kernel   : per uploaded chunk -- raw Block data -> dense property-index grid, y-packed light planes,
+//                     sunlight heights, chunk summary flags (streaming, HBM bound).
+//   classify_kernel : per task -- chunks whose summary flags prove "no faces" are answered immediately; the rest
+//                     go to a work list.
+//   mesh_kernel     : persistent CTAs, one chunk at a time, everything on chip:
+//                       TMA 3-D box load of the 36x34x36 halo'd voxel volume        (reference a2/a14: the gather)
+//                       bit-plane face candidates -> exact BlockTexture::Show        (a8/a9)
+//                       bit-parallel level-synchronous sunlight/torchlight flood     (a2-a4)
+//                       per-face AO + smoothed light keys                            (a7)
+//                       warp-parallel greedy merge in the reference's loop order     (a8)
+//                       ordered compaction + vectorised vertex/index emission        (a12)
+//                       custom and liquid-flow meshes                                (a6/a11/a13)
+//
+// (aN = row of SURVEY.md section 8a; reference file:line citations are at the individual functions.)
+#include "hcm_device.cuh"
+
+namespace hcm {
+
+typedef unsigned long long u64;
+typedef uint32_t u32;
+constexpr u32 FULL = 0xffffffffu;
+
+// ================================================================================================================
+// small PTX helpers: mbarrier + TMA (cp.async.bulk.tensor)
+// ================================================================================================================
+__device__ __forceinline__ u32 smem_u32(const void *p) { return (u32)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(u64 *bar, u32 count) {
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+	asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(u64 *bar, u32 bytes) {
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(u64 *bar, u32 phase) {
+	asm volatile("{\n"
+	             ".reg .pred p;\n"
+	             "WAIT_%=:\n"
+	             "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+	             "@p bra DONE_%=;\n"
+	             "bra WAIT_%=;\n"
+	             "DONE_%=:\n"
+	             "}" ::"r"(smem_u32(bar)),
+	             "r"(phase)
+	             : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, int c0, int c1, int c2, u64 *bar) {
+	asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+	                 smem_u32(dst)),
+	             "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+	             : "memory");
+}
+
+__device__ __forceinline__ u32 lanemask_lt() {
+	u32 m;
+	asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+	return m;
+}
+__device__ __forceinline__ u32 warp_excl_scan(u32 v, int lane) {
+	u32 x = v;
+#pragma unroll
+	for (int d = 1; d < 32; d <<= 1) {
+		u32 y = __shfl_up_sync(FULL, x, d);
+		if (lane >= d)
+			x += y;
+	}
+	return x - v;
+}
+
+// ================================================================================================================
+// derive kernel: one CTA per uploaded chunk, 256 threads; thread t owns columns x4..x4+3 of row z
+// ================================================================================================================
+__global__ void __launch_bounds__(256) derive_kernel(DevWorld w, const UploadEntry *__restrict__ entries, const uint8_t *__restrict__ prop_index,
+                                                     const DevTables *__restrict__ tables, const int8_t *__restrict__ raw_heights) {
+	__shared__ uint8_t s_pflags[256], s_pmisc[256];
+	__shared__ u32 s_and, s_or;
+	const int tid = threadIdx.x;
+	s_pflags[tid] = tables->pflags[tid];
+	s_pmisc[tid] = tables->pmisc[tid];
+	if (tid == 0)
+		s_and = 0xffffffffu, s_or = 0;
+	__syncthreads();
+
+	const UploadEntry e = entries[blockIdx.x];
+	const int z = tid >> 3, x4 = (tid & 7) << 2;
+	const uint16_t *raw = w.raw + (size_t)e.slot * HCM_CHUNK_VOXELS;
+	const size_t gx = (size_t)e.cx * 32 + x4, gz = (size_t)e.cz * 32 + z;
+
+	u32 pass[4] = {0, 0, 0, 0};
+	u32 torch[kMaxLightLevels][4];
+#pragma unroll
+	for (int l = 0; l < kMaxLightLevels; ++l)
+		torch[l][0] = torch[l][1] = torch[l][2] = torch[l][3] = 0;
+	u32 f_and = 0xffu, f_or = 0; // PF_* accumulated over the thread's voxels
+	u32 face_solid = 0x3f, face_empty = 0x3f; // per boundary side: all voxels of that layer seen by this thread are O / E
+
+	for (int y = 0; y < 32; ++y) {
+		const uint2 r = *reinterpret_cast<const uint2 *>(raw + x4 + (y * 32 + z) * 32);
+		const u32 d[4] = {r.x & 0xffffu, r.x >> 16, r.y & 0xffffu, r.y >> 16};
+		uint8_t pr[4];
+#pragma unroll
+		for (int i = 0; i < 4; ++i) {
+			pr[i] = __ldg(prop_index + d[i]);
+			const u32 fl = s_pflags[pr[i]];
+			const u32 lvl = s_pmisc[pr[i]] >> 4;
+			pass[i] |= (fl & PF_INDIRECT ? 1u : 0u) << y;
+			if (lvl) {
+				f_or |= 0x100u;
+#pragma unroll
+				for (int l = 0; l < kMaxLightLevels; ++l)
+					if (l < w.n_levels && w.levels[l] == lvl)
+						torch[l][i] |= 1u << y;
+			}
+			f_and &= fl;
+			f_or |= fl;
+			// boundary layers: side 0 +x (x=31), 1 -x (x=0), 2 +y, 3 -y, 4 +z, 5 -z
+			const int x = x4 + i;
+			u32 on = (x == 31 ? 1u : 0u) | (x == 0 ? 2u : 0u) | (y == 31 ? 4u : 0u) | (y == 0 ? 8u : 0u) | (z == 31 ? 16u : 0u) | (z == 0 ? 32u : 0u);
+			if (!(fl & PF_SOLID))
+				face_solid &= ~on;
+			if (!(fl & PF_EMPTY))
+				face_empty &= ~on;
+		}
+		uchar4 o = make_uchar4(pr[0], pr[1], pr[2], pr[3]);
+		*reinterpret_cast<uchar4 *>(w.prop8 + (((size_t)e.cy * 32 + y) * w.Z + gz) * w.X + gx) = o;
+	}
+	const size_t col = ((size_t)e.cy * w.Z + gz) * w.X + gx;
+	*reinterpret_cast<uint4 *>(w.pass + col) = make_uint4(pass[0], pass[1], pass[2], pass[3]);
+	const size_t plane = (size_t)w.wy * w.Z * w.X;
+	for (int l = 0; l < w.n_levels; ++l)
+		*reinterpret_cast<uint4 *>(w.torch + l * plane + col) = make_uint4(torch[l][0], torch[l][1], torch[l][2], torch[l][3]);
+	*reinterpret_cast<char4 *>(w.height + col) = *reinterpret_cast<const char4 *>(raw_heights + (size_t)e.slot * HCM_CHUNK_COLUMNS + z * 32 + x4);
+
+	// block-wide AND / OR of the per-thread summaries
+	u32 a = (f_and & 0xffu) | (face_solid << 8) | (face_empty << 16);
+	u32 o = f_or;
+	a = __reduce_and_sync(FULL, a);
+	o = __reduce_or_sync(FULL, o);
+	if ((tid & 31) == 0) {
+		atomicAnd(&s_and, a);
+		atomicOr(&s_or, o);
+	}
+	__syncthreads();
+	if (tid == 0) {
+		const u32 A = s_and, O = s_or;
+		u32 cf = CF_RESIDENT;
+		if (A & PF_EMPTY)
+			cf |= CF_ALL_EMPTY;
+		if (A & PF_SOLID)
+			cf |= CF_ALL_SOLID;
+		if (O & PF_CUSTOM)
+			cf |= CF_HAS_CUSTOM;
+		if (O & PF_DYNAMIC)
+			cf |= CF_HAS_DYNAMIC;
+		if (O & 0x100u)
+			cf |= CF_HAS_TORCH;
+		cf |= ((A >> 8) & 0x3f) * CF_FACE_SOLID0;
+		cf |= ((A >> 16) & 0x3f) * CF_FACE_EMPTY0;
+		const size_t ci = ((size_t)e.cy * w.wz + e.cz) * w.wx + e.cx;
+		w.cflags[ci] = cf;
+		w.slot[ci] = e.slot;
+	}
+}
+
+// Reset the dense grids of removed chunks to "air, nothing resident".
+__global__ void __launch_bounds__(256) clear_kernel(DevWorld w, const UploadEntry *__restrict__ entries) {
+	const UploadEntry e = entries[blockIdx.x];
+	const int tid = threadIdx.x, z = tid >> 3, x4 = (tid & 7) << 2;
+	const size_t gx = (size_t)e.cx * 32 + x4, gz = (size_t)e.cz * 32 + z;
+	for (int y = 0; y < 32; ++y)
+		*reinterpret_cast<u32 *>(w.prop8 + (((size_t)e.cy * 32 + y) * w.Z + gz) * w.X + gx) = 0;
+	const size_t col = ((size_t)e.cy * w.Z + gz) * w.X + gx;
+	*reinterpret_cast<uint4 *>(w.pass + col) = make_uint4(0, 0, 0, 0);
+	const size_t plane = (size_t)w.wy * w.Z * w.X;
+	for (int l = 0; l < w.n_levels; ++l)
+		*reinterpret_cast<uint4 *>(w.torch + l * plane + col) = make_uint4(0, 0, 0, 0);
+	*reinterpret_cast<u32 *>(w.height + col) = 0;
+	if (tid == 0) {
+		const size_t ci = ((size_t)e.cy * w.wz + e.cz) * w.wx + e.cx;
+		w.cflags[ci] = 0;
+		w.slot[ci] = -1;
+	}
+}
+
+// ================================================================================================================
+// classify kernel: thread per task
+// ================================================================================================================
+__global__ void __launch_bounds__(256)
+    classify_kernel(DevWorld w, const TaskIn *__restrict__ tasks, u32 n, u32 *__restrict__ worklist, BatchHeads *heads, hcm_task_result *task_out, int force_all) {
+	const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= n)
+		return;
+	const TaskIn ti = tasks[t];
+	auto cf = [&](int dx, int dy, int dz) { return w.cflags[((size_t)(ti.cy + dy) * w.wz + (ti.cz + dz)) * w.wx + (ti.cx + dx)]; };
+	const u32 c = cf(0, 0, 0);
+	bool trivial = false;
+	if ((c & CF_ALL_EMPTY) && !(c & CF_HAS_CUSTOM))
+		trivial = true; // no textured voxel and no custom mesh in the chunk: nothing can be emitted
+	else if (c & CF_ALL_SOLID) {
+		// every face is between two class-O voxels as long as the six touching neighbour layers are class O too
+		trivial = (cf(1, 0, 0) & (CF_FACE_SOLID0 << 1)) && (cf(-1, 0, 0) & (CF_FACE_SOLID0 << 0)) && (cf(0, 1, 0) & (CF_FACE_SOLID0 << 3)) &&
+		          (cf(0, -1, 0) & (CF_FACE_SOLID0 << 2)) && (cf(0, 0, 1) & (CF_FACE_SOLID0 << 5)) && (cf(0, 0, -1) & (CF_FACE_SOLID0 << 4));
+	}
+	if (trivial && !force_all) {
+		task_out[t] = hcm_task_result{0u, 0u};
+	} else {
+		const u32 i = atomicAdd(&heads->n_work, 1u);
+		worklist[i] = t;
+	}
+}
+
+// ================================================================================================================
+// mesh kernel
+// ================================================================================================================
+constexpr int SM_VOX = 0;
+constexpr int SM_LIGHT = SM_VOX + kVoxBytes;          // 58752
+constexpr int SM_F = SM_LIGHT + 39312;                // 98064
+constexpr int SM_CPLANE = SM_F + kMasks * 32 * 4;     // 123408
+constexpr int SM_REGION = SM_CPLANE + kInnerCols * 8; // 132656
+constexpr int kRegionBytes = kGroupCap * 12;          // 73728
+constexpr int SM_SMALL = SM_REGION + kRegionBytes;    // 206384
+
+// region views
+constexpr int RG_O = 0, RG_E = kInnerCols * 8, RG_D = 2 * kInnerCols * 8; // planes phase
+constexpr int kSB = 64;                                                   // flood buffer stride (zero border)
+constexpr int RG_SBUF = 0, RG_CNT = kSB * kSB * 8;                        // 32768, then 4 x 1156 x 8 = 36992
+static_assert(RG_CNT + 4 * kInnerCols * 8 <= kRegionBytes, "flood buffers must fit the phase region");
+static_assert(3 * kInnerCols * 8 <= kRegionBytes, "planes must fit the phase region");
+constexpr int RG_KEYS = 0, RG_GEO = kGroupCap * 8;
+
+struct Small {
+	DevTables tab;
+	u32 fc[kMasks + 2];    // visible faces per mask
+	u32 fcpre[kMasks + 2]; // exclusive prefix
+	u32 nq[kMasks + 2], nqo[kMasks + 2], nqt[kMasks + 2], baseo[kMasks + 2], baset[kMasks + 2];
+	u32 crow_o[1024], crow_t[1024]; // custom faces per (y,z) row and stream -> exclusive prefix
+	u32 aabb[2][kMaxSplits][6];
+	u32 split_other[2][kMaxSplits];
+	u32 wtmp[2][kWarps + 1];
+	u64 bar;
+	u32 work_item, n_custom, any_dyn, any_torch, Co, Ct, run_o, run_t, Qo, Qt, overflow, moff;
+	u64 voff, ioff;
+};
+constexpr int kSmemBytes = SM_SMALL + (int)sizeof(Small);
+static_assert(kSmemBytes <= 232448, "shared memory budget (227 KB per CTA)");
+
+__device__ __forceinline__ bool tex_show(const uint8_t *tf, u32 a, u32 b) { // BlockTexture::Show, BlockTexture.hpp:68-76
+	const u32 fa = tf[a], fb = tf[b];
+	if ((fa & TF_EMPTY) || a == b)
+		return false;
+	if (!(fa & HCM_TEX_TRANSPARENT) && !(fb & HCM_TEX_TRANSPARENT))
+		return false;
+	if ((fa & HCM_TEX_LIQUID) && !(fb & TF_EMPTY))
+		return false;
+	return !(fa & HCM_TEX_TRANSPARENT) || (fb & HCM_TEX_TRANSPARENT) || (fb & HCM_TEX_LIQUID);
+}
+
+__device__ __forceinline__ DynRec dyn_load(const DynRec *dyn, int x, int y, int z) {
+	const u64 raw = __ldcg(reinterpret_cast<const u64 *>(dyn + light_index(x, y, z)));
+	DynRec r;
+	*reinterpret_cast<u64 *>(&r) = raw;
+	return r;
+}
+
+// get_tex of generate_regular_mesh_axis (BlockMeshAlgo.hpp:321-325): dynamic override first, else the property table
+__device__ __forceinline__ u32 tex_code(const Small &S, const uint8_t *vox, const DynRec *dyn, int x, int y, int z, int face) {
+	const u32 pr = vox[vox_index(x, y, z)];
+	if (S.tab.pflags[pr] & PF_DYNAMIC) {
+		const DynRec r = dyn_load(dyn, x, y, z);
+		return ((r.texmask >> face) & 1) ? r.flow_code : 0u;
+	}
+	return S.tab.ptex[pr][face];
+}
+
+struct L4 { // Light4 of BlockMeshAlgo.hpp:18-46; byte v = corner v
+	u32 sun, torch, ao;
+};
+
+// light4_init, BlockMeshAlgo.hpp:48-163.  (x,y,z) is the voxel owning the face; all 9 cells of the layer in front of
+// the face are fetched once and shared by the four corners.
+__device__ __forceinline__ void light4_corner(u32 fP, u32 fQ, u32 fD, bool dF, u32 lF, u32 lP, u32 lQ, u32 lD, u32 &sun, u32 &torch, u32 &ao) {
+	const bool dP = fP & PF_DIRECT, dQ = fQ & PF_DIRECT, dD = fD & PF_DIRECT;
+	ao = ((!dP && !dQ) || (!dD && !dF)) ? 0u : (u32)max(3 - (int)!dP - (int)!dD - (int)!dQ - (int)!dF, 0); // :127-131
+	u32 cnt = 1, ss = lF & 15u, ts = lF >> 4; // :133-136
+	if ((fP | fQ) & PF_INDIRECT) {           // :137-159
+		if (fP & PF_INDIRECT)
+			++cnt, ss += lP & 15u, ts += lP >> 4;
+		if (fD & PF_INDIRECT)
+			++cnt, ss += lD & 15u, ts += lD >> 4;
+		if (fQ & PF_INDIRECT)
+			++cnt, ss += lQ & 15u, ts += lQ >> 4;
+	}
+	ss <<= 2, ts <<= 2; // <= 240; exact floor division by 1..4 ((n*171)>>9 == n/3 for n < 1024, tests/test_host_logic.py)
+	sun = cnt == 1 ? ss : (cnt == 2 ? ss >> 1 : (cnt == 3 ? (ss * 171u) >> 9 : ss >> 2)); // :160-161
+	torch = cnt == 1 ? ts : (cnt == 2 ? ts >> 1 : (cnt == 3 ? (ts * 171u) >> 9 : ts >> 2));
+}
+__device__ __forceinline__ L4 light4_init(const Small &S, const uint8_t *vox, const uint8_t *light, int face, int x, int y, int z) {
+	const int axis = face >> 1, dir = 1 - ((face & 1) << 1);
+	constexpr int VY = kVZ * kVX, LY = kLS * kLS;
+	// front cell (kLookup1v, :74) and the strides of the in-plane axes p < q
+	const int vb = vox_index(x, y, z) + dir * (axis == 0 ? 1 : (axis == 1 ? VY : kVX));
+	const int lb = light_index(x, y, z) + dir * (axis == 0 ? 1 : (axis == 1 ? LY : kLS));
+	const int vp = axis == 0 ? VY : 1, vq = axis == 2 ? VY : kVX;
+	const int lp = axis == 0 ? LY : 1, lq = axis == 2 ? LY : kLS;
+	u32 fl[3][3], li[3][3];
+#pragma unroll
+	for (int dp = 0; dp < 3; ++dp)
+#pragma unroll
+		for (int dq = 0; dq < 3; ++dq) {
+			fl[dp][dq] = S.tab.pflags[vox[vb + (dp - 1) * vp + (dq - 1) * vq]];
+			li[dp][dq] = light[lb + (dp - 1) * lp + (dq - 1) * lq];
+		}
+	const bool dF = fl[1][1] & PF_DIRECT;
+	// the four sign combinations along (p,q); kLookup3v (:75-108) orders them per face as
+	//   faces +x,-y,+z : (-,-) (+,-) (+,+) (-,+)      faces -x,+y,-z : (-,-) (-,+) (+,+) (+,-)
+	u32 s_mm, t_mm, a_mm, s_pm, t_pm, a_pm, s_pp, t_pp, a_pp, s_mp, t_mp, a_mp;
+	light4_corner(fl[0][1], fl[1][0], fl[0][0], dF, li[1][1], li[0][1], li[1][0], li[0][0], s_mm, t_mm, a_mm);
+	light4_corner(fl[2][1], fl[1][0], fl[2][0], dF, li[1][1], li[2][1], li[1][0], li[2][0], s_pm, t_pm, a_pm);
+	light4_corner(fl[2][1], fl[1][2], fl[2][2], dF, li[1][1], li[2][1], li[1][2], li[2][2], s_pp, t_pp, a_pp);
+	light4_corner(fl[0][1], fl[1][2], fl[0][2], dF, li[1][1], li[0][1], li[1][2], li[0][2], s_mp, t_mp, a_mp);
+	const bool alt = (0x26u >> face) & 1; // faces 1, 2, 5
+	const u32 s1 = alt ? s_mp : s_pm, t1 = alt ? t_mp : t_pm, a1 = alt ? a_mp : a_pm;
+	const u32 s3 = alt ? s_pm : s_mp, t3 = alt ? t_pm : t_mp, a3 = alt ? a_pm : a_mp;
+	L4 r;
+	r.sun = s_mm | (s1 << 8) | (s_pp << 16) | (s3 << 24);
+	r.torch = t_mm | (t1 << 8) | (t_pp << 16) | (t3 << 24);
+	r.ao = a_mm | (a1 << 8) | (a_pp << 16) | (a3 << 24);
+	return r;
+}
+
+// key of a regular face: 14 bits per corner (sun 6, torch 6, ao 2) + texture code in the top byte.
+// Two faces merge iff texture and Light4 are equal (BlockMeshAlgo.hpp:364-378) iff their keys are equal.
+__device__ __forceinline__ u64 pack_key(const L4 &l, u32 code) {
+	u64 k = (u64)code << 56;
+#pragma unroll
+	for (int v = 0; v < 4; ++v) {
+		const u64 c = ((l.sun >> (8 * v)) & 63u) | (((l.torch >> (8 * v)) & 63u) << 6) | (((l.ao >> (8 * v)) & 3u) << 12);
+		k |= c << (14 * v);
+	}
+	return k;
+}
+
+__device__ __forceinline__ void aabb_atomic(Small &S, u32 s, u32 k, const u32 mn[3], const u32 mx[3]) {
+#pragma unroll
+	for (int c = 0; c < 3; ++c) {
+		atomicMin(&S.aabb[s][k][c], mn[c]);
+		atomicMax(&S.aabb[s][k][3 + c], mx[c]);
+	}
+}
+
+// indices of one quad (BlockMeshAlgo.hpp:295-301 and :434-460) incl. the stale cur_vertex of a continuation mesh
+__device__ __forceinline__ void store_indices(const MeshParams &p, u64 ioff, u32 qpos, u32 q, bool flip) {
+	const u32 k = q / kQuadsPerMesh, j = q - k * kQuadsPerMesh;
+	const u32 b = (j == 0 && k > 0) ? HCM_MESH_MAX_VERTICES : 4u * j;
+	u32 i0, i1, i2, i3, i4, i5;
+	if (flip)
+		i0 = b, i1 = b + 1, i2 = b + 2, i3 = b, i4 = b + 2, i5 = b + 3;
+	else
+		i0 = b + 1, i1 = b + 2, i2 = b + 3, i3 = b, i4 = b + 1, i5 = b + 3;
+	u32 *dst = reinterpret_cast<u32 *>(p.idx + ioff + 6ull * qpos);
+	dst[0] = (i0 & 0xffffu) | (i1 << 16);
+	dst[1] = (i2 & 0xffffu) | (i3 << 16);
+	dst[2] = (i4 & 0xffffu) | (i5 << 16);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// liquid flow: restatement of flow_mesh_gen<Config,Variant>, block/block/public/Liquid.hpp:171-282
+// ---------------------------------------------------------------------------------------------------------------
+__device__ DynRec flow_record(const MeshParams &p, const Small &S, const uint8_t *vox, const TaskIn &ti, int x, int y, int z) {
+	const u32 pr = vox[vox_index(x, y, z)];
+	const DevMeshInfo mi = p.mesh_info[S.tab.pmesh[pr] - 1];
+	const u32 unit = mi.height_unit;
+	const int8_t nbh = (int8_t)(uint8_t)max(mi.variant * unit, 1u); // get_flow_height(Variant), Liquid.hpp:164-169,185
+	int8_t nh[8];
+	u32 liq = 0; // bit i: neighbour i is this liquid
+	const int dxs[8] = {-1, 0, 1, -1, 1, -1, 0, 1}, dzs[8] = {-1, -1, -1, 0, 0, 1, 1, 1}; // Liquid.hpp:291-301
+#pragma unroll
+	for (int i = 0; i < 8; ++i) {
+		const int nx = x + dxs[i], nz = z + dzs[i];
+		const u32 q = vox[vox_index(nx, y, nz)];
+		const u32 fl = S.tab.pflags[q];
+		int8_t h;
+		if (fl & PF_LIQ_SOURCE) {
+			h = 16, liq |= 1u << i;
+		} else if (fl & PF_LIQ_FLOW) {
+			// raw meta, not the table-clamped variant (Liquid.hpp:181-182): fetch the uploaded Block data
+			const int gx = ti.cx * 32 + nx, gy = ti.cy * 32 + y, gz = ti.cz * 32 + nz;
+			const int32_t slot = p.w.slot[((size_t)(gy >> 5) * p.w.wz + (gz >> 5)) * p.w.wx + (gx >> 5)];
+			const u32 data = p.w.raw[(size_t)slot * HCM_CHUNK_VOXELS + (gx & 31) + (((gy & 31) * 32 + (gz & 31)) * 32)];
+			h = (int8_t)(uint8_t)max((data >> 8) * unit, 1u);
+			liq |= 1u << i;
+		} else
+			h = (S.tab.pmisc[q] & 1) ? -1 : 0;
+		nh[i] = h;
+	}
+	auto vh = [&](int a, int b, int c) -> uint8_t { // get_vh, Liquid.hpp:198-203
+		const uint8_t mx = (uint8_t)max(max((int)nbh, (int)nh[a]), max((int)nh[b], (int)nh[c]));
+		if (mx != 16 && ((nbh == 0) + (nh[a] == 0) + (nh[b] == 0) + (nh[c] == 0)) >= 3)
+			return 0;
+		return mx;
+	};
+	DynRec r;
+	const uint8_t h0 = vh(0, 1, 3), h1 = vh(1, 2, 4), h2 = vh(3, 5, 6), h3 = vh(4, 6, 7);
+	r.h[0] = h0, r.h[1] = h1, r.h[2] = h2, r.h[3] = h3;
+	r.flow_code = mi.flow_code, r.flow_trans = mi.flow_trans;
+	if (h0 == 16 && h1 == 16 && h2 == 16 && h3 == 16) { // Liquid.hpp:210-212
+		r.texmask = 0x3f, r.faces = 0;
+		return r;
+	}
+	const bool lf = h0 == 16 && h2 == 16, le = h0 == 0 && h2 == 0, rf = h1 == 16 && h3 == 16, re = h1 == 0 && h3 == 0;
+	const bool ff = h2 == 16 && h3 == 16, fe = h2 == 0 && h3 == 0, bf = h0 == 16 && h1 == 16, be = h0 == 0 && h1 == 0;
+	u32 faces = 1; // top
+	if (!lf && !le && !((liq >> 3) & 1))
+		faces |= 2;
+	if (!rf && !re && !((liq >> 4) & 1))
+		faces |= 4;
+	if (!bf && !be && !((liq >> 1) & 1))
+		faces |= 8;
+	if (!ff && !fe && !((liq >> 6) & 1))
+		faces |= 16;
+	r.faces = (uint8_t)faces;
+	// textures: right, left, top(none), bottom(flow), front, back -- Liquid.hpp:287-292
+	r.texmask = (uint8_t)((rf ? 1u : 0u) | (lf ? 2u : 0u) | 8u | (ff ? 16u : 0u) | (bf ? 32u : 0u));
+	return r;
+}
+
+// one face of a custom/dynamic mesh as the emitter consumes it
+struct CFace {
+	u32 axis, light_face, render_face, tex16;
+	uint8_t v[4][4];
+};
+__device__ __forceinline__ void flow_face(const DynRec &r, u32 tex16, int which, CFace &f) { // Liquid.hpp:214-286
+	const uint8_t h0 = r.h[0], h1 = r.h[1], h2 = r.h[2], h3 = r.h[3];
+	f.tex16 = tex16;
+	auto set = [&](int i, uint8_t a, uint8_t b, uint8_t c) { f.v[i][0] = a, f.v[i][1] = b, f.v[i][2] = c, f.v[i][3] = 4; };
+	switch (which) {
+	case 0: f.axis = 1, f.light_face = f.render_face = 2; set(0, 0, h0, 0), set(1, 0, h2, 16), set(2, 16, h3, 16), set(3, 16, h1, 0); break;
+	case 1: f.axis = 0, f.light_face = f.render_face = 1; set(0, 0, h0, 0), set(1, 0, 0, 0), set(2, 0, 0, 16), set(3, 0, h2, 16); break;
+	case 2: f.axis = 0, f.light_face = f.render_face = 0; set(0, 16, 0, 0), set(1, 16, h1, 0), set(2, 16, h3, 16), set(3, 16, 0, 16); break;
+	case 3: f.axis = 2, f.light_face = f.render_face = 5; set(0, 0, 0, 0), set(1, 0, h0, 0), set(2, 16, h1, 0), set(3, 16, 0, 0); break;
+	default: f.axis = 2, f.light_face = f.render_face = 4; set(0, 0, h2, 16), set(1, 0, 0, 16), set(2, 16, 0, 16), set(3, 16, h3, 16); break;
+	}
+}
+
+// light4_interpolate, BlockMeshAlgo.hpp:165-196 (u32 arithmetic, ceil division by 16^3)
+__device__ __forceinline__ u32 lerp16(u32 a, u32 b, u32 t) { return a * (u32)((int)16 - (int)t) + b * t; }
+__device__ __forceinline__ u32 tri_interp(u32 lo, u32 hi, u32 du, u32 dv, u32 dw) {
+	auto c = [](u32 w, int i) { return (w >> (8 * i)) & 0xffu; };
+	const u32 s = lerp16(lerp16(lerp16(c(lo, 0), c(lo, 1), du), lerp16(c(lo, 3), c(lo, 2), du), dv),
+	                     lerp16(lerp16(c(hi, 0), c(hi, 1), du), lerp16(c(hi, 3), c(hi, 2), du), dv), dw);
+	return (s >> 12) + ((s & 4095u) ? 1u : 0u);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// bit-parallel flood of one light channel (reference a2-a4: ChunkMeshTask.cpp:48-111 + BlockLightAlgo.hpp:44-73).
+// Level sets G_l = {cells with light >= l}: G_15 = sources(15), G_l = sources(l) | G_{l+1} | (N6(G_{l+1}) & passable).
+// light(c) = #{l in 1..15 : c in G_l}, accumulated bit-sliced in four planes for the inner 34x34 columns.
+// Each thread owns up to 8 of the 62x62 columns as 62-bit words (bit = y+15); x/z neighbours go through `sbuf`.
+// Only columns within L1 distance 14-step of the inner square can still matter at `step` (IsBorderLightInterfere).
+// ---------------------------------------------------------------------------------------------------------------
+struct ColInfo {
+	int c[kColsPerThread];     // sbuf index (with zero border), -1 if unused
+	int inner[kColsPerThread]; // index into the count planes or -1
+	int lim[kColsPerThread];   // last step at which the column is still relevant
+	size_t g[kColsPerThread];  // element index of the lower chunk's word in the dense planes
+};
+
+__device__ __forceinline__ void cnt_add(u64 *cnt, int ii, u64 m) {
+#pragma unroll
+	for (int b = 0; b < 4; ++b) {
+		const u64 c = cnt[b * kInnerCols + ii];
+		cnt[b * kInnerCols + ii] = c ^ m;
+		m &= c;
+	}
+}
+__device__ __forceinline__ void cnt_add_from(u64 *cnt, int ii, u64 m, int b0) {
+	for (int b = b0; b < 4; ++b) {
+		const u64 c = cnt[b * kInnerCols + ii];
+		cnt[b * kInnerCols + ii] = c ^ m;
+		m &= c;
+	}
+}
+
+__device__ __forceinline__ u64 combine3(u32 lo, u32 mid, u32 hi) { // chunk words y-1, y, y+1 -> bits of y in [-15,46]
+	return (u64)(lo >> 17) | ((u64)mid << 15) | ((u64)(hi & 0x7fffu) << 47);
+}
+
+template <bool kTorch>
+__device__ __forceinline__ void flood_channel(const MeshParams &p, const ColInfo &ci, const u64 (&P)[kColsPerThread], u64 *sbuf, u64 *cnt, int tid) {
+	const size_t plane_stride = (size_t)p.w.Z * p.w.X; // one chunk layer of columns
+	u64 G[kColsPerThread];
+#pragma unroll
+	for (int k = 0; k < kColsPerThread; ++k)
+		G[k] = 0;
+	for (int i = tid; i < 4 * kInnerCols; i += kThreads)
+		cnt[i] = 0;
+	__syncthreads();
+	const int last_inject_step = kTorch ? 15 - (int)p.w.levels[p.w.n_levels - 1] : 0;
+	bool any_set = false; // block-uniform: some G bit is set anywhere
+	for (int step = 0; step <= 14; ++step) {
+		bool changed = false;
+		if (step > 0 && any_set) {
+#pragma unroll
+			for (int k = 0; k < kColsPerThread; ++k)
+				if (ci.c[k] >= 0)
+					sbuf[ci.c[k]] = G[k];
+			__syncthreads();
+#pragma unroll
+			for (int k = 0; k < kColsPerThread; ++k)
+				if (ci.c[k] >= 0 && step <= ci.lim[k]) {
+					const int c = ci.c[k];
+					const u64 g = G[k];
+					const u64 n = sbuf[c - 1] | sbuf[c + 1] | sbuf[c - kSB] | sbuf[c + kSB];
+					const u64 ng = g | (((g << 1) | (g >> 1) | n) & P[k]);
+					changed |= ng != g;
+					G[k] = ng;
+				}
+		}
+		// sources of level 15 - step
+		if (!kTorch) {
+			if (step == 0) {
+#pragma unroll
+				for (int k = 0; k < kColsPerThread; ++k)
+					if (ci.c[k] >= 0) {
+						u32 s[3];
+#pragma unroll
+						for (int d = 0; d < 3; ++d) {
+							const int h = p.w.height[ci.g[k] + d * plane_stride];
+							s[d] = h >= 32 ? 0u : (h <= 0 ? 0xffffffffu : (0xffffffffu << h)); // sunlit: y >= height, Chunk.hpp:73-76
+						}
+						G[k] = combine3(s[0], s[1], s[2]);
+						changed |= G[k] != 0;
+					}
+			}
+		} else {
+			const u32 lvl = 15 - step;
+			for (int l = 0; l < p.w.n_levels; ++l)
+				if (p.w.levels[l] == lvl) {
+					const u32 *src = p.w.torch + (size_t)l * p.w.wy * plane_stride;
+#pragma unroll
+					for (int k = 0; k < kColsPerThread; ++k)
+						if (ci.c[k] >= 0) {
+							const u64 s = combine3(src[ci.g[k]], src[ci.g[k] + plane_stride], src[ci.g[k] + 2 * plane_stride]);
+							changed |= (s & ~G[k]) != 0;
+							G[k] |= s;
+						}
+				}
+		}
+#pragma unroll
+		for (int k = 0; k < kColsPerThread; ++k)
+			if (ci.inner[k] >= 0)
+				cnt_add(cnt, ci.inner[k], G[k]);
+		const bool any_changed = __syncthreads_or(changed);
+		any_set |= any_changed;
+		if (!any_changed && step >= last_inject_step) {
+			// fixed point: the remaining 14 - step level sets are identical -> add them at once
+			const int rem = 14 - step;
+#pragma unroll
+			for (int k = 0; k < kColsPerThread; ++k)
+				if (ci.inner[k] >= 0)
+					for (int b = 0; b < 4; ++b)
+						if ((rem >> b) & 1)
+							cnt_add_from(cnt, ci.inner[k], G[k], b);
+			break;
+		}
+	}
+	__syncthreads();
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// greedy merge of one mask by one warp, in the reference's scan order (BlockMeshAlgo.hpp:345-477).
+// Lane = v (column).  Rows are visited in order; unconsumed equal-key neighbours form runs (width), a run grows
+// downwards while every cell below matches (height), consumed cells are cleared from the row bit masks.
+// Quad records replace the (already consumed) key slots of the mask, in emission order.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ void merge_mask(Small &S, const u32 *F, u64 *keys, u32 *geo, int m, int g0, int lane) {
+	const u32 lt = lanemask_lt();
+	const u32 Forig = F[m * 32 + lane]; // lane = row here
+	const u32 pre = warp_excl_scan(__popc(Forig), lane);
+	const u32 base = S.fcpre[m] - S.fcpre[g0];
+	u32 Arow = Forig;
+	u32 nq = 0, nqt = 0;
+	for (int u = 0; u < 32; ++u) {
+		const u32 rowbits = __shfl_sync(FULL, Arow, u);
+		if (!rowbits)
+			continue;
+		const u32 Fr = __shfl_sync(FULL, Forig, u), pr = __shfl_sync(FULL, pre, u);
+		const bool active = (rowbits >> lane) & 1;
+		const u64 key = active ? keys[base + pr + __popc(Fr & lt)] : 0ull;
+		const u64 keyL = __shfl_up_sync(FULL, key, 1);
+		const bool activeL = lane > 0 && ((rowbits >> (lane - 1)) & 1);
+		const bool start = active && !(activeL && keyL == key);
+		const u32 startmask = __ballot_sync(FULL, start);
+		u32 runmask = 0, width = 0;
+		if (active) {
+			const int s = 31 - __clz(startmask & (lt | (1u << lane)));
+			const u32 above_s = ~((2u << s) - 1u);
+			const u32 stop = (startmask | ~rowbits) & above_s;
+			const int e = stop ? (__ffs(stop) - 1) : 32;
+			runmask = (e == 32 ? 0u : (1u << e)) - (1u << s);
+			width = e - s;
+		}
+		u32 height = 1;
+		bool alive = active;
+		for (int hh = 1; u + hh < 32; ++hh) {
+			const u32 rb = __shfl_sync(FULL, Arow, u + hh);
+			const u32 Fr2 = __shfl_sync(FULL, Forig, u + hh), pr2 = __shfl_sync(FULL, pre, u + hh);
+			bool match = false;
+			if (alive && ((rb >> lane) & 1))
+				match = keys[base + pr2 + __popc(Fr2 & lt)] == key;
+			const u32 mb = __ballot_sync(FULL, match);
+			const bool cont = alive && ((mb & runmask) == runmask);
+			const u32 contmask = __ballot_sync(FULL, cont);
+			if (!contmask)
+				break;
+			if (lane == u + hh)
+				Arow &= ~contmask;
+			alive = cont;
+			if (cont)
+				height = hh + 1;
+		}
+		__syncwarp();
+		const bool tr = start && (S.tab.texflags[key >> 56] & HCM_TEX_TRANS_PASS); // UseTransparentPass, BlockMeshAlgo.hpp:394
+		if (start) {
+			const u32 slot = base + nq + __popc(startmask & lt);
+			keys[slot] = key;
+			geo[slot] = (u32)u | ((u32)lane << 5) | ((width - 1) << 10) | ((height - 1) << 15) | ((tr ? 1u : 0u) << 20);
+		}
+		nq += __popc(startmask);
+		nqt += __popc(__ballot_sync(FULL, tr));
+		__syncwarp();
+	}
+	if (lane == 0)
+		S.nq[m] = nq, S.nqt[m] = nqt, S.nqo[m] = nq - nqt;
+}
+
+// emission of the quads of one mask by one warp (lane per quad)
+__device__ void emit_mask(const MeshParams &p, Small &S, const u64 *keys, const u32 *geo, int m, int g0, int lane) {
+	const u32 lt = lanemask_lt();
+	const u32 nqm = S.nq[m];
+	if (!nqm)
+		return;
+	const u32 base = S.fcpre[m] - S.fcpre[g0];
+	const u32 bo = S.baseo[m], bt = S.baset[m];
+	const int axis = m / 66, rem = m - axis * 66, xa = rem >> 1, dir = rem & 1;
+	const int ua = axis == 1 ? 2 : 1, va = axis == 0 ? 2 : 0; // BlockAlgo.hpp:70-81 with swizzle YZX
+	const bool uv_order = dir ^ (axis != 2 ? 1 : 0);          // BlockMeshAlgo.hpp:382: quad_face_inv ^ ((U+1)%3 == V)
+	u32 co = 0, ct = 0;
+	for (u32 i0 = 0; i0 < nqm; i0 += 32) {
+		const u32 i = i0 + lane;
+		const bool valid = i < nqm;
+		const u64 key = valid ? keys[base + i] : 0ull;
+		const u32 g = valid ? geo[base + i] : 0u;
+		const bool tr = (g >> 20) & 1;
+		const u32 tm = __ballot_sync(FULL, valid && tr), om = __ballot_sync(FULL, valid && !tr);
+		const u32 qo_before = bo + co + __popc(om & lt), qt_before = bt + ct + __popc(tm & lt);
+		co += __popc(om), ct += __popc(tm);
+		const u32 s = tr ? 1u : 0u;
+		const u32 q = tr ? qt_before : qo_before;
+		const u32 k = q / kQuadsPerMesh;
+		u32 mn[3] = {0xffffffffu, 0xffffffffu, 0xffffffffu}, mx[3] = {0, 0, 0};
+		if (valid) {
+			const u32 u = g & 31u, v = (g >> 5) & 31u, width = ((g >> 10) & 31u) + 1, height = ((g >> 15) & 31u) + 1;
+			// origin = ToXYZ<Axis>(xa,u,v); the two edge vectors (BlockMeshAlgo.hpp:380-390)
+			const u32 P0[3] = {axis == 0 ? (u32)xa : v, axis == 1 ? (u32)xa : u, axis == 2 ? (u32)xa : (axis == 0 ? v : u)};
+			const int a1 = uv_order ? ua : va, a2 = uv_order ? va : ua;
+			const u32 l1 = uv_order ? height : width, l2 = uv_order ? width : height;
+			const u32 uvec[3] = {a1 == 0 ? l1 : 0u, a1 == 1 ? l1 : 0u, a1 == 2 ? l1 : 0u};
+			const u32 vvec[3] = {a2 == 0 ? l2 : 0u, a2 == 1 ? l2 : 0u, a2 == 2 ? l2 : 0u};
+			const u32 code = (u32)(key >> 56);
+			const u32 t16 = S.tab.tex16[code];
+			const u32 face = (u32)(axis << 1) | (u32)dir;
+			const u32 w1base = ((t16 & 0x1fffu) - 1u) | ((t16 >> 13) << 10) | (face << 13); // BlockVertex.hpp:16-17
+			u32 sun[4], ao[4];
+			uint2 vert[4];
+#pragma unroll
+			for (int c = 0; c < 4; ++c) {
+				const u32 f = (u32)(key >> (14 * c)) & 0x3fffu;
+				sun[c] = f & 63u, ao[c] = f >> 12;
+				const u32 torch = (f >> 6) & 63u;
+				u32 X = P0[0], Y = P0[1], Z = P0[2];
+				if (c == 1 || c == 2)
+					X += uvec[0], Y += uvec[1], Z += uvec[2];
+				if (c == 2 || c == 3)
+					X += vvec[0], Y += vvec[1], Z += vvec[2];
+				vert[c].x = (X << 4) | (Y << 14) | (Z << 24) | ((u32)axis << 30);
+				vert[c].y = w1base | (ao[c] << 16) | (sun[c] << 18) | (torch << 24);
+			}
+			uint4 *dst = reinterpret_cast<uint4 *>(p.vtx + S.voff + (s ? 4ull * S.Qo : 0ull) + 4ull * q);
+			dst[0] = make_uint4(vert[0].x, vert[0].y, vert[1].x, vert[1].y);
+			dst[1] = make_uint4(vert[2].x, vert[2].y, vert[3].x, vert[3].y);
+			// Light4::GetFlip, BlockMeshAlgo.hpp:38-43
+			const int d02 = abs((int)((ao[0] + 1) * (sun[0] + 1)) - (int)((ao[2] + 1) * (sun[2] + 1)));
+			const int d13 = abs((int)((ao[1] + 1) * (sun[1] + 1)) - (int)((ao[3] + 1) * (sun[3] + 1)));
+			store_indices(p, S.ioff, (s ? S.Qo : 0u) + q, q, d02 < d13);
+#pragma unroll
+			for (int c = 0; c < 3; ++c)
+				mn[c] = P0[c] << 4, mx[c] = (P0[c] + uvec[c] + vvec[c]) << 4; // BlockMeshAlgo.hpp:404-409
+			if (q == k * kQuadsPerMesh && k > 0)
+				S.split_other[s][k - 1] = s ? qo_before : qt_before; // who was ahead when this stream's mesh was cut
+		}
+		// AABB: reduce within lanes that target the same (stream, mesh) before touching shared memory
+		const u32 grp = __match_any_sync(FULL, valid ? (s * 64u + k) : 0xffffffffu);
+		u32 rmn[3], rmx[3];
+#pragma unroll
+		for (int c = 0; c < 3; ++c)
+			rmn[c] = __reduce_min_sync(grp, mn[c]), rmx[c] = __reduce_max_sync(grp, mx[c]);
+		if (valid && lane == __ffs(grp) - 1)
+			aabb_atomic(S, s, k, rmn, rmx);
+	}
+}
+
+// custom + dynamic faces of one in-chunk voxel (generate_custom_mesh, BlockMeshAlgo.hpp:238-303)
+__device__ void emit_custom_voxel(const MeshParams &p, Small &S, const uint8_t *vox, const uint8_t *light, const DynRec *dyn, int x, int y, int z, u32 qo,
+                                  u32 qt) {
+	const u32 pr = vox[vox_index(x, y, z)];
+	const u32 mesh = S.tab.pmesh[pr] - 1u;
+	const hcm_custom_mesh *cm = p.meshes + mesh;
+	const DevMeshInfo mi = p.mesh_info[mesh];
+	DynRec rec{};
+	u32 nfaces = cm->face_count, dynfaces = 0;
+	if (mi.dynamic_kind == HCM_DYNAMIC_LIQUID_FLOW) {
+		rec = dyn_load(dyn, x, y, z);
+		dynfaces = rec.faces;
+		nfaces = __popc(dynfaces);
+	}
+	const u32 base[3] = {(u32)x << 4, (u32)y << 4, (u32)z << 4};
+	int cur_lf = -1;
+	u32 w_ax = 0, u_ax = 0, v_ax = 0;
+	L4 lo{}, hi{};
+	for (u32 i = 0; i < nfaces; ++i) {
+		CFace f;
+		bool tr;
+		if (mi.dynamic_kind == HCM_DYNAMIC_LIQUID_FLOW) {
+			const int which = __ffs(dynfaces) - 1;
+			dynfaces &= dynfaces - 1;
+			flow_face(rec, S.tab.tex16[rec.flow_code], which, f);
+			tr = rec.flow_trans;
+		} else {
+			const hcm_mesh_face *mf = cm->faces + i;
+			f.axis = mf->axis, f.light_face = mf->light_face, f.render_face = mf->render_face, f.tex16 = mf->texture;
+			const uint2 va_ = *reinterpret_cast<const uint2 *>(&mf->verts[0][0]), vb_ = *reinterpret_cast<const uint2 *>(&mf->verts[2][0]);
+			const u32 vw[4] = {va_.x, va_.y, vb_.x, vb_.y};
+#pragma unroll
+			for (int c = 0; c < 4; ++c)
+				f.v[c][0] = vw[c] & 0xff, f.v[c][1] = (vw[c] >> 8) & 0xff, f.v[c][2] = (vw[c] >> 16) & 0xff, f.v[c][3] = vw[c] >> 24;
+			tr = (mi.trans_mask >> i) & 1;
+		}
+		if ((int)f.light_face != cur_lf) { // BlockMeshAlgo.hpp:247-268
+			cur_lf = (int)f.light_face;
+			w_ax = cur_lf >> 1, u_ax = (w_ax + 1) % 3, v_ax = (w_ax + 2) % 3;
+			if (cur_lf & 1) {
+				const u32 t = u_ax;
+				u_ax = v_ax, v_ax = t;
+			}
+			const int step = 1 - ((cur_lf & 1) << 1);
+			const int sx = w_ax == 0 ? step : 0, sy = w_ax == 1 ? step : 0, sz = w_ax == 2 ? step : 0;
+			lo = light4_init(S, vox, light, cur_lf, x - sx, y - sy, z - sz);
+			if (S.tab.pflags[vox[vox_index(x + sx, y + sy, z + sz)]] & PF_INDIRECT)
+				hi = light4_init(S, vox, light, cur_lf, x, y, z);
+			else
+				hi = lo;
+		}
+		const u32 s = tr ? 1u : 0u;
+		const u32 q = tr ? qt : qo;
+		const u32 k = q / kQuadsPerMesh;
+		if (q == k * kQuadsPerMesh && k > 0)
+			S.split_other[s][k - 1] = tr ? qo : qt;
+		u32 mn[3] = {0xffffffffu, 0xffffffffu, 0xffffffffu}, mx[3] = {0, 0, 0};
+		uint2 vert[4];
+#pragma unroll
+		for (int c = 0; c < 4; ++c) {
+			const u32 px = base[0] + f.v[c][0], py = base[1] + f.v[c][1], pz = base[2] + f.v[c][2];
+			mn[0] = min(mn[0], px), mn[1] = min(mn[1], py), mn[2] = min(mn[2], pz);
+			mx[0] = max(mx[0], px), mx[1] = max(mx[1], py), mx[2] = max(mx[2], pz);
+			auto comp = [&](u32 a) -> u32 { return a == 0 ? f.v[c][0] : (a == 1 ? f.v[c][1] : f.v[c][2]); };
+			const u32 du = comp(u_ax), dv = comp(v_ax);
+			u32 dw = min(comp(w_ax), 16u);
+			if (cur_lf & 1)
+				dw = (u32)(uint8_t)(16 - (int)dw);
+			u32 ao = f.v[c][3];
+			if (ao == 4)
+				ao = (uint8_t)tri_interp(lo.ao, hi.ao, du, dv, dw);
+			const u32 sun = (uint8_t)tri_interp(lo.sun, hi.sun, du, dv, dw);
+			const u32 torch = (uint8_t)tri_interp(lo.torch, hi.torch, du, dv, dw);
+			vert[c].x = px | (py << 10) | (pz << 20) | (f.axis << 30);
+			vert[c].y = ((f.tex16 & 0x1fffu) - 1u) | ((f.tex16 >> 13) << 10) | (f.render_face << 13) | (ao << 16) | (sun << 18) | (torch << 24);
+		}
+		uint4 *dst = reinterpret_cast<uint4 *>(p.vtx + S.voff + (s ? 4ull * S.Qo : 0ull) + 4ull * q);
+		dst[0] = make_uint4(vert[0].x, vert[0].y, vert[1].x, vert[1].y);
+		dst[1] = make_uint4(vert[2].x, vert[2].y, vert[3].x, vert[3].y);
+		store_indices(p, S.ioff, (s ? S.Qo : 0u) + q, q, true);
+		aabb_atomic(S, s, k, mn, mx);
+		if (tr)
+			++qt;
+		else
+			++qo;
+	}
+}
+
+__global__ void __launch_bounds__(kThreads, 1) mesh_kernel(const __grid_constant__ CUtensorMap tmap, const MeshParams p) {
+	extern __shared__ __align__(128) uint8_t smem[];
+	uint8_t *vox = smem + SM_VOX;
+	uint8_t *light = smem + SM_LIGHT;
+	u32 *F = reinterpret_cast<u32 *>(smem + SM_F);
+	u64 *Cpl = reinterpret_cast<u64 *>(smem + SM_CPLANE);
+	uint8_t *region = smem + SM_REGION;
+	Small &S = *reinterpret_cast<Small *>(smem + SM_SMALL);
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const u32 lt = lanemask_lt();
+
+	for (int i = tid; i < (int)(sizeof(DevTables) / 4); i += kThreads)
+		reinterpret_cast<u32 *>(&S.tab)[i] = reinterpret_cast<const u32 *>(p.tables)[i];
+	if (tid == 0)
+		mbar_init(&S.bar, 1);
+	__syncthreads();
+	u32 phase = 0;
+	DynRec *dyn = p.dyn_scratch + (size_t)blockIdx.x * kLightBytes;
+	const u32 n_work = p.heads->n_work;
+
+	for (;;) {
+		__syncthreads(); // previous task fully retired (smem reuse, S.work_item)
+		if (tid == 0)
+			S.work_item = atomicAdd(&p.heads->cursor, 1u);
+		__syncthreads();
+		const u32 wi = S.work_item;
+		if (wi >= n_work)
+			break;
+		const u32 task = p.worklist[wi];
+		const TaskIn ti = p.tasks[task];
+
+		// ---- phase 0: halo gather -- one TMA box of the dense property grid ---------------------------------------
+		if (tid == 0) {
+			mbar_expect_tx(&S.bar, kVoxBytes);
+			tma_load_3d(vox, &tmap, ti.cx * 32 - 2, ti.cz * 32 - 2, ti.cy * 32 - 1, &S.bar);
+		}
+		for (int i = tid; i < kMasks * 32; i += kThreads)
+			F[i] = 0;
+		for (int i = tid; i < 2 * kMaxSplits * 6; i += kThreads)
+			(&S.aabb[0][0][0])[i] = (i % 6) < 3 ? 0xffffffffu : 0u; // dep/AABB.hpp:11
+		if (tid == 0) {
+			S.n_custom = 0, S.any_dyn = 0, S.overflow = 0;
+			u32 cfo = 0; // torch sources anywhere in the 27 chunks?
+			for (int dy = -1; dy <= 1; ++dy)
+				for (int dz = -1; dz <= 1; ++dz)
+					for (int dx = -1; dx <= 1; ++dx)
+						cfo |= p.w.cflags[((size_t)(ti.cy + dy) * p.w.wz + (ti.cz + dz)) * p.w.wx + (ti.cx + dx)];
+			S.any_torch = (cfo & CF_HAS_TORCH) ? 1u : 0u;
+		}
+		mbar_wait(&S.bar, phase);
+		phase ^= 1;
+
+		// ---- phase 1: class bit planes (bit x+1 of row (y,z)) -------------------------------------------------------
+		{
+			u64 *Opl = reinterpret_cast<u64 *>(region + RG_O), *Epl = reinterpret_cast<u64 *>(region + RG_E), *Dpl = reinterpret_cast<u64 *>(region + RG_D);
+			u32 ncust = 0, anyd = 0;
+			for (int row = warp; row < kInnerCols; row += kWarps) {
+				const int y = row / kInner - 1, z = row % kInner - 1;
+				const uint8_t *r = vox + vox_index(0, y, z);
+				const u32 fl = S.tab.pflags[r[lane]];
+				const u32 fx = lane < 2 ? S.tab.pflags[r[lane == 0 ? -1 : 32]] : 0u;
+				auto plane = [&](u32 bit) -> u64 {
+					const u32 b = __ballot_sync(FULL, fl & bit), e = __ballot_sync(FULL, fx & bit);
+					return ((u64)b << 1) | (u64)(e & 1u) | ((u64)((e >> 1) & 1u) << 33);
+				};
+				const u64 o = plane(PF_SOLID), e = plane(PF_EMPTY), c = plane(PF_CUSTOM), d = plane(PF_DYNAMIC);
+				if (lane == 0) {
+					Opl[row] = o, Epl[row] = e, Cpl[row] = c, Dpl[row] = d;
+					if (y >= 0 && y < 32 && z >= 0 && z < 32)
+						ncust += __popc((u32)(c >> 1));
+					anyd |= d != 0;
+				}
+			}
+			if (lane == 0 && (ncust | anyd)) {
+				atomicAdd(&S.n_custom, ncust);
+				if (anyd)
+					S.any_dyn = 1;
+			}
+		}
+		__syncthreads();
+
+		// ---- phase 1b: liquid-flow voxels of [-1,32]^3 -> heights + per-voxel face textures --------------------------
+		if (S.any_dyn) {
+			const u64 *Dpl = reinterpret_cast<const u64 *>(region + RG_D);
+			for (int row = tid; row < kInnerCols; row += kThreads) {
+				u64 w = Dpl[row];
+				const int y = row / kInner - 1, z = row % kInner - 1;
+				while (w) {
+					const int x = __ffsll((long long)w) - 2;
+					w &= w - 1;
+					const DynRec r = flow_record(p, S, vox, ti, x, y, z);
+					*reinterpret_cast<u64 *>(dyn + light_index(x, y, z)) = *reinterpret_cast<const u64 *>(&r);
+				}
+			}
+			__syncthreads();
+		}
+
+		// ---- phase 2: face candidates from the planes, exact Show() on the survivors -> F --------------------------
+		{
+			const u64 *Opl = reinterpret_cast<const u64 *>(region + RG_O), *Epl = reinterpret_cast<const u64 *>(region + RG_E);
+			const uint8_t *tf = S.tab.texflags;
+			for (int unit = tid; unit < 1024 + 2 * 1056; unit += kThreads) {
+				if (unit < 1024) { // axis 0: row (y,z); bit xa <-> voxel pair (xa-1, xa)
+					const int y = unit >> 5, z = unit & 31;
+					const u64 o = Opl[(y + 1) * kInner + z + 1], e = Epl[(y + 1) * kInner + z + 1];
+					u64 cand = ~((o & (o >> 1)) | (e & (e >> 1))) & ((1ull << 33) - 1);
+					while (cand) {
+						const int xa = __ffsll((long long)cand) - 1;
+						cand &= cand - 1;
+						const u32 ta = tex_code(S, vox, dyn, xa - 1, y, z, 0), tb = tex_code(S, vox, dyn, xa, y, z, 1);
+						if (xa != 0 && tex_show(tf, ta, tb))
+							atomicOr(&F[mask_id(0, xa, 0) * 32 + y], 1u << z);
+						if (xa != 32 && tex_show(tf, tb, ta))
+							atomicOr(&F[mask_id(0, xa, 1) * 32 + y], 1u << z);
+					}
+				} else {
+					const int axis = unit < 1024 + 1056 ? 1 : 2;
+					const int k = unit - (axis == 1 ? 1024 : 1024 + 1056);
+					const int xa = k >> 5, u = k & 31;
+					// axis 1: slice y = xa, row u = z ; axis 2: slice z = xa, row u = y ; v = x for both
+					const int ya = axis == 1 ? xa - 1 : u, za = axis == 1 ? u : xa - 1;
+					const int yb = axis == 1 ? xa : u, zb = axis == 1 ? u : xa;
+					const int ra = (ya + 1) * kInner + za + 1, rb = (yb + 1) * kInner + zb + 1;
+					u32 cand = (u32)((~((Opl[ra] & Opl[rb]) | (Epl[ra] & Epl[rb]))) >> 1);
+					while (cand) {
+						const int x = __ffs(cand) - 1;
+						cand &= cand - 1;
+						const u32 ta = tex_code(S, vox, dyn, x, ya, za, axis * 2), tb = tex_code(S, vox, dyn, x, yb, zb, axis * 2 + 1);
+						if (xa != 0 && tex_show(tf, ta, tb))
+							atomicOr(&F[mask_id(axis, xa, 0) * 32 + u], 1u << x);
+						if (xa != 32 && tex_show(tf, tb, ta))
+							atomicOr(&F[mask_id(axis, xa, 1) * 32 + u], 1u << x);
+					}
+				}
+			}
+		}
+		__syncthreads();
+
+		// ---- phase 3: faces per mask, prefix; early out ----------------------------------------------------------------
+		for (int m = warp; m < kMasks; m += kWarps) {
+			const u32 c = __reduce_add_sync(FULL, (u32)__popc(F[m * 32 + lane]));
+			if (lane == 0)
+				S.fc[m] = c;
+		}
+		__syncthreads();
+		if (warp == 0) {
+			u32 carry = 0;
+			for (int b = 0; b < kMasks; b += 32) {
+				const u32 v = (b + lane < kMasks) ? S.fc[b + lane] : 0u;
+				const u32 ex = warp_excl_scan(v, lane);
+				if (b + lane < kMasks)
+					S.fcpre[b + lane] = carry + ex;
+				carry += __shfl_sync(FULL, ex + v, 31);
+			}
+			if (lane == 0)
+				S.fcpre[kMasks] = carry;
+		}
+		__syncthreads();
+		const u32 n_faces = S.fcpre[kMasks];
+		const u32 n_custom = S.n_custom;
+		const bool want_light = p.debug_light != nullptr;
+		if (n_faces == 0 && n_custom == 0 && !want_light) {
+			if (tid == 0)
+				p.task_out[task] = hcm_task_result{0u, 0u};
+			continue;
+		}
+
+		// ---- phase 4: light ---------------------------------------------------------------------------------------------
+		{
+			u64 *sbuf = reinterpret_cast<u64 *>(region + RG_SBUF);
+			u64 *cnt = reinterpret_cast<u64 *>(region + RG_CNT);
+			for (int i = tid; i < kSB * kSB; i += kThreads)
+				sbuf[i] = 0; // zero border (and interior)
+			ColInfo ci;
+			u64 P[kColsPerThread];
+			const size_t plane_stride = (size_t)p.w.Z * p.w.X;
+#pragma unroll
+			for (int k = 0; k < kColsPerThread; ++k) {
+				const int c = tid + k * kThreads;
+				if (c < kFCols) {
+					const int x = c % kFD, z = c / kFD; // domain coords: world x = x - 15
+					ci.c[k] = (z + 1) * kSB + (x + 1);
+					const int dx = x < 14 ? 14 - x : (x > 47 ? x - 47 : 0), dz = z < 14 ? 14 - z : (z > 47 ? z - 47 : 0);
+					ci.lim[k] = 14 - dx - dz;
+					ci.inner[k] = (dx == 0 && dz == 0) ? (z - 14) * kInner + (x - 14) : -1;
+					ci.g[k] = ((size_t)(ti.cy - 1) * p.w.Z + (size_t)(ti.cz * 32 - 15 + z)) * p.w.X + (size_t)(ti.cx * 32 - 15 + x);
+					P[k] = combine3(p.w.pass[ci.g[k]], p.w.pass[ci.g[k] + plane_stride], p.w.pass[ci.g[k] + 2 * plane_stride]);
+				} else {
+					ci.c[k] = -1, ci.lim[k] = -1, ci.inner[k] = -1, ci.g[k] = 0, P[k] = 0;
+				}
+			}
+			__syncthreads();
+			flood_channel<false>(p, ci, P, sbuf, cnt, tid);
+			// unpack the sunlight planes: light[x,y,z] = sun (torch nibble filled below)
+			for (int ii = tid; ii < kInnerCols; ii += kThreads) {
+				const u64 c0 = cnt[ii], c1 = cnt[kInnerCols + ii], c2 = cnt[2 * kInnerCols + ii], c3 = cnt[3 * kInnerCols + ii];
+				const int x = ii % kInner - 1, z = ii / kInner - 1;
+				for (int y = -1; y <= 32; ++y) {
+					const int b = y + 15;
+					light[light_index(x, y, z)] = (uint8_t)(((c0 >> b) & 1) | (((c1 >> b) & 1) << 1) | (((c2 >> b) & 1) << 2) | (((c3 >> b) & 1) << 3));
+				}
+			}
+			__syncthreads();
+			if (S.any_torch && p.w.n_levels > 0) {
+				for (int i = tid; i < kSB * kSB; i += kThreads)
+					sbuf[i] = 0;
+				__syncthreads();
+				flood_channel<true>(p, ci, P, sbuf, cnt, tid);
+				for (int ii = tid; ii < kInnerCols; ii += kThreads) {
+					const u64 c0 = cnt[ii], c1 = cnt[kInnerCols + ii], c2 = cnt[2 * kInnerCols + ii], c3 = cnt[3 * kInnerCols + ii];
+					const int x = ii % kInner - 1, z = ii / kInner - 1;
+					for (int y = -1; y <= 32; ++y) {
+						const int b = y + 15;
+						const u32 t = (u32)(((c0 >> b) & 1) | (((c1 >> b) & 1) << 1) | (((c2 >> b) & 1) << 2) | (((c3 >> b) & 1) << 3));
+						light[light_index(x, y, z)] |= (uint8_t)(t << 4);
+					}
+				}
+				__syncthreads();
+			}
+			if (want_light)
+				for (int i = tid; i < kLightBytes; i += kThreads)
+					p.debug_light[(size_t)task * kLightBytes + i] = light[i];
+		}
+
+		// ---- phase 5: custom faces per row and stream (count), exclusive prefix in (y,z) row order -------------------
+		if (n_custom) {
+			u32 co2[2] = {0, 0}, ct2[2] = {0, 0};
+#pragma unroll
+			for (int j = 0; j < 2; ++j) {
+				const int r = 2 * tid + j, y = r >> 5, z = r & 31;
+				u32 w = (u32)(Cpl[(y + 1) * kInner + z + 1] >> 1);
+				while (w) {
+					const int x = __ffs(w) - 1;
+					w &= w - 1;
+					const DevMeshInfo mi = p.mesh_info[S.tab.pmesh[vox[vox_index(x, y, z)]] - 1];
+					if (mi.dynamic_kind == HCM_DYNAMIC_LIQUID_FLOW) {
+						const DynRec rec = dyn_load(dyn, x, y, z);
+						const u32 nf = __popc((u32)rec.faces);
+						if (rec.flow_trans)
+							ct2[j] += nf;
+						else
+							co2[j] += nf;
+					} else
+						co2[j] += mi.n_opaque, ct2[j] += mi.n_trans;
+				}
+			}
+			const u32 so = co2[0] + co2[1], st = ct2[0] + ct2[1];
+			const u32 exo = warp_excl_scan(so, lane), ext = warp_excl_scan(st, lane);
+			if (lane == 31)
+				S.wtmp[0][warp] = exo + so, S.wtmp[1][warp] = ext + st;
+			__syncthreads();
+			if (warp == 0) {
+				const u32 vo = lane < kWarps ? S.wtmp[0][lane] : 0u, vt = lane < kWarps ? S.wtmp[1][lane] : 0u;
+				const u32 eo = warp_excl_scan(vo, lane), et = warp_excl_scan(vt, lane);
+				if (lane < kWarps)
+					S.wtmp[0][lane] = eo, S.wtmp[1][lane] = et;
+				if (lane == kWarps - 1)
+					S.Co = eo + vo, S.Ct = et + vt;
+			}
+			__syncthreads();
+			const u32 bo = S.wtmp[0][warp] + exo, bt = S.wtmp[1][warp] + ext;
+			S.crow_o[2 * tid] = bo, S.crow_o[2 * tid + 1] = bo + co2[0];
+			S.crow_t[2 * tid] = bt, S.crow_t[2 * tid + 1] = bt + ct2[0];
+		} else if (tid == 0)
+			S.Co = 0, S.Ct = 0;
+		__syncthreads();
+
+		// ---- phases 6/7: keys -> merge -> (count) -> allocate -> emit ---------------------------------------------------
+		u64 *keys = reinterpret_cast<u64 *>(region + RG_KEYS);
+		u32 *geo = reinterpret_cast<u32 *>(region + RG_GEO);
+		const bool single = n_faces <= (u32)kGroupCap;
+		const int n_pass = single ? 1 : 2;
+		for (int pass = 0; pass < n_pass; ++pass) {
+			const bool emit = pass == n_pass - 1;
+			if (tid == 0)
+				S.run_o = S.Co, S.run_t = S.Ct;
+			__syncthreads();
+			int g0 = 0;
+			while (g0 < kMasks) {
+				// largest g1 with faces(g0..g1) <= cap, at least one mask
+				int g1;
+				{
+					const u32 lim = S.fcpre[g0] + (u32)kGroupCap;
+					int lo = g0 + 1, hi = kMasks;
+					while (lo < hi) { // upper bound on the monotone prefix
+						const int mid = (lo + hi + 1) >> 1;
+						if (S.fcpre[mid] <= lim)
+							lo = mid;
+						else
+							hi = mid - 1;
+					}
+					g1 = lo;
+				}
+				const u32 nf = S.fcpre[g1] - S.fcpre[g0];
+				if (nf) {
+					// (a) face locations into the key slots, in mask/row/column order
+					for (int m = g0 + warp; m < g1; m += kWarps) {
+						u32 fw = F[m * 32 + lane];
+						u32 at = S.fcpre[m] - S.fcpre[g0] + warp_excl_scan(__popc(fw), lane);
+						while (fw) {
+							const u32 v = __ffs(fw) - 1;
+							fw &= fw - 1;
+							keys[at++] = ((u64)m << 10) | ((u64)lane << 5) | v;
+						}
+					}
+					__syncthreads();
+					// (b) one thread per visible face: texture + Light4 -> key
+					for (u32 f = tid; f < nf; f += kThreads) {
+						const u32 loc = (u32)keys[f];
+						const int m = loc >> 10, u = (loc >> 5) & 31, v = loc & 31;
+						const int axis = m / 66, rem = m - axis * 66, xa = rem >> 1, dir = rem & 1;
+						const int sl = xa - (dir ? 0 : 1); // the voxel owning the face: xa-1 for the + face, xa for the - face
+						const int q[3] = {axis == 0 ? sl : v, axis == 1 ? sl : u, axis == 2 ? sl : (axis == 0 ? v : u)};
+						const int face = axis * 2 + dir;
+						const u32 code = tex_code(S, vox, dyn, q[0], q[1], q[2], face);
+						const L4 l4 = light4_init(S, vox, light, face, q[0], q[1], q[2]);
+						keys[f] = pack_key(l4, code);
+					}
+					__syncthreads();
+					// (c) greedy merge, warp per mask
+					for (int m = g0 + warp; m < g1; m += kWarps) {
+						if (S.fc[m])
+							merge_mask(S, F, keys, geo, m, g0, lane);
+						else if (lane == 0)
+							S.nq[m] = 0, S.nqo[m] = 0, S.nqt[m] = 0;
+					}
+					__syncthreads();
+					// (d) ordered offsets: exclusive scan of the per-mask quad counts of both streams
+					if (warp == 0) {
+						u32 ro = S.run_o, rt = S.run_t;
+						for (int b = g0; b < g1; b += 32) {
+							const int m = b + lane;
+							const u32 vo = m < g1 ? S.nqo[m] : 0u, vt = m < g1 ? S.nqt[m] : 0u;
+							const u32 eo = warp_excl_scan(vo, lane), et = warp_excl_scan(vt, lane);
+							if (m < g1)
+								S.baseo[m] = ro + eo, S.baset[m] = rt + et;
+							ro += __shfl_sync(FULL, eo + vo, 31), rt += __shfl_sync(FULL, et + vt, 31);
+						}
+						if (lane == 0)
+							S.run_o = ro, S.run_t = rt;
+					}
+					__syncthreads();
+				}
+				if (single) {
+					// totals are known after the only group: allocate now
+					if (tid == 0) {
+						S.Qo = S.run_o, S.Qt = S.run_t;
+						const u64 nv = 4ull * (S.Qo + S.Qt), ni = 6ull * (S.Qo + S.Qt);
+						const u32 nm = (S.Qo + kQuadsPerMesh - 1) / kQuadsPerMesh + (S.Qt + kQuadsPerMesh - 1) / kQuadsPerMesh;
+						S.voff = atomicAdd(&p.heads->vtx, nv);
+						S.ioff = atomicAdd(&p.heads->idx, ni);
+						S.moff = atomicAdd(&p.heads->meshes, nm);
+						if (S.voff + nv > p.vtx_cap || S.ioff + ni > p.idx_cap || S.moff + nm > p.mesh_cap)
+							S.overflow = 1, atomicExch(&p.heads->overflow, 1u);
+					}
+					__syncthreads();
+				}
+				if (emit && nf && !S.overflow) {
+					for (int m = g0 + warp; m < g1; m += kWarps)
+						emit_mask(p, S, keys, geo, m, g0, lane);
+				}
+				__syncthreads();
+				g0 = g1;
+			}
+			if (!single && pass == 0) {
+				if (tid == 0) {
+					S.Qo = S.run_o, S.Qt = S.run_t;
+					const u64 nv = 4ull * (S.Qo + S.Qt), ni = 6ull * (S.Qo + S.Qt);
+					const u32 nm = (S.Qo + kQuadsPerMesh - 1) / kQuadsPerMesh + (S.Qt + kQuadsPerMesh - 1) / kQuadsPerMesh;
+					S.voff = atomicAdd(&p.heads->vtx, nv);
+					S.ioff = atomicAdd(&p.heads->idx, ni);
+					S.moff = atomicAdd(&p.heads->meshes, nm);
+					if (S.voff + nv > p.vtx_cap || S.ioff + ni > p.idx_cap || S.moff + nm > p.mesh_cap)
+						S.overflow = 1, atomicExch(&p.heads->overflow, 1u);
+				}
+				__syncthreads();
+			}
+		}
+
+		// ---- custom / dynamic faces: warp per (y,z) row, lane per voxel --------------------------------------------------
+		if (n_custom && !S.overflow) {
+			for (int r = warp; r < 1024; r += kWarps) {
+				const int y = r >> 5, z = r & 31;
+				const u32 w = (u32)(Cpl[(y + 1) * kInner + z + 1] >> 1);
+				if (!w)
+					continue;
+				u32 no = 0, nt = 0;
+				const bool mine = (w >> lane) & 1;
+				if (mine) {
+					const DevMeshInfo mi = p.mesh_info[S.tab.pmesh[vox[vox_index(lane, y, z)]] - 1];
+					if (mi.dynamic_kind == HCM_DYNAMIC_LIQUID_FLOW) {
+						const DynRec rec = dyn_load(dyn, lane, y, z);
+						const u32 nf = __popc((u32)rec.faces);
+						if (rec.flow_trans)
+							nt = nf;
+						else
+							no = nf;
+					} else
+						no = mi.n_opaque, nt = mi.n_trans;
+				}
+				const u32 qo = S.crow_o[r] + warp_excl_scan(no, lane), qt = S.crow_t[r] + warp_excl_scan(nt, lane);
+				if (mine)
+					emit_custom_voxel(p, S, vox, light, dyn, lane, y, z, qo, qt);
+			}
+		}
+		__syncthreads();
+
+		// ---- mesh descriptors in the order BlockMeshAlgo::Generate returns them (BlockMeshAlgo.hpp:397-403, :515-518) ----
+		if (tid == 0) {
+			if (S.overflow) {
+				p.task_out[task] = hcm_task_result{0u, 0u};
+			} else {
+				const u32 Q[2] = {S.Qo, S.Qt};
+				const u32 M[2] = {(Q[0] + kQuadsPerMesh - 1) / kQuadsPerMesh, (Q[1] + kQuadsPerMesh - 1) / kQuadsPerMesh};
+				const u32 full[2] = {M[0] ? M[0] - 1 : 0u, M[1] ? M[1] - 1 : 0u};
+				u32 out = S.moff;
+				auto put = [&](u32 s, u32 k) {
+					hcm_mesh_desc d;
+					const u32 nq = min(Q[s] - k * kQuadsPerMesh, kQuadsPerMesh);
+					d.task = task, d.transparent = s;
+					d.vertex_offset = S.voff + (s ? 4ull * Q[0] : 0ull) + 4ull * kQuadsPerMesh * k;
+					d.index_offset = S.ioff + 6ull * ((s ? Q[0] : 0u) + (u64)kQuadsPerMesh * k);
+					d.vertex_count = 4 * nq, d.index_count = 6 * nq;
+					for (int c = 0; c < 3; ++c)
+						d.aabb_min[c] = S.aabb[s][k][c], d.aabb_max[c] = S.aabb[s][k][3 + c];
+					p.mesh_out[out++] = d;
+				};
+				u32 i = 0, j = 0; // cut meshes, interleaved by the time of the cut
+				while (i < full[0] || j < full[1]) {
+					bool take_opaque;
+					if (i >= full[0])
+						take_opaque = false;
+					else if (j >= full[1])
+						take_opaque = true;
+					else // the opaque quad that triggers cut i is quad number 16383*(i+1); it precedes transparent trigger j iff
+					     // more opaque quads than that were already emitted when trigger j arrived
+						take_opaque = S.split_other[1][j] > kQuadsPerMesh * (i + 1);
+					if (take_opaque)
+						put(0, i++);
+					else
+						put(1, j++);
+				}
+				if (M[0])
+					put(0, M[0] - 1);
+				if (M[1])
+					put(1, M[1] - 1);
+				p.task_out[task] = hcm_task_result{S.moff, M[0] + M[1]};
+			}
+		}
+	}
+}
+
+// ================================================================================================================
+// host-callable launchers (used by hcm_api.cu)
+// ================================================================================================================
+void launch_derive(const DevWorld &w, const UploadEntry *entries, u32 n, const uint8_t *prop_index, const DevTables *tables, const int8_t *raw_heights,
+                   cudaStream_t st) {
+	if (n)
+		derive_kernel<<<n, 256, 0, st>>>(w, entries, prop_index, tables, raw_heights);
+}
+void launch_clear(const DevWorld &w, const UploadEntry *entries, u32 n, cudaStream_t st) {
+	if (n)
+		clear_kernel<<<n, 256, 0, st>>>(w, entries);
+}
+void launch_classify(const DevWorld &w, const TaskIn *tasks, u32 n, u32 *worklist, BatchHeads *heads, hcm_task_result *task_out, int force_all,
+                     cudaStream_t st) {
+	if (n)
+		classify_kernel<<<(n + 255) / 256, 256, 0, st>>>(w, tasks, n, worklist, heads, task_out, force_all);
+}
+cudaError_t mesh_kernel_prepare() { return cudaFuncSetAttribute(mesh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes); }
+int mesh_kernel_smem_bytes() { return kSmemBytes; }
+void launch_mesh(const CUtensorMap &tmap, const MeshParams &p, int grid, cudaStream_t st) { mesh_kernel<<<grid, kThreads, kSmemBytes, st>>>(tmap, p); }
+
+} // namespace hcm

@@ -1,0 +1,268 @@
+"""ctypes binding of csrc/libhcm.so (the C ABI of include/hcm.h).  Plumbing only: every call goes straight to the
+CUDA library; there is no Python or CPU implementation of the mesher behind it, and importing this module fails
+loudly when the extension has not been built."""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import registry as _registry
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(_HERE, "csrc")
+LIB_PATH = os.path.join(CSRC, "libhcm.so")
+
+_vp = ctypes.c_void_p
+
+
+class HcmError(RuntimeError):
+    def __init__(self, status: int, text: str):
+        super().__init__(f"hcm status {status}: {text}")
+        self.status = status
+
+
+class _Registry(ctypes.Structure):
+    _fields_ = [("n_props", ctypes.c_uint32), ("n_meshes", ctypes.c_uint32), ("n_textures", ctypes.c_uint32), ("_pad", ctypes.c_uint32),
+                ("prop_index", _vp), ("props", _vp), ("meshes", _vp), ("tex_flags", _vp)]
+
+
+class _Config(ctypes.Structure):
+    _fields_ = [("device", ctypes.c_int32), ("origin", ctypes.c_int16 * 3), ("extent", ctypes.c_uint16 * 3),
+                ("max_chunks", ctypes.c_uint32), ("max_tasks", ctypes.c_uint32), ("vertex_capacity", ctypes.c_uint64)]
+
+
+class _BatchView(ctypes.Structure):
+    _fields_ = [("n_tasks", ctypes.c_uint32), ("n_meshes", ctypes.c_uint32), ("n_vertices", ctypes.c_uint64), ("n_indices", ctypes.c_uint64),
+                ("tasks", _vp), ("meshes", _vp), ("vertices", _vp), ("indices", _vp)]
+
+
+class _BatchCounts(ctypes.Structure):
+    _fields_ = [("n_tasks", ctypes.c_uint32), ("n_meshes", ctypes.c_uint32), ("n_vertices", ctypes.c_uint64), ("n_indices", ctypes.c_uint64),
+                ("n_worked", ctypes.c_uint32), ("_pad", ctypes.c_uint32)]
+
+
+class _Stats(ctypes.Structure):
+    _fields_ = [("upload_copy_ms", ctypes.c_float), ("derive_ms", ctypes.c_float), ("classify_ms", ctypes.c_float), ("mesh_ms", ctypes.c_float),
+                ("fetch_copy_ms", ctypes.c_float), ("kernel_launches", ctypes.c_uint32), ("h2d_bytes", ctypes.c_uint64),
+                ("d2h_bytes", ctypes.c_uint64), ("device_bytes", ctypes.c_uint64)]
+
+
+MESH_DESC_DTYPE = np.dtype([("task", np.uint32), ("transparent", np.uint32), ("vertex_offset", np.uint64), ("index_offset", np.uint64),
+                            ("vertex_count", np.uint32), ("index_count", np.uint32), ("aabb_min", np.uint32, 3), ("aabb_max", np.uint32, 3)])
+TASK_RESULT_DTYPE = np.dtype([("first_mesh", np.uint32), ("n_meshes", np.uint32)])
+assert MESH_DESC_DTYPE.itemsize == 56
+
+EXPORTS = ["hcm_registry_from_blob", "hcm_create", "hcm_destroy", "hcm_last_error", "hcm_status_string", "hcm_host_alloc", "hcm_host_free",
+           "hcm_upload_chunks", "hcm_remove_chunks", "hcm_is_resident", "hcm_sync", "hcm_mesh_batch", "hcm_mesh_fetch", "hcm_mesh_wait",
+           "hcm_get_stats", "hcm_stream", "hcm_debug_light"]
+
+_lib = None
+
+
+def build_library(force: bool = False) -> str:
+    """Compile csrc/libhcm.so for sm_100a with nvcc (in-tree; cross-compiles without a GPU)."""
+    if force:
+        subprocess.run(["make", "-C", CSRC, "clean"], check=True, stdout=subprocess.DEVNULL)
+    subprocess.run(["make", "-C", CSRC], check=True, stdout=subprocess.DEVNULL)
+    return LIB_PATH
+
+
+def load_library():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` (nvcc, sm_100a). "
+                              "There is no CPU fallback.")
+        L = ctypes.CDLL(LIB_PATH)
+        L.hcm_last_error.restype = ctypes.c_char_p
+        L.hcm_last_error.argtypes = [_vp]
+        L.hcm_status_string.restype = ctypes.c_char_p
+        L.hcm_host_alloc.restype = _vp
+        L.hcm_host_alloc.argtypes = [ctypes.c_size_t]
+        L.hcm_host_free.argtypes = [_vp]
+        L.hcm_stream.restype = _vp
+        L.hcm_stream.argtypes = [_vp]
+        L.hcm_create.argtypes = [ctypes.POINTER(_Registry), ctypes.POINTER(_Config), ctypes.POINTER(_vp)]
+        L.hcm_destroy.argtypes = [_vp]
+        L.hcm_registry_from_blob.argtypes = [_vp, ctypes.c_size_t, ctypes.POINTER(_Registry)]
+        L.hcm_upload_chunks.argtypes = [_vp, ctypes.c_uint32, _vp, _vp, _vp]
+        L.hcm_remove_chunks.argtypes = [_vp, ctypes.c_uint32, _vp]
+        L.hcm_is_resident.argtypes = [_vp, _vp]
+        L.hcm_sync.argtypes = [_vp]
+        L.hcm_mesh_batch.argtypes = [_vp, ctypes.c_uint32, _vp]
+        L.hcm_mesh_fetch.argtypes = [_vp, ctypes.POINTER(_BatchView)]
+        L.hcm_mesh_wait.argtypes = [_vp, ctypes.POINTER(_BatchCounts)]
+        L.hcm_get_stats.argtypes = [_vp, ctypes.POINTER(_Stats)]
+        L.hcm_debug_light.argtypes = [_vp, _vp, _vp]
+        _lib = L
+    return _lib
+
+
+def _ptr(a: np.ndarray):
+    return a.ctypes.data_as(_vp)
+
+
+class PinnedArray:
+    """numpy view over pinned host memory from hcm_host_alloc (truly asynchronous upload source)."""
+
+    def __init__(self, shape, dtype):
+        L = load_library()
+        self.nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        self.ptr = L.hcm_host_alloc(max(self.nbytes, 1))
+        if not self.ptr:
+            raise MemoryError("hcm_host_alloc failed")
+        buf = (ctypes.c_uint8 * max(self.nbytes, 1)).from_address(self.ptr)
+        self.array = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+    def free(self):
+        if self.ptr:
+            self.array = None
+            load_library().hcm_host_free(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+@dataclass
+class BatchResult:
+    """Host views of one fetched batch (valid until the next batch on the same Mesher)."""
+    tasks: np.ndarray  # TASK_RESULT_DTYPE[n_tasks]
+    meshes: np.ndarray  # MESH_DESC_DTYPE[n_meshes]
+    vertices: np.ndarray  # u64[n_vertices]
+    indices: np.ndarray  # u16[n_indices]
+
+    def task_meshes(self, t: int) -> list[dict]:
+        """The std::vector<BlockMesh> of task t, as PushChunkMesh would receive it."""
+        first, n = int(self.tasks[t]["first_mesh"]), int(self.tasks[t]["n_meshes"])
+        out = []
+        for d in self.meshes[first:first + n]:
+            vo, io = int(d["vertex_offset"]), int(d["index_offset"])
+            out.append(dict(transparent=int(d["transparent"]), aabb_min=d["aabb_min"].copy(), aabb_max=d["aabb_max"].copy(),
+                            vertices=self.vertices[vo:vo + int(d["vertex_count"])], indices=self.indices[io:io + int(d["index_count"])]))
+        return out
+
+    def serialise(self, t: int) -> np.ndarray:
+        """Task t in the oracle's serialised mesh-list layout (oracle/ref_shim.cpp) for byte-for-byte comparison."""
+        ms = self.task_meshes(t)
+        parts = [np.array([len(ms)], dtype=np.uint32).view(np.uint8)]
+        for m in ms:
+            hdr = np.concatenate([[m["transparent"]], m["aabb_min"], m["aabb_max"], [len(m["vertices"]), len(m["indices"])]]).astype(np.uint32)
+            parts.append(hdr.view(np.uint8))
+        for m in ms:
+            parts.append(np.ascontiguousarray(m["vertices"]).view(np.uint8))
+            ib = np.ascontiguousarray(m["indices"]).view(np.uint8)
+            parts.append(ib)
+            if ib.size & 3:
+                parts.append(np.zeros(4 - (ib.size & 3), dtype=np.uint8))
+        return np.concatenate(parts)
+
+
+class Mesher:
+    """One hcm_ctx: a device-resident world window on one GPU plus its batch output arenas."""
+
+    def __init__(self, origin, extent, device: int = 0, max_chunks: int = 0, max_tasks: int = 0, vertex_capacity: int = 0,
+                 registry_blob: np.ndarray | None = None):
+        self.L = load_library()
+        self.blob = np.ascontiguousarray(registry_blob if registry_blob is not None else _registry.load().blob, dtype=np.uint8)
+        reg = _Registry()
+        rc = self.L.hcm_registry_from_blob(_ptr(self.blob), self.blob.size, ctypes.byref(reg))
+        if rc:
+            raise HcmError(rc, "bad registry blob")
+        cfg = _Config()
+        cfg.device = device
+        for i in range(3):
+            cfg.origin[i] = int(origin[i])
+            cfg.extent[i] = int(extent[i])
+        cfg.max_chunks, cfg.max_tasks, cfg.vertex_capacity = int(max_chunks), int(max_tasks), int(vertex_capacity)
+        ctx = _vp()
+        rc = self.L.hcm_create(ctypes.byref(reg), ctypes.byref(cfg), ctypes.byref(ctx))
+        if rc:
+            raise HcmError(rc, (self.L.hcm_last_error(None) or b"").decode())
+        self.ctx = ctx
+        self.origin = tuple(int(v) for v in origin)
+        self.extent = tuple(int(v) for v in extent)
+
+    def close(self):
+        if getattr(self, "ctx", None):
+            self.L.hcm_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int):
+        if rc:
+            raise HcmError(rc, (self.L.hcm_last_error(self.ctx) or b"").decode())
+
+    # ---- residency -------------------------------------------------------------------------------------------------
+    def upload(self, positions, blocks, heights) -> None:
+        pos = np.ascontiguousarray(positions, dtype=np.int16).reshape(-1, 3)
+        b = np.ascontiguousarray(blocks, dtype=np.uint16).reshape(len(pos), 32768)
+        h = np.ascontiguousarray(heights, dtype=np.int8).reshape(len(pos), 1024)
+        self._keep = (pos, b, h)  # the C side reads them asynchronously until the next sync
+        self._check(self.L.hcm_upload_chunks(self.ctx, len(pos), _ptr(pos), _ptr(b), _ptr(h)))
+
+    def remove(self, positions) -> None:
+        pos = np.ascontiguousarray(positions, dtype=np.int16).reshape(-1, 3)
+        self._check(self.L.hcm_remove_chunks(self.ctx, len(pos), _ptr(pos)))
+
+    def is_resident(self, pos) -> bool:
+        p = np.ascontiguousarray(pos, dtype=np.int16)
+        return bool(self.L.hcm_is_resident(self.ctx, _ptr(p)))
+
+    def sync(self) -> None:
+        self._check(self.L.hcm_sync(self.ctx))
+
+    # ---- meshing ---------------------------------------------------------------------------------------------------
+    def mesh_async(self, positions) -> None:
+        pos = np.ascontiguousarray(positions, dtype=np.int16).reshape(-1, 3)
+        self._check(self.L.hcm_mesh_batch(self.ctx, len(pos), _ptr(pos)))
+
+    def wait(self) -> dict:
+        c = _BatchCounts()
+        self._check(self.L.hcm_mesh_wait(self.ctx, ctypes.byref(c)))
+        return dict(n_tasks=c.n_tasks, n_meshes=c.n_meshes, n_vertices=c.n_vertices, n_indices=c.n_indices, n_worked=c.n_worked)
+
+    def fetch(self) -> BatchResult:
+        v = _BatchView()
+        self._check(self.L.hcm_mesh_fetch(self.ctx, ctypes.byref(v)))
+
+        def view(ptr, count, dtype):
+            if not count:
+                return np.zeros(0, dtype=dtype)
+            nbytes = count * np.dtype(dtype).itemsize
+            buf = (ctypes.c_uint8 * nbytes).from_address(ptr)
+            return np.frombuffer(buf, dtype=dtype, count=count)
+
+        return BatchResult(view(v.tasks, v.n_tasks, TASK_RESULT_DTYPE), view(v.meshes, v.n_meshes, MESH_DESC_DTYPE),
+                           view(v.vertices, v.n_vertices, np.uint64), view(v.indices, v.n_indices, np.uint16))
+
+    def mesh(self, positions) -> BatchResult:
+        self.mesh_async(positions)
+        return self.fetch()
+
+    # ---- measurement / debugging -----------------------------------------------------------------------------------
+    def stats(self) -> dict:
+        s = _Stats()
+        self._check(self.L.hcm_get_stats(self.ctx, ctypes.byref(s)))
+        return {f[0]: getattr(s, f[0]) for f in _Stats._fields_}
+
+    def stream_ptr(self) -> int:
+        return int(self.L.hcm_stream(self.ctx) or 0)
+
+    def debug_light(self, pos) -> np.ndarray:
+        p = np.ascontiguousarray(pos, dtype=np.int16)
+        out = np.zeros(34 * 34 * 34, dtype=np.uint8)
+        self._check(self.L.hcm_debug_light(self.ctx, _ptr(p), _ptr(out)))
+        return out

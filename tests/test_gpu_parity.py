@@ -1,0 +1,128 @@
+"""GPU parity: the CUDA mesher (through the C ABI) against the CPU oracle, byte for byte.
+
+Bar (BASELINE.json north_star): bit-exact per chunk on mesh count, transparent flags, AABBs, vertex bytes and index
+bytes.  Inputs are seeded synthetic chunks (machine independent) and, where oracle/_ref is present, terrain from the
+reference's own generator meshed by the unmodified reference mesher."""
+import numpy as np
+import pytest
+
+from util import describe_diff, synth_world
+
+pytestmark = pytest.mark.gpu
+
+KINDS = ["air", "stone", "checker", "transparent", "mix", "rawmeta", "caves", "flow"]
+
+
+@pytest.fixture(scope="module")
+def mesher():
+    from hypercraft_b200 import mesher as M
+
+    m = M.Mesher(origin=(-2, -2, -2), extent=(5, 5, 5))
+    yield m
+    m.close()
+
+
+@pytest.mark.parametrize("kind", KINDS)
+@pytest.mark.parametrize("seed", [1, 2])
+def test_light_stage_matches_oracle(mesher, port, kind, seed):
+    pos, blocks, heights, chunks = synth_world(kind, seed)
+    mesher.upload(pos, blocks, heights)
+    got = mesher.debug_light((0, 0, 0))
+    want = port.light34(chunks, (0, 0, 0))
+    bad = np.nonzero(got != want)[0]
+    assert len(bad) == 0, f"{len(bad)} light bytes differ, first at {bad[0]}: {got[bad[0]]:#x} vs {want[bad[0]]:#x}"
+
+
+@pytest.mark.parametrize("kind", KINDS)
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_mesh_matches_oracle(mesher, port, kind, seed):
+    pos, blocks, heights, chunks = synth_world(kind, seed)
+    mesher.upload(pos, blocks, heights)
+    res = mesher.mesh(np.array([[0, 0, 0]], dtype=np.int16))
+    got = res.serialise(0)
+    want = port.mesh(chunks, (0, 0, 0))
+    assert got.size == want.size and (got == want).all(), describe_diff(got, want)
+
+
+def test_mixed_neighbourhood(mesher, port):
+    """Centre of one kind, neighbours of others: halo faces, halo flowing water, halo light sources."""
+    combos = [("stone", {(1, 0, 0): "air", (0, 1, 0): "mix", (0, 0, -1): "flow"}),
+              ("air", {(0, -1, 0): "stone", (1, 0, 0): "mix"}),
+              ("flow", {(1, 0, 0): "mix", (-1, 0, 0): "flow", (0, 0, 1): "stone", (0, 0, -1): "rawmeta"}),
+              ("caves", {(0, 1, 0): "air", (0, -1, 0): "stone", (1, 1, 0): "mix"})]
+    for seed, (kind, by_off) in enumerate(combos):
+        pos, blocks, heights, chunks = synth_world(kind, 10 + seed, kinds_by_offset=by_off)
+        mesher.upload(pos, blocks, heights)
+        res = mesher.mesh(np.array([[0, 0, 0]], dtype=np.int16))
+        got, want = res.serialise(0), port.mesh(chunks, (0, 0, 0))
+        assert got.size == want.size and (got == want).all(), f"{kind} {by_off}\n" + describe_diff(got, want)
+
+
+def test_batch_of_many_tasks_and_reupload(port):
+    """A 3x3x3 block of tasks in one batch inside a 5^3 resident window; then edit one chunk and remesh."""
+    from hypercraft_b200 import mesher as M, worldgen
+
+    m = M.Mesher(origin=(-2, -2, -2), extent=(5, 5, 5))
+    allpos = np.array([[x, y, z] for x in range(-2, 3) for y in range(-2, 3) for z in range(-2, 3)], dtype=np.int16)
+    kinds = ["caves", "mix", "air", "stone", "transparent", "flow"]
+    blocks = np.zeros((len(allpos), 32768), dtype=np.uint16)
+    heights = np.zeros((len(allpos), 1024), dtype=np.int8)
+    chunks = {}
+    for i, p in enumerate(allpos):
+        blocks[i], heights[i] = worldgen.synth_chunk(kinds[(int(p[0]) * 7 + int(p[1]) * 3 + int(p[2])) % len(kinds)], 5, p)
+        chunks[tuple(int(c) for c in p)] = (blocks[i], heights[i])
+    m.upload(allpos, blocks, heights)
+    tasks = np.array([[x, y, z] for x in (-1, 0, 1) for y in (-1, 0, 1) for z in (-1, 0, 1)], dtype=np.int16)
+    res = m.mesh(tasks)
+    for t, p in enumerate(tasks):
+        got, want = res.serialise(t), port.mesh(chunks, p)
+        assert got.size == want.size and (got == want).all(), f"task {p}\n" + describe_diff(got, want)
+    # edit: replace the centre chunk, remesh it and a neighbour
+    nb, nh = worldgen.synth_chunk("checker", 9, (0, 0, 0))
+    chunks[(0, 0, 0)] = (nb, nh)
+    m.upload(np.array([[0, 0, 0]], dtype=np.int16), nb[None], nh[None])
+    tasks2 = np.array([[0, 0, 0], [1, 0, 0], [0, -1, 1]], dtype=np.int16)
+    res = m.mesh(tasks2)
+    for t, p in enumerate(tasks2):
+        got, want = res.serialise(t), port.mesh(chunks, p)
+        assert got.size == want.size and (got == want).all(), f"after edit, task {p}\n" + describe_diff(got, want)
+    m.close()
+
+
+def test_errors(mesher):
+    from hypercraft_b200 import mesher as M
+
+    with pytest.raises(M.HcmError) as e:
+        mesher.mesh(np.array([[2, 0, 0]], dtype=np.int16))  # window border: neighbour cannot be resident
+    assert e.value.status == -4
+    with pytest.raises(M.HcmError) as e:
+        mesher.mesh(np.array([[40, 0, 0]], dtype=np.int16))
+    assert e.value.status == -5
+    m2 = M.Mesher(origin=(0, 0, 0), extent=(3, 3, 3))
+    with pytest.raises(M.HcmError) as e:
+        m2.mesh(np.array([[1, 1, 1]], dtype=np.int16))  # nothing uploaded
+    assert e.value.status == -4
+    m2.close()
+
+
+def test_reference_terrain(have_ref, port):
+    """Reference terrain (seed 12314524) radius 3: every meshed chunk equals the unmodified reference mesher."""
+    if not have_ref:
+        pytest.skip("oracle/_ref/libhcref.so not present")
+    import hcoracle
+    from hypercraft_b200 import mesher as M, worldgen
+
+    meshed, resident = worldgen.load_radius_positions(3)
+    ref = hcoracle.RefWorld()
+    ref.generate(resident)
+    blocks, heights = ref.get_chunks(resident)
+    m = M.Mesher(origin=(-4, -4, -4), extent=(9, 9, 9))
+    m.upload(resident, blocks, heights)
+    res = m.mesh(meshed)
+    n_nonempty = 0
+    for t, p in enumerate(meshed):
+        got, want = res.serialise(t), ref.mesh(p)
+        assert got.size == want.size and (got == want).all(), f"terrain chunk {p}\n" + describe_diff(got, want)
+        n_nonempty += int(res.tasks[t]["n_meshes"]) > 0
+    assert n_nonempty > 10
+    m.close()
