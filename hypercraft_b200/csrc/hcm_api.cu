@@ -441,20 +441,21 @@ int hcm_create(const hcm_registry *registry, const hcm_config *cfg, hcm_ctx **ou
 	DevWorld &w = c->w;
 	w.ox = cfg->origin[0], w.oy = cfg->origin[1], w.oz = cfg->origin[2];
 	w.wx = cfg->extent[0], w.wy = cfg->extent[1], w.wz = cfg->extent[2];
-	w.X = 32 * w.wx, w.Z = 32 * w.wz;
+	w.X = 32 * w.wx, w.Z = 32 * w.wz, w.XP = 32 * w.wx + 16;
 	c->n_cells = (size_t)w.wx * w.wy * w.wz;
 	c->max_chunks = cfg->max_chunks ? cfg->max_chunks : (uint32_t)c->n_cells;
 	c->max_tasks = cfg->max_tasks ? cfg->max_tasks : (uint32_t)c->n_cells;
 	const size_t n_cols = (size_t)w.wy * w.Z * w.X;
 
-	CUB(dev_alloc(c, &w.prop8, n_cols * 32));
+	const size_t n_vox = (size_t)w.wy * 32 * w.Z * w.XP;
+	CUB(dev_alloc(c, &w.prop8, n_vox));
 	CUB(dev_alloc(c, &w.pass, n_cols));
 	if (w.n_levels)
 		CUB(dev_alloc(c, &w.torch, n_cols * w.n_levels));
 	CUB(dev_alloc(c, &w.height, n_cols));
 	CUB(dev_alloc(c, &w.cflags, c->n_cells));
 	CUB(dev_alloc(c, &w.slot, c->n_cells));
-	CUB(cudaMemsetAsync(w.prop8, 0, n_cols * 32, c->stream));
+	CUB(cudaMemsetAsync(w.prop8, 0, n_vox, c->stream));
 	CUB(cudaMemsetAsync(w.pass, 0, n_cols * 4, c->stream));
 	if (w.n_levels)
 		CUB(cudaMemsetAsync(w.torch, 0, n_cols * 4 * w.n_levels, c->stream));
@@ -505,8 +506,8 @@ int hcm_create(const hcm_registry *registry, const hcm_config *cfg, hcm_ctx **ou
 			fail(c, HCM_ERR_CUDA, "cuTensorMapEncodeTiled not available in this driver");
 			return bail(HCM_ERR_CUDA);
 		}
-		const cuuint64_t dims[3] = {(cuuint64_t)w.X, (cuuint64_t)w.Z, (cuuint64_t)w.wy * 32};
-		const cuuint64_t strides[2] = {(cuuint64_t)w.X, (cuuint64_t)w.X * w.Z};
+		const cuuint64_t dims[3] = {(cuuint64_t)w.XP, (cuuint64_t)w.Z, (cuuint64_t)w.wy * 32};
+		const cuuint64_t strides[2] = {(cuuint64_t)w.XP, (cuuint64_t)w.XP * w.Z};
 		const cuuint32_t box[3] = {(cuuint32_t)kVX, (cuuint32_t)kVZ, (cuuint32_t)kVY};
 		const cuuint32_t estr[3] = {1, 1, 1};
 		CUresult r = ((PFN_encodeTiled)fn)(&c->tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, w.prop8, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,

@@ -13,11 +13,13 @@ constexpr int kThreads = 512; // mesh kernel: 16 warps, one persistent CTA per S
 constexpr int kWarps = kThreads / 32;
 
 // ---- shared-memory voxel volume (property index per voxel), filled by ONE 3-D TMA box -----------------------------
-// x,z in [-2,33] (the +-2 reach is only read by the liquid-flow generator), y in [-1,32].  The innermost box extent
-// must be a multiple of 16 bytes, hence 48.
+// z in [-2,33] (the +-2 reach is only read by the liquid-flow generator), y in [-1,32].  TMA needs the innermost box
+// extent AND the innermost start coordinate to be multiples of 16 bytes (measured: a start of 32c-2 raises "illegal
+// instruction"), so the dense grid stores world column x at x + kXMargin and the box starts at 32c: x in [-4,43].
 constexpr int kVX = 48, kVZ = 36, kVY = 34;
+constexpr int kXMargin = 4;
 constexpr int kVoxBytes = kVX * kVZ * kVY; // 58752
-__host__ __device__ constexpr int vox_index(int x, int y, int z) { return ((y + 1) * kVZ + (z + 2)) * kVX + (x + 2); }
+__host__ __device__ constexpr int vox_index(int x, int y, int z) { return ((y + 1) * kVZ + (z + 2)) * kVX + (x + kXMargin); }
 
 // ---- light volume on [-1,32]^3: byte = torch << 4 | sun (block/include/block/Light.hpp:20-24) --------------------
 constexpr int kLS = 34;
@@ -92,7 +94,8 @@ struct DevWorld {
 	int ox, oy, oz; // window origin (chunk coordinates)
 	int wx, wy, wz; // window extent (chunks)
 	int X, Z;       // voxel extents of the dense grids along x and z (32*wx, 32*wz)
-	uint8_t *prop8;       // [32*wy][Z][X]   property index per voxel (x fastest, then z, then y -- the chunk order)
+	int XP;         // row pitch of prop8: 32*wx + 16 (world column x is stored at x + kXMargin)
+	uint8_t *prop8;       // [32*wy][Z][XP]  property index per voxel (x fastest, then z, then y -- the chunk order)
 	uint32_t *pass;       // [wy][Z][X]      bit y_local: voxel lets indirect light pass
 	uint32_t *torch;      // [levels][wy][Z][X] bit y_local: voxel emits light level levels[l]
 	int8_t *height;       // [wy][Z][X]      sunlight height of the column within its chunk

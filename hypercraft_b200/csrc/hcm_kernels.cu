@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(256) derive_kernel(DevWorld w, const UploadEnt
 				face_empty &= ~on;
 		}
 		uchar4 o = make_uchar4(pr[0], pr[1], pr[2], pr[3]);
-		*reinterpret_cast<uchar4 *>(w.prop8 + (((size_t)e.cy * 32 + y) * w.Z + gz) * w.X + gx) = o;
+		*reinterpret_cast<uchar4 *>(w.prop8 + (((size_t)e.cy * 32 + y) * w.Z + gz) * w.XP + gx + kXMargin) = o;
 	}
 	const size_t col = ((size_t)e.cy * w.Z + gz) * w.X + gx;
 	*reinterpret_cast<uint4 *>(w.pass + col) = make_uint4(pass[0], pass[1], pass[2], pass[3]);
@@ -169,7 +169,7 @@ __global__ void __launch_bounds__(256) clear_kernel(DevWorld w, const UploadEntr
 	const int tid = threadIdx.x, z = tid >> 3, x4 = (tid & 7) << 2;
 	const size_t gx = (size_t)e.cx * 32 + x4, gz = (size_t)e.cz * 32 + z;
 	for (int y = 0; y < 32; ++y)
-		*reinterpret_cast<u32 *>(w.prop8 + (((size_t)e.cy * 32 + y) * w.Z + gz) * w.X + gx) = 0;
+		*reinterpret_cast<u32 *>(w.prop8 + (((size_t)e.cy * 32 + y) * w.Z + gz) * w.XP + gx + kXMargin) = 0;
 	const size_t col = ((size_t)e.cy * w.Z + gz) * w.X + gx;
 	*reinterpret_cast<uint4 *>(w.pass + col) = make_uint4(0, 0, 0, 0);
 	const size_t plane = (size_t)w.wy * w.Z * w.X;
@@ -833,7 +833,7 @@ __global__ void __launch_bounds__(kThreads, 1) mesh_kernel(const __grid_constant
 		// ---- phase 0: halo gather -- one TMA box of the dense property grid ---------------------------------------
 		if (tid == 0) {
 			mbar_expect_tx(&S.bar, kVoxBytes);
-			tma_load_3d(vox, &tmap, ti.cx * 32 - 2, ti.cz * 32 - 2, ti.cy * 32 - 1, &S.bar);
+			tma_load_3d(vox, &tmap, ti.cx * 32, ti.cz * 32 - 2, ti.cy * 32 - 1, &S.bar); // stored column = x + kXMargin
 		}
 		for (int i = tid; i < kMasks * 32; i += kThreads)
 			F[i] = 0;
