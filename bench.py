@@ -1,0 +1,332 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200 chunk mesher (metric and config from BASELINE.json).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]                    # this repo's CUDA path
+  python bench.py --impl reference [--gpus N] [--steps K] [--warmup W]   # the reference's own CPU mesher (oracle/_ref)
+
+Workload (BASELINE.json configs[1]): full load-radius remesh -- every chunk p with |p|^2 <= r^2 around a centre is
+meshed, its 26 neighbours coming from the one-chunk dilation of that sphere (misc/load_radius.cpp:16-35), r = 20 =
+kWorldMaxLoadRadius (client/include/client/Config.hpp:14), terrain from the reference's DefaultTerrain(12314524)
+(client/src/LocalClient.cpp:37).  One STEP = one full remesh of that world:
+    hcm_rederive_chunks(all resident) + hcm_mesh_batch(all tasks)            -> `value`   (inputs resident in HBM)
+    hcm_upload_chunks(host) + hcm_mesh_batch + hcm_mesh_fetch(host)          -> `e2e`     (host buffers both sides)
+Multi-GPU (--gpus N under torchrun): chunks are independent given their halo, so every rank meshes its own sphere
+(centre shifted by 3r chunks per rank) with no collective on the data path -> weak scaling; value = total chunks of
+all ranks / max-over-ranks time.
+
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+
+SEED = 12314524  # client/src/LocalClient.cpp:37
+H_BYTES = 34 ** 3 * 3  # blocks (2 B) + light (1 B) on [-1,32]^3: SURVEY.md section 8d
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--radius", type=int, default=20)
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU work of the cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index), "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
+
+
+def build_world(radius: int, centre, threads: int):
+    """(meshed positions, resident positions, pinned blocks, pinned heights, data label, RefWorld or None)."""
+    import hcoracle
+    from hypercraft_b200 import mesher, worldgen
+
+    meshed, resident = worldgen.load_radius_positions(radius)
+    c = np.asarray(centre, dtype=np.int16)
+    meshed = (meshed + c).astype(np.int16)
+    resident = (resident + c).astype(np.int16)
+    pb = mesher.PinnedArray((len(resident), 32768), np.uint16)
+    ph = mesher.PinnedArray((len(resident), 1024), np.int8)
+    ref = None
+    if hcoracle.have_ref():
+        ref = hcoracle.RefWorld()
+        ref.generate(resident, seed=SEED, threads=threads)
+        ref.get_chunks(resident, pb.array, ph.array)
+        label = f"synthetic: reference DefaultTerrain(seed {SEED}) run on this host via oracle/_ref (no dataset)"
+    else:
+        for i, p in enumerate(resident):
+            pb.array[i], ph.array[i] = worldgen.synth_terrain_chunk(SEED, p)
+        label = "synthetic: repo height-field terrain (oracle/_ref terrain generator not available)"
+    return meshed, resident, pb, ph, label, ref
+
+
+def run_reference(args, rank, world):
+    """The reference's own CPU implementation of the path (unmodified ChunkTaskRunner<kMesh>::Run, all host threads)."""
+    if rank != 0:
+        return
+    import hcoracle
+    from hypercraft_b200 import worldgen
+
+    if not hcoracle.have_ref():
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libhcref.so not built (needs /root/reference at build time)"}))
+        return
+    threads = os.cpu_count() or 1
+    radius = args.radius
+    meshed, resident = worldgen.load_radius_positions(radius)
+    # bounded sample: a contiguous-in-list stride of the task list, neighbours generated on demand
+    ref = hcoracle.RefWorld()
+    probe = meshed[:: max(1, len(meshed) // 256)][:256]
+    need = np.unique(np.concatenate([worldgen.neighbourhood(p) for p in probe]), axis=0)
+    ref.generate(need, seed=SEED, threads=threads)
+    st, _ = ref.mesh_batch(probe, threads=threads)
+    rate = st["chunks"] / max(st["seconds"], 1e-6)
+    per_step = int(min(len(meshed), max(256, rate * args.cpu_seconds / max(1, args.steps + args.warmup) * 2)))
+    sample = meshed[:: max(1, len(meshed) // per_step)][:per_step]
+    need = np.unique(np.concatenate([worldgen.neighbourhood(p) for p in sample]), axis=0)
+    ref.generate(need, seed=SEED, threads=threads)
+    for _ in range(args.warmup):
+        ref.mesh_batch(sample, threads=threads)
+    secs, quads = 0.0, 0
+    for _ in range(args.steps):
+        st, _ = ref.mesh_batch(sample, threads=threads)
+        secs += st["seconds"]
+        quads = st["vertices"] // 4
+    ms = secs / args.steps * 1e3
+    value = len(sample) / (ms / 1e3)
+    sample_txt = f"{len(sample)} of the {len(meshed)} chunks of the r={radius} load sphere (every {max(1, len(meshed) // per_step)}th), per step"
+    out = {"impl": "reference", "metric": "chunks meshed/sec", "value": value, "unit": "chunks/s", "n_gpus": args.gpus, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/u16 integer",
+           "data": f"synthetic: reference DefaultTerrain(seed {SEED})",
+           "config": {"workload": f"load-radius remesh r={radius} (misc/load_radius.cpp, kWorldMaxLoadRadius), bounded sample", "radius": radius,
+                      "chunks_per_step": len(sample)},
+           "quads_per_s": quads / (ms / 1e3),
+           "cpu_baseline": {"value": value, "unit": "chunks/s", "cores": threads, "kind": "reference", "sample": sample_txt},
+           "e2e": {"value": value, "unit": "chunks/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out))
+
+
+def main():
+    args = parse_args()
+    rank, world, local = dist_env()
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the mesher has no CPU path (use --impl reference for the CPU baseline)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    from hypercraft_b200 import mesher as M
+
+    radius = args.radius
+    threads = max(1, (os.cpu_count() or 1) // world)
+    centre = (3 * radius * rank, 0, 0)
+    t_setup = time.time()
+    meshed, resident, pb, ph, data_label, ref = build_world(radius, centre, threads)
+    ext = 2 * radius + 3
+    m = M.Mesher(origin=(centre[0] - radius - 1, -radius - 1, -radius - 1), extent=(ext, ext, ext), device=local, max_chunks=len(resident),
+                 max_tasks=len(meshed))
+    m.upload(resident, pb.array, ph.array)
+    m.sync()
+    setup_s = time.time() - t_setup
+
+    stream = torch.cuda.ExternalStream(m.stream_ptr(), device=torch.device("cuda", local))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident():
+        m.rederive()
+        m.mesh_async(meshed)
+        return m.wait()
+
+    # ---- warm-up (also sizes the output arenas) -------------------------------------------------------------------
+    counts = None
+    for _ in range(max(args.warmup, 3)):
+        counts = step_resident()
+    n_quads = counts["n_vertices"] // 4
+    algo_bytes = len(meshed) * H_BYTES + 8 * counts["n_vertices"]
+
+    # ---- timed: K steps, device timed on the ctx stream, max over ranks --------------------------------------------
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    launches0 = m.stats()["kernel_launches"]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    mesh_ms, derive_ms, classify_ms = [], [], []
+    e0.record(stream)
+    for _ in range(args.steps):
+        step_resident()
+        s = m.stats()
+        mesh_ms.append(s["mesh_ms"]), derive_ms.append(s["derive_ms"]), classify_ms.append(s["classify_ms"])
+    e1.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    launches = m.stats()["kernel_launches"] - launches0
+    ms_total = e0.elapsed_time(e1)
+    t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
+    tot = torch.tensor([len(meshed), int(n_quads), int(launches)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    ms_per_step = float(t.item()) / args.steps
+    total_chunks, total_quads, total_launches = (float(x) for x in tot.tolist())
+    value = total_chunks / (ms_per_step / 1e3)
+
+    # ---- end to end: host buffers in, host meshes out, every step ---------------------------------------------------
+    res = None
+    for _ in range(1):
+        m.upload(resident, pb.array, ph.array)
+        res = m.mesh(meshed)
+    d2h0, h2d0 = m.stats()["d2h_bytes"], m.stats()["h2d_bytes"]
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        m.upload(resident, pb.array, ph.array)
+        res = m.mesh(meshed)
+    torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - t0) * 1e3
+    t = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms_step = float(t.item()) / args.steps
+    s = m.stats()
+    h2d_step = (s["h2d_bytes"] - h2d0) // args.steps
+    d2h_step = (s["d2h_bytes"] - d2h0) // args.steps
+    e2e_value = total_chunks / (e2e_ms_step / 1e3)
+
+    # ---- parity gate + CPU baseline on rank 0 (bounded sample of the same workload) -----------------------------------
+    cpu_baseline, parity = None, None
+    if rank == 0 and ref is not None and not args.no_cpu_baseline:
+        import hcoracle
+
+        cpu_threads = os.cpu_count() or 1
+        probe = meshed[:: max(1, len(meshed) // 128)][:128]
+        st, _ = ref.mesh_batch(probe, threads=cpu_threads)
+        rate = st["chunks"] / max(st["seconds"], 1e-6)
+        n_s = int(min(len(meshed), max(128, rate * args.cpu_seconds)))
+        stride = max(1, len(meshed) // n_s)
+        idx = np.arange(0, len(meshed), stride)[:n_s]
+        st, per = ref.mesh_batch(meshed[idx], threads=cpu_threads, per_chunk=True)
+        cpu_baseline = {"value": st["chunks"] / st["seconds"], "unit": "chunks/s", "cores": cpu_threads, "kind": "reference",
+                        "quads_per_s": st["vertices"] / 4 / st["seconds"],
+                        "sample": f"{len(idx)} of {len(meshed)} chunks (every {stride}th of the r={radius} task list), unmodified "
+                                  f"ChunkTaskRunner<kMesh>::Run, one runner per thread"}
+        # parity: mesh/vertex/index counts of every sampled chunk + full bytes of the heaviest ones against the reference
+        got_m = res.tasks["n_meshes"][idx].astype(np.uint64)
+        first = res.tasks["first_mesh"][idx]
+        gv = np.array([int(res.meshes["vertex_count"][f:f + n].sum()) for f, n in zip(first, got_m)], dtype=np.uint64)
+        gi = np.array([int(res.meshes["index_count"][f:f + n].sum()) for f, n in zip(first, got_m)], dtype=np.uint64)
+        count_bad = int(((got_m != per[:, 0]) | (gv != per[:, 1]) | (gi != per[:, 2])).sum())
+        heavy = idx[np.argsort(-per[:, 1].astype(np.int64))[:48]]
+        byte_bad = 0
+        for t_i in heavy:
+            a, b = res.serialise(int(t_i)), ref.mesh(meshed[t_i])
+            byte_bad += not (a.size == b.size and (a == b).all())
+        parity = {"sampled_chunks": int(len(idx)), "count_mismatches": count_bad, "byte_compared_chunks": int(len(heavy)), "byte_mismatches": int(byte_bad)}
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak_gbs, peak_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json)") if "hbm_gbs" in peaks else (6650.0, "fallback (B200_PROFILING.md)")
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_summary.json"))).get("mesh_kernel_dram_bytes_per_launch")
+        except Exception:
+            pass
+        k_ms = float(np.mean(mesh_ms))
+        achieved = algo_bytes / (k_ms / 1e3) / 1e9
+        out = {
+            "metric": "chunks meshed/sec", "value": value, "unit": "chunks/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/u16 integer",
+            "data": data_label,
+            "config": {"workload": f"full load-radius remesh r={radius} (misc/load_radius.cpp; kWorldMaxLoadRadius) per GPU", "radius": radius,
+                       "chunks_meshed_per_gpu": int(len(meshed)), "chunks_resident_per_gpu": int(len(resident)),
+                       "tasks_through_full_kernel_per_gpu": int(counts["n_worked"]), "parallelism": f"{world} independent spheres (no collective)",
+                       "l2": "inputs (5.4 GB resident per GPU) larger than L2; no flush needed", "setup_seconds": setup_s},
+            "quads_per_s": total_quads / (ms_per_step / 1e3), "quads_per_step": total_quads, "vertices_per_step_per_gpu": int(counts["n_vertices"]),
+            "e2e": {"value": e2e_value, "unit": "chunks/s", "ms_per_step": e2e_ms_step, "h2d_bytes_per_step": int(h2d_step),
+                    "d2h_bytes_per_step": int(d2h_step)},
+            "gpu_launches": int(total_launches),
+            "kernel_ms": {"derive": float(np.mean(derive_ms)), "classify": float(np.mean(classify_ms)), "mesh": k_ms},
+            "roofline": {"bound": "hbm", "kernel": "hcm::mesh_kernel", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
+                         "traffic": traffic, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": int(algo_bytes), "formula": "sum over chunks of 34^3*3 + 8*vertices (SURVEY 8d)"},
+            "cpu_baseline": cpu_baseline, "parity": parity, "clocks": clocks,
+        }
+        print(json.dumps(out))
+    m.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -623,6 +623,47 @@ int hcm_remove_chunks(hcm_ctx *c, uint32_t n, const int16_t *pos) {
 	return HCM_OK;
 }
 
+int hcm_rederive_chunks(hcm_ctx *c, uint32_t n, const int16_t *pos) {
+	if (!c)
+		return HCM_ERR_INVALID;
+	if (n && !pos)
+		return fail(c, HCM_ERR_INVALID, "null positions");
+	CU(cudaSetDevice(c->device));
+	std::vector<UploadEntry> entries;
+	if (n == 0) {
+		for (int cy = 0; cy < c->w.wy; ++cy)
+			for (int cz = 0; cz < c->w.wz; ++cz)
+				for (int cx = 0; cx < c->w.wx; ++cx) {
+					const int32_t slot = c->slot_of[cell(c, cx, cy, cz)];
+					if (slot >= 0)
+						entries.push_back(UploadEntry{slot, (int16_t)cx, (int16_t)cy, (int16_t)cz, 0});
+				}
+	} else {
+		for (uint32_t i = 0; i < n; ++i) {
+			int cx, cy, cz;
+			if (!in_window(c, pos + 3 * i, &cx, &cy, &cz))
+				return fail(c, HCM_ERR_OUT_OF_WINDOW, "chunk (%d,%d,%d) is outside the window", pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]);
+			const int32_t slot = c->slot_of[cell(c, cx, cy, cz)];
+			if (slot < 0)
+				return fail(c, HCM_ERR_NOT_RESIDENT, "chunk (%d,%d,%d) is not resident", pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]);
+			entries.push_back(UploadEntry{slot, (int16_t)cx, (int16_t)cy, (int16_t)cz, 0});
+		}
+	}
+	if (entries.empty())
+		return HCM_OK;
+	cudaStream_t st = c->stream;
+	CU(cudaEventRecord(c->ev[EV_UP0], st));
+	CU(cudaMemcpyAsync(c->d_entries, entries.data(), entries.size() * sizeof(UploadEntry), cudaMemcpyHostToDevice, st));
+	c->stats.h2d_bytes += entries.size() * sizeof(UploadEntry);
+	CU(cudaEventRecord(c->ev[EV_UP1], st));
+	launch_derive(c->w, c->d_entries, (uint32_t)entries.size(), c->d_prop_index, c->d_tables, c->d_rawh, st);
+	CU(cudaGetLastError());
+	CU(cudaEventRecord(c->ev[EV_UP2], st));
+	c->stats.kernel_launches += 1;
+	c->ev_upload = true;
+	return HCM_OK;
+}
+
 int hcm_sync(hcm_ctx *c) {
 	if (!c)
 		return HCM_ERR_INVALID;

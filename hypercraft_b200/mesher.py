@@ -57,7 +57,7 @@ TASK_RESULT_DTYPE = np.dtype([("first_mesh", np.uint32), ("n_meshes", np.uint32)
 assert MESH_DESC_DTYPE.itemsize == 56
 
 EXPORTS = ["hcm_registry_from_blob", "hcm_create", "hcm_destroy", "hcm_last_error", "hcm_status_string", "hcm_host_alloc", "hcm_host_free",
-           "hcm_upload_chunks", "hcm_remove_chunks", "hcm_is_resident", "hcm_sync", "hcm_mesh_batch", "hcm_mesh_fetch", "hcm_mesh_wait",
+           "hcm_upload_chunks", "hcm_remove_chunks", "hcm_rederive_chunks", "hcm_is_resident", "hcm_sync", "hcm_mesh_batch", "hcm_mesh_fetch", "hcm_mesh_wait",
            "hcm_get_stats", "hcm_stream", "hcm_debug_light"]
 
 _lib = None
@@ -91,6 +91,7 @@ def load_library():
         L.hcm_registry_from_blob.argtypes = [_vp, ctypes.c_size_t, ctypes.POINTER(_Registry)]
         L.hcm_upload_chunks.argtypes = [_vp, ctypes.c_uint32, _vp, _vp, _vp]
         L.hcm_remove_chunks.argtypes = [_vp, ctypes.c_uint32, _vp]
+        L.hcm_rederive_chunks.argtypes = [_vp, ctypes.c_uint32, _vp]
         L.hcm_is_resident.argtypes = [_vp, _vp]
         L.hcm_sync.argtypes = [_vp]
         L.hcm_mesh_batch.argtypes = [_vp, ctypes.c_uint32, _vp]
@@ -216,6 +217,14 @@ class Mesher:
     def remove(self, positions) -> None:
         pos = np.ascontiguousarray(positions, dtype=np.int16).reshape(-1, 3)
         self._check(self.L.hcm_remove_chunks(self.ctx, len(pos), _ptr(pos)))
+
+    def rederive(self, positions=None) -> None:
+        """Re-run the derivation kernel from device-resident Block data (None: every resident chunk)."""
+        if positions is None:
+            self._check(self.L.hcm_rederive_chunks(self.ctx, 0, None))
+        else:
+            pos = np.ascontiguousarray(positions, dtype=np.int16).reshape(-1, 3)
+            self._check(self.L.hcm_rederive_chunks(self.ctx, len(pos), _ptr(pos)))
 
     def is_resident(self, pos) -> bool:
         p = np.ascontiguousarray(pos, dtype=np.int16)

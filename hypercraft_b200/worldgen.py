@@ -200,3 +200,51 @@ def _vertical_pass_table() -> np.ndarray:
         reg = registry.load()
         _VPASS = reg.props["transparency"][reg.prop_index] == 2
     return _VPASS
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# fallback terrain (only used by bench.py when the reference terrain generator, oracle/_ref, is not available)
+# ---------------------------------------------------------------------------------------------------------------
+def _lattice(seed: int, ix: np.ndarray, iz: np.ndarray) -> np.ndarray:
+    with np.errstate(over="ignore"):
+        k = (ix.astype(np.int64) & 0xFFFFF).astype(np.uint64) | ((iz.astype(np.int64) & 0xFFFFF).astype(np.uint64) << np.uint64(20))
+        return (_splitmix64(k ^ np.uint64(seed * 0x9E3779B1)) & np.uint64(0xFFFF)).astype(np.int64)
+
+
+def _value_noise(seed: int, wx: np.ndarray, wz: np.ndarray, cell: int) -> np.ndarray:
+    """integer bilinear value noise in [0, 65535]"""
+    ix, iz = np.floor_divide(wx, cell), np.floor_divide(wz, cell)
+    fx, fz = wx - ix * cell, wz - iz * cell
+    a, b = _lattice(seed, ix, iz), _lattice(seed, ix + 1, iz)
+    c, d = _lattice(seed, ix, iz + 1), _lattice(seed, ix + 1, iz + 1)
+    top = a * (cell - fx) + b * fx
+    bot = c * (cell - fx) + d * fx
+    return (top * (cell - fz) + bot * fz) // (cell * cell)
+
+
+def synth_terrain_chunk(seed: int, pos) -> tuple[np.ndarray, np.ndarray]:
+    """Deterministic height-field terrain (stone/dirt/grass, oceans, plants, a few glowstones)."""
+    cx, cy, cz = (int(c) for c in pos)
+    lx = np.arange(CHUNK)
+    wx, wz = np.meshgrid(cx * CHUNK + lx, cz * CHUNK + lx, indexing="xy")  # [z][x]
+    h = (_value_noise(seed, wx, wz, 64) - 32768) // 400 + (_value_noise(seed + 1, wx, wz, 16) - 32768) // 2600  # about +-95
+    wy = (cy * CHUNK + np.arange(CHUNK)).reshape(CHUNK, 1, 1)  # [y][z][x]
+    hh = h[None, :, :]
+    blocks = np.zeros((CHUNK, CHUNK, CHUNK), dtype=np.uint16)
+    blocks[wy < hh - 3] = STONE
+    blocks[(wy >= hh - 3) & (wy < hh)] = DIRT
+    top = np.broadcast_to(wy == hh, blocks.shape)
+    blocks[top] = np.broadcast_to(np.where(hh > 1, GRASS_BLOCK, SAND), blocks.shape)[top].astype(np.uint16)
+    blocks[(wy > hh) & (wy <= 0)] = WATER
+    r = voxel_hash(seed, pos).reshape(CHUNK, CHUNK, CHUNK)
+    plant = np.broadcast_to((wy == hh + 1) & (hh > 1), blocks.shape) & ((r % np.uint64(23)) == 0)
+    blocks[plant] = GRASS
+    lamp = np.broadcast_to(wy == hh + 1, blocks.shape) & ((r % np.uint64(4099)) == 1) & np.broadcast_to(hh > 1, blocks.shape)
+    blocks[lamp] = GLOWSTONE
+    surface = np.maximum(h, np.where(h < 0, 0, h))  # water is not vertical-light-pass: the ocean surface shades
+    heights = np.clip(surface + 1 - cy * CHUNK, 0, CHUNK).astype(np.int8)
+    lampcol = lamp.any(axis=0)
+    if lampcol.any():
+        lamp_top = np.max(np.where(lamp, np.arange(1, CHUNK + 1).reshape(CHUNK, 1, 1), 0), axis=0)
+        heights = np.where(lampcol, np.maximum(heights, lamp_top), heights).astype(np.int8)
+    return blocks.reshape(-1), heights.reshape(-1)

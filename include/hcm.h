@@ -155,6 +155,10 @@ void hcm_host_free(void *p);
 int hcm_upload_chunks(hcm_ctx *ctx, uint32_t n, const int16_t *pos /* n x 3 */, const uint16_t *blocks /* n x 32768 */,
                       const int8_t *heights /* n x 1024 */);
 int hcm_remove_chunks(hcm_ctx *ctx, uint32_t n, const int16_t *pos /* n x 3 */);
+/* Re-run the derivation kernel on chunks whose Block data is already device resident (n == 0: every resident chunk).
+ * This is the device-side half of hcm_upload_chunks; a full remesh "with inputs resident in HBM" is
+ * hcm_rederive_chunks(ctx, 0, NULL) followed by hcm_mesh_batch. */
+int hcm_rederive_chunks(hcm_ctx *ctx, uint32_t n, const int16_t *pos /* n x 3 */);
 int hcm_is_resident(const hcm_ctx *ctx, const int16_t pos[3]); /* 1 / 0 */
 int hcm_sync(hcm_ctx *ctx);
 

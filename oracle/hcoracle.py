@@ -109,13 +109,15 @@ class RefWorld:
             raise KeyError(tuple(int(x) for x in p))
         return b, h
 
-    def get_chunks(self, positions: np.ndarray):
+    def get_chunks(self, positions: np.ndarray, blocks_out: np.ndarray | None = None, heights_out: np.ndarray | None = None):
         pos = np.ascontiguousarray(positions, dtype=np.int16).reshape(-1, 3)
-        b = np.empty((len(pos), 32768), dtype=np.uint16)
-        h = np.empty((len(pos), 1024), dtype=np.int8)
-        for i in range(len(pos)):
-            if self.L.hcref_world_get_chunk(self.w, _ptr(pos[i]), _ptr(b[i]), _ptr(h[i])) != 0:
-                raise KeyError(tuple(int(x) for x in pos[i]))
+        b = blocks_out if blocks_out is not None else np.empty((len(pos), 32768), dtype=np.uint16)
+        h = heights_out if heights_out is not None else np.empty((len(pos), 1024), dtype=np.int8)
+        assert b.flags.c_contiguous and h.flags.c_contiguous and b.dtype == np.uint16 and h.dtype == np.int8
+        self.L.hcref_world_get_chunks.restype = ctypes.c_int64
+        missing = self.L.hcref_world_get_chunks(self.w, _ptr(pos), ctypes.c_uint64(len(pos)), _ptr(b), _ptr(h))
+        if missing:
+            raise KeyError(f"{missing} chunks missing")
         return b, h
 
     def mesh(self, pos) -> np.ndarray:

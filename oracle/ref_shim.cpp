@@ -165,6 +165,23 @@ int hcref_world_get_chunk(void *wp, const int16_t pos[3], uint16_t *blocks, int8
 	return 0;
 }
 
+// bulk variant of hcref_world_get_chunk; returns the number of positions that were missing (left untouched)
+int64_t hcref_world_get_chunks(void *wp, const int16_t *pos, uint64_t n, uint16_t *blocks, int8_t *heights) {
+	auto *w = (RefWorld *)wp;
+	int64_t missing = 0;
+	for (uint64_t i = 0; i < n; ++i) {
+		auto it = w->chunks.find(PosKey{pos[i * 3], pos[i * 3 + 1], pos[i * 3 + 2]});
+		if (it == w->chunks.end()) {
+			++missing;
+			continue;
+		}
+		memcpy(blocks + i * 32768, it->second->GetBlockData(), 32768 * 2);
+		for (uint32_t k = 0; k < 1024; ++k)
+			heights[i * 1024 + k] = it->second->GetSunlightHeight(k);
+	}
+	return missing;
+}
+
 // Reference terrain: DefaultTerrain(seed).Generate for every listed position, n_threads workers.
 // (LocalClient.cpp:37 uses seed 12314524.)  Positions already present are regenerated.
 void hcref_world_generate(void *wp, uint32_t seed, const int16_t *pos, uint64_t n, int n_threads) {
