@@ -291,9 +291,9 @@ __device__ __forceinline__ void light4_corner(u32 fP, u32 fQ, u32 fD, bool dF, u
 		if (fQ & PF_INDIRECT)
 			++cnt, ss += lQ & 15u, ts += lQ >> 4;
 	}
-	ss <<= 2, ts <<= 2; // <= 240; exact floor division by 1..4 ((n*171)>>9 == n/3 for n < 1024, tests/test_host_logic.py)
-	sun = cnt == 1 ? ss : (cnt == 2 ? ss >> 1 : (cnt == 3 ? (ss * 171u) >> 9 : ss >> 2)); // :160-161
-	torch = cnt == 1 ? ts : (cnt == 2 ? ts >> 1 : (cnt == 3 ? (ts * 171u) >> 9 : ts >> 2));
+	ss <<= 2, ts <<= 2; // <= 240; exact floor division by 1..4 ((n*683)>>11 == n/3 for n < 1024, tests/test_host_logic.py)
+	sun = cnt == 1 ? ss : (cnt == 2 ? ss >> 1 : (cnt == 3 ? (ss * 683u) >> 11 : ss >> 2)); // :160-161
+	torch = cnt == 1 ? ts : (cnt == 2 ? ts >> 1 : (cnt == 3 ? (ts * 683u) >> 11 : ts >> 2));
 }
 __device__ __forceinline__ L4 light4_init(const Small &S, const uint8_t *vox, const uint8_t *light, int face, int x, int y, int z) {
 	const int axis = face >> 1, dir = 1 - ((face & 1) << 1);

@@ -1,0 +1,54 @@
+"""Multi-GPU partitioning of a mesh-task list.
+
+Chunks are independent given their 26 neighbours, so G GPUs need no exchange step: the task list is cut into G
+contiguous x-slabs of (nearly) equal task count, and each GPU's resident set is its slab dilated by one chunk
+(boundary chunk planes are simply uploaded to both neighbours).  No collective is involved on the data path."""
+from __future__ import annotations
+
+import numpy as np
+
+
+def slab_bounds(positions: np.ndarray, world: int) -> list[tuple[int, int]]:
+    """Per rank [x_lo, x_hi) such that the slabs tile the x-range and hold balanced task counts."""
+    pos = np.asarray(positions, dtype=np.int64).reshape(-1, 3)
+    if len(pos) == 0:
+        return [(0, 0)] * world
+    xs = np.sort(pos[:, 0])
+    x_min, x_max = int(xs[0]), int(xs[-1]) + 1
+    cuts = [x_min]
+    for r in range(1, world):
+        target = (len(xs) * r) // world
+        c = int(xs[min(target, len(xs) - 1)])
+        cuts.append(max(c, cuts[-1]))
+    cuts.append(x_max)
+    return [(cuts[r], cuts[r + 1]) for r in range(world)]
+
+
+def shard_tasks(positions: np.ndarray, world: int, rank: int) -> np.ndarray:
+    pos = np.asarray(positions, dtype=np.int16).reshape(-1, 3)
+    lo, hi = slab_bounds(pos, world)[rank]
+    sel = (pos[:, 0] >= lo) & (pos[:, 0] < hi)
+    return pos[sel]
+
+
+def resident_for(tasks: np.ndarray) -> np.ndarray:
+    """The one-chunk dilation of a task set: every position a task reads."""
+    t = np.asarray(tasks, dtype=np.int32).reshape(-1, 3)
+    if len(t) == 0:
+        return np.zeros((0, 3), dtype=np.int16)
+    lo = t.min(axis=0) - 1
+    span = t.max(axis=0) - lo + 2
+    occ = np.zeros(tuple(int(s) for s in span), dtype=bool)
+    ti = t - lo
+    for dx in (-1, 0, 1):
+        for dy in (-1, 0, 1):
+            for dz in (-1, 0, 1):
+                occ[ti[:, 0] + dx, ti[:, 1] + dy, ti[:, 2] + dz] = True
+    return (np.argwhere(occ) + lo).astype(np.int16)
+
+
+def window_for(resident: np.ndarray) -> tuple[tuple[int, int, int], tuple[int, int, int]]:
+    """(origin, extent) of the smallest hcm world window holding `resident`."""
+    r = np.asarray(resident, dtype=np.int32).reshape(-1, 3)
+    lo, hi = r.min(axis=0), r.max(axis=0)
+    return tuple(int(v) for v in lo), tuple(int(v) for v in (hi - lo + 1))

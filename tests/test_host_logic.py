@@ -1,0 +1,128 @@
+"""Host-side logic and the C-ABI surface (no GPU needed)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_load_radius_counts_match_reference_list():
+    """client/src/WorldLoadingList.inl end table: r=11 -> 8121 resident, r=20 -> 41443."""
+    from hypercraft_b200 import worldgen
+
+    for r, meshed, resident in [(0, 1, 27), (11, 5575, 8121), (20, 33401, 41443)]:
+        m, res = worldgen.load_radius_positions(r)
+        assert (len(m), len(res)) == (meshed, resident)
+        s = {tuple(p) for p in res.tolist()}
+        for p in m[:: max(1, len(m) // 50)]:
+            assert all(tuple(q) in s for q in worldgen.neighbourhood(p).tolist())
+
+
+def test_make_block_follows_block_ctor():
+    from hypercraft_b200 import worldgen as w
+
+    assert w.make_block(w.STONE) == 1
+    assert w.make_block(w.LOG, 2, 1) == 17 | ((2 | (1 << 3)) << 8)
+    assert w.make_block(w.FLOWING_WATER, 8) == 15 | (8 << 8)
+    assert w.make_block(w.VINE, 0, 5) == 21 | (5 << 8)
+
+
+def test_registry_blob_is_consistent():
+    from hypercraft_b200 import registry
+
+    reg = registry.load()
+    assert len(reg.props) == 67 and len(reg.meshes) == 24 and len(reg.tex_flags) == 53
+    air = reg.props[reg.prop_index[0]]
+    assert air["transparency"] == 2 and air["light_level"] == 0 and not air["tex"].any() and air["liquid_obstacle"] == 0  # block/test/test_block.cpp:10-23
+    glow = reg.props[reg.prop_index[24]]
+    assert glow["light_level"] == 15 and glow["transparency"] == 0
+    # vertical-pass => indirect-pass for every property (block/test/test_block.cpp:58-67)
+    assert ((reg.props["transparency"] == 2) <= (reg.props["transparency"] != 0)).all()
+    flow = reg.meshes[reg.props[reg.prop_index[15 | (3 << 8)]]["custom_mesh"] - 1]
+    assert flow["dynamic_kind"] == 1 and flow["liquid_variant"] == 3 and flow["liquid_height_unit"] == 2
+    # meta above the table clamps to the last variant, raw meta is still kept by the ABI (Block.cpp.in:9-16)
+    assert reg.prop_index[15 | (200 << 8)] == reg.prop_index[15 | (8 << 8)]
+
+
+def test_divide_by_three_trick_is_exact():
+    """light4_init divides (sum << 2) by 1..4 (BlockMeshAlgo.hpp:160-161); the kernel uses (n*683)>>11 for /3."""
+    n = np.arange(0, 1024, dtype=np.int64)
+    assert ((n * 683) >> 11 == n // 3).all()
+
+
+def test_shard_partition_is_exact():
+    from hypercraft_b200 import shard, worldgen
+
+    meshed, resident = worldgen.load_radius_positions(6)
+    for world in (1, 2, 4, 8):
+        parts = [shard.shard_tasks(meshed, world, r) for r in range(world)]
+        allp = np.concatenate(parts)
+        assert len(allp) == len(meshed) and len({tuple(p) for p in allp.tolist()}) == len(meshed)
+        assert max(len(p) for p in parts) - min(len(p) for p in parts) <= len(meshed) // world  # slabs are plane-granular
+        for p in parts:
+            res = {tuple(q) for q in shard.resident_for(p).tolist()}
+            for t in p[:: max(1, len(p) // 20)]:
+                assert all(tuple(q) in res for q in worldgen.neighbourhood(t).tolist())
+            origin, extent = shard.window_for(shard.resident_for(p))
+            assert all(e >= 3 for e in extent)
+
+
+def test_library_exports_every_declared_symbol():
+    """libhcm.so loads and exports exactly the entry points include/hcm.h declares (no compute call)."""
+    from hypercraft_b200 import mesher
+
+    if not os.path.exists(mesher.LIB_PATH):
+        mesher.build_library()
+    lib = ctypes.CDLL(mesher.LIB_PATH)
+    header = open(os.path.join(ROOT, "include", "hcm.h")).read()
+    declared = sorted(set(re.findall(r"\b(hcm_[a-z_0-9]+)\s*\(", header)))
+    assert set(declared) == set(mesher.EXPORTS), (declared, mesher.EXPORTS)
+    for name in declared:
+        assert hasattr(lib, name), f"libhcm.so does not export {name}"
+    lib.hcm_status_string.restype = ctypes.c_char_p
+    assert lib.hcm_status_string(0) == b"ok"
+
+
+def test_struct_sizes_match_header():
+    from hypercraft_b200 import mesher, registry
+
+    assert registry.PROP_DTYPE.itemsize == 20 and registry.FACE_DTYPE.itemsize == 24 and registry.MESH_DTYPE.itemsize == 400
+    assert mesher.MESH_DESC_DTYPE.itemsize == 56 and mesher.TASK_RESULT_DTYPE.itemsize == 8
+    assert ctypes.sizeof(mesher._Config) == 32 and ctypes.sizeof(mesher._Registry) == 48
+
+
+def test_create_fails_loudly_without_gpu():
+    """No CPU fallback: without a CUDA device hcm_create returns HCM_ERR_CUDA."""
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from hypercraft_b200 import mesher
+
+    with pytest.raises(mesher.HcmError) as e:
+        mesher.Mesher(origin=(0, 0, 0), extent=(3, 3, 3))
+    assert e.value.status == -2 and "no CPU fallback" in str(e.value)
+
+
+def test_rejects_bad_registry_blob():
+    from hypercraft_b200 import mesher
+
+    lib = mesher.load_library()
+    reg = mesher._Registry()
+    bad = np.zeros(64, dtype=np.uint8)
+    assert lib.hcm_registry_from_blob(bad.ctypes.data_as(ctypes.c_void_p), bad.size, ctypes.byref(reg)) == -1
+
+
+def test_synthetic_chunks_are_deterministic():
+    from hypercraft_b200 import worldgen
+
+    a = worldgen.synth_chunk("mix", 3, (1, -2, 0))
+    b = worldgen.synth_chunk("mix", 3, (1, -2, 0))
+    c = worldgen.synth_chunk("mix", 3, (1, -2, 1))
+    assert (a[0] == b[0]).all() and (a[1] == b[1]).all() and not (a[0] == c[0]).all()
+    import hashlib
+
+    assert hashlib.sha256(a[0].tobytes()).hexdigest()[:16] == hashlib.sha256(b[0].tobytes()).hexdigest()[:16]
