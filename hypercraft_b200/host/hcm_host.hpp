@@ -1,0 +1,161 @@
+// hcm_host.hpp -- C++ host side above the C ABI (include/hcm.h), mirroring the reference's mesh-task interface.
+//
+// The reference runs one `ChunkTaskRunner<ChunkTaskType::kMesh>::Run(pool, ChunkTaskRunnerData<kMesh>&&)` per chunk
+// on N worker threads (client/src/ChunkMeshTask.cpp:41-127, client/include/client/ChunkTaskPool.hpp:187-194) and ends
+// with `renderer->PushChunkMesh(chunk->GetPosition(), std::move(meshes))` (:124-126).  On a GPU the unit of dispatch is
+// a BATCH of popped tasks: `MeshTaskDispatcher::Submit` takes the same 27-chunk array `ChunkTaskData<kMesh>::Pop`
+// captures (ChunkMeshTask.cpp:14-39; index 26 = centre, order = NeighbourIndex2CmpXYZ, Position.hpp:146-152) and
+// `Flush` hands every task's `std::vector<BlockMesh>` to a sink with PushChunkMesh's signature.
+//
+// `ChunkT` is any type with the reference Chunk's accessors (client/include/client/Chunk.hpp:45-66):
+//     const uint16_t*-compatible  GetBlockData()      (Block is a 2-byte POD, Block.hpp:89)
+//     int8_t                      GetSunlightHeight(uint32_t idx)
+//     position with .x .y .z      GetPosition()
+// so the reference's own `hc::client::Chunk` plugs in unchanged.
+#pragma once
+
+#include <array>
+#include <cstdint>
+#include <cstring>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/hcm.h"
+
+namespace hcm_host {
+
+// layout-compatible with hc::client::BlockVertex (client/include/client/BlockVertex.hpp:8-18)
+struct BlockVertex {
+	uint32_t x10_y10_z10_axis2, tex10_trans3_face3_ao2_sl6_tl6;
+};
+static_assert(sizeof(BlockVertex) == 8, "BlockVertex is 8 bytes (R32G32_UINT, rg/ChunkOpaquePass.hpp:70-71)");
+
+struct U32AABB { // AABB<uint32_t>, dep/AABB.hpp:9-12
+	uint32_t min[3]{UINT32_MAX, UINT32_MAX, UINT32_MAX}, max[3]{0, 0, 0};
+};
+
+// hc::client::BlockMesh (BlockVertex.hpp:20-25)
+struct BlockMesh {
+	std::vector<BlockVertex> vertices;
+	std::vector<uint16_t> indices;
+	U32AABB aabb{};
+	bool transparent{};
+};
+
+struct ChunkPos3 {
+	int16_t x, y, z;
+	bool operator==(const ChunkPos3 &r) const { return x == r.x && y == r.y && z == r.z; }
+};
+struct ChunkPos3Hash {
+	size_t operator()(const ChunkPos3 &p) const {
+		return (size_t)(uint16_t)p.x * 73856093u ^ (size_t)(uint16_t)p.y * 19349663u ^ (size_t)(uint16_t)p.z * 83492791u;
+	}
+};
+
+class Error : public std::runtime_error {
+public:
+	int status;
+	Error(int s, const std::string &what) : std::runtime_error(what), status(s) {}
+};
+
+template <typename ChunkT> class MeshTaskDispatcher {
+public:
+	// registry_blob: the serialised hcm_registry (INTEGRATION.md shows the exporter); window: chunks the device may hold
+	MeshTaskDispatcher(const void *registry_blob, size_t blob_size, int device, ChunkPos3 window_origin, std::array<uint16_t, 3> window_extent) {
+		hcm_registry reg{};
+		if (int rc = hcm_registry_from_blob(registry_blob, blob_size, &reg))
+			throw Error(rc, "bad registry blob");
+		hcm_config cfg{};
+		cfg.device = device;
+		cfg.origin[0] = window_origin.x, cfg.origin[1] = window_origin.y, cfg.origin[2] = window_origin.z;
+		cfg.extent[0] = window_extent[0], cfg.extent[1] = window_extent[1], cfg.extent[2] = window_extent[2];
+		if (int rc = hcm_create(&reg, &cfg, &m_ctx))
+			throw Error(rc, hcm_last_error(nullptr));
+	}
+	~MeshTaskDispatcher() { hcm_destroy(m_ctx); }
+	MeshTaskDispatcher(const MeshTaskDispatcher &) = delete;
+	MeshTaskDispatcher &operator=(const MeshTaskDispatcher &) = delete;
+
+	// A chunk whose blocks or sunlight heights changed since it was last seen (the SetBlock / SetSunlight tasks that
+	// `Push<kMesh>`, ChunkSetBlockTask.cpp:119, ChunkSetSunlightTask.cpp:84) must be re-uploaded before its remesh.
+	void MarkDirty(const ChunkPos3 &pos) { m_resident.erase(pos); }
+
+	// Same input as ChunkTaskRunnerData<kMesh> (ChunkMeshTask.inl:17-29).  Like Run(), the chunks are read-only snapshots
+	// held by shared_ptr until Flush() returns.
+	void Submit(const std::array<std::shared_ptr<ChunkT>, 27> &chunks) {
+		for (const auto &c : chunks) {
+			const auto p = c->GetPosition();
+			ChunkPos3 pos{(int16_t)p.x, (int16_t)p.y, (int16_t)p.z};
+			auto it = m_resident.find(pos);
+			if (it == m_resident.end() || it->second != c.get()) {
+				m_resident[pos] = c.get();
+				m_upload.push_back(c);
+			}
+		}
+		const auto p = chunks[26]->GetPosition();
+		m_tasks.push_back(ChunkPos3{(int16_t)p.x, (int16_t)p.y, (int16_t)p.z});
+		m_keepalive.insert(m_keepalive.end(), chunks.begin(), chunks.end());
+	}
+
+	size_t Pending() const { return m_tasks.size(); }
+
+	// Runs the batch and calls sink(const ChunkPos3&, std::vector<BlockMesh>&&) once per submitted task, in submission
+	// order -- the place where Run() calls WorldRenderer::PushChunkMesh.  Zero meshes is a valid result and is pushed too
+	// (it clears the chunk's old handles, WorldRenderer.hpp:81-86).
+	template <typename Sink> void Flush(Sink &&sink) {
+		if (m_tasks.empty())
+			return;
+		if (!m_upload.empty()) {
+			const size_t n = m_upload.size();
+			m_pos.resize(n * 3), m_blocks.resize(n * HCM_CHUNK_VOXELS), m_heights.resize(n * HCM_CHUNK_COLUMNS);
+			for (size_t i = 0; i < n; ++i) {
+				const auto p = m_upload[i]->GetPosition();
+				m_pos[3 * i] = (int16_t)p.x, m_pos[3 * i + 1] = (int16_t)p.y, m_pos[3 * i + 2] = (int16_t)p.z;
+				std::memcpy(m_blocks.data() + i * HCM_CHUNK_VOXELS, m_upload[i]->GetBlockData(), HCM_CHUNK_VOXELS * 2);
+				for (uint32_t k = 0; k < HCM_CHUNK_COLUMNS; ++k)
+					m_heights[i * HCM_CHUNK_COLUMNS + k] = (int8_t)m_upload[i]->GetSunlightHeight(k);
+			}
+			check(hcm_upload_chunks(m_ctx, (uint32_t)n, m_pos.data(), m_blocks.data(), m_heights.data()));
+		}
+		std::vector<int16_t> tp(m_tasks.size() * 3);
+		for (size_t i = 0; i < m_tasks.size(); ++i)
+			tp[3 * i] = m_tasks[i].x, tp[3 * i + 1] = m_tasks[i].y, tp[3 * i + 2] = m_tasks[i].z;
+		check(hcm_mesh_batch(m_ctx, (uint32_t)m_tasks.size(), tp.data()));
+		hcm_batch_view v{};
+		check(hcm_mesh_fetch(m_ctx, &v));
+		for (uint32_t t = 0; t < v.n_tasks; ++t) {
+			std::vector<BlockMesh> meshes(v.tasks[t].n_meshes);
+			for (uint32_t k = 0; k < v.tasks[t].n_meshes; ++k) {
+				const hcm_mesh_desc &d = v.meshes[v.tasks[t].first_mesh + k];
+				BlockMesh &m = meshes[k];
+				m.vertices.resize(d.vertex_count);
+				std::memcpy(m.vertices.data(), v.vertices + d.vertex_offset, (size_t)d.vertex_count * 8);
+				m.indices.assign(v.indices + d.index_offset, v.indices + d.index_offset + d.index_count);
+				std::memcpy(m.aabb.min, d.aabb_min, 12), std::memcpy(m.aabb.max, d.aabb_max, 12);
+				m.transparent = d.transparent != 0;
+			}
+			sink(m_tasks[t], std::move(meshes));
+		}
+		m_tasks.clear(), m_upload.clear(), m_keepalive.clear();
+	}
+
+	hcm_ctx *Context() { return m_ctx; }
+
+private:
+	void check(int rc) {
+		if (rc)
+			throw Error(rc, hcm_last_error(m_ctx));
+	}
+	hcm_ctx *m_ctx{};
+	std::unordered_map<ChunkPos3, const ChunkT *, ChunkPos3Hash> m_resident;
+	std::vector<std::shared_ptr<ChunkT>> m_upload, m_keepalive;
+	std::vector<ChunkPos3> m_tasks;
+	std::vector<int16_t> m_pos;
+	std::vector<uint16_t> m_blocks;
+	std::vector<int8_t> m_heights;
+};
+
+} // namespace hcm_host

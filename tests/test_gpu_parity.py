@@ -126,3 +126,21 @@ def test_reference_terrain(have_ref, port):
         n_nonempty += int(res.tasks[t]["n_meshes"]) > 0
     assert n_nonempty > 10
     m.close()
+
+
+def test_cpp_host_mirror_dispatcher():
+    """hypercraft_b200/host/hcm_host.hpp (the C++ side a HyperCraft build would compile in): Submit 27-chunk arrays,
+    Flush into a PushChunkMesh-shaped sink, compare with the oracle -- see tests/cpp/test_dispatcher.cpp."""
+    import os
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "tests", "cpp", "test_dispatcher")
+    src = exe + ".cpp"
+    lib = os.path.join(root, "hypercraft_b200", "csrc")
+    subprocess.run(["g++", "-std=c++20", "-O2", "-o", exe, src, f"-L{lib}", "-lhcm", "-ldl", f"-Wl,-rpath,{lib}"], check=True)
+    import hcoracle
+
+    hcoracle.build(ref=False, port=True)
+    r = subprocess.run([exe, os.path.join(root, "hypercraft_b200", "data", "registry.bin"), hcoracle.PORT_SO], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.startswith("PASS"), r.stdout + r.stderr
