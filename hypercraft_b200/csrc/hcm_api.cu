@@ -446,6 +446,10 @@ int hcm_create(const hcm_registry *registry, const hcm_config *cfg, hcm_ctx **ou
 	c->max_chunks = cfg->max_chunks ? cfg->max_chunks : (uint32_t)c->n_cells;
 	c->max_tasks = cfg->max_tasks ? cfg->max_tasks : (uint32_t)c->n_cells;
 	const size_t n_cols = (size_t)w.wy * w.Z * w.X;
+	if (n_cols >= (1ull << 32)) {
+		fail(c, HCM_ERR_INVALID, "window too large: %zu columns (the kernels index columns with 32 bits)", n_cols);
+		return bail(HCM_ERR_INVALID);
+	}
 
 	const size_t n_vox = (size_t)w.wy * 32 * w.Z * w.XP;
 	CUB(dev_alloc(c, &w.prop8, n_vox));

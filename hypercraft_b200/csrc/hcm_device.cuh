@@ -21,10 +21,16 @@ constexpr int kXMargin = 4;
 constexpr int kVoxBytes = kVX * kVZ * kVY; // 58752
 __host__ __device__ constexpr int vox_index(int x, int y, int z) { return ((y + 1) * kVZ + (z + 2)) * kVX + (x + kXMargin); }
 
-// ---- light volume on [-1,32]^3: byte = torch << 4 | sun (block/include/block/Light.hpp:20-24) --------------------
+// ---- canonical cell order on [-1,32]^3 (debug light output, liquid scratch records) ---------------------------------
 constexpr int kLS = 34;
 constexpr int kLightBytes = kLS * kLS * kLS; // 39304
-__host__ __device__ constexpr int light_index(int x, int y, int z) { return (x + 1) + ((z + 1) + (y + 1) * kLS) * kLS; }
+__host__ __device__ constexpr int cell_index(int x, int y, int z) { return (x + 1) + ((z + 1) + (y + 1) * kLS) * kLS; }
+
+// ---- shared-memory light volume on [-1,32]^3: byte = torch << 4 | sun (block/include/block/Light.hpp:20-24) -------
+// y is the fastest axis (padded to 36) so that a flood column unpacks into nine aligned 32-bit stores.
+constexpr int kLY = 36;
+constexpr int kLvolBytes = kLY * kLS * kLS; // 41616
+__host__ __device__ constexpr int lvol_index(int x, int y, int z) { return (y + 1) + kLY * ((x + 1) + kLS * (z + 1)); }
 
 // ---- face masks: one 32x32 bit mask per (axis, slice 0..32, direction) --------------------------------------------
 constexpr int kMasks = 3 * 33 * 2; // 198
@@ -36,7 +42,9 @@ constexpr int kGroupCap = 6144; // faces per group (key 8 B + geometry 4 B each)
 // ---- flood domain: 62 x 62 columns (x,z in [-15,46]) of 62-bit words (bit = y + 15) -------------------------------
 constexpr int kFD = 62;
 constexpr int kFCols = kFD * kFD;       // 3844
-constexpr int kColsPerThread = 8;       // 8 * 512 >= 3844
+constexpr int kInnerSlots = 3;          // 3 * 512 >= 1156 inner columns (their light planes live in registers)
+constexpr int kOuterSlots = 6;          // 6 * 512 >= 2688 outer columns
+constexpr int kColsPerThread = kInnerSlots + kOuterSlots;
 constexpr int kInner = 34;              // columns x,z in [-1,32] carry the result
 constexpr int kInnerCols = kInner * kInner;
 

@@ -215,7 +215,7 @@ __global__ void __launch_bounds__(256)
 // ================================================================================================================
 constexpr int SM_VOX = 0;
 constexpr int SM_LIGHT = SM_VOX + kVoxBytes;          // 58752
-constexpr int SM_F = SM_LIGHT + 39312;                // 98064
+constexpr int SM_F = SM_LIGHT + kLvolBytes;           // 100368
 constexpr int SM_CPLANE = SM_F + kMasks * 32 * 4;     // 123408
 constexpr int SM_REGION = SM_CPLANE + kInnerCols * 8; // 132656
 constexpr int kRegionBytes = kGroupCap * 12;          // 73728
@@ -224,8 +224,8 @@ constexpr int SM_SMALL = SM_REGION + kRegionBytes;    // 206384
 // region views
 constexpr int RG_O = 0, RG_E = kInnerCols * 8, RG_D = 2 * kInnerCols * 8; // planes phase
 constexpr int kSB = 64;                                                   // flood buffer stride (zero border)
-constexpr int RG_SBUF = 0, RG_CNT = kSB * kSB * 8;                        // 32768, then 4 x 1156 x 8 = 36992
-static_assert(RG_CNT + 4 * kInnerCols * 8 <= kRegionBytes, "flood buffers must fit the phase region");
+constexpr int RG_SBUF = 0;                                                // 64 x 64 x 8 = 32768
+static_assert(kSB * kSB * 8 <= kRegionBytes, "flood buffer must fit the phase region");
 static_assert(3 * kInnerCols * 8 <= kRegionBytes, "planes must fit the phase region");
 constexpr int RG_KEYS = 0, RG_GEO = kGroupCap * 8;
 
@@ -257,7 +257,7 @@ __device__ __forceinline__ bool tex_show(const uint8_t *tf, u32 a, u32 b) { // B
 }
 
 __device__ __forceinline__ DynRec dyn_load(const DynRec *dyn, int x, int y, int z) {
-	const u64 raw = __ldcg(reinterpret_cast<const u64 *>(dyn + light_index(x, y, z)));
+	const u64 raw = __ldcg(reinterpret_cast<const u64 *>(dyn + cell_index(x, y, z)));
 	DynRec r;
 	*reinterpret_cast<u64 *>(&r) = raw;
 	return r;
@@ -297,12 +297,12 @@ __device__ __forceinline__ void light4_corner(u32 fP, u32 fQ, u32 fD, bool dF, u
 }
 __device__ __forceinline__ L4 light4_init(const Small &S, const uint8_t *vox, const uint8_t *light, int face, int x, int y, int z) {
 	const int axis = face >> 1, dir = 1 - ((face & 1) << 1);
-	constexpr int VY = kVZ * kVX, LY = kLS * kLS;
+	constexpr int VY = kVZ * kVX, LX = kLY, LZ = kLY * kLS; // light volume strides: y 1, x 36, z 36*34
 	// front cell (kLookup1v, :74) and the strides of the in-plane axes p < q
 	const int vb = vox_index(x, y, z) + dir * (axis == 0 ? 1 : (axis == 1 ? VY : kVX));
-	const int lb = light_index(x, y, z) + dir * (axis == 0 ? 1 : (axis == 1 ? LY : kLS));
+	const int lb = lvol_index(x, y, z) + dir * (axis == 0 ? LX : (axis == 1 ? 1 : LZ));
 	const int vp = axis == 0 ? VY : 1, vq = axis == 2 ? VY : kVX;
-	const int lp = axis == 0 ? LY : 1, lq = axis == 2 ? LY : kLS;
+	const int lp = axis == 0 ? 1 : LX, lq = axis == 2 ? 1 : LZ;
 	u32 fl[3][3], li[3][3];
 #pragma unroll
 	for (int dp = 0; dp < 3; ++dp)
@@ -455,66 +455,88 @@ __device__ __forceinline__ u32 tri_interp(u32 lo, u32 hi, u32 du, u32 dv, u32 dw
 // ---------------------------------------------------------------------------------------------------------------
 // bit-parallel flood of one light channel (reference a2-a4: ChunkMeshTask.cpp:48-111 + BlockLightAlgo.hpp:44-73).
 // Level sets G_l = {cells with light >= l}: G_15 = sources(15), G_l = sources(l) | G_{l+1} | (N6(G_{l+1}) & passable).
-// light(c) = #{l in 1..15 : c in G_l}, accumulated bit-sliced in four planes for the inner 34x34 columns.
-// Each thread owns up to 8 of the 62x62 columns as 62-bit words (bit = y+15); x/z neighbours go through `sbuf`.
-// Only columns within L1 distance 14-step of the inner square can still matter at `step` (IsBorderLightInterfere).
+// light(c) = 15 - (first step at which c enters G), step = 15 - l; the four bit planes of that value are kept in
+// registers for the inner 34x34 columns and unpacked straight into the shared light volume.
+// A column (x,z) of the 62^3 region is one 62-bit word (bit = y+15): y-neighbours are two shifts, x/z-neighbours four
+// word loads from `sbuf`.  Each thread owns up to 3 inner + 6 outer columns.  Only columns within L1 distance
+// 14-step of the inner square can still matter at `step` (the reference's IsBorderLightInterfere pruning), columns
+// with nothing left to light are skipped, and the loop ends at the fixed point.
 // ---------------------------------------------------------------------------------------------------------------
 struct ColInfo {
-	int c[kColsPerThread];     // sbuf index (with zero border), -1 if unused
-	int inner[kColsPerThread]; // index into the count planes or -1
-	int lim[kColsPerThread];   // last step at which the column is still relevant
-	size_t g[kColsPerThread];  // element index of the lower chunk's word in the dense planes
+	int c[kColsPerThread];    // sbuf index (with zero border), -1 if unused
+	int lim[kColsPerThread];  // last step at which the column is still relevant
+	u32 g[kColsPerThread];    // element index of the lower chunk's word in the dense planes (< 2^32: checked in hcm_create)
 };
-
-__device__ __forceinline__ void cnt_add(u64 *cnt, int ii, u64 m) {
-#pragma unroll
-	for (int b = 0; b < 4; ++b) {
-		const u64 c = cnt[b * kInnerCols + ii];
-		cnt[b * kInnerCols + ii] = c ^ m;
-		m &= c;
-	}
-}
-__device__ __forceinline__ void cnt_add_from(u64 *cnt, int ii, u64 m, int b0) {
-	for (int b = b0; b < 4; ++b) {
-		const u64 c = cnt[b * kInnerCols + ii];
-		cnt[b * kInnerCols + ii] = c ^ m;
-		m &= c;
-	}
-}
 
 __device__ __forceinline__ u64 combine3(u32 lo, u32 mid, u32 hi) { // chunk words y-1, y, y+1 -> bits of y in [-15,46]
 	return (u64)(lo >> 17) | ((u64)mid << 15) | ((u64)(hi & 0x7fffu) << 47);
 }
 
+// slot k of thread tid -> domain column (x,z) in [0,62)^2, or false
+__device__ __forceinline__ bool slot_column(int tid, int k, int &x, int &z) {
+	if (k < kInnerSlots) {
+		const int ii = tid + k * kThreads;
+		if (ii >= kInnerCols)
+			return false;
+		x = ii % kInner + 14, z = ii / kInner + 14;
+		return true;
+	}
+	const int o = tid + (k - kInnerSlots) * kThreads;
+	if (o < 14 * kFD) {
+		z = o / kFD, x = o % kFD;
+	} else if (o < 28 * kFD) {
+		z = 48 + (o - 14 * kFD) / kFD, x = (o - 14 * kFD) % kFD;
+	} else if (o < 28 * kFD + kInner * 28) {
+		const int q = o - 28 * kFD;
+		z = 14 + q / 28;
+		const int xx = q % 28;
+		x = xx < 14 ? xx : xx + kInner;
+	} else
+		return false;
+	return true;
+}
+
+// spread the 4 low bits of n to bit 0 of 4 bytes
+__device__ __forceinline__ u32 spread4(u32 n) { return (n * 0x00204081u) & 0x01010101u; }
+
 template <bool kTorch>
-__device__ __forceinline__ void flood_channel(const MeshParams &p, const ColInfo &ci, const u64 (&P)[kColsPerThread], u64 *sbuf, u64 *cnt, int tid) {
+__device__ __forceinline__ void flood_channel(const MeshParams &p, const ColInfo &ci, const u64 (&P)[kColsPerThread], u64 *sbuf, uint8_t *light, int tid) {
 	const size_t plane_stride = (size_t)p.w.Z * p.w.X; // one chunk layer of columns
 	u64 G[kColsPerThread];
+	u64 pl[kInnerSlots][4]; // bit planes of the light value of the inner columns
+	bool dirty[kColsPerThread];
 #pragma unroll
 	for (int k = 0; k < kColsPerThread; ++k)
-		G[k] = 0;
-	for (int i = tid; i < 4 * kInnerCols; i += kThreads)
-		cnt[i] = 0;
-	__syncthreads();
+		G[k] = 0, dirty[k] = false;
+#pragma unroll
+	for (int k = 0; k < kInnerSlots; ++k)
+		pl[k][0] = pl[k][1] = pl[k][2] = pl[k][3] = 0;
 	const int last_inject_step = kTorch ? 15 - (int)p.w.levels[p.w.n_levels - 1] : 0;
 	bool any_set = false; // block-uniform: some G bit is set anywhere
 	for (int step = 0; step <= 14; ++step) {
 		bool changed = false;
+		u64 nw[kInnerSlots];
+#pragma unroll
+		for (int k = 0; k < kInnerSlots; ++k)
+			nw[k] = 0;
 		if (step > 0 && any_set) {
 #pragma unroll
 			for (int k = 0; k < kColsPerThread; ++k)
-				if (ci.c[k] >= 0)
-					sbuf[ci.c[k]] = G[k];
+				if (dirty[k])
+					sbuf[ci.c[k]] = G[k], dirty[k] = false;
 			__syncthreads();
 #pragma unroll
 			for (int k = 0; k < kColsPerThread; ++k)
-				if (ci.c[k] >= 0 && step <= ci.lim[k]) {
+				if (ci.c[k] >= 0 && step <= ci.lim[k] && (P[k] & ~G[k])) {
 					const int c = ci.c[k];
 					const u64 g = G[k];
 					const u64 n = sbuf[c - 1] | sbuf[c + 1] | sbuf[c - kSB] | sbuf[c + kSB];
-					const u64 ng = g | (((g << 1) | (g >> 1) | n) & P[k]);
-					changed |= ng != g;
-					G[k] = ng;
+					const u64 add = (((g << 1) | (g >> 1) | n) & P[k]) & ~g;
+					if (add) {
+						G[k] = g | add, dirty[k] = true, changed = true;
+						if (k < kInnerSlots)
+							nw[k] = add;
+					}
 				}
 		}
 		// sources of level 15 - step
@@ -530,7 +552,11 @@ __device__ __forceinline__ void flood_channel(const MeshParams &p, const ColInfo
 							s[d] = h >= 32 ? 0u : (h <= 0 ? 0xffffffffu : (0xffffffffu << h)); // sunlit: y >= height, Chunk.hpp:73-76
 						}
 						G[k] = combine3(s[0], s[1], s[2]);
-						changed |= G[k] != 0;
+						if (G[k]) {
+							dirty[k] = true, changed = true;
+							if (k < kInnerSlots)
+								nw[k] = G[k];
+						}
 					}
 			}
 		} else {
@@ -541,28 +567,45 @@ __device__ __forceinline__ void flood_channel(const MeshParams &p, const ColInfo
 #pragma unroll
 					for (int k = 0; k < kColsPerThread; ++k)
 						if (ci.c[k] >= 0) {
-							const u64 s = combine3(src[ci.g[k]], src[ci.g[k] + plane_stride], src[ci.g[k] + 2 * plane_stride]);
-							changed |= (s & ~G[k]) != 0;
-							G[k] |= s;
+							const u64 s = combine3(src[ci.g[k]], src[ci.g[k] + plane_stride], src[ci.g[k] + 2 * plane_stride]) & ~G[k];
+							if (s) {
+								G[k] |= s, dirty[k] = true, changed = true;
+								if (k < kInnerSlots)
+									nw[k] |= s;
+							}
 						}
 				}
 		}
+		// cells that entered G at this step get the value 15 - step
+		const u32 val = 15 - step;
 #pragma unroll
-		for (int k = 0; k < kColsPerThread; ++k)
-			if (ci.inner[k] >= 0)
-				cnt_add(cnt, ci.inner[k], G[k]);
+		for (int k = 0; k < kInnerSlots; ++k)
+#pragma unroll
+			for (int b = 0; b < 4; ++b)
+				if ((val >> b) & 1)
+					pl[k][b] |= nw[k];
 		const bool any_changed = __syncthreads_or(changed);
 		any_set |= any_changed;
-		if (!any_changed && step >= last_inject_step) {
-			// fixed point: the remaining 14 - step level sets are identical -> add them at once
-			const int rem = 14 - step;
+		if (!any_changed && step >= last_inject_step)
+			break; // fixed point
+	}
+	// unpack: 34 cells of a column = nine 32-bit words of the y-fastest light volume (cell y at byte y+1)
 #pragma unroll
-			for (int k = 0; k < kColsPerThread; ++k)
-				if (ci.inner[k] >= 0)
-					for (int b = 0; b < 4; ++b)
-						if ((rem >> b) & 1)
-							cnt_add_from(cnt, ci.inner[k], G[k], b);
-			break;
+	for (int k = 0; k < kInnerSlots; ++k) {
+		const int ii = tid + k * kThreads;
+		if (ii < kInnerCols) {
+			u32 *dst = reinterpret_cast<u32 *>(light + kLY * ii); // lvol_index(x,-1,z) = 36 * ((x+1) + 34*(z+1)) = 36 * ii
+#pragma unroll
+			for (int j = 0; j < 9; ++j) {
+				// word j holds volume bytes 4j..4j+3 = cells y = 4j-1 .. 4j+2 = plane bits 4j+14 .. 4j+17
+				const int sh = 4 * j + 14;
+				u32 w = spread4((u32)(pl[k][0] >> sh) & 15u) | (spread4((u32)(pl[k][1] >> sh) & 15u) << 1) | (spread4((u32)(pl[k][2] >> sh) & 15u) << 2) |
+				        (spread4((u32)(pl[k][3] >> sh) & 15u) << 3);
+				if (kTorch)
+					dst[j] |= w << 4;
+				else
+					dst[j] = w;
+			}
 		}
 	}
 	__syncthreads();
@@ -581,10 +624,10 @@ __device__ void merge_mask(Small &S, const u32 *F, u64 *keys, u32 *geo, int m, i
 	const u32 base = S.fcpre[m] - S.fcpre[g0];
 	u32 Arow = Forig;
 	u32 nq = 0, nqt = 0;
-	for (int u = 0; u < 32; ++u) {
+	u32 todo = __ballot_sync(FULL, Arow != 0); // rows that still hold unconsumed faces
+	while (todo) {
+		const int u = __ffs(todo) - 1;
 		const u32 rowbits = __shfl_sync(FULL, Arow, u);
-		if (!rowbits)
-			continue;
 		const u32 Fr = __shfl_sync(FULL, Forig, u), pr = __shfl_sync(FULL, pre, u);
 		const bool active = (rowbits >> lane) & 1;
 		const u64 key = active ? keys[base + pr + __popc(Fr & lt)] : 0ull;
@@ -629,7 +672,7 @@ __device__ void merge_mask(Small &S, const u32 *F, u64 *keys, u32 *geo, int m, i
 		}
 		nq += __popc(startmask);
 		nqt += __popc(__ballot_sync(FULL, tr));
-		__syncwarp();
+		todo = __ballot_sync(FULL, Arow != 0) & ~((2u << u) - 1u); // rows below u that are not fully consumed
 	}
 	if (lane == 0)
 		S.nq[m] = nq, S.nqt[m] = nqt, S.nqo[m] = nq - nqt;
@@ -851,27 +894,36 @@ __global__ void __launch_bounds__(kThreads, 1) mesh_kernel(const __grid_constant
 		mbar_wait(&S.bar, phase);
 		phase ^= 1;
 
-		// ---- phase 1: class bit planes (bit x+1 of row (y,z)) -------------------------------------------------------
+		// ---- phase 1: class bit planes (bit x+1 of row (y,z)); one lane builds one row from three 16-byte loads -------
 		{
 			u64 *Opl = reinterpret_cast<u64 *>(region + RG_O), *Epl = reinterpret_cast<u64 *>(region + RG_E), *Dpl = reinterpret_cast<u64 *>(region + RG_D);
 			u32 ncust = 0, anyd = 0;
-			for (int row = warp; row < kInnerCols; row += kWarps) {
-				const int y = row / kInner - 1, z = row % kInner - 1;
-				const uint8_t *r = vox + vox_index(0, y, z);
-				const u32 fl = S.tab.pflags[r[lane]];
-				const u32 fx = lane < 2 ? S.tab.pflags[r[lane == 0 ? -1 : 32]] : 0u;
-				auto plane = [&](u32 bit) -> u64 {
-					const u32 b = __ballot_sync(FULL, fl & bit), e = __ballot_sync(FULL, fx & bit);
-					return ((u64)b << 1) | (u64)(e & 1u) | ((u64)((e >> 1) & 1u) << 33);
-				};
-				const u64 o = plane(PF_SOLID), e = plane(PF_EMPTY), c = plane(PF_CUSTOM), d = plane(PF_DYNAMIC);
-				if (lane == 0) {
-					Opl[row] = o, Epl[row] = e, Cpl[row] = c, Dpl[row] = d;
-					if (y >= 0 && y < 32 && z >= 0 && z < 32)
-						ncust += __popc((u32)(c >> 1));
-					anyd |= d != 0;
+			for (int row = tid; row < kInnerCols; row += kThreads) {
+				const int yy = row / kInner, zz = row % kInner; // y + 1, z + 1
+				const uint4 *r = reinterpret_cast<const uint4 *>(vox + (yy * kVZ + zz + 1) * kVX);
+				const uint4 q0 = r[0], q1 = r[1], q2 = r[2];
+				const u32 w[12] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w};
+				u32 lo[4] = {0, 0, 0, 0}, hi[4] = {0, 0, 0, 0};
+#pragma unroll
+				for (int i = 0; i < 34; ++i) { // stored byte i + 3 <-> world x = i - 1 <-> plane bit i
+					const u32 pr = (w[(i + 3) >> 2] >> (8 * ((i + 3) & 3))) & 0xffu;
+					const u32 cls = (u32)S.tab.pflags[pr] >> 2; // bit0 O, bit1 E, bit2 C, bit3 D
+#pragma unroll
+					for (int k = 0; k < 4; ++k) {
+						if (i < 32)
+							lo[k] |= ((cls >> k) & 1u) << i;
+						else
+							hi[k] |= ((cls >> k) & 1u) << (i - 32);
+					}
 				}
+				Opl[row] = ((u64)hi[0] << 32) | lo[0], Epl[row] = ((u64)hi[1] << 32) | lo[1];
+				Cpl[row] = ((u64)hi[2] << 32) | lo[2], Dpl[row] = ((u64)hi[3] << 32) | lo[3];
+				if (yy >= 1 && yy <= 32 && zz >= 1 && zz <= 32)
+					ncust += __popc((lo[2] >> 1) | (hi[2] << 31));
+				anyd |= lo[3] | hi[3];
 			}
+			ncust = __reduce_add_sync(FULL, ncust);
+			anyd = __reduce_or_sync(FULL, anyd);
 			if (lane == 0 && (ncust | anyd)) {
 				atomicAdd(&S.n_custom, ncust);
 				if (anyd)
@@ -890,7 +942,7 @@ __global__ void __launch_bounds__(kThreads, 1) mesh_kernel(const __grid_constant
 					const int x = __ffsll((long long)w) - 2;
 					w &= w - 1;
 					const DynRec r = flow_record(p, S, vox, ti, x, y, z);
-					*reinterpret_cast<u64 *>(dyn + light_index(x, y, z)) = *reinterpret_cast<const u64 *>(&r);
+					*reinterpret_cast<u64 *>(dyn + cell_index(x, y, z)) = *reinterpret_cast<const u64 *>(&r);
 				}
 			}
 			__syncthreads();
@@ -969,7 +1021,6 @@ __global__ void __launch_bounds__(kThreads, 1) mesh_kernel(const __grid_constant
 		// ---- phase 4: light ---------------------------------------------------------------------------------------------
 		{
 			u64 *sbuf = reinterpret_cast<u64 *>(region + RG_SBUF);
-			u64 *cnt = reinterpret_cast<u64 *>(region + RG_CNT);
 			for (int i = tid; i < kSB * kSB; i += kThreads)
 				sbuf[i] = 0; // zero border (and interior)
 			ColInfo ci;
@@ -977,50 +1028,32 @@ __global__ void __launch_bounds__(kThreads, 1) mesh_kernel(const __grid_constant
 			const size_t plane_stride = (size_t)p.w.Z * p.w.X;
 #pragma unroll
 			for (int k = 0; k < kColsPerThread; ++k) {
-				const int c = tid + k * kThreads;
-				if (c < kFCols) {
-					const int x = c % kFD, z = c / kFD; // domain coords: world x = x - 15
+				int x = 0, z = 0; // domain coords: world x = x - 15
+				bool ok = slot_column(tid, k, x, z);
+				const int dx = x < 14 ? 14 - x : (x > 47 ? x - 47 : 0), dz = z < 14 ? 14 - z : (z > 47 ? z - 47 : 0);
+				ok = ok && dx + dz <= 14; // farther columns can never reach the inner square
+				if (ok) {
 					ci.c[k] = (z + 1) * kSB + (x + 1);
-					const int dx = x < 14 ? 14 - x : (x > 47 ? x - 47 : 0), dz = z < 14 ? 14 - z : (z > 47 ? z - 47 : 0);
 					ci.lim[k] = 14 - dx - dz;
-					ci.inner[k] = (dx == 0 && dz == 0) ? (z - 14) * kInner + (x - 14) : -1;
-					ci.g[k] = ((size_t)(ti.cy - 1) * p.w.Z + (size_t)(ti.cz * 32 - 15 + z)) * p.w.X + (size_t)(ti.cx * 32 - 15 + x);
+					ci.g[k] = (u32)(((size_t)(ti.cy - 1) * p.w.Z + (size_t)(ti.cz * 32 - 15 + z)) * p.w.X + (size_t)(ti.cx * 32 - 15 + x));
 					P[k] = combine3(p.w.pass[ci.g[k]], p.w.pass[ci.g[k] + plane_stride], p.w.pass[ci.g[k] + 2 * plane_stride]);
 				} else {
-					ci.c[k] = -1, ci.lim[k] = -1, ci.inner[k] = -1, ci.g[k] = 0, P[k] = 0;
+					ci.c[k] = -1, ci.lim[k] = -1, ci.g[k] = 0, P[k] = 0;
 				}
 			}
 			__syncthreads();
-			flood_channel<false>(p, ci, P, sbuf, cnt, tid);
-			// unpack the sunlight planes: light[x,y,z] = sun (torch nibble filled below)
-			for (int ii = tid; ii < kInnerCols; ii += kThreads) {
-				const u64 c0 = cnt[ii], c1 = cnt[kInnerCols + ii], c2 = cnt[2 * kInnerCols + ii], c3 = cnt[3 * kInnerCols + ii];
-				const int x = ii % kInner - 1, z = ii / kInner - 1;
-				for (int y = -1; y <= 32; ++y) {
-					const int b = y + 15;
-					light[light_index(x, y, z)] = (uint8_t)(((c0 >> b) & 1) | (((c1 >> b) & 1) << 1) | (((c2 >> b) & 1) << 2) | (((c3 >> b) & 1) << 3));
-				}
-			}
-			__syncthreads();
+			flood_channel<false>(p, ci, P, sbuf, light, tid);
 			if (S.any_torch && p.w.n_levels > 0) {
 				for (int i = tid; i < kSB * kSB; i += kThreads)
 					sbuf[i] = 0;
 				__syncthreads();
-				flood_channel<true>(p, ci, P, sbuf, cnt, tid);
-				for (int ii = tid; ii < kInnerCols; ii += kThreads) {
-					const u64 c0 = cnt[ii], c1 = cnt[kInnerCols + ii], c2 = cnt[2 * kInnerCols + ii], c3 = cnt[3 * kInnerCols + ii];
-					const int x = ii % kInner - 1, z = ii / kInner - 1;
-					for (int y = -1; y <= 32; ++y) {
-						const int b = y + 15;
-						const u32 t = (u32)(((c0 >> b) & 1) | (((c1 >> b) & 1) << 1) | (((c2 >> b) & 1) << 2) | (((c3 >> b) & 1) << 3));
-						light[light_index(x, y, z)] |= (uint8_t)(t << 4);
-					}
-				}
-				__syncthreads();
+				flood_channel<true>(p, ci, P, sbuf, light, tid);
 			}
-			if (want_light)
-				for (int i = tid; i < kLightBytes; i += kThreads)
-					p.debug_light[(size_t)task * kLightBytes + i] = light[i];
+			if (want_light) // canonical order (x fastest, then z, then y) for hcm_debug_light
+				for (int i = tid; i < kLightBytes; i += kThreads) {
+					const int x = i % kLS - 1, z = (i / kLS) % kLS - 1, y = i / (kLS * kLS) - 1;
+					p.debug_light[(size_t)task * kLightBytes + i] = light[lvol_index(x, y, z)];
+				}
 		}
 
 		// ---- phase 5: custom faces per row and stream (count), exclusive prefix in (y,z) row order -------------------
@@ -1096,6 +1129,8 @@ __global__ void __launch_bounds__(kThreads, 1) mesh_kernel(const __grid_constant
 				if (nf) {
 					// (a) face locations into the key slots, in mask/row/column order
 					for (int m = g0 + warp; m < g1; m += kWarps) {
+						if (!S.fc[m])
+							continue;
 						u32 fw = F[m * 32 + lane];
 						u32 at = S.fcpre[m] - S.fcpre[g0] + warp_excl_scan(__popc(fw), lane);
 						while (fw) {
@@ -1126,19 +1161,26 @@ __global__ void __launch_bounds__(kThreads, 1) mesh_kernel(const __grid_constant
 							S.nq[m] = 0, S.nqo[m] = 0, S.nqt[m] = 0;
 					}
 					__syncthreads();
-					// (d) ordered offsets: exclusive scan of the per-mask quad counts of both streams
-					if (warp == 0) {
-						u32 ro = S.run_o, rt = S.run_t;
-						for (int b = g0; b < g1; b += 32) {
-							const int m = b + lane;
-							const u32 vo = m < g1 ? S.nqo[m] : 0u, vt = m < g1 ? S.nqt[m] : 0u;
-							const u32 eo = warp_excl_scan(vo, lane), et = warp_excl_scan(vt, lane);
-							if (m < g1)
-								S.baseo[m] = ro + eo, S.baset[m] = rt + et;
-							ro += __shfl_sync(FULL, eo + vo, 31), rt += __shfl_sync(FULL, et + vt, 31);
+					// (d) ordered offsets: exclusive scan of the per-mask quad counts of both streams (masks <= 198 <= 7 warps)
+					{
+						const int m = g0 + tid;
+						const u32 vo = m < g1 ? S.nqo[m] : 0u, vt = m < g1 ? S.nqt[m] : 0u;
+						const u32 eo = warp_excl_scan(vo, lane), et = warp_excl_scan(vt, lane);
+						if (lane == 31 && warp < 8)
+							S.wtmp[0][warp] = eo + vo, S.wtmp[1][warp] = et + vt;
+						__syncthreads();
+						u32 co = S.run_o, ct = S.run_t;
+						for (int w2 = 0; w2 < warp && w2 < 8; ++w2)
+							co += S.wtmp[0][w2], ct += S.wtmp[1][w2];
+						if (m < g1)
+							S.baseo[m] = co + eo, S.baset[m] = ct + et;
+						__syncthreads();
+						if (tid == 0) {
+							u32 to = 0, tt = 0;
+							for (int w2 = 0; w2 < 8; ++w2)
+								to += S.wtmp[0][w2], tt += S.wtmp[1][w2];
+							S.run_o += to, S.run_t += tt;
 						}
-						if (lane == 0)
-							S.run_o = ro, S.run_t = rt;
 					}
 					__syncthreads();
 				}
