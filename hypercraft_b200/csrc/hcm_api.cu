@@ -194,7 +194,7 @@ int build_tables(hcm_ctx *c, const hcm_registry *reg, DevTables &t, std::vector<
 				all_solid = false;
 			else
 				all_empty = false;
-			if (fl & HCM_TEX_TRANSPARENT)
+			if (fl & (HCM_TEX_TRANSPARENT | HCM_TEX_LIQUID))
 				all_solid = false;
 		}
 		const bool dynamic = p.custom_mesh && reg->meshes[p.custom_mesh - 1].dynamic_kind != HCM_DYNAMIC_NONE;

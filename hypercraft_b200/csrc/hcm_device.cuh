@@ -54,12 +54,14 @@ constexpr int kMaxSplits = 40;                                 // >= ceil(622592
 // ---- per-property flags (DevTables::pflags) ------------------------------------------------------------------------
 constexpr uint8_t PF_INDIRECT = 1;  // Block::GetIndirectLightPass  (transparency != opaque), Block.hpp:70
 constexpr uint8_t PF_DIRECT = 2;    // GetVerticalLightPass || collision != solid, BlockMeshAlgo.hpp:119,124
-constexpr uint8_t PF_SOLID = 4;     // class O: six non-empty, non-transparent face textures, no dynamic mesh
+constexpr uint8_t PF_SOLID = 4;     // class O: six non-empty, non-transparent, non-liquid face textures, no custom mesh
 constexpr uint8_t PF_EMPTY = 8;     // class E: six empty face textures, no dynamic mesh
 constexpr uint8_t PF_CUSTOM = 16;   // has a custom mesh
 constexpr uint8_t PF_DYNAMIC = 32;  // custom mesh is dynamic (liquid flow)
 constexpr uint8_t PF_LIQ_SOURCE = 64;
 constexpr uint8_t PF_LIQ_FLOW = 128;
+
+static_assert(PF_INDIRECT == 1 && PF_SOLID == 4 && PF_EMPTY == 8, "derive_kernel relies on these bit positions");
 
 // texture code flags (DevTables::texflags): HCM_TEX_* plus
 constexpr uint8_t TF_EMPTY = 8; // BlockTexture::Empty(): id == 0

@@ -73,38 +73,88 @@ __device__ __forceinline__ u32 warp_excl_scan(u32 v, int lane) {
 // ================================================================================================================
 __global__ void __launch_bounds__(256) derive_kernel(DevWorld w, const UploadEntry *__restrict__ entries, const uint8_t *__restrict__ prop_index,
                                                      const DevTables *__restrict__ tables, const int8_t *__restrict__ raw_heights) {
-	__shared__ uint8_t s_pflags[256], s_pmisc[256];
+	__shared__ uint16_t s_pinfo[256]; // pflags | light level << 8
 	__shared__ u32 s_and, s_or;
 	const int tid = threadIdx.x;
-	s_pflags[tid] = tables->pflags[tid];
-	s_pmisc[tid] = tables->pmisc[tid];
+	s_pinfo[tid] = (uint16_t)(tables->pflags[tid] | ((tables->pmisc[tid] >> 4) << 8));
 	if (tid == 0)
 		s_and = 0xffffffffu, s_or = 0;
-	__syncthreads();
 
 	const UploadEntry e = entries[blockIdx.x];
 	const int z = tid >> 3, x4 = (tid & 7) << 2;
 	const uint16_t *raw = w.raw + (size_t)e.slot * HCM_CHUNK_VOXELS;
 	const size_t gx = (size_t)e.cx * 32 + x4, gz = (size_t)e.cz * 32 + z;
+	uint8_t *prow = w.prop8 + (((size_t)e.cy * 32) * w.Z + gz) * w.XP + gx + kXMargin; // + y * Z * XP
+	const size_t pstride = (size_t)w.Z * w.XP;
+	const size_t col = ((size_t)e.cy * w.Z + gz) * w.X + gx;
+	const size_t plane = (size_t)w.wy * w.Z * w.X;
+	const size_t ci = ((size_t)e.cy * w.wz + e.cz) * w.wx + e.cx;
 
+	// ---- uniform chunks (all air, all stone: most of a load sphere) need one table lookup, not 32768 ----------------
+	const u32 d0 = raw[0];
+	const u32 pat = d0 | (d0 << 16);
+	u32 acc_and = 0xffffffffu, acc_or = 0; // all 32 loads are independent: uniform <=> AND == OR == pattern
+#pragma unroll
+	for (int y = 0; y < 32; ++y) {
+		const uint2 r = __ldg(reinterpret_cast<const uint2 *>(raw + x4 + (y * 32 + z) * 32));
+		acc_and &= r.x & r.y, acc_or |= r.x | r.y;
+	}
+	const bool same = acc_and == pat && acc_or == pat;
+	*reinterpret_cast<char4 *>(w.height + col) = *reinterpret_cast<const char4 *>(raw_heights + (size_t)e.slot * HCM_CHUNK_COLUMNS + z * 32 + x4);
+	if (__syncthreads_and(same)) {
+		const u32 pr = __ldg(prop_index + d0);
+		const u32 info = s_pinfo[pr], fl = info & 0xffu, lvl = info >> 8;
+		const u32 p4 = pr * 0x01010101u;
+#pragma unroll 8
+		for (int y = 0; y < 32; ++y)
+			*reinterpret_cast<u32 *>(prow + y * pstride) = p4;
+		const u32 pw = (fl & PF_INDIRECT) ? 0xffffffffu : 0u;
+		*reinterpret_cast<uint4 *>(w.pass + col) = make_uint4(pw, pw, pw, pw);
+		for (int l = 0; l < w.n_levels; ++l) {
+			const u32 tw = (lvl && w.levels[l] == lvl) ? 0xffffffffu : 0u;
+			*reinterpret_cast<uint4 *>(w.torch + l * plane + col) = make_uint4(tw, tw, tw, tw);
+		}
+		if (tid == 0) {
+			u32 cf = CF_RESIDENT;
+			if (fl & PF_EMPTY)
+				cf |= CF_ALL_EMPTY | 0x3fu * CF_FACE_EMPTY0;
+			if (fl & PF_SOLID)
+				cf |= CF_ALL_SOLID | 0x3fu * CF_FACE_SOLID0;
+			if (fl & PF_CUSTOM)
+				cf |= CF_HAS_CUSTOM;
+			if (fl & PF_DYNAMIC)
+				cf |= CF_HAS_DYNAMIC;
+			if (lvl)
+				cf |= CF_HAS_TORCH;
+			w.cflags[ci] = cf;
+			w.slot[ci] = e.slot;
+		}
+		return;
+	}
+
+	// ---- general chunk -----------------------------------------------------------------------------------------------
 	u32 pass[4] = {0, 0, 0, 0};
 	u32 torch[kMaxLightLevels][4];
 #pragma unroll
 	for (int l = 0; l < kMaxLightLevels; ++l)
 		torch[l][0] = torch[l][1] = torch[l][2] = torch[l][3] = 0;
-	u32 f_and = 0xffu, f_or = 0; // PF_* accumulated over the thread's voxels
-	u32 face_solid = 0x3f, face_empty = 0x3f; // per boundary side: all voxels of that layer seen by this thread are O / E
-
+	u32 f_and = 0xffu, f_or = 0;              // PF_* accumulated over the thread's voxels (bit 8 of f_or: some voxel emits light)
+	u32 face_solid = 0x3f, face_empty = 0x3f; // per boundary side: every voxel of that layer seen by this thread is class O / E
+	// boundary layers: side 0 +x (x=31), 1 -x (x=0), 2 +y, 3 -y, 4 +z, 5 -z
+	const u32 on_z = (z == 31 ? 16u : 0u) | (z == 0 ? 32u : 0u);
+	const u32 on_x[4] = {on_z | (x4 == 0 ? 2u : 0u), on_z, on_z, on_z | (x4 == 28 ? 1u : 0u)};
 	for (int y = 0; y < 32; ++y) {
 		const uint2 r = *reinterpret_cast<const uint2 *>(raw + x4 + (y * 32 + z) * 32);
 		const u32 d[4] = {r.x & 0xffffu, r.x >> 16, r.y & 0xffffu, r.y >> 16};
-		uint8_t pr[4];
+		const u32 on_y = (y == 31 ? 4u : 0u) | (y == 0 ? 8u : 0u);
+		u32 pr[4];
+#pragma unroll
+		for (int i = 0; i < 4; ++i)
+			pr[i] = __ldg(prop_index + d[i]);
 #pragma unroll
 		for (int i = 0; i < 4; ++i) {
-			pr[i] = __ldg(prop_index + d[i]);
-			const u32 fl = s_pflags[pr[i]];
-			const u32 lvl = s_pmisc[pr[i]] >> 4;
-			pass[i] |= (fl & PF_INDIRECT ? 1u : 0u) << y;
+			const u32 info = s_pinfo[pr[i]], fl = info & 0xffu, lvl = info >> 8;
+			pass[i] |= (fl & PF_INDIRECT) << y; // PF_INDIRECT == 1
 			if (lvl) {
 				f_or |= 0x100u;
 #pragma unroll
@@ -114,23 +164,15 @@ __global__ void __launch_bounds__(256) derive_kernel(DevWorld w, const UploadEnt
 			}
 			f_and &= fl;
 			f_or |= fl;
-			// boundary layers: side 0 +x (x=31), 1 -x (x=0), 2 +y, 3 -y, 4 +z, 5 -z
-			const int x = x4 + i;
-			u32 on = (x == 31 ? 1u : 0u) | (x == 0 ? 2u : 0u) | (y == 31 ? 4u : 0u) | (y == 0 ? 8u : 0u) | (z == 31 ? 16u : 0u) | (z == 0 ? 32u : 0u);
-			if (!(fl & PF_SOLID))
-				face_solid &= ~on;
-			if (!(fl & PF_EMPTY))
-				face_empty &= ~on;
+			const u32 on = on_x[i] | on_y;
+			face_solid &= ~(on & (((fl >> 2) & 1u) - 1u)); // PF_SOLID == 4
+			face_empty &= ~(on & (((fl >> 3) & 1u) - 1u)); // PF_EMPTY == 8
 		}
-		uchar4 o = make_uchar4(pr[0], pr[1], pr[2], pr[3]);
-		*reinterpret_cast<uchar4 *>(w.prop8 + (((size_t)e.cy * 32 + y) * w.Z + gz) * w.XP + gx + kXMargin) = o;
+		*reinterpret_cast<u32 *>(prow + y * pstride) = pr[0] | (pr[1] << 8) | (pr[2] << 16) | (pr[3] << 24);
 	}
-	const size_t col = ((size_t)e.cy * w.Z + gz) * w.X + gx;
 	*reinterpret_cast<uint4 *>(w.pass + col) = make_uint4(pass[0], pass[1], pass[2], pass[3]);
-	const size_t plane = (size_t)w.wy * w.Z * w.X;
 	for (int l = 0; l < w.n_levels; ++l)
 		*reinterpret_cast<uint4 *>(w.torch + l * plane + col) = make_uint4(torch[l][0], torch[l][1], torch[l][2], torch[l][3]);
-	*reinterpret_cast<char4 *>(w.height + col) = *reinterpret_cast<const char4 *>(raw_heights + (size_t)e.slot * HCM_CHUNK_COLUMNS + z * 32 + x4);
 
 	// block-wide AND / OR of the per-thread summaries
 	u32 a = (f_and & 0xffu) | (face_solid << 8) | (face_empty << 16);
@@ -157,7 +199,6 @@ __global__ void __launch_bounds__(256) derive_kernel(DevWorld w, const UploadEnt
 			cf |= CF_HAS_TORCH;
 		cf |= ((A >> 8) & 0x3f) * CF_FACE_SOLID0;
 		cf |= ((A >> 16) & 0x3f) * CF_FACE_EMPTY0;
-		const size_t ci = ((size_t)e.cy * w.wz + e.cz) * w.wx + e.cx;
 		w.cflags[ci] = cf;
 		w.slot[ci] = e.slot;
 	}
@@ -224,8 +265,8 @@ constexpr int SM_SMALL = SM_REGION + kRegionBytes;    // 206384
 // region views
 constexpr int RG_O = 0, RG_E = kInnerCols * 8, RG_D = 2 * kInnerCols * 8; // planes phase
 constexpr int kSB = 64;                                                   // flood buffer stride (zero border)
-constexpr int RG_SBUF = 0;                                                // 64 x 64 x 8 = 32768
-static_assert(kSB * kSB * 8 <= kRegionBytes, "flood buffer must fit the phase region");
+constexpr int RG_SBUF = 0;                                                // 2 x 64 x 64 x 8 = 65536 (double buffered)
+static_assert(2 * kSB * kSB * 8 <= kRegionBytes, "flood buffers must fit the phase region");
 static_assert(3 * kInnerCols * 8 <= kRegionBytes, "planes must fit the phase region");
 constexpr int RG_KEYS = 0, RG_GEO = kGroupCap * 8;
 
@@ -504,10 +545,12 @@ __device__ __forceinline__ void flood_channel(const MeshParams &p, const ColInfo
 	const size_t plane_stride = (size_t)p.w.Z * p.w.X; // one chunk layer of columns
 	u64 G[kColsPerThread];
 	u64 pl[kInnerSlots][4]; // bit planes of the light value of the inner columns
-	bool dirty[kColsPerThread];
+	// sbuf is double buffered: step s reads buffer (s-1)&1 and publishes into buffer s&1, so one barrier per step is
+	// enough.  A column that changed at step s must be published at steps s and s+1 (once into each buffer).
+	int dirty[kColsPerThread];
 #pragma unroll
 	for (int k = 0; k < kColsPerThread; ++k)
-		G[k] = 0, dirty[k] = false;
+		G[k] = 0, dirty[k] = 0;
 #pragma unroll
 	for (int k = 0; k < kInnerSlots; ++k)
 		pl[k][0] = pl[k][1] = pl[k][2] = pl[k][3] = 0;
@@ -519,21 +562,18 @@ __device__ __forceinline__ void flood_channel(const MeshParams &p, const ColInfo
 #pragma unroll
 		for (int k = 0; k < kInnerSlots; ++k)
 			nw[k] = 0;
+		const u64 *rd = sbuf + ((step - 1) & 1) * (kSB * kSB);
+		u64 *wr = sbuf + (step & 1) * (kSB * kSB);
 		if (step > 0 && any_set) {
-#pragma unroll
-			for (int k = 0; k < kColsPerThread; ++k)
-				if (dirty[k])
-					sbuf[ci.c[k]] = G[k], dirty[k] = false;
-			__syncthreads();
 #pragma unroll
 			for (int k = 0; k < kColsPerThread; ++k)
 				if (ci.c[k] >= 0 && step <= ci.lim[k] && (P[k] & ~G[k])) {
 					const int c = ci.c[k];
 					const u64 g = G[k];
-					const u64 n = sbuf[c - 1] | sbuf[c + 1] | sbuf[c - kSB] | sbuf[c + kSB];
+					const u64 n = rd[c - 1] | rd[c + 1] | rd[c - kSB] | rd[c + kSB];
 					const u64 add = (((g << 1) | (g >> 1) | n) & P[k]) & ~g;
 					if (add) {
-						G[k] = g | add, dirty[k] = true, changed = true;
+						G[k] = g | add, dirty[k] = 2, changed = true;
 						if (k < kInnerSlots)
 							nw[k] = add;
 					}
@@ -553,7 +593,7 @@ __device__ __forceinline__ void flood_channel(const MeshParams &p, const ColInfo
 						}
 						G[k] = combine3(s[0], s[1], s[2]);
 						if (G[k]) {
-							dirty[k] = true, changed = true;
+							dirty[k] = 2, changed = true;
 							if (k < kInnerSlots)
 								nw[k] = G[k];
 						}
@@ -569,7 +609,7 @@ __device__ __forceinline__ void flood_channel(const MeshParams &p, const ColInfo
 						if (ci.c[k] >= 0) {
 							const u64 s = combine3(src[ci.g[k]], src[ci.g[k] + plane_stride], src[ci.g[k] + 2 * plane_stride]) & ~G[k];
 							if (s) {
-								G[k] |= s, dirty[k] = true, changed = true;
+								G[k] |= s, dirty[k] = 2, changed = true;
 								if (k < kInnerSlots)
 									nw[k] |= s;
 							}
@@ -584,6 +624,10 @@ __device__ __forceinline__ void flood_channel(const MeshParams &p, const ColInfo
 			for (int b = 0; b < 4; ++b)
 				if ((val >> b) & 1)
 					pl[k][b] |= nw[k];
+#pragma unroll
+		for (int k = 0; k < kColsPerThread; ++k)
+			if (dirty[k] > 0)
+				wr[ci.c[k]] = G[k], --dirty[k];
 		const bool any_changed = __syncthreads_or(changed);
 		any_set |= any_changed;
 		if (!any_changed && step >= last_inject_step)
@@ -878,8 +922,8 @@ __global__ void __launch_bounds__(kThreads, 1) mesh_kernel(const __grid_constant
 			mbar_expect_tx(&S.bar, kVoxBytes);
 			tma_load_3d(vox, &tmap, ti.cx * 32, ti.cz * 32 - 2, ti.cy * 32 - 1, &S.bar); // stored column = x + kXMargin
 		}
-		for (int i = tid; i < kMasks * 32; i += kThreads)
-			F[i] = 0;
+		for (int i = tid; i < 66 * 32; i += kThreads)
+			F[i] = 0; // axis-0 masks are filled with atomicOr; the others are overwritten
 		for (int i = tid; i < 2 * kMaxSplits * 6; i += kThreads)
 			(&S.aabb[0][0][0])[i] = (i % 6) < 3 ? 0xffffffffu : 0u; // dep/AABB.hpp:11
 		if (tid == 0) {
@@ -948,23 +992,39 @@ __global__ void __launch_bounds__(kThreads, 1) mesh_kernel(const __grid_constant
 			__syncthreads();
 		}
 
-		// ---- phase 2: face candidates from the planes, exact Show() on the survivors -> F --------------------------
+		// ---- phase 2: faces from the planes -------------------------------------------------------------------------
+		// A pair (a,b) of voxels across a slice: O|E (opaque cube next to textureless voxel) always shows a's face and
+		// never b's (Show(): a non-empty, b = kNone is transparent, a opaque); O|O and E|E never show anything; only
+		// pairs with a voxel that is neither (water, leaves, glass, cactus, flowing water ...) need the exact Show().
 		{
 			const u64 *Opl = reinterpret_cast<const u64 *>(region + RG_O), *Epl = reinterpret_cast<const u64 *>(region + RG_E);
 			const uint8_t *tf = S.tab.texflags;
 			for (int unit = tid; unit < 1024 + 2 * 1056; unit += kThreads) {
-				if (unit < 1024) { // axis 0: row (y,z); bit xa <-> voxel pair (xa-1, xa)
+				if (unit < 1024) { // axis 0: row (y,z); bit xa of the shifted words <-> voxel pair (xa-1, xa)
 					const int y = unit >> 5, z = unit & 31;
 					const u64 o = Opl[(y + 1) * kInner + z + 1], e = Epl[(y + 1) * kInner + z + 1];
-					u64 cand = ~((o & (o >> 1)) | (e & (e >> 1))) & ((1ull << 33) - 1);
+					const u64 x_ = ~(o | e) & ((1ull << 34) - 1);
+					u64 s0 = o & (e >> 1) & 0x1fffffffeull; // + faces: slices 1..32
+					u64 s1 = e & (o >> 1) & 0x0ffffffffull; // - faces: slices 0..31
+					u64 cand = (x_ | (x_ >> 1)) & ((1ull << 33) - 1);
 					while (cand) {
 						const int xa = __ffsll((long long)cand) - 1;
 						cand &= cand - 1;
 						const u32 ta = tex_code(S, vox, dyn, xa - 1, y, z, 0), tb = tex_code(S, vox, dyn, xa, y, z, 1);
 						if (xa != 0 && tex_show(tf, ta, tb))
-							atomicOr(&F[mask_id(0, xa, 0) * 32 + y], 1u << z);
+							s0 |= 1ull << xa;
 						if (xa != 32 && tex_show(tf, tb, ta))
-							atomicOr(&F[mask_id(0, xa, 1) * 32 + y], 1u << z);
+							s1 |= 1ull << xa;
+					}
+					while (s0) {
+						const int xa = __ffsll((long long)s0) - 1;
+						s0 &= s0 - 1;
+						atomicOr(&F[mask_id(0, xa, 0) * 32 + y], 1u << z);
+					}
+					while (s1) {
+						const int xa = __ffsll((long long)s1) - 1;
+						s1 &= s1 - 1;
+						atomicOr(&F[mask_id(0, xa, 1) * 32 + y], 1u << z);
 					}
 				} else {
 					const int axis = unit < 1024 + 1056 ? 1 : 2;
@@ -974,16 +1034,20 @@ __global__ void __launch_bounds__(kThreads, 1) mesh_kernel(const __grid_constant
 					const int ya = axis == 1 ? xa - 1 : u, za = axis == 1 ? u : xa - 1;
 					const int yb = axis == 1 ? xa : u, zb = axis == 1 ? u : xa;
 					const int ra = (ya + 1) * kInner + za + 1, rb = (yb + 1) * kInner + zb + 1;
-					u32 cand = (u32)((~((Opl[ra] & Opl[rb]) | (Epl[ra] & Epl[rb]))) >> 1);
+					const u32 oa = (u32)(Opl[ra] >> 1), ea = (u32)(Epl[ra] >> 1), ob = (u32)(Opl[rb] >> 1), eb = (u32)(Epl[rb] >> 1);
+					u32 f0 = xa != 0 ? (oa & eb) : 0u, f1 = xa != 32 ? (ea & ob) : 0u;
+					u32 cand = ~(oa | ea) | ~(ob | eb);
 					while (cand) {
 						const int x = __ffs(cand) - 1;
 						cand &= cand - 1;
 						const u32 ta = tex_code(S, vox, dyn, x, ya, za, axis * 2), tb = tex_code(S, vox, dyn, x, yb, zb, axis * 2 + 1);
 						if (xa != 0 && tex_show(tf, ta, tb))
-							atomicOr(&F[mask_id(axis, xa, 0) * 32 + u], 1u << x);
+							f0 |= 1u << x;
 						if (xa != 32 && tex_show(tf, tb, ta))
-							atomicOr(&F[mask_id(axis, xa, 1) * 32 + u], 1u << x);
+							f1 |= 1u << x;
 					}
+					F[mask_id(axis, xa, 0) * 32 + u] = f0; // every (mask,row) word of axes 1 and 2 has exactly one writer
+					F[mask_id(axis, xa, 1) * 32 + u] = f1;
 				}
 			}
 		}
@@ -1021,8 +1085,8 @@ __global__ void __launch_bounds__(kThreads, 1) mesh_kernel(const __grid_constant
 		// ---- phase 4: light ---------------------------------------------------------------------------------------------
 		{
 			u64 *sbuf = reinterpret_cast<u64 *>(region + RG_SBUF);
-			for (int i = tid; i < kSB * kSB; i += kThreads)
-				sbuf[i] = 0; // zero border (and interior)
+			for (int i = tid; i < 2 * kSB * kSB; i += kThreads)
+				sbuf[i] = 0; // both buffers: zero border and interior
 			ColInfo ci;
 			u64 P[kColsPerThread];
 			const size_t plane_stride = (size_t)p.w.Z * p.w.X;
@@ -1044,7 +1108,7 @@ __global__ void __launch_bounds__(kThreads, 1) mesh_kernel(const __grid_constant
 			__syncthreads();
 			flood_channel<false>(p, ci, P, sbuf, light, tid);
 			if (S.any_torch && p.w.n_levels > 0) {
-				for (int i = tid; i < kSB * kSB; i += kThreads)
+				for (int i = tid; i < 2 * kSB * kSB; i += kThreads)
 					sbuf[i] = 0;
 				__syncthreads();
 				flood_channel<true>(p, ci, P, sbuf, light, tid);
