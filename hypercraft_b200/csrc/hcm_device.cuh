@@ -9,7 +9,11 @@
 namespace hcm {
 
 // ---- launch geometry ------------------------------------------------------------------------------------------
-constexpr int kThreads = 512; // mesh kernel: 16 warps, one persistent CTA per SM (shared memory bound)
+#ifndef HCM_MESH_THREADS
+#define HCM_MESH_THREADS 1024
+#endif
+constexpr int kThreads = HCM_MESH_THREADS; // mesh kernel: one persistent CTA per SM (shared memory bound); the phases are
+                                           // latency bound, so as many warps as a CTA can hold
 constexpr int kWarps = kThreads / 32;
 
 // ---- shared-memory voxel volume (property index per voxel), filled by ONE 3-D TMA box -----------------------------
@@ -42,8 +46,8 @@ constexpr int kGroupCap = 6144; // faces per group (key 8 B + geometry 4 B each)
 // ---- flood domain: 62 x 62 columns (x,z in [-15,46]) of 62-bit words (bit = y + 15) -------------------------------
 constexpr int kFD = 62;
 constexpr int kFCols = kFD * kFD;       // 3844
-constexpr int kInnerSlots = 3;          // 3 * 512 >= 1156 inner columns (their light planes live in registers)
-constexpr int kOuterSlots = 6;          // 6 * 512 >= 2688 outer columns
+constexpr int kInnerSlots = (1156 + kThreads - 1) / kThreads; // inner columns per thread (their light planes live in registers)
+constexpr int kOuterSlots = (2688 + kThreads - 1) / kThreads; // outer columns per thread
 constexpr int kColsPerThread = kInnerSlots + kOuterSlots;
 constexpr int kInner = 34;              // columns x,z in [-1,32] carry the result
 constexpr int kInnerCols = kInner * kInner;

@@ -254,10 +254,33 @@ __global__ void __launch_bounds__(256)
 // ================================================================================================================
 // mesh kernel
 // ================================================================================================================
+#ifdef HCM_PHASE_TIMING // developer build: cycles per phase, summed over tasks (tools/phase_timing.py)
+__device__ unsigned long long g_phase_cycles[32];
+#define PHASE_MARK(i)                                                                                                  \
+	do {                                                                                                               \
+		if (tid == 0) {                                                                                                \
+			const long long now_ = clock64();                                                                          \
+			atomicAdd(&g_phase_cycles[i], (unsigned long long)(now_ - t_phase));                                       \
+			t_phase = now_;                                                                                            \
+		}                                                                                                              \
+	} while (0)
+#define PHASE_COUNT(i, n)                                                                                              \
+	do {                                                                                                               \
+		atomicAdd(&g_phase_cycles[i], (unsigned long long)(n));                                                        \
+	} while (0)
+#else
+#define PHASE_COUNT(i, n)                                                                                              \
+	do {                                                                                                               \
+	} while (0)
+#define PHASE_MARK(i)                                                                                                  \
+	do {                                                                                                               \
+	} while (0)
+#endif
 constexpr int SM_VOX = 0;
 constexpr int SM_LIGHT = SM_VOX + kVoxBytes;          // 58752
 constexpr int SM_F = SM_LIGHT + kLvolBytes;           // 100368
-constexpr int SM_CPLANE = SM_F + kMasks * 32 * 4;     // 123408
+constexpr int kFS = 33;                               // row stride of F (padded: lanes that walk different masks hit different banks)
+constexpr int SM_CPLANE = SM_F + kMasks * kFS * 4;
 constexpr int SM_REGION = SM_CPLANE + kInnerCols * 8; // 132656
 constexpr int kRegionBytes = kGroupCap * 12;          // 73728
 constexpr int SM_SMALL = SM_REGION + kRegionBytes;    // 206384
@@ -275,6 +298,10 @@ struct Small {
 	u32 fc[kMasks + 2];    // visible faces per mask
 	u32 fcpre[kMasks + 2]; // exclusive prefix
 	u32 nq[kMasks + 2], nqo[kMasks + 2], nqt[kMasks + 2], baseo[kMasks + 2], baset[kMasks + 2];
+	u32 qpre[kMasks + 2];                    // exclusive prefix of nq within the current group
+	u32 n_quads;
+	uint8_t order[2][kMasks + 2]; // non-empty masks of the current group: [0] heavy, [1] light (dynamic merge scheduling)
+	u32 n_order[2], next_mask;
 	u32 crow_o[1024], crow_t[1024]; // custom faces per (y,z) row and stream -> exclusive prefix
 	u32 aabb[2][kMaxSplits][6];
 	u32 split_other[2][kMaxSplits];
@@ -661,25 +688,57 @@ __device__ __forceinline__ void flood_channel(const MeshParams &p, const ColInfo
 // downwards while every cell below matches (height), consumed cells are cleared from the row bit masks.
 // Quad records replace the (already consumed) key slots of the mask, in emission order.
 // ---------------------------------------------------------------------------------------------------------------
+// geo word of a quad record: u | v<<5 | (width-1)<<10 | (height-1)<<15 | transparent<<20 | rank-in-stream-within-mask<<21
+__device__ __forceinline__ u32 pack_geo(u32 u, u32 v, u32 w, u32 h, bool tr, u32 rank) {
+	return u | (v << 5) | ((w - 1) << 10) | ((h - 1) << 15) | ((tr ? 1u : 0u) << 20) | (rank << 21);
+}
+
+// Lane = column v.  A set-up pass turns the mask into three words per lane -- fcol (bit u: cell (u,v) is a face),
+// eql (bit u: same key as the face to its left) and eqd (bit u: same key as the face below) -- with all key loads
+// independent of each other; the sequential part then runs on registers only:
+//   run starts   = ballot(active && !(left active && eql))           (width,  BlockMeshAlgo.hpp:364-368)
+//   run height   = 1 + redux.min over the run of the number of consecutive eqd bits from row u   (:371-379)
+//   consumption  = each lane sets bits u..u+height-1 of its own `cons` word                        (:462-466)
+// A cell below an unconsumed cell can only be consumed by the very quad that starts at that cell, so the height test
+// needs no activity check.  Records overwrite the mask's (already read) key slots in emission order.
 __device__ void merge_mask(Small &S, const u32 *F, u64 *keys, u32 *geo, int m, int g0, int lane) {
 	const u32 lt = lanemask_lt();
-	const u32 Forig = F[m * 32 + lane]; // lane = row here
-	const u32 pre = warp_excl_scan(__popc(Forig), lane);
+	const u32 Frow = F[m * kFS + lane]; // lane = row for these two
+	const u32 pre = warp_excl_scan(__popc(Frow), lane);
 	const u32 base = S.fcpre[m] - S.fcpre[g0];
-	u32 Arow = Forig;
-	u32 nq = 0, nqt = 0;
-	u32 todo = __ballot_sync(FULL, Arow != 0); // rows that still hold unconsumed faces
-	while (todo) {
-		const int u = __ffs(todo) - 1;
-		const u32 rowbits = __shfl_sync(FULL, Arow, u);
-		const u32 Fr = __shfl_sync(FULL, Forig, u), pr = __shfl_sync(FULL, pre, u);
-		const bool active = (rowbits >> lane) & 1;
-		const u64 key = active ? keys[base + pr + __popc(Fr & lt)] : 0ull;
-		const u64 keyL = __shfl_up_sync(FULL, key, 1);
+	u32 fcol = 0, eql = 0, eqd = 0;
+	{
+		u64 kprev = 0;
+		bool fprev = false;
+		u32 rows = __ballot_sync(FULL, Frow != 0);
+		int uprev = -2;
+		while (rows) {
+			const int u = __ffs(rows) - 1;
+			rows &= rows - 1;
+			const u32 Fu = __shfl_sync(FULL, Frow, u), pu = __shfl_sync(FULL, pre, u);
+			const bool f = (Fu >> lane) & 1;
+			const u64 k = f ? keys[base + pu + __popc(Fu & lt)] : 0ull;
+			const u64 kl = __shfl_up_sync(FULL, k, 1);
+			const bool fl = lane > 0 && ((Fu >> (lane - 1)) & 1);
+			fcol |= (f ? 1u : 0u) << u;
+			eql |= ((f && fl && kl == k) ? 1u : 0u) << u;
+			if (uprev == u - 1)
+				eqd |= ((f && fprev && kprev == k) ? 1u : 0u) << (u - 1);
+			kprev = k, fprev = f, uprev = u;
+		}
+	}
+	u32 cons = 0, nq = 0, nqt = 0;
+	for (;;) {
+		const u32 mine = fcol & ~cons;
+		const int u = (int)__reduce_min_sync(FULL, mine ? (u32)(__ffs(mine) - 1) : 32u); // rows above are fully consumed
+		if (u >= 32)
+			break;
+		const bool active = (mine >> u) & 1;
+		const u32 rowbits = __ballot_sync(FULL, active);
 		const bool activeL = lane > 0 && ((rowbits >> (lane - 1)) & 1);
-		const bool start = active && !(activeL && keyL == key);
+		const bool start = active && !(activeL && ((eql >> u) & 1));
 		const u32 startmask = __ballot_sync(FULL, start);
-		u32 runmask = 0, width = 0;
+		u32 runmask = 1u << lane, width = 0, vlen = 0;
 		if (active) {
 			const int s = 31 - __clz(startmask & (lt | (1u << lane)));
 			const u32 above_s = ~((2u << s) - 1u);
@@ -687,67 +746,71 @@ __device__ void merge_mask(Small &S, const u32 *F, u64 *keys, u32 *geo, int m, i
 			const int e = stop ? (__ffs(stop) - 1) : 32;
 			runmask = (e == 32 ? 0u : (1u << e)) - (1u << s);
 			width = e - s;
+			vlen = __ffs(~(eqd >> u)) - 1; // consecutive equal faces below (bit 31 of eqd is never set)
 		}
-		u32 height = 1;
-		bool alive = active;
-		for (int hh = 1; u + hh < 32; ++hh) {
-			const u32 rb = __shfl_sync(FULL, Arow, u + hh);
-			const u32 Fr2 = __shfl_sync(FULL, Forig, u + hh), pr2 = __shfl_sync(FULL, pre, u + hh);
-			bool match = false;
-			if (alive && ((rb >> lane) & 1))
-				match = keys[base + pr2 + __popc(Fr2 & lt)] == key;
-			const u32 mb = __ballot_sync(FULL, match);
-			const bool cont = alive && ((mb & runmask) == runmask);
-			const u32 contmask = __ballot_sync(FULL, cont);
-			if (!contmask)
-				break;
-			if (lane == u + hh)
-				Arow &= ~contmask;
-			alive = cont;
-			if (cont)
-				height = hh + 1;
+		// height - 1 = min of vlen over the run, bit-serial from the top with ballots (every lane of a run gets the same result)
+		u32 cand = runmask, hmin = 0;
+#pragma unroll
+		for (int b = 4; b >= 0; --b) {
+			const u32 zeros = __ballot_sync(FULL, active && !((vlen >> b) & 1)) & cand;
+			if (zeros)
+				cand = zeros;
+			else
+				hmin |= 1u << b;
 		}
-		__syncwarp();
+		const u32 height = hmin + 1;
+		if (active)
+			cons |= (height == 32 ? 0xffffffffu : ((1u << height) - 1u)) << u;
+		const u32 Fu = __shfl_sync(FULL, Frow, u), pu = __shfl_sync(FULL, pre, u);
+		const u64 key = start ? keys[base + pu + __popc(Fu & lt)] : 0ull;
 		const bool tr = start && (S.tab.texflags[key >> 56] & HCM_TEX_TRANS_PASS); // UseTransparentPass, BlockMeshAlgo.hpp:394
+		const u32 trmask = __ballot_sync(FULL, tr);
+		__syncwarp();
 		if (start) {
 			const u32 slot = base + nq + __popc(startmask & lt);
+			const u32 rank = tr ? nqt + __popc(trmask & lt) : (nq - nqt) + __popc(startmask & ~trmask & lt);
 			keys[slot] = key;
-			geo[slot] = (u32)u | ((u32)lane << 5) | ((width - 1) << 10) | ((height - 1) << 15) | ((tr ? 1u : 0u) << 20);
+			geo[slot] = pack_geo((u32)u, (u32)lane, width, height, tr, rank);
 		}
 		nq += __popc(startmask);
-		nqt += __popc(__ballot_sync(FULL, tr));
-		todo = __ballot_sync(FULL, Arow != 0) & ~((2u << u) - 1u); // rows below u that are not fully consumed
+		nqt += __popc(trmask);
+		__syncwarp();
 	}
 	if (lane == 0)
 		S.nq[m] = nq, S.nqt[m] = nqt, S.nqo[m] = nq - nqt;
 }
 
-// emission of the quads of one mask by one warp (lane per quad)
-__device__ void emit_mask(const MeshParams &p, Small &S, const u64 *keys, const u32 *geo, int m, int g0, int lane) {
-	const u32 lt = lanemask_lt();
-	const u32 nqm = S.nq[m];
-	if (!nqm)
-		return;
-	const u32 base = S.fcpre[m] - S.fcpre[g0];
-	const u32 bo = S.baseo[m], bt = S.baset[m];
-	const int axis = m / 66, rem = m - axis * 66, xa = rem >> 1, dir = rem & 1;
-	const int ua = axis == 1 ? 2 : 1, va = axis == 0 ? 2 : 0; // BlockAlgo.hpp:70-81 with swizzle YZX
-	const bool uv_order = dir ^ (axis != 2 ? 1 : 0);          // BlockMeshAlgo.hpp:382: quad_face_inv ^ ((U+1)%3 == V)
-	u32 co = 0, ct = 0;
-	for (u32 i0 = 0; i0 < nqm; i0 += 32) {
-		const u32 i = i0 + lane;
-		const bool valid = i < nqm;
-		const u64 key = valid ? keys[base + i] : 0ull;
-		const u32 g = valid ? geo[base + i] : 0u;
-		const bool tr = (g >> 20) & 1;
-		const u32 tm = __ballot_sync(FULL, valid && tr), om = __ballot_sync(FULL, valid && !tr);
-		const u32 qo_before = bo + co + __popc(om & lt), qt_before = bt + ct + __popc(tm & lt);
-		co += __popc(om), ct += __popc(tm);
-		const u32 s = tr ? 1u : 0u;
-		const u32 q = tr ? qt_before : qo_before;
-		const u32 k = q / kQuadsPerMesh;
+// emission: one thread per quad of the group (j = rank in the group's quad list)
+__device__ void emit_quads(const MeshParams &p, Small &S, const u64 *keys, const u32 *geo, int g0, int g1, int tid, int lane) {
+	const u32 nquads = S.n_quads;
+	for (u32 j0 = (u32)(tid - lane); j0 < nquads; j0 += kThreads) { // warp-uniform trip count
+		const u32 j = j0 + lane;
+		const bool valid = j < nquads;
+		u32 s = 0, k = 0;
 		u32 mn[3] = {0xffffffffu, 0xffffffffu, 0xffffffffu}, mx[3] = {0, 0, 0};
 		if (valid) {
+			int lo = g0, hi = g1 - 1; // last mask with qpre[m] <= j
+			while (lo < hi) {
+				const int mid = (lo + hi + 1) >> 1;
+				if (S.qpre[mid] <= j)
+					lo = mid;
+				else
+					hi = mid - 1;
+			}
+			const int m = lo;
+			const u32 i = j - S.qpre[m];
+			const u32 slot = S.fcpre[m] - S.fcpre[g0] + i;
+			const u64 key = keys[slot];
+			const u32 g = geo[slot];
+			const int axis = m / 66, rem = m - axis * 66, xa = rem >> 1, dir = rem & 1;
+			const int ua = axis == 1 ? 2 : 1, va = axis == 0 ? 2 : 0; // BlockAlgo.hpp:70-81 with swizzle YZX
+			const bool uv_order = dir ^ (axis != 2 ? 1 : 0);          // BlockMeshAlgo.hpp:382: quad_face_inv ^ ((U+1)%3 == V)
+			const bool tr = (g >> 20) & 1;
+			const u32 rank = g >> 21;
+			s = tr ? 1u : 0u;
+			const u32 q = (tr ? S.baset[m] : S.baseo[m]) + rank;
+			const u32 other_before = (tr ? S.baseo[m] : S.baset[m]) + (i - rank);
+			k = q / kQuadsPerMesh;
 			const u32 u = g & 31u, v = (g >> 5) & 31u, width = ((g >> 10) & 31u) + 1, height = ((g >> 15) & 31u) + 1;
 			// origin = ToXYZ<Axis>(xa,u,v); the two edge vectors (BlockMeshAlgo.hpp:380-390)
 			const u32 P0[3] = {axis == 0 ? (u32)xa : v, axis == 1 ? (u32)xa : u, axis == 2 ? (u32)xa : (axis == 0 ? v : u)};
@@ -785,7 +848,7 @@ __device__ void emit_mask(const MeshParams &p, Small &S, const u64 *keys, const 
 			for (int c = 0; c < 3; ++c)
 				mn[c] = P0[c] << 4, mx[c] = (P0[c] + uvec[c] + vvec[c]) << 4; // BlockMeshAlgo.hpp:404-409
 			if (q == k * kQuadsPerMesh && k > 0)
-				S.split_other[s][k - 1] = s ? qo_before : qt_before; // who was ahead when this stream's mesh was cut
+				S.split_other[s][k - 1] = other_before; // who was ahead when this stream's mesh was cut
 		}
 		// AABB: reduce within lanes that target the same (stream, mesh) before touching shared memory
 		const u32 grp = __match_any_sync(FULL, valid ? (s * 64u + k) : 0xffffffffu);
@@ -903,6 +966,9 @@ __global__ void __launch_bounds__(kThreads, 1) mesh_kernel(const __grid_constant
 		mbar_init(&S.bar, 1);
 	__syncthreads();
 	u32 phase = 0;
+#ifdef HCM_PHASE_TIMING
+	long long t_phase = clock64();
+#endif
 	DynRec *dyn = p.dyn_scratch + (size_t)blockIdx.x * kLightBytes;
 	const u32 n_work = p.heads->n_work;
 
@@ -912,6 +978,7 @@ __global__ void __launch_bounds__(kThreads, 1) mesh_kernel(const __grid_constant
 			S.work_item = atomicAdd(&p.heads->cursor, 1u);
 		__syncthreads();
 		const u32 wi = S.work_item;
+		PHASE_MARK(0); // task fetch
 		if (wi >= n_work)
 			break;
 		const u32 task = p.worklist[wi];
@@ -922,7 +989,7 @@ __global__ void __launch_bounds__(kThreads, 1) mesh_kernel(const __grid_constant
 			mbar_expect_tx(&S.bar, kVoxBytes);
 			tma_load_3d(vox, &tmap, ti.cx * 32, ti.cz * 32 - 2, ti.cy * 32 - 1, &S.bar); // stored column = x + kXMargin
 		}
-		for (int i = tid; i < 66 * 32; i += kThreads)
+		for (int i = tid; i < 66 * kFS; i += kThreads)
 			F[i] = 0; // axis-0 masks are filled with atomicOr; the others are overwritten
 		for (int i = tid; i < 2 * kMaxSplits * 6; i += kThreads)
 			(&S.aabb[0][0][0])[i] = (i % 6) < 3 ? 0xffffffffu : 0u; // dep/AABB.hpp:11
@@ -937,6 +1004,7 @@ __global__ void __launch_bounds__(kThreads, 1) mesh_kernel(const __grid_constant
 		}
 		mbar_wait(&S.bar, phase);
 		phase ^= 1;
+		PHASE_MARK(1); // TMA + zeroing
 
 		// ---- phase 1: class bit planes (bit x+1 of row (y,z)); one lane builds one row from three 16-byte loads -------
 		{
@@ -976,6 +1044,7 @@ __global__ void __launch_bounds__(kThreads, 1) mesh_kernel(const __grid_constant
 		}
 		__syncthreads();
 
+		PHASE_MARK(2); // planes
 		// ---- phase 1b: liquid-flow voxels of [-1,32]^3 -> heights + per-voxel face textures --------------------------
 		if (S.any_dyn) {
 			const u64 *Dpl = reinterpret_cast<const u64 *>(region + RG_D);
@@ -992,6 +1061,7 @@ __global__ void __launch_bounds__(kThreads, 1) mesh_kernel(const __grid_constant
 			__syncthreads();
 		}
 
+		PHASE_MARK(3); // liquid
 		// ---- phase 2: faces from the planes -------------------------------------------------------------------------
 		// A pair (a,b) of voxels across a slice: O|E (opaque cube next to textureless voxel) always shows a's face and
 		// never b's (Show(): a non-empty, b = kNone is transparent, a opaque); O|O and E|E never show anything; only
@@ -1019,12 +1089,12 @@ __global__ void __launch_bounds__(kThreads, 1) mesh_kernel(const __grid_constant
 					while (s0) {
 						const int xa = __ffsll((long long)s0) - 1;
 						s0 &= s0 - 1;
-						atomicOr(&F[mask_id(0, xa, 0) * 32 + y], 1u << z);
+						atomicOr(&F[mask_id(0, xa, 0) * kFS + y], 1u << z);
 					}
 					while (s1) {
 						const int xa = __ffsll((long long)s1) - 1;
 						s1 &= s1 - 1;
-						atomicOr(&F[mask_id(0, xa, 1) * 32 + y], 1u << z);
+						atomicOr(&F[mask_id(0, xa, 1) * kFS + y], 1u << z);
 					}
 				} else {
 					const int axis = unit < 1024 + 1056 ? 1 : 2;
@@ -1046,16 +1116,17 @@ __global__ void __launch_bounds__(kThreads, 1) mesh_kernel(const __grid_constant
 						if (xa != 32 && tex_show(tf, tb, ta))
 							f1 |= 1u << x;
 					}
-					F[mask_id(axis, xa, 0) * 32 + u] = f0; // every (mask,row) word of axes 1 and 2 has exactly one writer
-					F[mask_id(axis, xa, 1) * 32 + u] = f1;
+					F[mask_id(axis, xa, 0) * kFS + u] = f0; // every (mask,row) word of axes 1 and 2 has exactly one writer
+					F[mask_id(axis, xa, 1) * kFS + u] = f1;
 				}
 			}
 		}
 		__syncthreads();
 
+		PHASE_MARK(4); // faces
 		// ---- phase 3: faces per mask, prefix; early out ----------------------------------------------------------------
 		for (int m = warp; m < kMasks; m += kWarps) {
-			const u32 c = __reduce_add_sync(FULL, (u32)__popc(F[m * 32 + lane]));
+			const u32 c = __reduce_add_sync(FULL, (u32)__popc(F[m * kFS + lane]));
 			if (lane == 0)
 				S.fc[m] = c;
 		}
@@ -1073,6 +1144,7 @@ __global__ void __launch_bounds__(kThreads, 1) mesh_kernel(const __grid_constant
 				S.fcpre[kMasks] = carry;
 		}
 		__syncthreads();
+		PHASE_MARK(5); // face counts + prefix
 		const u32 n_faces = S.fcpre[kMasks];
 		const u32 n_custom = S.n_custom;
 		const bool want_light = p.debug_light != nullptr;
@@ -1106,6 +1178,7 @@ __global__ void __launch_bounds__(kThreads, 1) mesh_kernel(const __grid_constant
 				}
 			}
 			__syncthreads();
+			PHASE_MARK(6); // flood setup (plane loads)
 			flood_channel<false>(p, ci, P, sbuf, light, tid);
 			if (S.any_torch && p.w.n_levels > 0) {
 				for (int i = tid; i < 2 * kSB * kSB; i += kThreads)
@@ -1120,12 +1193,15 @@ __global__ void __launch_bounds__(kThreads, 1) mesh_kernel(const __grid_constant
 				}
 		}
 
+		PHASE_MARK(7); // flood + unpack
 		// ---- phase 5: custom faces per row and stream (count), exclusive prefix in (y,z) row order -------------------
 		if (n_custom) {
+			constexpr int kRPT = 1024 / kThreads; // (y,z) rows per thread
+			static_assert(kRPT == 1 || kRPT == 2, "phase 5 handles 1 or 2 rows per thread");
 			u32 co2[2] = {0, 0}, ct2[2] = {0, 0};
 #pragma unroll
-			for (int j = 0; j < 2; ++j) {
-				const int r = 2 * tid + j, y = r >> 5, z = r & 31;
+			for (int j = 0; j < kRPT; ++j) {
+				const int r = kRPT * tid + j, y = r >> 5, z = r & 31;
 				u32 w = (u32)(Cpl[(y + 1) * kInner + z + 1] >> 1);
 				while (w) {
 					const int x = __ffs(w) - 1;
@@ -1157,12 +1233,14 @@ __global__ void __launch_bounds__(kThreads, 1) mesh_kernel(const __grid_constant
 			}
 			__syncthreads();
 			const u32 bo = S.wtmp[0][warp] + exo, bt = S.wtmp[1][warp] + ext;
-			S.crow_o[2 * tid] = bo, S.crow_o[2 * tid + 1] = bo + co2[0];
-			S.crow_t[2 * tid] = bt, S.crow_t[2 * tid + 1] = bt + ct2[0];
+			S.crow_o[kRPT * tid] = bo, S.crow_t[kRPT * tid] = bt;
+			if (kRPT == 2)
+				S.crow_o[2 * tid + 1] = bo + co2[0], S.crow_t[2 * tid + 1] = bt + ct2[0];
 		} else if (tid == 0)
 			S.Co = 0, S.Ct = 0;
 		__syncthreads();
 
+		PHASE_MARK(8); // custom count
 		// ---- phases 6/7: keys -> merge -> (count) -> allocate -> emit ---------------------------------------------------
 		u64 *keys = reinterpret_cast<u64 *>(region + RG_KEYS);
 		u32 *geo = reinterpret_cast<u32 *>(region + RG_GEO);
@@ -1195,7 +1273,7 @@ __global__ void __launch_bounds__(kThreads, 1) mesh_kernel(const __grid_constant
 					for (int m = g0 + warp; m < g1; m += kWarps) {
 						if (!S.fc[m])
 							continue;
-						u32 fw = F[m * 32 + lane];
+						u32 fw = F[m * kFS + lane];
 						u32 at = S.fcpre[m] - S.fcpre[g0] + warp_excl_scan(__popc(fw), lane);
 						while (fw) {
 							const u32 v = __ffs(fw) - 1;
@@ -1204,6 +1282,7 @@ __global__ void __launch_bounds__(kThreads, 1) mesh_kernel(const __grid_constant
 						}
 					}
 					__syncthreads();
+					PHASE_MARK(9); // fill
 					// (b) one thread per visible face: texture + Light4 -> key
 					for (u32 f = tid; f < nf; f += kThreads) {
 						const u32 loc = (u32)keys[f];
@@ -1217,15 +1296,60 @@ __global__ void __launch_bounds__(kThreads, 1) mesh_kernel(const __grid_constant
 						keys[f] = pack_key(l4, code);
 					}
 					__syncthreads();
-					// (c) greedy merge, warp per mask
-					for (int m = g0 + warp; m < g1; m += kWarps) {
-						if (S.fc[m])
-							merge_mask(S, F, keys, geo, m, g0, lane);
-						else if (lane == 0)
+					PHASE_MARK(10); // keys
+					// (c) greedy merge, one warp per mask.  A mask costs ~ its non-empty rows, and the heavy ones (terrain tops)
+					// cluster on every other mask id, so warps pull masks from a shared counter, heavy masks first.
+					if (tid == 0)
+						S.n_order[0] = 0, S.n_order[1] = 0, S.next_mask = 0;
+					__syncthreads();
+					if (g0 + tid < g1) {
+						const int m = g0 + tid;
+						const u32 c = S.fc[m];
+						if (c == 0)
 							S.nq[m] = 0, S.nqo[m] = 0, S.nqt[m] = 0;
+						else {
+							const int cls = c >= 128 ? 0 : 1;
+							S.order[cls][atomicAdd(&S.n_order[cls], 1u)] = (uint8_t)m;
+						}
 					}
 					__syncthreads();
-					// (d) ordered offsets: exclusive scan of the per-mask quad counts of both streams (masks <= 198 <= 7 warps)
+					{
+						const u32 nh = S.n_order[0], ntot = nh + S.n_order[1];
+						for (;;) {
+							u32 j = 0;
+							if (lane == 0)
+								j = atomicAdd(&S.next_mask, 1u);
+							j = __shfl_sync(FULL, j, 0);
+							if (j >= ntot)
+								break;
+							const int m = j < nh ? S.order[0][j] : S.order[1][j - nh];
+#ifdef HCM_PHASE_TIMING
+							{
+								const u32 nr_ = __popc(__ballot_sync(FULL, F[m * kFS + lane] != 0));
+								if (lane == 0) {
+									PHASE_COUNT(20, 1);       // masks merged
+									PHASE_COUNT(21, S.fc[m]); // faces
+									PHASE_COUNT(22, nr_);     // non-empty rows
+								}
+							}
+#endif
+#ifdef HCM_PHASE_TIMING
+							const long long tm0_ = clock64();
+#endif
+							merge_mask(S, F, keys, geo, m, g0, lane);
+#ifdef HCM_PHASE_TIMING
+							if (lane == 0)
+								PHASE_COUNT(24, clock64() - tm0_); // cycles inside merge_mask, summed over warps
+#endif
+						}
+#ifdef HCM_PHASE_TIMING
+						if (lane == 0)
+							PHASE_COUNT(25, clock64() - t_phase); // per-warp time from phase start to running out of masks
+#endif
+					}
+					__syncthreads();
+					PHASE_MARK(11); // merge
+					// (d) ordered offsets: exclusive scans of the per-mask quad counts (both streams, and all quads)
 					{
 						const int m = g0 + tid;
 						const u32 vo = m < g1 ? S.nqo[m] : 0u, vt = m < g1 ? S.nqt[m] : 0u;
@@ -1233,17 +1357,20 @@ __global__ void __launch_bounds__(kThreads, 1) mesh_kernel(const __grid_constant
 						if (lane == 31 && warp < 8)
 							S.wtmp[0][warp] = eo + vo, S.wtmp[1][warp] = et + vt;
 						__syncthreads();
-						u32 co = S.run_o, ct = S.run_t;
+						u32 co = 0, ct = 0;
 						for (int w2 = 0; w2 < warp && w2 < 8; ++w2)
 							co += S.wtmp[0][w2], ct += S.wtmp[1][w2];
-						if (m < g1)
-							S.baseo[m] = co + eo, S.baset[m] = ct + et;
+						if (m < g1) {
+							S.baseo[m] = S.run_o + co + eo, S.baset[m] = S.run_t + ct + et;
+							S.qpre[m] = co + eo + ct + et;
+						}
 						__syncthreads();
 						if (tid == 0) {
 							u32 to = 0, tt = 0;
 							for (int w2 = 0; w2 < 8; ++w2)
 								to += S.wtmp[0][w2], tt += S.wtmp[1][w2];
-							S.run_o += to, S.run_t += tt;
+							S.run_o += to, S.run_t += tt, S.n_quads = to + tt;
+							PHASE_COUNT(23, to + tt); // quads
 						}
 					}
 					__syncthreads();
@@ -1262,10 +1389,9 @@ __global__ void __launch_bounds__(kThreads, 1) mesh_kernel(const __grid_constant
 					}
 					__syncthreads();
 				}
-				if (emit && nf && !S.overflow) {
-					for (int m = g0 + warp; m < g1; m += kWarps)
-						emit_mask(p, S, keys, geo, m, g0, lane);
-				}
+				PHASE_MARK(13); // alloc
+				if (emit && nf && !S.overflow)
+					emit_quads(p, S, keys, geo, g0, g1, tid, lane);
 				__syncthreads();
 				g0 = g1;
 			}
@@ -1284,6 +1410,7 @@ __global__ void __launch_bounds__(kThreads, 1) mesh_kernel(const __grid_constant
 			}
 		}
 
+		PHASE_MARK(14); // emit
 		// ---- custom / dynamic faces: warp per (y,z) row, lane per voxel --------------------------------------------------
 		if (n_custom && !S.overflow) {
 			for (int r = warp; r < 1024; r += kWarps) {
@@ -1312,6 +1439,7 @@ __global__ void __launch_bounds__(kThreads, 1) mesh_kernel(const __grid_constant
 		}
 		__syncthreads();
 
+		PHASE_MARK(15); // custom emit
 		// ---- mesh descriptors in the order BlockMeshAlgo::Generate returns them (BlockMeshAlgo.hpp:397-403, :515-518) ----
 		if (tid == 0) {
 			if (S.overflow) {
@@ -1354,6 +1482,7 @@ __global__ void __launch_bounds__(kThreads, 1) mesh_kernel(const __grid_constant
 				p.task_out[task] = hcm_task_result{S.moff, M[0] + M[1]};
 			}
 		}
+		PHASE_MARK(16); // descriptors
 	}
 }
 
@@ -1374,6 +1503,16 @@ void launch_classify(const DevWorld &w, const TaskIn *tasks, u32 n, u32 *worklis
 	if (n)
 		classify_kernel<<<(n + 255) / 256, 256, 0, st>>>(w, tasks, n, worklist, heads, task_out, force_all);
 }
+#ifdef HCM_PHASE_TIMING
+extern "C" __attribute__((visibility("default"))) int hcm_debug_phase_cycles(unsigned long long *out, int reset) {
+	cudaMemcpyFromSymbol(out, g_phase_cycles, sizeof(g_phase_cycles));
+	if (reset) {
+		unsigned long long z[32] = {};
+		cudaMemcpyToSymbol(g_phase_cycles, z, sizeof(z));
+	}
+	return 0;
+}
+#endif
 cudaError_t mesh_kernel_prepare() { return cudaFuncSetAttribute(mesh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes); }
 int mesh_kernel_smem_bytes() { return kSmemBytes; }
 void launch_mesh(const CUtensorMap &tmap, const MeshParams &p, int grid, cudaStream_t st) { mesh_kernel<<<grid, kThreads, kSmemBytes, st>>>(tmap, p); }
