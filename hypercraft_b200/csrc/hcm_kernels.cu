@@ -292,6 +292,9 @@ constexpr int RG_SBUF = 0;                                                // 2 x
 static_assert(2 * kSB * kSB * 8 <= kRegionBytes, "flood buffers must fit the phase region");
 static_assert(3 * kInnerCols * 8 <= kRegionBytes, "planes must fit the phase region");
 constexpr int RG_KEYS = 0, RG_GEO = kGroupCap * 8;
+constexpr int RG_CLIST = 32768;                                           // exact-pair list behind the planes
+constexpr int kCandCap = (kRegionBytes - RG_CLIST) / 4;
+static_assert(3 * kInnerCols * 8 <= RG_CLIST, "planes overlap the candidate list");
 
 struct Small {
 	DevTables tab;
@@ -299,7 +302,7 @@ struct Small {
 	u32 fcpre[kMasks + 2]; // exclusive prefix
 	u32 nq[kMasks + 2], nqo[kMasks + 2], nqt[kMasks + 2], baseo[kMasks + 2], baset[kMasks + 2];
 	u32 qpre[kMasks + 2];                    // exclusive prefix of nq within the current group
-	u32 n_quads;
+	u32 n_quads, n_cand, cand_overflow;
 	uint8_t order[2][kMasks + 2]; // non-empty masks of the current group: [0] heavy, [1] light (dynamic merge scheduling)
 	u32 n_order[2], next_mask;
 	u32 crow_o[1024], crow_t[1024]; // custom faces per (y,z) row and stream -> exclusive prefix
@@ -735,35 +738,37 @@ __device__ void merge_mask(Small &S, const u32 *F, u64 *keys, u32 *geo, int m, i
 			break;
 		const bool active = (mine >> u) & 1;
 		const u32 rowbits = __ballot_sync(FULL, active);
-		const bool activeL = lane > 0 && ((rowbits >> (lane - 1)) & 1);
-		const bool start = active && !(activeL && ((eql >> u) & 1));
-		const u32 startmask = __ballot_sync(FULL, start);
-		u32 runmask = 1u << lane, width = 0, vlen = 0;
-		if (active) {
-			const int s = 31 - __clz(startmask & (lt | (1u << lane)));
-			const u32 above_s = ~((2u << s) - 1u);
-			const u32 stop = (startmask | ~rowbits) & above_s;
-			const int e = stop ? (__ffs(stop) - 1) : 32;
-			runmask = (e == 32 ? 0u : (1u << e)) - (1u << s);
-			width = e - s;
-			vlen = __ffs(~(eqd >> u)) - 1; // consecutive equal faces below (bit 31 of eqd is never set)
-		}
-		// height - 1 = min of vlen over the run, bit-serial from the top with ballots (every lane of a run gets the same result)
-		u32 cand = runmask, hmin = 0;
+		const u32 eqlrow = __ballot_sync(FULL, (eql >> u) & 1);
+		const u32 startmask = rowbits & ~((rowbits << 1) & eqlrow); // unconsumed, and not continuing an equal unconsumed left neighbour
+		const u32 brk = startmask | ~rowbits;                       // run boundaries
+		u32 val = active ? (u32)(__ffs(~(eqd >> u)) - 1) : 31u;     // equal faces straight below (bit 31 of eqd is never set)
+		u32 hmin;
+		if ((startmask & (startmask - 1)) == 0) { // one run in this row
+			hmin = __reduce_min_sync(FULL, val);
+		} else { // segmented suffix-min: a lane joins lane+d when no run boundary lies in (lane, lane+d]
 #pragma unroll
-		for (int b = 4; b >= 0; --b) {
-			const u32 zeros = __ballot_sync(FULL, active && !((vlen >> b) & 1)) & cand;
-			if (zeros)
-				cand = zeros;
-			else
-				hmin |= 1u << b;
+			for (int d = 1; d < 32; d <<= 1) {
+				const u32 other = __shfl_down_sync(FULL, val, d);
+				if ((((u64)brk >> (lane + 1)) & ((1u << d) - 1u)) == 0)
+					val = min(val, other);
+			}
+			const int s = 31 - __clz(startmask & (lt | (1u << lane))); // leader of my run (meaningful for active lanes)
+			hmin = __shfl_sync(FULL, val, s & 31);
 		}
 		const u32 height = hmin + 1;
 		if (active)
 			cons |= (height == 32 ? 0xffffffffu : ((1u << height) - 1u)) << u;
+		const bool start = (startmask >> lane) & 1;
 		const u32 Fu = __shfl_sync(FULL, Frow, u), pu = __shfl_sync(FULL, pre, u);
-		const u64 key = start ? keys[base + pu + __popc(Fu & lt)] : 0ull;
-		const bool tr = start && (S.tab.texflags[key >> 56] & HCM_TEX_TRANS_PASS); // UseTransparentPass, BlockMeshAlgo.hpp:394
+		u64 key = 0;
+		bool tr = false;
+		u32 width = 0;
+		if (start) {
+			key = keys[base + pu + __popc(Fu & lt)];
+			tr = S.tab.texflags[key >> 56] & HCM_TEX_TRANS_PASS; // UseTransparentPass, BlockMeshAlgo.hpp:394
+			const u64 rest = (u64)brk >> (lane + 1);
+			width = rest ? (u32)__ffsll((long long)rest) : 32u - lane;
+		}
 		const u32 trmask = __ballot_sync(FULL, tr);
 		__syncwarp();
 		if (start) {
@@ -994,7 +999,7 @@ __global__ void __launch_bounds__(kThreads, 1) mesh_kernel(const __grid_constant
 		for (int i = tid; i < 2 * kMaxSplits * 6; i += kThreads)
 			(&S.aabb[0][0][0])[i] = (i % 6) < 3 ? 0xffffffffu : 0u; // dep/AABB.hpp:11
 		if (tid == 0) {
-			S.n_custom = 0, S.any_dyn = 0, S.overflow = 0;
+			S.n_custom = 0, S.any_dyn = 0, S.overflow = 0, S.n_cand = 0, S.cand_overflow = 0;
 			u32 cfo = 0; // torch sources anywhere in the 27 chunks?
 			for (int dy = -1; dy <= 1; ++dy)
 				for (int dz = -1; dz <= 1; ++dz)
@@ -1066,9 +1071,22 @@ __global__ void __launch_bounds__(kThreads, 1) mesh_kernel(const __grid_constant
 		// A pair (a,b) of voxels across a slice: O|E (opaque cube next to textureless voxel) always shows a's face and
 		// never b's (Show(): a non-empty, b = kNone is transparent, a opaque); O|O and E|E never show anything; only
 		// pairs with a voxel that is neither (water, leaves, glass, cactus, flowing water ...) need the exact Show().
+		// Those pairs are first collected into a list so that the exact test runs with every lane busy.
 		{
 			const u64 *Opl = reinterpret_cast<const u64 *>(region + RG_O), *Epl = reinterpret_cast<const u64 *>(region + RG_E);
+			u32 *clist = reinterpret_cast<u32 *>(region + RG_CLIST);
 			const uint8_t *tf = S.tab.texflags;
+			// exact Show() of one pair; entry = axis<<16 | slice<<10 | u<<5 | v
+			auto exact = [&](u32 ent) {
+				const int axis = ent >> 16, xa = (ent >> 10) & 63, u = (ent >> 5) & 31, v = ent & 31;
+				const int ax = axis == 0 ? xa - 1 : v, ay = axis == 1 ? xa - 1 : u, az = axis == 2 ? xa - 1 : (axis == 0 ? v : u);
+				const int bx = axis == 0 ? xa : v, by = axis == 1 ? xa : u, bz = axis == 2 ? xa : (axis == 0 ? v : u);
+				const u32 ta = tex_code(S, vox, dyn, ax, ay, az, axis * 2), tb = tex_code(S, vox, dyn, bx, by, bz, axis * 2 + 1);
+				if (xa != 0 && tex_show(tf, ta, tb))
+					atomicOr(&F[mask_id(axis, xa, 0) * kFS + u], 1u << v);
+				if (xa != 32 && tex_show(tf, tb, ta))
+					atomicOr(&F[mask_id(axis, xa, 1) * kFS + u], 1u << v);
+			};
 			for (int unit = tid; unit < 1024 + 2 * 1056; unit += kThreads) {
 				if (unit < 1024) { // axis 0: row (y,z); bit xa of the shifted words <-> voxel pair (xa-1, xa)
 					const int y = unit >> 5, z = unit & 31;
@@ -1077,15 +1095,6 @@ __global__ void __launch_bounds__(kThreads, 1) mesh_kernel(const __grid_constant
 					u64 s0 = o & (e >> 1) & 0x1fffffffeull; // + faces: slices 1..32
 					u64 s1 = e & (o >> 1) & 0x0ffffffffull; // - faces: slices 0..31
 					u64 cand = (x_ | (x_ >> 1)) & ((1ull << 33) - 1);
-					while (cand) {
-						const int xa = __ffsll((long long)cand) - 1;
-						cand &= cand - 1;
-						const u32 ta = tex_code(S, vox, dyn, xa - 1, y, z, 0), tb = tex_code(S, vox, dyn, xa, y, z, 1);
-						if (xa != 0 && tex_show(tf, ta, tb))
-							s0 |= 1ull << xa;
-						if (xa != 32 && tex_show(tf, tb, ta))
-							s1 |= 1ull << xa;
-					}
 					while (s0) {
 						const int xa = __ffsll((long long)s0) - 1;
 						s0 &= s0 - 1;
@@ -1096,6 +1105,19 @@ __global__ void __launch_bounds__(kThreads, 1) mesh_kernel(const __grid_constant
 						s1 &= s1 - 1;
 						atomicOr(&F[mask_id(0, xa, 1) * kFS + y], 1u << z);
 					}
+					if (cand) {
+						u32 pos = atomicAdd(&S.n_cand, (u32)__popcll(cand));
+						while (cand) {
+							const u32 xa = __ffsll((long long)cand) - 1;
+							cand &= cand - 1;
+							const u32 ent = (xa << 10) | ((u32)y << 5) | (u32)z;
+							if (pos < (u32)kCandCap)
+								clist[pos] = ent;
+							else
+								exact(ent); // list full (stress chunks): evaluate in place
+							++pos;
+						}
+					}
 				} else {
 					const int axis = unit < 1024 + 1056 ? 1 : 2;
 					const int k = unit - (axis == 1 ? 1024 : 1024 + 1056);
@@ -1105,19 +1127,45 @@ __global__ void __launch_bounds__(kThreads, 1) mesh_kernel(const __grid_constant
 					const int yb = axis == 1 ? xa : u, zb = axis == 1 ? u : xa;
 					const int ra = (ya + 1) * kInner + za + 1, rb = (yb + 1) * kInner + zb + 1;
 					const u32 oa = (u32)(Opl[ra] >> 1), ea = (u32)(Epl[ra] >> 1), ob = (u32)(Opl[rb] >> 1), eb = (u32)(Epl[rb] >> 1);
-					u32 f0 = xa != 0 ? (oa & eb) : 0u, f1 = xa != 32 ? (ea & ob) : 0u;
+					// every (mask,row) word of axes 1 and 2 is initialised by exactly one unit
+					F[mask_id(axis, xa, 0) * kFS + u] = xa != 0 ? (oa & eb) : 0u;
+					F[mask_id(axis, xa, 1) * kFS + u] = xa != 32 ? (ea & ob) : 0u;
 					u32 cand = ~(oa | ea) | ~(ob | eb);
-					while (cand) {
-						const int x = __ffs(cand) - 1;
-						cand &= cand - 1;
-						const u32 ta = tex_code(S, vox, dyn, x, ya, za, axis * 2), tb = tex_code(S, vox, dyn, x, yb, zb, axis * 2 + 1);
-						if (xa != 0 && tex_show(tf, ta, tb))
-							f0 |= 1u << x;
-						if (xa != 32 && tex_show(tf, tb, ta))
-							f1 |= 1u << x;
+					if (cand) {
+						u32 pos = atomicAdd(&S.n_cand, (u32)__popc(cand));
+						while (cand) {
+							const u32 x = __ffs(cand) - 1;
+							cand &= cand - 1;
+							const u32 ent = ((u32)axis << 16) | ((u32)xa << 10) | ((u32)u << 5) | x;
+							if (pos < (u32)kCandCap)
+								clist[pos] = ent;
+							else
+								S.cand_overflow = 1; // handled below, after F is initialised everywhere
+							++pos;
+						}
 					}
-					F[mask_id(axis, xa, 0) * kFS + u] = f0; // every (mask,row) word of axes 1 and 2 has exactly one writer
-					F[mask_id(axis, xa, 1) * kFS + u] = f1;
+				}
+			}
+			__syncthreads();
+			const u32 nc = min(S.n_cand, (u32)kCandCap);
+			for (u32 i = tid; i < nc; i += kThreads)
+				exact(clist[i]);
+			if (S.cand_overflow) {
+				// stress chunks: more exact pairs on axes 1/2 than the list holds.  Redo those units in place (every pair again:
+				// atomicOr is idempotent), now that all F words have been initialised.
+				for (int unit = 1024 + tid; unit < 1024 + 2 * 1056; unit += kThreads) {
+					const int axis = unit < 1024 + 1056 ? 1 : 2;
+					const int k = unit - (axis == 1 ? 1024 : 1024 + 1056);
+					const int xa = k >> 5, u = k & 31;
+					const int ya = axis == 1 ? xa - 1 : u, za = axis == 1 ? u : xa - 1;
+					const int yb = axis == 1 ? xa : u, zb = axis == 1 ? u : xa;
+					const int ra = (ya + 1) * kInner + za + 1, rb = (yb + 1) * kInner + zb + 1;
+					u32 cand = ~((u32)(Opl[ra] >> 1) | (u32)(Epl[ra] >> 1)) | ~((u32)(Opl[rb] >> 1) | (u32)(Epl[rb] >> 1));
+					while (cand) {
+						const u32 x = __ffs(cand) - 1;
+						cand &= cand - 1;
+						exact(((u32)axis << 16) | ((u32)xa << 10) | ((u32)u << 5) | x);
+					}
 				}
 			}
 		}

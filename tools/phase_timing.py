@@ -31,6 +31,7 @@ names = ["task fetch", "TMA+zero", "planes", "liquid", "faces", "counts+prefix",
 tot = sum(out[:17]); n = c["n_worked"]
 print(f"r={R}: {n} worked tasks, mesh_ms {st['mesh_ms']:.3f}, cycles/task {tot / n:.0f}")
 print(f"  per task: masks merged {out[20]/n:.1f}, faces {out[21]/n:.0f}, non-empty rows {out[22]/n:.0f}, quads {out[23]/n:.0f}")
+print(f"  exact Show() candidate pairs per task: {out[26]/n:.0f}")
 print(f"  merge_mask cycles summed over warps {out[24]/n:.0f}/task ; per-warp busy-until sum {out[25]/n:.0f}/task (16 warps)")
 for i, nm in enumerate(names):
     print(f"  {nm:14s} {out[i] / n:9.0f} cyc/task  {100 * out[i] / tot:5.1f}%")
