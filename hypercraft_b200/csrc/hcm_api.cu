@@ -1,6 +1,8 @@
 // C ABI of the B200 chunk mesher (include/hcm.h): context, residency, batching, output arenas.
 // All device work is enqueued on the ctx stream; there is no CPU fallback anywhere in this file.
 #include <algorithm>
+#include <atomic>
+#include <thread>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -28,6 +30,9 @@ static thread_local std::string g_create_error;
 struct hcm_ctx {
 	int device = 0;
 	cudaStream_t stream = nullptr;
+	cudaStream_t copy_stream = nullptr; // host->device copies of large uploads overlap the host-side scan and the derive kernel
+	std::vector<cudaEvent_t> block_events;
+	bool use_batch_copy = true;
 	DevWorld w{};
 	size_t n_cells = 0; // window chunks
 	uint32_t max_chunks = 0, max_tasks = 0;
@@ -112,6 +117,15 @@ bool in_window(const hcm_ctx *c, const int16_t *pos, int *cx, int *cy, int *cz) 
 	return *cx >= 0 && *cx < c->w.wx && *cy >= 0 && *cy < c->w.wy && *cz >= 0 && *cz < c->w.wz;
 }
 size_t cell(const hcm_ctx *c, int cx, int cy, int cz) { return ((size_t)cy * c->w.wz + cz) * c->w.wx + cx; }
+
+// true when all 32768 voxels hold the same Block value (period-4 array whose first four elements are equal)
+inline bool chunk_is_uniform(const uint16_t *b) {
+	const uint16_t v = b[0];
+	return b[1] == v && b[2] == v && b[3] == v && memcmp(b, b + 4, (HCM_CHUNK_VOXELS - 4) * 2) == 0;
+}
+
+constexpr uint32_t kUploadBlock = 2048; // chunks per pipeline stage (128 MB of Block data)
+constexpr uint32_t kScanGrain = 32;     // chunks per work item of the scan threads
 
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
                                     const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -385,6 +399,10 @@ void hcm_destroy(hcm_ctx *c) {
 	for (auto &e : c->ev)
 		if (e)
 			cudaEventDestroy(e);
+	for (auto &e : c->block_events)
+		cudaEventDestroy(e);
+	if (c->copy_stream)
+		cudaStreamDestroy(c->copy_stream);
 	if (c->stream)
 		cudaStreamDestroy(c->stream);
 	delete c;
@@ -435,6 +453,7 @@ int hcm_create(const hcm_registry *registry, const hcm_config *cfg, hcm_ctx **ou
 
 	CUB(cudaSetDevice(c->device));
 	CUB(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+	CUB(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
 	for (int i = 0; i < EV_COUNT; ++i)
 		CUB(cudaEventCreate(&c->ev[i]));
 
@@ -571,29 +590,115 @@ int hcm_upload_chunks(hcm_ctx *c, uint32_t n, const int16_t *pos, const uint16_t
 			}
 			return rc;
 		}
-		entries[i] = UploadEntry{slot, (int16_t)cx, (int16_t)cy, (int16_t)cz, 0};
+		entries[i] = UploadEntry{slot, (int16_t)cx, (int16_t)cy, (int16_t)cz, 0, 0};
 	}
-	cudaStream_t st = c->stream;
+	cudaStream_t st = c->stream, cs = c->copy_stream;
 	CU(cudaEventRecord(c->ev[EV_UP0], st));
-	// host -> device, one copy per run of consecutive slots
-	for (uint32_t i = 0; i < n;) {
-		uint32_t j = i + 1;
-		while (j < n && entries[j].slot == entries[j - 1].slot + 1)
-			++j;
-		const size_t cnt = j - i;
-		CU(cudaMemcpyAsync(c->d_raw + (size_t)entries[i].slot * HCM_CHUNK_VOXELS, blocks + (size_t)i * HCM_CHUNK_VOXELS, cnt * HCM_CHUNK_VOXELS * 2,
-		                   cudaMemcpyHostToDevice, st));
-		CU(cudaMemcpyAsync(c->d_rawh + (size_t)entries[i].slot * HCM_CHUNK_COLUMNS, heights + (size_t)i * HCM_CHUNK_COLUMNS, cnt * HCM_CHUNK_COLUMNS,
-		                   cudaMemcpyHostToDevice, st));
-		i = j;
+	CU(cudaStreamWaitEvent(cs, c->ev[EV_UP0], 0)); // earlier kernels may still read the raw slots
+	// Uniform chunks (all air / all stone: most of a load sphere) cross the bus as one Block value instead of 64 KB.
+	// Pipeline per block of kUploadBlock chunks: host threads scan block b+1 (memcmp, early exit at the first difference)
+	// while the copy engine moves block b and the derive kernel runs on block b-1.
+	const uint32_t n_blocks = (n + kUploadBlock - 1) / kUploadBlock;
+	while (c->block_events.size() < n_blocks) {
+		cudaEvent_t e;
+		CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+		c->block_events.push_back(e);
 	}
-	CU(cudaMemcpyAsync(c->d_entries, entries.data(), n * sizeof(UploadEntry), cudaMemcpyHostToDevice, st)); // pageable: staged before return
-	c->stats.h2d_bytes += (uint64_t)n * (HCM_CHUNK_VOXELS * 2 + HCM_CHUNK_COLUMNS + sizeof(UploadEntry));
-	CU(cudaEventRecord(c->ev[EV_UP1], st));
-	launch_derive(c->w, c->d_entries, n, c->d_prop_index, c->d_tables, c->d_rawh, st);
-	CU(cudaGetLastError());
+	const uint32_t n_items = (n + kScanGrain - 1) / kScanGrain;
+	std::vector<std::atomic<uint8_t>> item_done(n_items);
+	for (auto &d : item_done)
+		d.store(0, std::memory_order_relaxed);
+	std::atomic<uint32_t> next{0};
+	UploadEntry *ent = entries.data();
+	auto scan_work = [&]() {
+		for (;;) {
+			const uint32_t it = next.fetch_add(1);
+			if (it >= n_items)
+				break;
+			const uint32_t lo = it * kScanGrain, hi = std::min(n, lo + kScanGrain);
+			for (uint32_t i = lo; i < hi; ++i) {
+				const uint16_t *b = blocks + (size_t)i * HCM_CHUNK_VOXELS;
+				if (chunk_is_uniform(b))
+					ent[i].flags |= UE_UNIFORM, ent[i].value = b[0];
+			}
+			item_done[it].store(1, std::memory_order_release);
+		}
+	};
+	const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+	const uint32_t n_threads = n < 256 ? 0u : (uint32_t)std::min<size_t>({(size_t)hw - 1, (size_t)15, (size_t)n_items});
+	std::vector<std::thread> scanners;
+	for (uint32_t t = 0; t < n_threads; ++t)
+		scanners.emplace_back(scan_work);
+	struct Joiner {
+		std::vector<std::thread> &ts;
+		~Joiner() {
+			for (auto &t : ts)
+				t.join();
+		}
+	} joiner{scanners};
+	if (n_threads == 0)
+		scan_work();
+
+	uint64_t copied = 0;
+	std::vector<void *> cp_dst, cp_src;
+	std::vector<size_t> cp_size;
+	for (uint32_t blk = 0; blk < n_blocks; ++blk) {
+		const uint32_t lo = blk * kUploadBlock, hi = std::min(n, lo + kUploadBlock);
+		for (uint32_t it = lo / kScanGrain; it < (hi + kScanGrain - 1) / kScanGrain; ++it) // kUploadBlock is a multiple of kScanGrain
+			while (!item_done[it].load(std::memory_order_acquire))
+				std::this_thread::yield();
+		// heights for every chunk, blocks for the non-uniform ones; one copy per run of consecutive slots, all runs of the
+		// block submitted with ONE cudaMemcpyBatchAsync (thousands of single calls would cost more than the transfer)
+		cp_dst.clear(), cp_src.clear(), cp_size.clear();
+		for (uint32_t i = lo; i < hi;) {
+			uint32_t j = i + 1;
+			while (j < hi && ent[j].slot == ent[j - 1].slot + 1)
+				++j;
+			cp_dst.push_back(c->d_rawh + (size_t)ent[i].slot * HCM_CHUNK_COLUMNS), cp_src.push_back((void *)(heights + (size_t)i * HCM_CHUNK_COLUMNS));
+			cp_size.push_back((size_t)(j - i) * HCM_CHUNK_COLUMNS);
+			for (uint32_t a = i; a < j;) {
+				if (ent[a].flags & UE_UNIFORM) {
+					++a;
+					continue;
+				}
+				uint32_t b = a + 1;
+				while (b < j && !(ent[b].flags & UE_UNIFORM))
+					++b;
+				cp_dst.push_back(c->d_raw + (size_t)ent[a].slot * HCM_CHUNK_VOXELS), cp_src.push_back((void *)(blocks + (size_t)a * HCM_CHUNK_VOXELS));
+				cp_size.push_back((size_t)(b - a) * HCM_CHUNK_VOXELS * 2);
+				a = b;
+			}
+			i = j;
+		}
+		for (size_t k = 0; k < cp_size.size(); ++k)
+			copied += cp_size[k];
+		bool batched = false;
+		if (c->use_batch_copy && cp_size.size() > 4) {
+			cudaMemcpyAttributes attr{};
+			attr.srcAccessOrder = cudaMemcpySrcAccessOrderStream;
+			size_t attr_idx = 0, fail_idx = 0;
+			cudaError_t be = cudaMemcpyBatchAsync(cp_dst.data(), cp_src.data(), cp_size.data(), cp_size.size(), &attr, &attr_idx, 1, &fail_idx, cs);
+			if (be == cudaSuccess)
+				batched = true;
+			else {
+				(void)cudaGetLastError();
+				c->use_batch_copy = false; // driver/runtime without batch copies: fall back for good
+			}
+		}
+		if (!batched)
+			for (size_t k = 0; k < cp_size.size(); ++k)
+				CU(cudaMemcpyAsync(cp_dst[k], cp_src[k], cp_size[k], cudaMemcpyHostToDevice, cs));
+		CU(cudaMemcpyAsync(c->d_entries + lo, ent + lo, (size_t)(hi - lo) * sizeof(UploadEntry), cudaMemcpyHostToDevice, cs)); // pageable: staged before return
+		CU(cudaEventRecord(c->block_events[blk], cs));
+		CU(cudaStreamWaitEvent(st, c->block_events[blk], 0));
+		if (blk == 0)
+			CU(cudaEventRecord(c->ev[EV_UP1], st));
+		launch_derive(c->w, c->d_entries + lo, hi - lo, c->d_prop_index, c->d_tables, c->d_rawh, st);
+		CU(cudaGetLastError());
+		c->stats.kernel_launches += 1;
+	}
+	c->stats.h2d_bytes += copied + (uint64_t)n * sizeof(UploadEntry);
 	CU(cudaEventRecord(c->ev[EV_UP2], st));
-	c->stats.kernel_launches += 1;
 	c->ev_upload = true;
 	return HCM_OK;
 }
@@ -614,7 +719,7 @@ int hcm_remove_chunks(hcm_ctx *c, uint32_t n, const int16_t *pos) {
 		int32_t &slot = c->slot_of[cell(c, cx, cy, cz)];
 		if (slot < 0)
 			continue;
-		entries.push_back(UploadEntry{slot, (int16_t)cx, (int16_t)cy, (int16_t)cz, 0});
+		entries.push_back(UploadEntry{slot, (int16_t)cx, (int16_t)cy, (int16_t)cz, 0, 0});
 		c->free_slots.push_back(slot);
 		slot = -1;
 	}
@@ -640,7 +745,7 @@ int hcm_rederive_chunks(hcm_ctx *c, uint32_t n, const int16_t *pos) {
 				for (int cx = 0; cx < c->w.wx; ++cx) {
 					const int32_t slot = c->slot_of[cell(c, cx, cy, cz)];
 					if (slot >= 0)
-						entries.push_back(UploadEntry{slot, (int16_t)cx, (int16_t)cy, (int16_t)cz, 0});
+						entries.push_back(UploadEntry{slot, (int16_t)cx, (int16_t)cy, (int16_t)cz, 0, 0});
 				}
 	} else {
 		for (uint32_t i = 0; i < n; ++i) {
@@ -650,7 +755,7 @@ int hcm_rederive_chunks(hcm_ctx *c, uint32_t n, const int16_t *pos) {
 			const int32_t slot = c->slot_of[cell(c, cx, cy, cz)];
 			if (slot < 0)
 				return fail(c, HCM_ERR_NOT_RESIDENT, "chunk (%d,%d,%d) is not resident", pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]);
-			entries.push_back(UploadEntry{slot, (int16_t)cx, (int16_t)cy, (int16_t)cz, 0});
+			entries.push_back(UploadEntry{slot, (int16_t)cx, (int16_t)cy, (int16_t)cz, 0, 0});
 		}
 	}
 	if (entries.empty())

@@ -123,8 +123,10 @@ struct DevWorld {
 struct UploadEntry {
 	int32_t slot;
 	int16_t cx, cy, cz; // window-relative chunk coordinates
-	int16_t _pad;
+	uint16_t value;     // UE_UNIFORM: the Block value every voxel of the chunk holds
+	uint32_t flags;
 };
+constexpr uint32_t UE_UNIFORM = 1; // host found the chunk uniform: its 64 KB were not copied, the kernel fills the raw slot
 
 struct TaskIn {
 	int16_t cx, cy, cz; // window-relative chunk coordinates

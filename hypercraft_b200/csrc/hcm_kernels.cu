@@ -91,15 +91,25 @@ __global__ void __launch_bounds__(256) derive_kernel(DevWorld w, const UploadEnt
 	const size_t ci = ((size_t)e.cy * w.wz + e.cz) * w.wx + e.cx;
 
 	// ---- uniform chunks (all air, all stone: most of a load sphere) need one table lookup, not 32768 ----------------
-	const u32 d0 = raw[0];
-	const u32 pat = d0 | (d0 << 16);
-	u32 acc_and = 0xffffffffu, acc_or = 0; // all 32 loads are independent: uniform <=> AND == OR == pattern
+	u32 d0, pat;
+	bool same;
+	if (e.flags & UE_UNIFORM) {
+		// the host skipped the 64 KB copy: materialise the raw slot here (the liquid generator reads raw meta of neighbours)
+		d0 = e.value, pat = d0 | (d0 << 16), same = true;
+		uint16_t *rw = const_cast<uint16_t *>(raw);
+#pragma unroll 8
+		for (int y = 0; y < 32; ++y)
+			*reinterpret_cast<uint2 *>(rw + x4 + (y * 32 + z) * 32) = make_uint2(pat, pat);
+	} else {
+		d0 = raw[0], pat = d0 | (d0 << 16);
+		u32 acc_and = 0xffffffffu, acc_or = 0; // all 32 loads are independent: uniform <=> AND == OR == pattern
 #pragma unroll
-	for (int y = 0; y < 32; ++y) {
-		const uint2 r = __ldg(reinterpret_cast<const uint2 *>(raw + x4 + (y * 32 + z) * 32));
-		acc_and &= r.x & r.y, acc_or |= r.x | r.y;
+		for (int y = 0; y < 32; ++y) {
+			const uint2 r = __ldg(reinterpret_cast<const uint2 *>(raw + x4 + (y * 32 + z) * 32));
+			acc_and &= r.x & r.y, acc_or |= r.x | r.y;
+		}
+		same = acc_and == pat && acc_or == pat;
 	}
-	const bool same = acc_and == pat && acc_or == pat;
 	*reinterpret_cast<char4 *>(w.height + col) = *reinterpret_cast<const char4 *>(raw_heights + (size_t)e.slot * HCM_CHUNK_COLUMNS + z * 32 + x4);
 	if (__syncthreads_and(same)) {
 		const u32 pr = __ldg(prop_index + d0);
