@@ -68,6 +68,29 @@ __device__ __forceinline__ u32 warp_excl_scan(u32 v, int lane) {
 	return x - v;
 }
 
+#ifdef HCM_PHASE_TIMING // developer build: cycles per phase, summed over tasks (tools/phase_timing.py)
+__device__ unsigned long long g_phase_cycles[64];
+#define PHASE_MARK(i)                                                                                                  \
+	do {                                                                                                               \
+		if (tid == 0) {                                                                                                \
+			const long long now_ = clock64();                                                                          \
+			atomicAdd(&g_phase_cycles[i], (unsigned long long)(now_ - t_phase));                                       \
+			t_phase = now_;                                                                                            \
+		}                                                                                                              \
+	} while (0)
+#define PHASE_COUNT(i, n)                                                                                              \
+	do {                                                                                                               \
+		atomicAdd(&g_phase_cycles[i], (unsigned long long)(n));                                                        \
+	} while (0)
+#else
+#define PHASE_COUNT(i, n)                                                                                              \
+	do {                                                                                                               \
+	} while (0)
+#define PHASE_MARK(i)                                                                                                  \
+	do {                                                                                                               \
+	} while (0)
+#endif
+
 // ================================================================================================================
 // derive kernel: one CTA per uploaded chunk, 256 threads; thread t owns columns x4..x4+3 of row z
 // ================================================================================================================
@@ -264,28 +287,7 @@ __global__ void __launch_bounds__(256)
 // ================================================================================================================
 // mesh kernel
 // ================================================================================================================
-#ifdef HCM_PHASE_TIMING // developer build: cycles per phase, summed over tasks (tools/phase_timing.py)
-__device__ unsigned long long g_phase_cycles[32];
-#define PHASE_MARK(i)                                                                                                  \
-	do {                                                                                                               \
-		if (tid == 0) {                                                                                                \
-			const long long now_ = clock64();                                                                          \
-			atomicAdd(&g_phase_cycles[i], (unsigned long long)(now_ - t_phase));                                       \
-			t_phase = now_;                                                                                            \
-		}                                                                                                              \
-	} while (0)
-#define PHASE_COUNT(i, n)                                                                                              \
-	do {                                                                                                               \
-		atomicAdd(&g_phase_cycles[i], (unsigned long long)(n));                                                        \
-	} while (0)
-#else
-#define PHASE_COUNT(i, n)                                                                                              \
-	do {                                                                                                               \
-	} while (0)
-#define PHASE_MARK(i)                                                                                                  \
-	do {                                                                                                               \
-	} while (0)
-#endif
+
 constexpr int SM_VOX = 0;
 constexpr int SM_LIGHT = SM_VOX + kVoxBytes;          // 58752
 constexpr int SM_F = SM_LIGHT + kLvolBytes;           // 100368
@@ -313,8 +315,8 @@ struct Small {
 	u32 nq[kMasks + 2], nqo[kMasks + 2], nqt[kMasks + 2], baseo[kMasks + 2], baset[kMasks + 2];
 	u32 qpre[kMasks + 2];                    // exclusive prefix of nq within the current group
 	u32 n_quads, n_cand, cand_overflow;
-	uint8_t order[2][kMasks + 2]; // non-empty masks of the current group: [0] heavy, [1] light (dynamic merge scheduling)
-	u32 n_order[2], next_mask;
+	uint8_t order[3][kMasks + 2]; // non-empty masks of the current group: [0] heavy, [1] medium (dynamic warp scheduling), [2] tiny (one thread each)
+	u32 n_order[3], next_mask;
 	u32 crow_o[1024], crow_t[1024]; // custom faces per (y,z) row and stream -> exclusive prefix
 	u32 aabb[2][kMaxSplits][6];
 	u32 split_other[2][kMaxSplits];
@@ -596,6 +598,9 @@ __device__ __forceinline__ void flood_channel(const MeshParams &p, const ColInfo
 		pl[k][0] = pl[k][1] = pl[k][2] = pl[k][3] = 0;
 	const int last_inject_step = kTorch ? 15 - (int)p.w.levels[p.w.n_levels - 1] : 0;
 	bool any_set = false; // block-uniform: some G bit is set anywhere
+#ifdef HCM_PHASE_TIMING
+	long long tf0_ = clock64();
+#endif
 	for (int step = 0; step <= 14; ++step) {
 		bool changed = false;
 		u64 nw[kInnerSlots];
@@ -608,6 +613,7 @@ __device__ __forceinline__ void flood_channel(const MeshParams &p, const ColInfo
 #pragma unroll
 			for (int k = 0; k < kColsPerThread; ++k)
 				if (ci.c[k] >= 0 && step <= ci.lim[k] && (P[k] & ~G[k])) {
+					PHASE_COUNT(27, 1); // live column evaluations
 					const int c = ci.c[k];
 					const u64 g = G[k];
 					const u64 n = rd[c - 1] | rd[c + 1] | rd[c - kSB] | rd[c + kSB];
@@ -669,10 +675,18 @@ __device__ __forceinline__ void flood_channel(const MeshParams &p, const ColInfo
 			if (dirty[k] > 0)
 				wr[ci.c[k]] = G[k], --dirty[k];
 		const bool any_changed = __syncthreads_or(changed);
+		if (tid == 0)
+			PHASE_COUNT(28, 1); // flood steps executed
 		any_set |= any_changed;
 		if (!any_changed && step >= last_inject_step)
 			break; // fixed point
 	}
+#ifdef HCM_PHASE_TIMING
+	if (tid == 0) {
+		PHASE_COUNT(29, clock64() - tf0_); // flood step loop
+		tf0_ = clock64();
+	}
+#endif
 	// unpack: 34 cells of a column = nine 32-bit words of the y-fastest light volume (cell y at byte y+1)
 #pragma unroll
 	for (int k = 0; k < kInnerSlots; ++k) {
@@ -693,6 +707,10 @@ __device__ __forceinline__ void flood_channel(const MeshParams &p, const ColInfo
 		}
 	}
 	__syncthreads();
+#ifdef HCM_PHASE_TIMING
+	if (tid == 0)
+		PHASE_COUNT(30, clock64() - tf0_); // unpack
+#endif
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -720,6 +738,9 @@ __device__ void merge_mask(Small &S, const u32 *F, u64 *keys, u32 *geo, int m, i
 	const u32 pre = warp_excl_scan(__popc(Frow), lane);
 	const u32 base = S.fcpre[m] - S.fcpre[g0];
 	u32 fcol = 0, eql = 0, eqd = 0;
+#ifdef HCM_PHASE_TIMING
+	const long long tms0_ = clock64();
+#endif
 	{
 		u64 kprev = 0;
 		bool fprev = false;
@@ -740,8 +761,15 @@ __device__ void merge_mask(Small &S, const u32 *F, u64 *keys, u32 *geo, int m, i
 			kprev = k, fprev = f, uprev = u;
 		}
 	}
+#ifdef HCM_PHASE_TIMING
+	const long long tms1_ = clock64();
+	u32 iters_ = 0;
+#endif
 	u32 cons = 0, nq = 0, nqt = 0;
 	for (;;) {
+#ifdef HCM_PHASE_TIMING
+		++iters_;
+#endif
 		const u32 mine = fcol & ~cons;
 		const int u = (int)__reduce_min_sync(FULL, mine ? (u32)(__ffs(mine) - 1) : 32u); // rows above are fully consumed
 		if (u >= 32)
@@ -791,8 +819,65 @@ __device__ void merge_mask(Small &S, const u32 *F, u64 *keys, u32 *geo, int m, i
 		nqt += __popc(trmask);
 		__syncwarp();
 	}
+#ifdef HCM_PHASE_TIMING
+	if (lane == 0) {
+		PHASE_COUNT(37, tms1_ - tms0_);       // set-up loop cycles
+		PHASE_COUNT(38, clock64() - tms1_);   // main loop cycles
+		PHASE_COUNT(39, iters_);              // main loop iterations
+	}
+#endif
 	if (lane == 0)
 		S.nq[m] = nq, S.nqt[m] = nqt, S.nqo[m] = nq - nqt;
+}
+
+// The same scan done by ONE thread, for masks with a handful of faces (4 out of 5 masks of a terrain chunk have at most
+// 16): 32 such masks run side by side in one warp.  Consumed cells are marked in place with a key no face can have.
+constexpr u64 kConsumedKey = ~0ull; // sun field 63 > 60
+constexpr u32 kThreadMergeMax = 12; // faces
+constexpr int kTinyPerWarp = 8;     // tiny masks per warp: fewer lanes per warp = less divergence, and spare warps are plentiful here
+__device__ void merge_mask_thread(Small &S, const u32 *F, u64 *keys, u32 *geo, int m, int g0) {
+	const u32 *Fm = F + m * kFS;
+	const u32 base = S.fcpre[m] - S.fcpre[g0];
+	u32 nq = 0, nqt = 0, rowslot = base;
+	for (int u = 0; u < 32; ++u) {
+		const u32 Fu = Fm[u];
+		u32 bits = Fu;
+		while (bits) {
+			const int v = __ffs(bits) - 1;
+			const u32 idx = rowslot + __popc(Fu & ((1u << v) - 1u));
+			const u64 key = keys[idx];
+			if (key == kConsumedKey) {
+				bits &= bits - 1;
+				continue;
+			}
+			u32 w = 1; // BlockMeshAlgo.hpp:364-368 (consumed or missing cells never compare equal)
+			while (v + w < 32 && ((Fu >> (v + w)) & 1u) && keys[idx + w] == key)
+				++w;
+			const u32 runmask = (w == 32 ? 0xffffffffu : ((1u << w) - 1u)) << v;
+			u32 h = 1, ps = rowslot + __popc(Fu); // :371-379
+			for (int uu = u + 1; uu < 32; ++uu) {
+				const u32 Fr = Fm[uu];
+				if ((Fr & runmask) != runmask)
+					break;
+				const u32 i2 = ps + __popc(Fr & ((1u << v) - 1u));
+				bool ok = true;
+				for (u32 k = 0; k < w && ok; ++k)
+					ok = keys[i2 + k] == key;
+				if (!ok)
+					break;
+				for (u32 k = 0; k < w; ++k)
+					keys[i2 + k] = kConsumedKey; // :462-466
+				++h, ps += __popc(Fr);
+			}
+			const bool tr = S.tab.texflags[key >> 56] & HCM_TEX_TRANS_PASS;
+			keys[base + nq] = key; // record slot <= idx: never an unread cell
+			geo[base + nq] = pack_geo((u32)u, (u32)v, w, h, tr, tr ? nqt : nq - nqt);
+			++nq, nqt += tr ? 1u : 0u;
+			bits &= ~runmask;
+		}
+		rowslot += __popc(Fu);
+	}
+	S.nq[m] = nq, S.nqt[m] = nqt, S.nqo[m] = nq - nqt;
 }
 
 // emission: one thread per quad of the group (j = rank in the group's quad list)
@@ -1358,7 +1443,7 @@ __global__ void __launch_bounds__(kThreads, 1) mesh_kernel(const __grid_constant
 					// (c) greedy merge, one warp per mask.  A mask costs ~ its non-empty rows, and the heavy ones (terrain tops)
 					// cluster on every other mask id, so warps pull masks from a shared counter, heavy masks first.
 					if (tid == 0)
-						S.n_order[0] = 0, S.n_order[1] = 0, S.next_mask = 0;
+						S.n_order[0] = 0, S.n_order[1] = 0, S.n_order[2] = 0, S.next_mask = 0;
 					__syncthreads();
 					if (g0 + tid < g1) {
 						const int m = g0 + tid;
@@ -1366,12 +1451,31 @@ __global__ void __launch_bounds__(kThreads, 1) mesh_kernel(const __grid_constant
 						if (c == 0)
 							S.nq[m] = 0, S.nqo[m] = 0, S.nqt[m] = 0;
 						else {
-							const int cls = c >= 128 ? 0 : 1;
+							const int cls = c >= 128 ? 0 : (c > kThreadMergeMax ? 1 : 2);
 							S.order[cls][atomicAdd(&S.n_order[cls], 1u)] = (uint8_t)m;
 						}
 					}
 					__syncthreads();
 					{
+						// tiny masks: one thread each, on the last warps; everything else: warps pull from a shared counter
+						const u32 n_tiny = S.n_order[2];
+						const int tiny_warps = min((int)((n_tiny + kTinyPerWarp - 1) / kTinyPerWarp), kWarps);
+#ifdef HCM_PHASE_TIMING
+						const long long tw0_ = clock64();
+#endif
+						if (warp >= kWarps - tiny_warps) {
+							// warp w of the tiny group takes masks w, w + tiny_warps, ... on its first lanes
+							const int tw = warp - (kWarps - tiny_warps);
+							for (u32 j = (u32)(tw + lane * tiny_warps); j < n_tiny && lane < 32; j += 32u * tiny_warps)
+								merge_mask_thread(S, F, keys, geo, S.order[2][j], g0);
+							__syncwarp();
+#ifdef HCM_PHASE_TIMING
+							if (lane == 0) {
+								PHASE_COUNT(35, clock64() - tw0_); // tiny-mask warps
+								PHASE_COUNT(36, 1);
+							}
+#endif
+						}
 						const u32 nh = S.n_order[0], ntot = nh + S.n_order[1];
 						for (;;) {
 							u32 j = 0;
@@ -1382,27 +1486,23 @@ __global__ void __launch_bounds__(kThreads, 1) mesh_kernel(const __grid_constant
 								break;
 							const int m = j < nh ? S.order[0][j] : S.order[1][j - nh];
 #ifdef HCM_PHASE_TIMING
-							{
-								const u32 nr_ = __popc(__ballot_sync(FULL, F[m * kFS + lane] != 0));
-								if (lane == 0) {
-									PHASE_COUNT(20, 1);       // masks merged
-									PHASE_COUNT(21, S.fc[m]); // faces
-									PHASE_COUNT(22, nr_);     // non-empty rows
-								}
-							}
-#endif
-#ifdef HCM_PHASE_TIMING
 							const long long tm0_ = clock64();
+							const u32 nr_ = __popc(__ballot_sync(FULL, F[m * kFS + lane] != 0));
 #endif
 							merge_mask(S, F, keys, geo, m, g0, lane);
 #ifdef HCM_PHASE_TIMING
-							if (lane == 0)
-								PHASE_COUNT(24, clock64() - tm0_); // cycles inside merge_mask, summed over warps
+							if (lane == 0) {
+								const unsigned long long d_ = (unsigned long long)(clock64() - tm0_);
+								PHASE_COUNT(24, d_);
+								PHASE_COUNT(22, nr_);
+								PHASE_COUNT(20, 1);
+								atomicMax(&g_phase_cycles[33], d_);
+							}
 #endif
 						}
 #ifdef HCM_PHASE_TIMING
 						if (lane == 0)
-							PHASE_COUNT(25, clock64() - t_phase); // per-warp time from phase start to running out of masks
+							PHASE_COUNT(34, clock64() - tw0_); // per-warp time inside the merge section, summed over warps
 #endif
 					}
 					__syncthreads();
@@ -1565,7 +1665,7 @@ void launch_classify(const DevWorld &w, const TaskIn *tasks, u32 n, u32 *worklis
 extern "C" __attribute__((visibility("default"))) int hcm_debug_phase_cycles(unsigned long long *out, int reset) {
 	cudaMemcpyFromSymbol(out, g_phase_cycles, sizeof(g_phase_cycles));
 	if (reset) {
-		unsigned long long z[32] = {};
+		unsigned long long z[64] = {};
 		cudaMemcpyToSymbol(g_phase_cycles, z, sizeof(z));
 	}
 	return 0;

@@ -22,7 +22,7 @@ m.upload(resident, b, h)
 for _ in range(3):
     m.mesh_async(meshed); c = m.wait()
 L = M.load_library()
-out = (ctypes.c_ulonglong * 32)()
+out = (ctypes.c_ulonglong * 64)()
 L.hcm_debug_phase_cycles(out, 1)
 m.mesh_async(meshed); c = m.wait(); st = m.stats()
 L.hcm_debug_phase_cycles(out, 0)
@@ -31,7 +31,12 @@ names = ["task fetch", "TMA+zero", "planes", "liquid", "faces", "counts+prefix",
 tot = sum(out[:17]); n = c["n_worked"]
 print(f"r={R}: {n} worked tasks, mesh_ms {st['mesh_ms']:.3f}, cycles/task {tot / n:.0f}")
 print(f"  per task: masks merged {out[20]/n:.1f}, faces {out[21]/n:.0f}, non-empty rows {out[22]/n:.0f}, quads {out[23]/n:.0f}")
+print("  masks per task by face count (<=8,<=16,<=32,<=64,<=128,>128):", [round(out[40+i]/n,1) for i in range(6)], " rows:", [round(out[48+i]/n,1) for i in range(6)])
+print(f"  flood: steps executed per task {out[28]/n:.1f} (sun+torch), live column evaluations per task {out[27]/n:.0f} (of {15*3424} possible per channel)")
+print(f"  flood step loop {out[29]/n:.0f} cyc/task, unpack {out[30]/n:.0f} cyc/task")
 print(f"  exact Show() candidate pairs per task: {out[26]/n:.0f}")
-print(f"  merge_mask cycles summed over warps {out[24]/n:.0f}/task ; per-warp busy-until sum {out[25]/n:.0f}/task (16 warps)")
+print(f"  warp-level merges: {out[20]/n:.1f} masks/task, {out[22]/n:.0f} rows/task, {out[24]/max(out[22],1):.0f} cycles/row, longest single mask {out[33]} cycles")
+print(f"  warp merge: set-up {out[37]/max(out[20],1):.0f} cyc/mask, main loop {out[38]/max(out[39],1):.0f} cyc/iteration, {out[39]/n:.0f} iterations/task")
+print(f"  tiny-mask warps: {out[36]/n:.2f} per task, {out[35]/max(out[36],1):.0f} cycles each; merge section per-warp mean {out[34]/n/32:.0f} cycles")
 for i, nm in enumerate(names):
     print(f"  {nm:14s} {out[i] / n:9.0f} cyc/task  {100 * out[i] / tot:5.1f}%")
