@@ -546,9 +546,15 @@ __device__ __forceinline__ u32 tri_interp(u32 lo, u32 hi, u32 du, u32 dv, u32 dw
 // with nothing left to light are skipped, and the loop ends at the fixed point.
 // ---------------------------------------------------------------------------------------------------------------
 struct ColInfo {
-	int c[kColsPerThread];    // sbuf index (with zero border), -1 if unused
-	int lim[kColsPerThread];  // last step at which the column is still relevant
-	u32 g[kColsPerThread];    // element index of the lower chunk's word in the dense planes (< 2^32: checked in hcm_create)
+	int c[kColsPerThread]; // sbuf index (with zero border) | last relevant step << 16, or -1 if unused
+	u32 g0;                // element index in the dense planes of the lower chunk's word of domain column (0,0) (< 2^32: hcm_create)
+	u32 X;                 // row pitch of the dense planes
+	__device__ __forceinline__ int idx(int k) const { return c[k] & 0xffff; }
+	__device__ __forceinline__ int lim(int k) const { return c[k] >> 16; }
+	__device__ __forceinline__ u32 g(int k) const { // sbuf index = (z+1)*64 + (x+1)
+		const int i = idx(k);
+		return g0 + (u32)((i >> 6) - 1) * X + (u32)((i & 63) - 1);
+	}
 };
 
 __device__ __forceinline__ u64 combine3(u32 lo, u32 mid, u32 hi) { // chunk words y-1, y, y+1 -> bits of y in [-15,46]
@@ -585,98 +591,98 @@ __device__ __forceinline__ u32 spread4(u32 n) { return (n * 0x00204081u) & 0x010
 template <bool kTorch>
 __device__ __forceinline__ void flood_channel(const MeshParams &p, const ColInfo &ci, const u64 (&P)[kColsPerThread], u64 *sbuf, uint8_t *light, int tid) {
 	const size_t plane_stride = (size_t)p.w.Z * p.w.X; // one chunk layer of columns
-	u64 G[kColsPerThread];
 	u64 pl[kInnerSlots][4]; // bit planes of the light value of the inner columns
-	// sbuf is double buffered: step s reads buffer (s-1)&1 and publishes into buffer s&1, so one barrier per step is
-	// enough.  A column that changed at step s must be published at steps s and s+1 (once into each buffer).
-	int dirty[kColsPerThread];
-#pragma unroll
-	for (int k = 0; k < kColsPerThread; ++k)
-		G[k] = 0, dirty[k] = 0;
+	// The level-set words live in `sbuf`, double buffered: step s reads buffer (s-1)&1 and publishes into buffer s&1, so
+	// one barrier per step is enough.  A column that changed at step s is published at steps s and s+1 (once per buffer).
+	u32 dirty = 0; // bit k: slot k changed in the previous step and still has to reach the other buffer
+	u32 live = 0;  // bit k: slot k can still gain cells (valid, unlit passable cells left, still within reach of the inner square)
 #pragma unroll
 	for (int k = 0; k < kInnerSlots; ++k)
 		pl[k][0] = pl[k][1] = pl[k][2] = pl[k][3] = 0;
 	const int last_inject_step = kTorch ? 15 - (int)p.w.levels[p.w.n_levels - 1] : 0;
 	bool any_set = false; // block-uniform: some G bit is set anywhere
 #ifdef HCM_PHASE_TIMING
-	long long tf0_ = clock64();
+	long long tf0_ = clock64(), tfs_ = tf0_;
 #endif
 	for (int step = 0; step <= 14; ++step) {
 		bool changed = false;
-		u64 nw[kInnerSlots];
-#pragma unroll
-		for (int k = 0; k < kInnerSlots; ++k)
-			nw[k] = 0;
+		const u32 val = 15 - step; // cells that enter G at this step get this light value
 		const u64 *rd = sbuf + ((step - 1) & 1) * (kSB * kSB);
 		u64 *wr = sbuf + (step & 1) * (kSB * kSB);
-		if (step > 0 && any_set) {
+		u32 level_plane = ~0u; // torch: index of the source plane of this level, if any
+		if (kTorch) {
+			level_plane = ~0u;
+			for (int l = 0; l < p.w.n_levels; ++l)
+				if (p.w.levels[l] == val)
+					level_plane = (u32)l;
+		}
+		const bool inject = kTorch ? level_plane != ~0u : step == 0;
+		if (inject || (any_set && (live | dirty))) { // most threads have nothing left after a step or two: one test skips them
+			u32 next_dirty = 0;
 #pragma unroll
-			for (int k = 0; k < kColsPerThread; ++k)
-				if (ci.c[k] >= 0 && step <= ci.lim[k] && (P[k] & ~G[k])) {
-					PHASE_COUNT(27, 1); // live column evaluations
-					const int c = ci.c[k];
-					const u64 g = G[k];
-					const u64 n = rd[c - 1] | rd[c + 1] | rd[c - kSB] | rd[c + kSB];
-					const u64 add = (((g << 1) | (g >> 1) | n) & P[k]) & ~g;
-					if (add) {
-						G[k] = g | add, dirty[k] = 2, changed = true;
-						if (k < kInnerSlots)
-							nw[k] = add;
+			for (int k = 0; k < kColsPerThread; ++k) {
+				const bool lv = (live >> k) & 1, dt = (dirty >> k) & 1;
+				if (ci.c[k] < 0 || !(inject || lv || dt))
+					continue;
+				const int c = ci.idx(k);
+				const u64 g = step > 0 ? rd[c] : 0ull;
+				u64 add = 0;
+				if (lv && step > 0) {
+					if (step > ci.lim(k))
+						live &= ~(1u << k);
+					else {
+						const u64 n = rd[c - 1] | rd[c + 1] | rd[c - kSB] | rd[c + kSB];
+						add = (((g << 1) | (g >> 1) | n) & P[k]) & ~g;
 					}
 				}
-		}
-		// sources of level 15 - step
-		if (!kTorch) {
-			if (step == 0) {
-#pragma unroll
-				for (int k = 0; k < kColsPerThread; ++k)
-					if (ci.c[k] >= 0) {
-						u32 s[3];
+				if (inject) { // sources of level 15 - step
+					if (!kTorch) {
+						u32 sl[3];
 #pragma unroll
 						for (int d = 0; d < 3; ++d) {
-							const int h = p.w.height[ci.g[k] + d * plane_stride];
-							s[d] = h >= 32 ? 0u : (h <= 0 ? 0xffffffffu : (0xffffffffu << h)); // sunlit: y >= height, Chunk.hpp:73-76
+							const int h = p.w.height[ci.g(k) + d * plane_stride];
+							sl[d] = h >= 32 ? 0u : (h <= 0 ? 0xffffffffu : (0xffffffffu << h)); // sunlit: y >= height, Chunk.hpp:73-76
 						}
-						G[k] = combine3(s[0], s[1], s[2]);
-						if (G[k]) {
-							dirty[k] = 2, changed = true;
-							if (k < kInnerSlots)
-								nw[k] = G[k];
-						}
+						add |= combine3(sl[0], sl[1], sl[2]) & ~g;
+					} else {
+						const u32 *src = p.w.torch + (size_t)level_plane * p.w.wy * plane_stride;
+						const u32 gk = ci.g(k);
+						add |= combine3(src[gk], src[gk + plane_stride], src[gk + 2 * plane_stride]) & ~g;
 					}
-			}
-		} else {
-			const u32 lvl = 15 - step;
-			for (int l = 0; l < p.w.n_levels; ++l)
-				if (p.w.levels[l] == lvl) {
-					const u32 *src = p.w.torch + (size_t)l * p.w.wy * plane_stride;
-#pragma unroll
-					for (int k = 0; k < kColsPerThread; ++k)
-						if (ci.c[k] >= 0) {
-							const u64 s = combine3(src[ci.g[k]], src[ci.g[k] + plane_stride], src[ci.g[k] + 2 * plane_stride]) & ~G[k];
-							if (s) {
-								G[k] |= s, dirty[k] = 2, changed = true;
-								if (k < kInnerSlots)
-									nw[k] |= s;
-							}
-						}
 				}
+				const u64 ng = g | add;
+				if (add) {
+					changed = true, next_dirty |= 1u << k;
+					if (k < kInnerSlots) {
+#pragma unroll
+						for (int b = 0; b < 4; ++b)
+							if ((val >> b) & 1)
+								pl[k < kInnerSlots ? k : 0][b] |= add;
+					}
+				}
+				if (add || dt)
+					wr[c] = ng;
+				if (inject || add) { // (re)evaluate whether the slot can still change
+					if (P[k] & ~ng)
+						live |= 1u << k;
+					else
+						live &= ~(1u << k);
+				}
+			}
+			dirty = next_dirty;
 		}
-		// cells that entered G at this step get the value 15 - step
-		const u32 val = 15 - step;
-#pragma unroll
-		for (int k = 0; k < kInnerSlots; ++k)
-#pragma unroll
-			for (int b = 0; b < 4; ++b)
-				if ((val >> b) & 1)
-					pl[k][b] |= nw[k];
-#pragma unroll
-		for (int k = 0; k < kColsPerThread; ++k)
-			if (dirty[k] > 0)
-				wr[ci.c[k]] = G[k], --dirty[k];
 		const bool any_changed = __syncthreads_or(changed);
-		if (tid == 0)
+#ifdef HCM_PHASE_TIMING
+		if (tid == 0) {
 			PHASE_COUNT(28, 1); // flood steps executed
+			const long long now_ = clock64();
+			if (step == 0)
+				PHASE_COUNT(31, now_ - tf0_); // step 0 (sources from global memory)
+			else
+				PHASE_COUNT(32, now_ - tfs_);
+			tfs_ = now_;
+		}
+#endif
 		any_set |= any_changed;
 		if (!any_changed && step >= last_inject_step)
 			break; // fixed point
@@ -1303,6 +1309,8 @@ __global__ void __launch_bounds__(kThreads, 1) mesh_kernel(const __grid_constant
 			for (int i = tid; i < 2 * kSB * kSB; i += kThreads)
 				sbuf[i] = 0; // both buffers: zero border and interior
 			ColInfo ci;
+			ci.X = (u32)p.w.X;
+			ci.g0 = (u32)(((size_t)(ti.cy - 1) * p.w.Z + (size_t)(ti.cz * 32 - 15)) * p.w.X + (size_t)(ti.cx * 32 - 15));
 			u64 P[kColsPerThread];
 			const size_t plane_stride = (size_t)p.w.Z * p.w.X;
 #pragma unroll
@@ -1312,12 +1320,11 @@ __global__ void __launch_bounds__(kThreads, 1) mesh_kernel(const __grid_constant
 				const int dx = x < 14 ? 14 - x : (x > 47 ? x - 47 : 0), dz = z < 14 ? 14 - z : (z > 47 ? z - 47 : 0);
 				ok = ok && dx + dz <= 14; // farther columns can never reach the inner square
 				if (ok) {
-					ci.c[k] = (z + 1) * kSB + (x + 1);
-					ci.lim[k] = 14 - dx - dz;
-					ci.g[k] = (u32)(((size_t)(ti.cy - 1) * p.w.Z + (size_t)(ti.cz * 32 - 15 + z)) * p.w.X + (size_t)(ti.cx * 32 - 15 + x));
-					P[k] = combine3(p.w.pass[ci.g[k]], p.w.pass[ci.g[k] + plane_stride], p.w.pass[ci.g[k] + 2 * plane_stride]);
+					ci.c[k] = ((z + 1) * kSB + (x + 1)) | ((14 - dx - dz) << 16);
+					const u32 gk = ci.g(k);
+					P[k] = combine3(p.w.pass[gk], p.w.pass[gk + plane_stride], p.w.pass[gk + 2 * plane_stride]);
 				} else {
-					ci.c[k] = -1, ci.lim[k] = -1, ci.g[k] = 0, P[k] = 0;
+					ci.c[k] = -1, P[k] = 0;
 				}
 			}
 			__syncthreads();

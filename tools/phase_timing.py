@@ -33,6 +33,9 @@ print(f"r={R}: {n} worked tasks, mesh_ms {st['mesh_ms']:.3f}, cycles/task {tot /
 print(f"  per task: masks merged {out[20]/n:.1f}, faces {out[21]/n:.0f}, non-empty rows {out[22]/n:.0f}, quads {out[23]/n:.0f}")
 print("  masks per task by face count (<=8,<=16,<=32,<=64,<=128,>128):", [round(out[40+i]/n,1) for i in range(6)], " rows:", [round(out[48+i]/n,1) for i in range(6)])
 print(f"  flood: steps executed per task {out[28]/n:.1f} (sun+torch), live column evaluations per task {out[27]/n:.0f} (of {15*3424} possible per channel)")
+print(f"  flood: step 0 {out[31]/n:.0f} cyc/task, later steps {out[32]/max(out[28]-2*n,1):.0f} cyc/step")
+ls_ = max(out[28]-n,1)
+print(f"  flood later steps (tid 0): dilation {out[52]/ls_:.0f}, inject+planes+publish {out[53]/ls_:.0f}, barrier wait {out[54]/ls_:.0f} cycles/step ({ls_/n:.1f} later steps/task)")
 print(f"  flood step loop {out[29]/n:.0f} cyc/task, unpack {out[30]/n:.0f} cyc/task")
 print(f"  exact Show() candidate pairs per task: {out[26]/n:.0f}")
 print(f"  warp-level merges: {out[20]/n:.1f} masks/task, {out[22]/n:.0f} rows/task, {out[24]/max(out[22],1):.0f} cycles/row, longest single mask {out[33]} cycles")
