@@ -144,3 +144,99 @@ def test_cpp_host_mirror_dispatcher():
     hcoracle.build(ref=False, port=True)
     r = subprocess.run([exe, os.path.join(root, "hypercraft_b200", "data", "registry.bin"), hcoracle.PORT_SO], capture_output=True, text=True)
     assert r.returncode == 0 and r.stdout.startswith("PASS"), r.stdout + r.stderr
+
+
+def _terrain_world(radius):
+    """(meshed, resident, blocks, heights): reference terrain if oracle/_ref is present, else the repo's fallback terrain."""
+    import hcoracle
+    from hypercraft_b200 import worldgen
+
+    meshed, resident = worldgen.load_radius_positions(radius)
+    if hcoracle.have_ref():
+        ref = hcoracle.RefWorld()
+        ref.generate(resident)
+        blocks, heights = ref.get_chunks(resident)
+    else:
+        blocks = np.zeros((len(resident), 32768), dtype=np.uint16)
+        heights = np.zeros((len(resident), 1024), dtype=np.int8)
+        for i, p in enumerate(resident):
+            blocks[i], heights[i] = worldgen.synth_terrain_chunk(12314524, p)
+    return meshed, resident, blocks, heights
+
+
+def test_structural_invariants_at_scale():
+    """Size-independent properties on a whole load sphere (r = 8, 2 109 tasks): vertex/index/quad bookkeeping, the
+    16-bit cut, index ranges, AABBs that bound their vertices, idempotence and independence from task order."""
+    from hypercraft_b200 import mesher as M
+
+    meshed, resident, blocks, heights = _terrain_world(8)
+    m = M.Mesher(origin=(-9, -9, -9), extent=(19, 19, 19), max_chunks=len(resident), max_tasks=len(meshed))
+    m.upload(resident, blocks, heights)
+    res = m.mesh(meshed)
+    md = res.meshes
+    assert int(md["vertex_count"].sum()) == len(res.vertices) and int(md["index_count"].sum()) == len(res.indices)
+    assert (md["vertex_count"] % 4 == 0).all() and (md["index_count"] * 4 == md["vertex_count"] * 6).all()
+    assert (md["vertex_count"] <= 65532).all() and (md["vertex_count"] > 0).all()
+    assert int(res.tasks["n_meshes"].sum()) == len(md)
+    snap = {}
+    for t in range(len(meshed)):
+        ms = res.task_meshes(t)
+        for k, mesh in enumerate(ms):
+            v = mesh["vertices"]
+            w0 = (v & np.uint64(0xFFFFFFFF)).astype(np.uint32)
+            xyz = np.stack([w0 & 1023, (w0 >> 10) & 1023, (w0 >> 20) & 1023], axis=1)
+            assert (xyz.min(axis=0) == mesh["aabb_min"]).all() and (xyz.max(axis=0) == mesh["aabb_max"]).all()
+            assert (xyz <= 512).all()
+            idx = mesh["indices"].astype(np.int64)
+            assert idx.max() < len(v) or (idx[:6].max() == 65535 and idx[6:].max(initial=0) < len(v))  # stale base of a continuation mesh
+            assert mesh["transparent"] in (0, 1)
+        snap[t] = res.serialise(t).tobytes()
+    # idempotence
+    res2 = m.mesh(meshed)
+    assert all(res2.serialise(t).tobytes() == snap[t] for t in range(0, len(meshed), 7))
+    # task order does not matter
+    perm = np.random.default_rng(3).permutation(len(meshed))
+    res3 = m.mesh(meshed[perm])
+    assert all(res3.serialise(i).tobytes() == snap[int(perm[i])] for i in range(0, len(meshed), 5))
+    # re-deriving from the device-resident Block data changes nothing
+    m.rederive()
+    res4 = m.mesh(meshed)
+    assert all(res4.serialise(t).tobytes() == snap[t] for t in range(0, len(meshed), 11))
+    m.close()
+
+
+def test_translation_invariance_and_removal(port):
+    """The same 27 chunks give the same meshes wherever the window puts them; removed chunks stop being resident."""
+    from hypercraft_b200 import mesher as M
+
+    pos, blocks, heights, chunks = synth_world("mix", 4)
+    want = port.mesh(chunks, (0, 0, 0))
+    for origin, shift in [((-3, -2, -4), (0, 0, 0)), ((100, -50, 7), (102, -47, 9))]:
+        m = M.Mesher(origin=origin, extent=(7, 6, 8))
+        p2 = (pos.astype(np.int32) + np.array(shift)).astype(np.int16)
+        m.upload(p2, blocks, heights)
+        res = m.mesh(np.array([shift], dtype=np.int16))
+        got = res.serialise(0)
+        assert got.size == want.size and (got == want).all()
+        assert m.is_resident(shift)
+        m.remove(np.array([shift], dtype=np.int16))
+        assert not m.is_resident(shift)
+        with pytest.raises(M.HcmError) as e:
+            m.mesh(np.array([shift], dtype=np.int16))
+        assert e.value.status == -4
+        s = m.stats()
+        assert s["kernel_launches"] >= 3 and s["h2d_bytes"] > 0 and s["d2h_bytes"] > 0 and s["device_bytes"] > 0
+        m.close()
+
+
+def test_output_arena_grows_instead_of_truncating(port):
+    """A deliberately tiny vertex arena: the batch is re-run with a larger one, never cut short."""
+    from hypercraft_b200 import mesher as M
+
+    pos, blocks, heights, chunks = synth_world("checker", 2)
+    m = M.Mesher(origin=(-2, -2, -2), extent=(5, 5, 5), vertex_capacity=1024)
+    m.upload(pos, blocks, heights)
+    res = m.mesh(np.array([[0, 0, 0]], dtype=np.int16))
+    got, want = res.serialise(0), port.mesh(chunks, (0, 0, 0))
+    assert got.size == want.size and (got == want).all()
+    m.close()
