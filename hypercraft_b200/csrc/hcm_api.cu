@@ -47,6 +47,10 @@ struct hcm_ctx {
 	CUtensorMap tmap{};
 
 	std::vector<int32_t> slot_of; // host mirror of DevWorld::slot
+	std::vector<uint8_t> nbr_count; // per cell: resident chunks in its 3x3x3 neighbourhood (27 = a mesh task is possible)
+	uint64_t residency_version = 1, all_entries_version = 0; // cache of the "every resident chunk" entry list on the device
+	UploadEntry *d_all_entries = nullptr;
+	uint32_t n_all_entries = 0;
 	std::vector<int32_t> free_slots;
 
 	TaskIn *d_tasks = nullptr;
@@ -126,6 +130,18 @@ inline bool chunk_is_uniform(const uint16_t *b) {
 
 constexpr uint32_t kUploadBlock = 2048; // chunks per pipeline stage (128 MB of Block data)
 constexpr uint32_t kScanGrain = 32;     // chunks per work item of the scan threads
+
+// a chunk became resident (+1) or was removed (-1): update the 27 cells that see it as a neighbour
+void bump_neighbours(hcm_ctx *c, int cx, int cy, int cz, int delta) {
+	for (int dy = -1; dy <= 1; ++dy)
+		for (int dz = -1; dz <= 1; ++dz)
+			for (int dx = -1; dx <= 1; ++dx) {
+				const int x = cx + dx, y = cy + dy, z = cz + dz;
+				if (x >= 0 && x < c->w.wx && y >= 0 && y < c->w.wy && z >= 0 && z < c->w.wz)
+					c->nbr_count[cell(c, x, y, z)] = (uint8_t)(c->nbr_count[cell(c, x, y, z)] + delta);
+			}
+	++c->residency_version;
+}
 
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
                                     const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -388,7 +404,7 @@ void hcm_destroy(hcm_ctx *c) {
 	if (c->stream)
 		cudaStreamSynchronize(c->stream);
 	void *dev[] = {c->w.prop8, c->w.pass, c->w.torch, c->w.height, c->w.cflags, c->w.slot, c->d_tables, c->d_prop_index, c->d_meshes, c->d_mesh_info, c->d_raw,
-	               c->d_rawh, c->d_entries, c->d_tasks, c->d_worklist, c->d_heads, c->d_task_out, c->d_mesh_out, c->d_vtx, c->d_idx, c->d_dyn, c->d_debug_light};
+	               c->d_rawh, c->d_entries, c->d_all_entries, c->d_tasks, c->d_worklist, c->d_heads, c->d_task_out, c->d_mesh_out, c->d_vtx, c->d_idx, c->d_dyn, c->d_debug_light};
 	for (void *p : dev)
 		if (p)
 			cudaFree(p);
@@ -503,6 +519,7 @@ int hcm_create(const hcm_registry *registry, const hcm_config *cfg, hcm_ctx **ou
 	CUB(cudaStreamSynchronize(c->stream)); // `tables`/`minfo` are stack/heap temporaries
 
 	c->slot_of.assign(c->n_cells, -1);
+	c->nbr_count.assign(c->n_cells, 0);
 	c->free_slots.resize(c->max_chunks);
 	for (uint32_t i = 0; i < c->max_chunks; ++i)
 		c->free_slots[i] = (int32_t)(c->max_chunks - 1 - i); // pop_back hands out 0,1,2,... -> contiguous uploads
@@ -580,6 +597,7 @@ int hcm_upload_chunks(hcm_ctx *c, uint32_t n, const int16_t *pos, const uint16_t
 					c->free_slots.pop_back();
 					c->slot_of[cell(c, cx, cy, cz)] = slot;
 					fresh.push_back((int32_t)cell(c, cx, cy, cz));
+					bump_neighbours(c, cx, cy, cz, +1);
 				}
 			}
 		}
@@ -587,6 +605,8 @@ int hcm_upload_chunks(hcm_ctx *c, uint32_t n, const int16_t *pos, const uint16_t
 			for (auto it = fresh.rbegin(); it != fresh.rend(); ++it) {
 				c->free_slots.push_back(c->slot_of[*it]);
 				c->slot_of[*it] = -1;
+				const int fx = *it % c->w.wx, fz = (*it / c->w.wx) % c->w.wz, fy = *it / (c->w.wx * c->w.wz);
+				bump_neighbours(c, fx, fy, fz, -1);
 			}
 			return rc;
 		}
@@ -722,6 +742,7 @@ int hcm_remove_chunks(hcm_ctx *c, uint32_t n, const int16_t *pos) {
 		entries.push_back(UploadEntry{slot, (int16_t)cx, (int16_t)cy, (int16_t)cz, 0, 0});
 		c->free_slots.push_back(slot);
 		slot = -1;
+		bump_neighbours(c, cx, cy, cz, -1);
 	}
 	if (entries.empty())
 		return HCM_OK;
@@ -740,13 +761,33 @@ int hcm_rederive_chunks(hcm_ctx *c, uint32_t n, const int16_t *pos) {
 	CU(cudaSetDevice(c->device));
 	std::vector<UploadEntry> entries;
 	if (n == 0) {
-		for (int cy = 0; cy < c->w.wy; ++cy)
-			for (int cz = 0; cz < c->w.wz; ++cz)
-				for (int cx = 0; cx < c->w.wx; ++cx) {
-					const int32_t slot = c->slot_of[cell(c, cx, cy, cz)];
-					if (slot >= 0)
-						entries.push_back(UploadEntry{slot, (int16_t)cx, (int16_t)cy, (int16_t)cz, 0, 0});
-				}
+		cudaStream_t st0 = c->stream;
+		if (c->all_entries_version != c->residency_version) { // the list only changes with residency: keep it on the device
+			for (int cy = 0; cy < c->w.wy; ++cy)
+				for (int cz = 0; cz < c->w.wz; ++cz)
+					for (int cx = 0; cx < c->w.wx; ++cx) {
+						const int32_t slot = c->slot_of[cell(c, cx, cy, cz)];
+						if (slot >= 0)
+							entries.push_back(UploadEntry{slot, (int16_t)cx, (int16_t)cy, (int16_t)cz, 0, 0});
+					}
+			if (!c->d_all_entries)
+				CU(dev_alloc(c, &c->d_all_entries, (size_t)c->max_chunks));
+			if (!entries.empty())
+				CU(cudaMemcpyAsync(c->d_all_entries, entries.data(), entries.size() * sizeof(UploadEntry), cudaMemcpyHostToDevice, st0));
+			c->stats.h2d_bytes += entries.size() * sizeof(UploadEntry);
+			c->n_all_entries = (uint32_t)entries.size();
+			c->all_entries_version = c->residency_version;
+		}
+		if (!c->n_all_entries)
+			return HCM_OK;
+		CU(cudaEventRecord(c->ev[EV_UP0], st0));
+		CU(cudaEventRecord(c->ev[EV_UP1], st0));
+		launch_derive(c->w, c->d_all_entries, c->n_all_entries, c->d_prop_index, c->d_tables, c->d_rawh, st0);
+		CU(cudaGetLastError());
+		CU(cudaEventRecord(c->ev[EV_UP2], st0));
+		c->stats.kernel_launches += 1;
+		c->ev_upload = true;
+		return HCM_OK;
 	} else {
 		for (uint32_t i = 0; i < n; ++i) {
 			int cx, cy, cz;
@@ -796,12 +837,15 @@ static int submit(hcm_ctx *c, uint32_t n, const int16_t *pos, int force_all) {
 		if (cx < 1 || cy < 1 || cz < 1 || cx > c->w.wx - 2 || cy > c->w.wy - 2 || cz > c->w.wz - 2)
 			return fail(c, HCM_ERR_NOT_RESIDENT, "task (%d,%d,%d) touches the window border: a neighbour cannot be resident", pos[3 * i], pos[3 * i + 1],
 			            pos[3 * i + 2]);
-		for (int dy = -1; dy <= 1; ++dy)
-			for (int dz = -1; dz <= 1; ++dz)
-				for (int dx = -1; dx <= 1; ++dx)
-					if (c->slot_of[cell(c, cx + dx, cy + dy, cz + dz)] < 0)
-						return fail(c, HCM_ERR_NOT_RESIDENT, "task (%d,%d,%d): neighbour (%d,%d,%d) is not resident", pos[3 * i], pos[3 * i + 1],
-						            pos[3 * i + 2], pos[3 * i] + dx, pos[3 * i + 1] + dy, pos[3 * i + 2] + dz);
+		if (c->nbr_count[cell(c, cx, cy, cz)] != 27) {
+			for (int dy = -1; dy <= 1; ++dy)
+				for (int dz = -1; dz <= 1; ++dz)
+					for (int dx = -1; dx <= 1; ++dx)
+						if (c->slot_of[cell(c, cx + dx, cy + dy, cz + dz)] < 0)
+							return fail(c, HCM_ERR_NOT_RESIDENT, "task (%d,%d,%d): neighbour (%d,%d,%d) is not resident", pos[3 * i], pos[3 * i + 1],
+							            pos[3 * i + 2], pos[3 * i] + dx, pos[3 * i + 1] + dy, pos[3 * i + 2] + dz);
+			return fail(c, HCM_ERR_STATE, "internal: neighbour count out of sync");
+		}
 		c->tasks[i] = TaskIn{(int16_t)cx, (int16_t)cy, (int16_t)cz, 0};
 	}
 	c->batch_n = n;

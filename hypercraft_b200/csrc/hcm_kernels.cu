@@ -52,6 +52,13 @@ __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, i
 	             : "memory");
 }
 
+// 1-D TMA bulk copy global -> shared (size multiple of 16, both addresses 16-byte aligned)
+__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, u32 bytes, u64 *bar) {
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src), "r"(bytes),
+	             "r"(smem_u32(bar))
+	             : "memory");
+}
+
 __device__ __forceinline__ u32 lanemask_lt() {
 	u32 m;
 	asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
@@ -96,14 +103,25 @@ __device__ unsigned long long g_phase_cycles[64];
 // ================================================================================================================
 __global__ void __launch_bounds__(256) derive_kernel(DevWorld w, const UploadEntry *__restrict__ entries, const uint8_t *__restrict__ prop_index,
                                                      const DevTables *__restrict__ tables, const int8_t *__restrict__ raw_heights) {
-	__shared__ uint16_t s_pinfo[256]; // pflags | light level << 8
+	extern __shared__ __align__(128) uint8_t derive_smem[]; // the chunk's 64 KB of Block data, one TMA bulk copy
+	__shared__ uint16_t s_pinfo[256];                       // pflags | light level << 8
 	__shared__ u32 s_and, s_or;
+	__shared__ __align__(8) u64 s_bar;
 	const int tid = threadIdx.x;
-	s_pinfo[tid] = (uint16_t)(tables->pflags[tid] | ((tables->pmisc[tid] >> 4) << 8));
-	if (tid == 0)
-		s_and = 0xffffffffu, s_or = 0;
-
 	const UploadEntry e = entries[blockIdx.x];
+	const bool host_uniform = e.flags & UE_UNIFORM;
+	if (tid == 0) {
+		mbar_init(&s_bar, 1);
+		s_and = 0xffffffffu, s_or = 0;
+	}
+	s_pinfo[tid] = (uint16_t)(tables->pflags[tid] | ((tables->pmisc[tid] >> 4) << 8));
+	__syncthreads();
+	if (tid == 0 && !host_uniform) {
+		mbar_expect_tx(&s_bar, HCM_CHUNK_VOXELS * 2);
+		tma_load_1d(derive_smem, w.raw + (size_t)e.slot * HCM_CHUNK_VOXELS, HCM_CHUNK_VOXELS * 2, &s_bar);
+	}
+	const uint16_t *sraw = reinterpret_cast<const uint16_t *>(derive_smem);
+
 	const int z = tid >> 3, x4 = (tid & 7) << 2;
 	const uint16_t *raw = w.raw + (size_t)e.slot * HCM_CHUNK_VOXELS;
 	const size_t gx = (size_t)e.cx * 32 + x4, gz = (size_t)e.cz * 32 + z;
@@ -116,7 +134,7 @@ __global__ void __launch_bounds__(256) derive_kernel(DevWorld w, const UploadEnt
 	// ---- uniform chunks (all air, all stone: most of a load sphere) need one table lookup, not 32768 ----------------
 	u32 d0, pat;
 	bool same;
-	if (e.flags & UE_UNIFORM) {
+	if (host_uniform) {
 		// the host skipped the 64 KB copy: materialise the raw slot here (the liquid generator reads raw meta of neighbours)
 		d0 = e.value, pat = d0 | (d0 << 16), same = true;
 		uint16_t *rw = const_cast<uint16_t *>(raw);
@@ -124,11 +142,12 @@ __global__ void __launch_bounds__(256) derive_kernel(DevWorld w, const UploadEnt
 		for (int y = 0; y < 32; ++y)
 			*reinterpret_cast<uint2 *>(rw + x4 + (y * 32 + z) * 32) = make_uint2(pat, pat);
 	} else {
-		d0 = raw[0], pat = d0 | (d0 << 16);
-		u32 acc_and = 0xffffffffu, acc_or = 0; // all 32 loads are independent: uniform <=> AND == OR == pattern
+		mbar_wait(&s_bar, 0);
+		d0 = sraw[0], pat = d0 | (d0 << 16);
+		u32 acc_and = 0xffffffffu, acc_or = 0; // uniform <=> AND == OR == pattern
 #pragma unroll
 		for (int y = 0; y < 32; ++y) {
-			const uint2 r = __ldg(reinterpret_cast<const uint2 *>(raw + x4 + (y * 32 + z) * 32));
+			const uint2 r = *reinterpret_cast<const uint2 *>(sraw + x4 + (y * 32 + z) * 32);
 			acc_and &= r.x & r.y, acc_or |= r.x | r.y;
 		}
 		same = acc_and == pat && acc_or == pat;
@@ -177,7 +196,7 @@ __global__ void __launch_bounds__(256) derive_kernel(DevWorld w, const UploadEnt
 	const u32 on_z = (z == 31 ? 16u : 0u) | (z == 0 ? 32u : 0u);
 	const u32 on_x[4] = {on_z | (x4 == 0 ? 2u : 0u), on_z, on_z, on_z | (x4 == 28 ? 1u : 0u)};
 	for (int y = 0; y < 32; ++y) {
-		const uint2 r = *reinterpret_cast<const uint2 *>(raw + x4 + (y * 32 + z) * 32);
+		const uint2 r = *reinterpret_cast<const uint2 *>(sraw + x4 + (y * 32 + z) * 32);
 		const u32 d[4] = {r.x & 0xffffu, r.x >> 16, r.y & 0xffffu, r.y >> 16};
 		const u32 on_y = (y == 31 ? 4u : 0u) | (y == 0 ? 8u : 0u);
 		u32 pr[4];
@@ -1657,7 +1676,7 @@ __global__ void __launch_bounds__(kThreads, 1) mesh_kernel(const __grid_constant
 void launch_derive(const DevWorld &w, const UploadEntry *entries, u32 n, const uint8_t *prop_index, const DevTables *tables, const int8_t *raw_heights,
                    cudaStream_t st) {
 	if (n)
-		derive_kernel<<<n, 256, 0, st>>>(w, entries, prop_index, tables, raw_heights);
+		derive_kernel<<<n, 256, HCM_CHUNK_VOXELS * 2, st>>>(w, entries, prop_index, tables, raw_heights);
 }
 void launch_clear(const DevWorld &w, const UploadEntry *entries, u32 n, cudaStream_t st) {
 	if (n)
@@ -1678,7 +1697,12 @@ extern "C" __attribute__((visibility("default"))) int hcm_debug_phase_cycles(uns
 	return 0;
 }
 #endif
-cudaError_t mesh_kernel_prepare() { return cudaFuncSetAttribute(mesh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes); }
+cudaError_t mesh_kernel_prepare() {
+	cudaError_t e = cudaFuncSetAttribute(derive_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HCM_CHUNK_VOXELS * 2);
+	if (e != cudaSuccess)
+		return e;
+	return cudaFuncSetAttribute(mesh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+}
 int mesh_kernel_smem_bytes() { return kSmemBytes; }
 void launch_mesh(const CUtensorMap &tmap, const MeshParams &p, int grid, cudaStream_t st) { mesh_kernel<<<grid, kThreads, kSmemBytes, st>>>(tmap, p); }
 
