@@ -240,3 +240,37 @@ def test_output_arena_grows_instead_of_truncating(port):
     got, want = res.serialise(0), port.mesh(chunks, (0, 0, 0))
     assert got.size == want.size and (got == want).all()
     m.close()
+
+
+def test_edit_driven_incremental_remesh(port):
+    """Config 5: seeded single-block edits; after each, re-upload the edited chunk (blocks + recomputed sunlight column),
+    remesh exactly the reference's fan-out set and compare every remeshed chunk with the oracle on the updated world."""
+    from hypercraft_b200 import edits, mesher as M, registry, worldgen
+
+    reg = registry.load()
+    vpass = reg.props["transparency"][reg.prop_index] == 2
+    allpos = np.array([[x, y, z] for x in range(-2, 3) for y in range(-2, 3) for z in range(-2, 3)], dtype=np.int16)
+    chunks = {}
+    for p in allpos:
+        b, h = worldgen.synth_terrain_chunk(77, p)
+        chunks[tuple(int(c) for c in p)] = (b.copy(), h.copy())
+    m = M.Mesher(origin=(-2, -2, -2), extent=(5, 5, 5))
+    m.upload(allpos, np.stack([chunks[tuple(int(c) for c in p)][0] for p in allpos]), np.stack([chunks[tuple(int(c) for c in p)][1] for p in allpos]))
+    rng = np.random.default_rng(11)
+    new_blocks = [0, 1, 24, 14, worldgen.make_block(worldgen.FLOWING_WATER, 5), 9, worldgen.make_block(worldgen.LEAVES, 2)]
+    for it in range(10):
+        bx, bz = int(rng.integers(0, 32)), int(rng.integers(0, 32))
+        cpos = (0, int(rng.integers(-1, 1)), 0)
+        b, h = chunks[cpos]
+        by = int(np.clip(int(h[bx + bz * 32]) + int(rng.integers(-3, 2)), 0, 31)) if it % 3 else int(rng.integers(0, 32))
+        b[bx + (by * 32 + bz) * 32] = new_blocks[it % len(new_blocks)]
+        up_h = int(chunks[(cpos[0], cpos[1] + 1, cpos[2])][1][bx + bz * 32])
+        h[bx + bz * 32] = edits.column_sunlight_height(b, bx, bz, up_h, vpass)
+        m.upload(np.array([cpos], dtype=np.int16), b[None], h[None])
+        tasks = np.array([[cpos[0] + d[0], cpos[1] + d[1], cpos[2] + d[2]] for d in edits.remesh_offsets((bx, by, bz))], dtype=np.int16)
+        tasks = tasks[(np.abs(tasks) <= 1).all(axis=1)]  # tasks need their 26 neighbours inside the 5^3 window
+        res = m.mesh(tasks)
+        for t, p in enumerate(tasks):
+            got, want = res.serialise(t), port.mesh(chunks, p)
+            assert got.size == want.size and (got == want).all(), f"edit {it} at {(bx, by, bz)} in {cpos}: task {p}\n" + describe_diff(got, want)
+    m.close()

@@ -126,3 +126,32 @@ def test_synthetic_chunks_are_deterministic():
     import hashlib
 
     assert hashlib.sha256(a[0].tobytes()).hexdigest()[:16] == hashlib.sha256(b[0].tobytes()).hexdigest()[:16]
+
+
+def test_edit_fan_out_matches_reference_rule():
+    """ChunkShouldRemesh / remesh fan-out (ChunkMeshTask.inl:9-15, ChunkSetBlockTask.cpp:100-107)."""
+    from hypercraft_b200 import edits
+
+    assert edits.chunk_should_remesh((16, 16, 16)) and edits.chunk_should_remesh((-15, 0, 0)) and not edits.chunk_should_remesh((-16, 0, 0))
+    assert edits.chunk_should_remesh((33 + 14, 5, 5)) and not edits.chunk_should_remesh((33 + 15, 5, 5))
+    assert not edits.chunk_should_remesh((-8, -8, 40))  # 7 + 7 + 7 = 21
+    centre = edits.remesh_offsets((16, 16, 16))
+    assert centre == [(0, 0, 0)]  # 16 voxels from every face: no neighbour within 14 of its [-1,33] box
+    corner = edits.remesh_offsets((0, 0, 0))
+    assert (0, 0, 0) in corner and (-1, -1, -1) in corner and (1, 0, 0) not in corner and len(corner) == 8
+    edge = edits.remesh_offsets((31, 10, 16))
+    assert (1, 0, 0) in edge and (1, -1, 0) in edge and (-1, 0, 0) not in edge
+
+
+def test_column_sunlight_height_rule():
+    from hypercraft_b200 import edits, registry
+
+    reg = registry.load()
+    vpass = reg.props["transparency"][reg.prop_index] == 2
+    b = np.zeros(32768, dtype=np.uint16)
+    assert edits.column_sunlight_height(b, 3, 4, 0, vpass) == 0
+    b[3 + (10 * 32 + 4) * 32] = 1  # stone at y = 10
+    assert edits.column_sunlight_height(b, 3, 4, 0, vpass) == 11
+    b[3 + (20 * 32 + 4) * 32] = 14  # water (semi-transparent) at y = 20 blocks vertical light too
+    assert edits.column_sunlight_height(b, 3, 4, 0, vpass) == 21
+    assert edits.column_sunlight_height(b, 3, 4, 5, vpass) == 32

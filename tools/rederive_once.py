@@ -1,0 +1,16 @@
+import os, sys
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import hcoracle
+from hypercraft_b200 import mesher as M, worldgen
+R = int(os.environ.get("R", "11"))
+meshed, resident = worldgen.load_radius_positions(R)
+ref = hcoracle.RefWorld(); ref.generate(resident)
+b, h = ref.get_chunks(resident)
+ext = 2 * R + 3
+m = M.Mesher(origin=(-R - 1,) * 3, extent=(ext,) * 3, max_chunks=len(resident), max_tasks=len(meshed))
+m.upload(resident, b, h); m.sync()
+for _ in range(3):
+    m.rederive(); m.sync()
+print("chunks", len(resident), "derive_ms", m.stats()["derive_ms"])
