@@ -182,6 +182,7 @@ def main():
 
     radius = args.radius
     threads = max(1, (os.cpu_count() or 1) // world)
+    os.environ.setdefault("HCM_HOST_THREADS", str(max(1, min(15, threads - 1))))  # upload scan threads of this rank's hcm_ctx
     centre = (3 * radius * rank, 0, 0)
     t_setup = time.time()
     meshed, resident, pb, ph, data_label, ref = build_world(radius, centre, threads)

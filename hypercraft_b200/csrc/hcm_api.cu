@@ -5,6 +5,7 @@
 #include <thread>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -33,6 +34,7 @@ struct hcm_ctx {
 	cudaStream_t copy_stream = nullptr; // host->device copies of large uploads overlap the host-side scan and the derive kernel
 	std::vector<cudaEvent_t> block_events;
 	bool use_batch_copy = true;
+	uint32_t host_threads = 0; // scan threads of hcm_upload_chunks (env HCM_HOST_THREADS; 0 = hardware_concurrency - 1, at most 15)
 	DevWorld w{};
 	size_t n_cells = 0; // window chunks
 	uint32_t max_chunks = 0, max_tasks = 0;
@@ -453,6 +455,8 @@ int hcm_create(const hcm_registry *registry, const hcm_config *cfg, hcm_ctx **ou
 		return rc;
 	};
 	c->device = cfg->device;
+	if (const char *ht = getenv("HCM_HOST_THREADS"))
+		c->host_threads = (uint32_t)std::max(0, atoi(ht));
 	DevTables tables;
 	std::vector<DevMeshInfo> minfo;
 	if (int rc = build_tables(c, registry, tables, minfo))
@@ -644,8 +648,9 @@ int hcm_upload_chunks(hcm_ctx *c, uint32_t n, const int16_t *pos, const uint16_t
 			item_done[it].store(1, std::memory_order_release);
 		}
 	};
-	const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
-	const uint32_t n_threads = n < 256 ? 0u : (uint32_t)std::min<size_t>({(size_t)hw - 1, (size_t)15, (size_t)n_items});
+	const unsigned hw = std::max(2u, std::thread::hardware_concurrency());
+	const size_t want_threads = c->host_threads ? c->host_threads : std::min<size_t>(hw - 1, 15);
+	const uint32_t n_threads = n < 256 ? 0u : (uint32_t)std::min<size_t>(want_threads, (size_t)n_items);
 	std::vector<std::thread> scanners;
 	for (uint32_t t = 0; t < n_threads; ++t)
 		scanners.emplace_back(scan_work);
