@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <map>
 #include <string>
 #include <vector>
@@ -33,7 +34,15 @@ struct hcm_ctx {
 	cudaStream_t stream = nullptr;
 	cudaStream_t copy_stream = nullptr; // host->device copies of large uploads overlap the host-side scan and the derive kernel
 	std::vector<cudaEvent_t> block_events;
+	cudaStream_t fetch_stream = nullptr; // device->host copies of hcm_upload_and_mesh overlap uploads and kernels
+	std::vector<cudaEvent_t> sub_events;
+	BatchHeads *h_heads_ring = nullptr; // pinned: heads after each sub-batch
+	uint32_t heads_ring_cap = 0;
+	hcm_task_result *h_task_stage = nullptr; // pinned: task results in sub-batch order
+	uint64_t h_task_stage_cap = 0;
+	std::vector<int32_t> cell_block; // scratch of hcm_upload_and_mesh
 	bool use_batch_copy = true;
+	uint32_t upload_block = 2048, min_sub_batch = 512; // pipeline granularity (env HCM_UPLOAD_BLOCK, HCM_MIN_SUB_BATCH: test knobs)
 	uint32_t host_threads = 0; // scan threads of hcm_upload_chunks (env HCM_HOST_THREADS; 0 = hardware_concurrency - 1, at most 15)
 	DevWorld w{};
 	size_t n_cells = 0; // window chunks
@@ -130,7 +139,7 @@ inline bool chunk_is_uniform(const uint16_t *b) {
 	return b[1] == v && b[2] == v && b[3] == v && memcmp(b, b + 4, (HCM_CHUNK_VOXELS - 4) * 2) == 0;
 }
 
-constexpr uint32_t kUploadBlock = 2048; // chunks per pipeline stage (128 MB of Block data)
+constexpr uint32_t kUploadBlock = 2048; // default chunks per pipeline stage (128 MB of Block data); hcm_ctx::upload_block
 constexpr uint32_t kScanGrain = 32;     // chunks per work item of the scan threads
 
 // a chunk became resident (+1) or was removed (-1): update the 27 cells that see it as a neighbour
@@ -302,20 +311,41 @@ template <typename T> int host_reserve(hcm_ctx *c, T **p, uint64_t *cap, uint64_
 	return HCM_OK;
 }
 
+MeshParams mesh_params(const hcm_ctx *c, uint32_t first_task) {
+	MeshParams p{};
+	p.w = c->w;
+	p.tables = c->d_tables, p.meshes = c->d_meshes, p.mesh_info = c->d_mesh_info;
+	p.tasks = c->d_tasks + first_task, p.worklist = c->d_worklist, p.heads = c->d_heads;
+	p.task_out = c->d_task_out + first_task, p.mesh_out = c->d_mesh_out, p.vtx = c->d_vtx, p.idx = c->d_idx;
+	p.vtx_cap = c->vtx_cap, p.idx_cap = c->idx_cap, p.mesh_cap = c->mesh_cap;
+	p.dyn_scratch = c->d_dyn, p.debug_light = c->d_debug_light;
+	return p;
+}
+
+// grow a pinned host array, keeping its first `used` elements (copies into it may still be in flight on `st`)
+template <typename T> int host_reserve_keep(hcm_ctx *c, T **p, uint64_t *cap, uint64_t need, uint64_t used, cudaStream_t st) {
+	if (need <= *cap)
+		return HCM_OK;
+	T *np_ = nullptr;
+	const uint64_t ncap = std::max<uint64_t>({need + need / 4, *cap * 2, (uint64_t)1024});
+	CU(cudaHostAlloc((void **)&np_, ncap * sizeof(T), cudaHostAllocDefault));
+	if (*p) {
+		CU(cudaStreamSynchronize(st));
+		if (used)
+			memcpy(np_, *p, used * sizeof(T));
+		cudaFreeHost(*p);
+	}
+	*p = np_, *cap = ncap;
+	return HCM_OK;
+}
+
 int launch_batch(hcm_ctx *c) {
 	cudaStream_t st = c->stream;
 	CU(cudaEventRecord(c->ev[EV_B0], st));
 	CU(cudaMemsetAsync(c->d_heads, 0, sizeof(BatchHeads), st));
 	launch_classify(c->w, c->d_tasks, c->batch_n, c->d_worklist, c->d_heads, c->d_task_out, c->force_all, st);
 	CU(cudaEventRecord(c->ev[EV_B1], st));
-	MeshParams p{};
-	p.w = c->w;
-	p.tables = c->d_tables, p.meshes = c->d_meshes, p.mesh_info = c->d_mesh_info;
-	p.tasks = c->d_tasks, p.worklist = c->d_worklist, p.heads = c->d_heads;
-	p.task_out = c->d_task_out, p.mesh_out = c->d_mesh_out, p.vtx = c->d_vtx, p.idx = c->d_idx;
-	p.vtx_cap = c->vtx_cap, p.idx_cap = c->idx_cap, p.mesh_cap = c->mesh_cap;
-	p.dyn_scratch = c->d_dyn, p.debug_light = c->d_debug_light;
-	launch_mesh(c->tmap, p, c->grid, st);
+	launch_mesh(c->tmap, mesh_params(c, 0), c->grid, st);
 	CU(cudaGetLastError());
 	CU(cudaEventRecord(c->ev[EV_B2], st));
 	c->stats.kernel_launches += 2;
@@ -410,7 +440,7 @@ void hcm_destroy(hcm_ctx *c) {
 	for (void *p : dev)
 		if (p)
 			cudaFree(p);
-	void *host[] = {c->h_heads, c->h_task_out, c->h_mesh_out, c->h_vtx, c->h_idx};
+	void *host[] = {c->h_heads, c->h_task_out, c->h_mesh_out, c->h_vtx, c->h_idx, c->h_heads_ring, c->h_task_stage};
 	for (void *p : host)
 		if (p)
 			cudaFreeHost(p);
@@ -419,6 +449,10 @@ void hcm_destroy(hcm_ctx *c) {
 			cudaEventDestroy(e);
 	for (auto &e : c->block_events)
 		cudaEventDestroy(e);
+	for (auto &e : c->sub_events)
+		cudaEventDestroy(e);
+	if (c->fetch_stream)
+		cudaStreamDestroy(c->fetch_stream);
 	if (c->copy_stream)
 		cudaStreamDestroy(c->copy_stream);
 	if (c->stream)
@@ -457,6 +491,10 @@ int hcm_create(const hcm_registry *registry, const hcm_config *cfg, hcm_ctx **ou
 	c->device = cfg->device;
 	if (const char *ht = getenv("HCM_HOST_THREADS"))
 		c->host_threads = (uint32_t)std::max(0, atoi(ht));
+	if (const char *ub = getenv("HCM_UPLOAD_BLOCK"))
+		c->upload_block = std::max(32u, (uint32_t)atoi(ub) / 32u * 32u); // a multiple of the scan grain
+	if (const char *ms = getenv("HCM_MIN_SUB_BATCH"))
+		c->min_sub_batch = std::max(1u, (uint32_t)atoi(ms));
 	DevTables tables;
 	std::vector<DevMeshInfo> minfo;
 	if (int rc = build_tables(c, registry, tables, minfo))
@@ -474,6 +512,7 @@ int hcm_create(const hcm_registry *registry, const hcm_config *cfg, hcm_ctx **ou
 	CUB(cudaSetDevice(c->device));
 	CUB(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
 	CUB(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+	CUB(cudaStreamCreateWithFlags(&c->fetch_stream, cudaStreamNonBlocking));
 	for (int i = 0; i < EV_COUNT; ++i)
 		CUB(cudaEventCreate(&c->ev[i]));
 
@@ -573,11 +612,13 @@ int hcm_is_resident(const hcm_ctx *c, const int16_t pos[3]) {
 	return c->slot_of[cell(c, cx, cy, cz)] >= 0 ? 1 : 0;
 }
 
-int hcm_upload_chunks(hcm_ctx *c, uint32_t n, const int16_t *pos, const uint16_t *blocks, const int8_t *heights) {
-	if (!c)
-		return HCM_ERR_INVALID;
-	if (n == 0)
-		return HCM_OK;
+// Hooks of upload_impl: hcm_upload_and_mesh submits mesh sub-batches between the upload blocks.
+struct UploadHooks {
+	std::function<int(const std::vector<UploadEntry> &, uint32_t n_blocks)> assigned; // residency is updated, nothing enqueued yet
+	std::function<int(uint32_t blk, uint32_t n_blocks)> block_enqueued;               // copy + derive of block blk are in the streams
+};
+
+static int upload_impl(hcm_ctx *c, uint32_t n, const int16_t *pos, const uint16_t *blocks, const int8_t *heights, const UploadHooks *hooks) {
 	if (!pos || !blocks || !heights)
 		return fail(c, HCM_ERR_INVALID, "null upload arrays");
 	if (n > c->max_chunks)
@@ -585,6 +626,14 @@ int hcm_upload_chunks(hcm_ctx *c, uint32_t n, const int16_t *pos, const uint16_t
 	CU(cudaSetDevice(c->device));
 	std::vector<UploadEntry> entries(n);
 	std::vector<int32_t> fresh; // slots taken in this call (rolled back on error)
+	auto roll_back = [&]() {
+		for (auto it = fresh.rbegin(); it != fresh.rend(); ++it) {
+			c->free_slots.push_back(c->slot_of[*it]);
+			c->slot_of[*it] = -1;
+			const int fx = *it % c->w.wx, fz = (*it / c->w.wx) % c->w.wz, fy = *it / (c->w.wx * c->w.wz);
+			bump_neighbours(c, fx, fy, fz, -1);
+		}
+	};
 	for (uint32_t i = 0; i < n; ++i) {
 		int cx, cy, cz;
 		int rc = HCM_OK;
@@ -606,23 +655,23 @@ int hcm_upload_chunks(hcm_ctx *c, uint32_t n, const int16_t *pos, const uint16_t
 			}
 		}
 		if (rc) {
-			for (auto it = fresh.rbegin(); it != fresh.rend(); ++it) {
-				c->free_slots.push_back(c->slot_of[*it]);
-				c->slot_of[*it] = -1;
-				const int fx = *it % c->w.wx, fz = (*it / c->w.wx) % c->w.wz, fy = *it / (c->w.wx * c->w.wz);
-				bump_neighbours(c, fx, fy, fz, -1);
-			}
+			roll_back();
 			return rc;
 		}
 		entries[i] = UploadEntry{slot, (int16_t)cx, (int16_t)cy, (int16_t)cz, 0, 0};
 	}
+	const uint32_t n_blocks = (n + c->upload_block - 1) / c->upload_block;
+	if (hooks && hooks->assigned)
+		if (int rc = hooks->assigned(entries, n_blocks)) {
+			roll_back();
+			return rc;
+		}
 	cudaStream_t st = c->stream, cs = c->copy_stream;
 	CU(cudaEventRecord(c->ev[EV_UP0], st));
 	CU(cudaStreamWaitEvent(cs, c->ev[EV_UP0], 0)); // earlier kernels may still read the raw slots
 	// Uniform chunks (all air / all stone: most of a load sphere) cross the bus as one Block value instead of 64 KB.
 	// Pipeline per block of kUploadBlock chunks: host threads scan block b+1 (memcmp, early exit at the first difference)
 	// while the copy engine moves block b and the derive kernel runs on block b-1.
-	const uint32_t n_blocks = (n + kUploadBlock - 1) / kUploadBlock;
 	while (c->block_events.size() < n_blocks) {
 		cudaEvent_t e;
 		CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -668,8 +717,8 @@ int hcm_upload_chunks(hcm_ctx *c, uint32_t n, const int16_t *pos, const uint16_t
 	std::vector<void *> cp_dst, cp_src;
 	std::vector<size_t> cp_size;
 	for (uint32_t blk = 0; blk < n_blocks; ++blk) {
-		const uint32_t lo = blk * kUploadBlock, hi = std::min(n, lo + kUploadBlock);
-		for (uint32_t it = lo / kScanGrain; it < (hi + kScanGrain - 1) / kScanGrain; ++it) // kUploadBlock is a multiple of kScanGrain
+		const uint32_t lo = blk * c->upload_block, hi = std::min(n, lo + c->upload_block);
+		for (uint32_t it = lo / kScanGrain; it < (hi + kScanGrain - 1) / kScanGrain; ++it) // upload_block is a multiple of kScanGrain
 			while (!item_done[it].load(std::memory_order_acquire))
 				std::this_thread::yield();
 		// heights for every chunk, blocks for the non-uniform ones; one copy per run of consecutive slots, all runs of the
@@ -721,11 +770,23 @@ int hcm_upload_chunks(hcm_ctx *c, uint32_t n, const int16_t *pos, const uint16_t
 		launch_derive(c->w, c->d_entries + lo, hi - lo, c->d_prop_index, c->d_tables, c->d_rawh, st);
 		CU(cudaGetLastError());
 		c->stats.kernel_launches += 1;
+		if (blk + 1 == n_blocks)
+			CU(cudaEventRecord(c->ev[EV_UP2], st));
+		if (hooks && hooks->block_enqueued)
+			if (int rc = hooks->block_enqueued(blk, n_blocks))
+				return rc;
 	}
 	c->stats.h2d_bytes += copied + (uint64_t)n * sizeof(UploadEntry);
-	CU(cudaEventRecord(c->ev[EV_UP2], st));
 	c->ev_upload = true;
 	return HCM_OK;
+}
+
+int hcm_upload_chunks(hcm_ctx *c, uint32_t n, const int16_t *pos, const uint16_t *blocks, const int8_t *heights) {
+	if (!c)
+		return HCM_ERR_INVALID;
+	if (n == 0)
+		return HCM_OK;
+	return upload_impl(c, n, pos, blocks, heights, nullptr);
 }
 
 int hcm_remove_chunks(hcm_ctx *c, uint32_t n, const int16_t *pos) {
@@ -914,6 +975,194 @@ int hcm_mesh_fetch(hcm_ctx *c, hcm_batch_view *out) {
 	c->ev_fetch = true;
 	c->stats.d2h_bytes += (uint64_t)c->batch_n * sizeof(hcm_task_result) + (uint64_t)h.meshes * sizeof(hcm_mesh_desc) + h.vtx * 8 + h.idx * 2;
 	out->n_tasks = c->batch_n, out->n_meshes = h.meshes, out->n_vertices = h.vtx, out->n_indices = h.idx;
+	out->tasks = c->h_task_out, out->meshes = c->h_mesh_out, out->vertices = c->h_vtx, out->indices = c->h_idx;
+	return HCM_OK;
+}
+
+// ---- pipelined upload + mesh + fetch --------------------------------------------------------------------------------
+// The three stages of a world (re)load overlap: while the copy engine moves upload block b+1 to the device, the mesh
+// kernel works on the tasks whose 27 chunks arrived with blocks <= b, and the second copy engine returns the meshes of
+// earlier sub-batches.  Same kernels, same arenas (the allocation heads simply keep counting across sub-batches).
+constexpr uint32_t kMinSubBatch = 512; // default hcm_ctx::min_sub_batch: smaller ready sets wait for the next upload block
+
+int hcm_upload_and_mesh(hcm_ctx *c, uint32_t n_chunks, const int16_t *pos, const uint16_t *blocks, const int8_t *heights, uint32_t n_tasks,
+                        const int16_t *task_pos, hcm_batch_view *out) {
+	if (!c || !out)
+		return HCM_ERR_INVALID;
+	if (n_chunks == 0) { // nothing to overlap
+		if (int rc = submit(c, n_tasks, task_pos, 0))
+			return rc;
+		return hcm_mesh_fetch(c, out);
+	}
+	if (n_tasks > c->max_tasks)
+		return fail(c, HCM_ERR_CAPACITY, "batch of %u tasks exceeds max_tasks %u", n_tasks, c->max_tasks);
+	if (n_tasks && !task_pos)
+		return fail(c, HCM_ERR_INVALID, "null positions");
+	CU(cudaSetDevice(c->device));
+	const int wx = c->w.wx, wy = c->w.wy, wz = c->w.wz;
+	std::vector<TaskIn> tin(n_tasks);
+	for (uint32_t i = 0; i < n_tasks; ++i) {
+		int cx, cy, cz;
+		const int16_t *tp = task_pos + 3 * i;
+		if (!in_window(c, tp, &cx, &cy, &cz))
+			return fail(c, HCM_ERR_OUT_OF_WINDOW, "task (%d,%d,%d) is outside the window", tp[0], tp[1], tp[2]);
+		if (cx < 1 || cy < 1 || cz < 1 || cx > wx - 2 || cy > wy - 2 || cz > wz - 2)
+			return fail(c, HCM_ERR_NOT_RESIDENT, "task (%d,%d,%d) touches the window border: a neighbour cannot be resident", tp[0], tp[1], tp[2]);
+		tin[i] = TaskIn{(int16_t)cx, (int16_t)cy, (int16_t)cz, 0};
+	}
+	c->batch_pending = false, c->batch_done = false; // an unfetched earlier batch is dropped, like a second hcm_mesh_batch
+
+	std::vector<uint32_t> perm(n_tasks), bucket_start; // perm[k] = caller's index of the k-th task in sub-batch order
+	uint32_t submitted = 0, n_sub = 0, fetched = 0;
+	std::vector<std::pair<uint32_t, uint32_t>> sub_range;
+	BatchHeads prev{};
+	bool overflow = false;
+	uint64_t d2h = 0;
+	cudaStream_t st = c->stream, fs = c->fetch_stream;
+
+	auto fetch_completed = [&](bool block) -> int {
+		while (fetched < n_sub) {
+			if (block)
+				CU(cudaEventSynchronize(c->sub_events[fetched]));
+			else {
+				cudaError_t q = cudaEventQuery(c->sub_events[fetched]);
+				if (q == cudaErrorNotReady)
+					return HCM_OK;
+				CU(q);
+			}
+			const BatchHeads cur = c->h_heads_ring[fetched];
+			const uint32_t t0 = sub_range[fetched].first, t1 = sub_range[fetched].second;
+			if (cur.overflow)
+				overflow = true;
+			if (!overflow) {
+				uint64_t mcap = c->h_mesh_cap;
+				if (int rc = host_reserve_keep(c, &c->h_mesh_out, &mcap, cur.meshes, prev.meshes, fs))
+					return rc;
+				c->h_mesh_cap = (uint32_t)mcap;
+				if (int rc = host_reserve_keep(c, &c->h_vtx, &c->h_vtx_cap, cur.vtx, prev.vtx, fs))
+					return rc;
+				if (int rc = host_reserve_keep(c, &c->h_idx, &c->h_idx_cap, cur.idx, prev.idx, fs))
+					return rc;
+				if (t1 > t0)
+					CU(cudaMemcpyAsync(c->h_task_stage + t0, c->d_task_out + t0, (size_t)(t1 - t0) * sizeof(hcm_task_result), cudaMemcpyDeviceToHost, fs));
+				if (cur.meshes > prev.meshes)
+					CU(cudaMemcpyAsync(c->h_mesh_out + prev.meshes, c->d_mesh_out + prev.meshes, (size_t)(cur.meshes - prev.meshes) * sizeof(hcm_mesh_desc),
+					                   cudaMemcpyDeviceToHost, fs));
+				if (cur.vtx > prev.vtx)
+					CU(cudaMemcpyAsync(c->h_vtx + prev.vtx, c->d_vtx + prev.vtx, (cur.vtx - prev.vtx) * 8, cudaMemcpyDeviceToHost, fs));
+				if (cur.idx > prev.idx)
+					CU(cudaMemcpyAsync(c->h_idx + prev.idx, c->d_idx + prev.idx, (cur.idx - prev.idx) * 2, cudaMemcpyDeviceToHost, fs));
+				d2h += (uint64_t)(t1 - t0) * sizeof(hcm_task_result) + (uint64_t)(cur.meshes - prev.meshes) * sizeof(hcm_mesh_desc) + (cur.vtx - prev.vtx) * 8 +
+				       (cur.idx - prev.idx) * 2 + sizeof(BatchHeads);
+			}
+			prev = cur;
+			++fetched;
+		}
+		return HCM_OK;
+	};
+
+	UploadHooks hooks;
+	hooks.assigned = [&](const std::vector<UploadEntry> &entries, uint32_t n_blocks) -> int {
+		// every neighbour of every task must be resident once this upload is through (ChunkMeshTask.cpp:18-34)
+		for (uint32_t i = 0; i < n_tasks; ++i)
+			if (c->nbr_count[cell(c, tin[i].cx, tin[i].cy, tin[i].cz)] != 27)
+				return fail(c, HCM_ERR_NOT_RESIDENT, "task (%d,%d,%d): a neighbour is neither resident nor part of this upload", task_pos[3 * i], task_pos[3 * i + 1],
+				            task_pos[3 * i + 2]);
+		// block a task becomes ready with = latest upload block among its 27 chunks: separable 3x3x3 maximum
+		std::vector<int32_t> &cb = c->cell_block;
+		cb.assign(c->n_cells, -1);
+		for (size_t i = 0; i < entries.size(); ++i)
+			cb[cell(c, entries[i].cx, entries[i].cy, entries[i].cz)] = (int32_t)(i / c->upload_block);
+		std::vector<int32_t> tmp(c->n_cells);
+		const size_t sx = 1, sz = (size_t)wx, sy = (size_t)wx * wz;
+		auto pass = [&](const std::vector<int32_t> &a, std::vector<int32_t> &b, size_t stride, int extent, int which) {
+			for (int y = 0; y < wy; ++y)
+				for (int z = 0; z < wz; ++z)
+					for (int x = 0; x < wx; ++x) {
+						const size_t i = cell(c, x, y, z);
+						const int k = which == 0 ? x : which == 1 ? z : y;
+						int32_t m = a[i];
+						if (k > 0)
+							m = std::max(m, a[i - stride]);
+						if (k < extent - 1)
+							m = std::max(m, a[i + stride]);
+						b[i] = m;
+					}
+		};
+		pass(cb, tmp, sx, wx, 0), pass(tmp, cb, sz, wz, 1), pass(cb, tmp, sy, wy, 2);
+		bucket_start.assign(n_blocks + 1, 0);
+		for (uint32_t i = 0; i < n_tasks; ++i)
+			++bucket_start[std::max(tmp[cell(c, tin[i].cx, tin[i].cy, tin[i].cz)], 0) + 1];
+		for (uint32_t b = 0; b < n_blocks; ++b)
+			bucket_start[b + 1] += bucket_start[b];
+		std::vector<uint32_t> fill(bucket_start.begin(), bucket_start.end() - 1);
+		c->tasks.resize(n_tasks);
+		for (uint32_t i = 0; i < n_tasks; ++i) {
+			const uint32_t k = fill[std::max(tmp[cell(c, tin[i].cx, tin[i].cy, tin[i].cz)], 0)]++;
+			perm[k] = i, c->tasks[k] = tin[i];
+		}
+		while (c->sub_events.size() < n_blocks) {
+			cudaEvent_t e;
+			CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+			c->sub_events.push_back(e);
+		}
+		if (c->heads_ring_cap < n_blocks) {
+			if (c->h_heads_ring)
+				cudaFreeHost(c->h_heads_ring);
+			c->h_heads_ring = nullptr, c->heads_ring_cap = 0;
+			CU(cudaHostAlloc((void **)&c->h_heads_ring, (size_t)n_blocks * sizeof(BatchHeads), cudaHostAllocDefault));
+			c->heads_ring_cap = n_blocks;
+		}
+		if (int rc = host_reserve(c, &c->h_task_stage, &c->h_task_stage_cap, n_tasks))
+			return rc;
+		uint64_t tcap = c->h_task_cap;
+		if (int rc = host_reserve(c, &c->h_task_out, &tcap, n_tasks))
+			return rc;
+		c->h_task_cap = (uint32_t)tcap;
+		if (n_tasks)
+			CU(cudaMemcpyAsync(c->d_tasks, c->tasks.data(), (size_t)n_tasks * sizeof(TaskIn), cudaMemcpyHostToDevice, st));
+		CU(cudaMemsetAsync(c->d_heads, 0, sizeof(BatchHeads), st));
+		c->stats.h2d_bytes += (uint64_t)n_tasks * sizeof(TaskIn);
+		return HCM_OK;
+	};
+	hooks.block_enqueued = [&](uint32_t blk, uint32_t n_blocks) -> int {
+		const uint32_t ready = bucket_start[blk + 1];
+		const bool last = blk + 1 == n_blocks;
+		if (ready > submitted && (ready - submitted >= c->min_sub_batch || last)) {
+			const uint32_t t0 = submitted, t1 = ready;
+			CU(cudaMemsetAsync(&c->d_heads->n_work, 0, 2 * sizeof(unsigned int), st)); // n_work and cursor; the allocation heads keep counting
+			launch_classify(c->w, c->d_tasks + t0, t1 - t0, c->d_worklist, c->d_heads, c->d_task_out + t0, 0, st);
+			launch_mesh(c->tmap, mesh_params(c, t0), c->grid, st);
+			CU(cudaGetLastError());
+			CU(cudaMemcpyAsync(c->h_heads_ring + n_sub, c->d_heads, sizeof(BatchHeads), cudaMemcpyDeviceToHost, st));
+			CU(cudaEventRecord(c->sub_events[n_sub], st));
+			c->stats.kernel_launches += 2;
+			sub_range.emplace_back(t0, t1);
+			++n_sub;
+			submitted = ready;
+		}
+		return fetch_completed(false);
+	};
+	if (int rc = upload_impl(c, n_chunks, pos, blocks, heights, &hooks)) {
+		cudaStreamSynchronize(st), cudaStreamSynchronize(fs);
+		return rc;
+	}
+	if (int rc = fetch_completed(true))
+		return rc;
+	CU(cudaStreamSynchronize(fs));
+	if (overflow) { // rare: grow the arenas like hcm_mesh_wait does and take the plain path; every chunk is resident by now
+		CU(cudaStreamSynchronize(st));
+		const uint64_t need_v = std::max<uint64_t>(prev.vtx, prev.idx / 6 * 4);
+		if (int rc = alloc_arenas(c, std::max<uint64_t>(need_v + need_v / 8, c->vtx_cap), std::max<uint32_t>(prev.meshes + prev.meshes / 8 + 64, c->mesh_cap)))
+			return rc;
+		if (int rc = submit(c, n_tasks, task_pos, 0))
+			return rc;
+		return hcm_mesh_fetch(c, out);
+	}
+	for (uint32_t k = 0; k < n_tasks; ++k)
+		c->h_task_out[perm[k]] = c->h_task_stage[k];
+	c->stats.d2h_bytes += d2h;
+	out->n_tasks = n_tasks, out->n_meshes = prev.meshes, out->n_vertices = prev.vtx, out->n_indices = prev.idx;
 	out->tasks = c->h_task_out, out->meshes = c->h_mesh_out, out->vertices = c->h_vtx, out->indices = c->h_idx;
 	return HCM_OK;
 }

@@ -58,7 +58,7 @@ assert MESH_DESC_DTYPE.itemsize == 56
 
 EXPORTS = ["hcm_registry_from_blob", "hcm_create", "hcm_destroy", "hcm_last_error", "hcm_status_string", "hcm_host_alloc", "hcm_host_free",
            "hcm_upload_chunks", "hcm_remove_chunks", "hcm_rederive_chunks", "hcm_is_resident", "hcm_sync", "hcm_mesh_batch", "hcm_mesh_fetch", "hcm_mesh_wait",
-           "hcm_get_stats", "hcm_stream", "hcm_debug_light"]
+           "hcm_upload_and_mesh", "hcm_get_stats", "hcm_stream", "hcm_debug_light"]
 
 _lib = None
 
@@ -97,6 +97,7 @@ def load_library():
         L.hcm_mesh_batch.argtypes = [_vp, ctypes.c_uint32, _vp]
         L.hcm_mesh_fetch.argtypes = [_vp, ctypes.POINTER(_BatchView)]
         L.hcm_mesh_wait.argtypes = [_vp, ctypes.POINTER(_BatchCounts)]
+        L.hcm_upload_and_mesh.argtypes = [_vp, ctypes.c_uint32, _vp, _vp, _vp, ctypes.c_uint32, _vp, ctypes.POINTER(_BatchView)]
         L.hcm_get_stats.argtypes = [_vp, ctypes.POINTER(_Stats)]
         L.hcm_debug_light.argtypes = [_vp, _vp, _vp]
         _lib = L
@@ -243,10 +244,8 @@ class Mesher:
         self._check(self.L.hcm_mesh_wait(self.ctx, ctypes.byref(c)))
         return dict(n_tasks=c.n_tasks, n_meshes=c.n_meshes, n_vertices=c.n_vertices, n_indices=c.n_indices, n_worked=c.n_worked)
 
-    def fetch(self) -> BatchResult:
-        v = _BatchView()
-        self._check(self.L.hcm_mesh_fetch(self.ctx, ctypes.byref(v)))
-
+    @staticmethod
+    def _result(v: _BatchView) -> BatchResult:
         def view(ptr, count, dtype):
             if not count:
                 return np.zeros(0, dtype=dtype)
@@ -256,6 +255,22 @@ class Mesher:
 
         return BatchResult(view(v.tasks, v.n_tasks, TASK_RESULT_DTYPE), view(v.meshes, v.n_meshes, MESH_DESC_DTYPE),
                            view(v.vertices, v.n_vertices, np.uint64), view(v.indices, v.n_indices, np.uint16))
+
+    def fetch(self) -> BatchResult:
+        v = _BatchView()
+        self._check(self.L.hcm_mesh_fetch(self.ctx, ctypes.byref(v)))
+        return self._result(v)
+
+    def upload_and_mesh(self, positions, blocks, heights, task_positions) -> BatchResult:
+        """upload() + mesh_async() + fetch() with host->device copies, kernels and device->host copies overlapped
+        (hcm_upload_and_mesh).  Result rows follow ``task_positions``."""
+        pos = np.ascontiguousarray(positions, dtype=np.int16).reshape(-1, 3)
+        b = np.ascontiguousarray(blocks, dtype=np.uint16).reshape(len(pos), 32768)
+        h = np.ascontiguousarray(heights, dtype=np.int8).reshape(len(pos), 1024)
+        tp = np.ascontiguousarray(task_positions, dtype=np.int16).reshape(-1, 3)
+        v = _BatchView()
+        self._check(self.L.hcm_upload_and_mesh(self.ctx, len(pos), _ptr(pos), _ptr(b), _ptr(h), len(tp), _ptr(tp), ctypes.byref(v)))
+        return self._result(v)
 
     def mesh(self, positions) -> BatchResult:
         self.mesh_async(positions)

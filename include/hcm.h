@@ -214,6 +214,17 @@ typedef struct hcm_batch_counts {
 } hcm_batch_counts;
 int hcm_mesh_wait(hcm_ctx *ctx, hcm_batch_counts *out);
 
+/* World (re)load in one call: hcm_upload_chunks + hcm_mesh_batch + hcm_mesh_fetch with the three stages overlapped.
+ * The reference streams in the same way: a mesh task is pushed as soon as the 27 chunks around it exist
+ * (client/src/ChunkMeshTask.cpp:18-34, World::update pushes tasks per finished neighbour) and WorldRenderer takes each
+ * mesh as it completes (ChunkMeshTask.cpp:66-74).  Here the upload is cut into blocks; after block b is on the device
+ * the tasks whose neighbourhood is complete are meshed while block b+1 crosses the bus, and finished meshes return on
+ * the second copy engine.  `out` is what hcm_mesh_fetch would return: out->tasks[i] belongs to task_pos[i]; mesh
+ * bytes per task are identical to the unpipelined calls (mesh order inside the arrays may differ).  Every neighbour of
+ * every task must be resident already or be part of this upload. */
+int hcm_upload_and_mesh(hcm_ctx *ctx, uint32_t n_chunks, const int16_t *pos /* n_chunks x 3 */, const uint16_t *blocks,
+                        const int8_t *heights, uint32_t n_tasks, const int16_t *task_pos /* n_tasks x 3 */, hcm_batch_view *out);
+
 /* ------------------------------------------------------------------------------------------------------------
  * Measurement and debugging
  * ---------------------------------------------------------------------------------------------------------- */

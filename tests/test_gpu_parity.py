@@ -274,3 +274,88 @@ def test_edit_driven_incremental_remesh(port):
             got, want = res.serialise(t), port.mesh(chunks, p)
             assert got.size == want.size and (got == want).all(), f"edit {it} at {(bx, by, bz)} in {cpos}: task {p}\n" + describe_diff(got, want)
     m.close()
+
+
+def _small_world():
+    from hypercraft_b200 import worldgen
+
+    allpos = np.array([[x, y, z] for x in range(-2, 3) for y in range(-2, 3) for z in range(-2, 3)], dtype=np.int16)
+    kinds = ["caves", "mix", "air", "stone", "transparent", "flow", "checker"]
+    blocks = np.zeros((len(allpos), 32768), dtype=np.uint16)
+    heights = np.zeros((len(allpos), 1024), dtype=np.int8)
+    chunks = {}
+    for i, p in enumerate(allpos):
+        blocks[i], heights[i] = worldgen.synth_chunk(kinds[(int(p[0]) * 5 + int(p[1]) * 3 + int(p[2])) % len(kinds)], 11, p)
+        chunks[tuple(int(c) for c in p)] = (blocks[i], heights[i])
+    tasks = np.array([[x, y, z] for x in (-1, 0, 1) for y in (-1, 0, 1) for z in (-1, 0, 1)], dtype=np.int16)
+    return allpos, blocks, heights, chunks, tasks
+
+
+def test_pipelined_upload_and_mesh_small(port, monkeypatch):
+    """hcm_upload_and_mesh on a 5^3 world cut into 4 upload blocks: oracle parity per task, rows in the caller's task
+    order, chunks that were resident before the call, an empty upload, the arena-overflow fallback and the error path."""
+    from hypercraft_b200 import mesher as M
+
+    monkeypatch.setenv("HCM_UPLOAD_BLOCK", "32")
+    monkeypatch.setenv("HCM_MIN_SUB_BATCH", "1")
+    allpos, blocks, heights, chunks, tasks = _small_world()
+    order = np.random.default_rng(5).permutation(len(tasks))
+
+    def check(res, tlist, what):
+        assert len(res.tasks) == len(tlist)
+        for t, p in enumerate(tlist):
+            got, want = res.serialise(t), port.mesh(chunks, p)
+            assert got.size == want.size and (got == want).all(), f"{what}: task {p}\n" + describe_diff(got, want)
+
+    m = M.Mesher(origin=(-2, -2, -2), extent=(5, 5, 5))
+    check(m.upload_and_mesh(allpos, blocks, heights, tasks[order]), tasks[order], "fresh world")
+    check(m.upload_and_mesh(allpos[:0], blocks[:0], heights[:0], tasks), tasks, "empty upload")
+    check(m.upload_and_mesh(allpos[40:90], blocks[40:90], heights[40:90], tasks), tasks, "partial re-upload")
+    m.close()
+    # half of the world resident beforehand, the other half arrives with the call (in reverse order)
+    m = M.Mesher(origin=(-2, -2, -2), extent=(5, 5, 5))
+    m.upload(allpos[:60], blocks[:60], heights[:60])
+    rest = np.arange(60, len(allpos))[::-1]
+    check(m.upload_and_mesh(allpos[rest], blocks[rest], heights[rest], tasks), tasks, "half resident")
+    m.close()
+    # a vertex arena that is far too small: the call falls back to the growing path, nothing is truncated
+    m = M.Mesher(origin=(-2, -2, -2), extent=(5, 5, 5), vertex_capacity=1024)
+    check(m.upload_and_mesh(allpos, blocks, heights, tasks), tasks, "tiny arena")
+    m.close()
+    # a task whose neighbourhood stays incomplete: error, and the upload is rolled back
+    m = M.Mesher(origin=(-2, -2, -2), extent=(5, 5, 5))
+    with pytest.raises(M.HcmError) as e:
+        m.upload_and_mesh(allpos[:100], blocks[:100], heights[:100], tasks)
+    assert e.value.status == -4
+    assert not any(m.is_resident(p) for p in allpos)
+    with pytest.raises(M.HcmError) as e:
+        m.upload_and_mesh(allpos, blocks, heights, np.array([[2, 0, 0]], dtype=np.int16))
+    assert e.value.status == -4
+    check(m.upload_and_mesh(allpos, blocks, heights, tasks), tasks, "after errors")
+    m.close()
+
+
+def test_pipelined_world_load_equals_plain_calls(monkeypatch):
+    """A whole load sphere (r = 8) through hcm_upload_and_mesh in ~16 upload blocks and in a shuffled chunk order gives,
+    task by task, the bytes of upload + mesh + fetch."""
+    from hypercraft_b200 import mesher as M
+
+    meshed, resident, blocks, heights = _terrain_world(8)
+    kw = dict(origin=(-9, -9, -9), extent=(19, 19, 19), max_chunks=len(resident), max_tasks=len(meshed))
+    m = M.Mesher(**kw)
+    m.upload(resident, blocks, heights)
+    plain = m.mesh(meshed)
+    want = [plain.serialise(t).tobytes() for t in range(len(meshed))]
+    m.close()
+    monkeypatch.setenv("HCM_UPLOAD_BLOCK", "256")
+    monkeypatch.setenv("HCM_MIN_SUB_BATCH", "64")
+    m = M.Mesher(**kw)
+    res = m.upload_and_mesh(resident, blocks, heights, meshed)
+    assert len(res.vertices) == len(plain.vertices) and len(res.indices) == len(plain.indices) and len(res.meshes) == len(plain.meshes)
+    assert all(res.serialise(t).tobytes() == want[t] for t in range(len(meshed)))
+    launches = m.stats()["kernel_launches"]
+    assert launches >= 3 * 8, f"expected a pipeline of many sub-batches, saw {launches} kernel launches"
+    perm = np.random.default_rng(9).permutation(len(resident))
+    res = m.upload_and_mesh(resident[perm], blocks[perm], heights[perm], meshed)  # everything resident already, re-uploaded shuffled
+    assert all(res.serialise(t).tobytes() == want[t] for t in range(len(meshed)))
+    m.close()
