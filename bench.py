@@ -242,8 +242,9 @@ def main():
     # ---- end to end: host buffers in, host meshes out, every step ---------------------------------------------------
     res = None
     barrier()
-    t0 = time.perf_counter()
-    for _ in range(2):  # the three calls one after the other (also the warm-up of the pinned result buffers)
+    for it in range(3):  # the three calls one after the other (first pass: warm-up of the pinned result buffers)
+        if it == 1:
+            t0 = time.perf_counter()
         m.upload(resident, pb.array, ph.array)
         res = m.mesh(meshed)
     e2e_serial_ms = (time.perf_counter() - t0) * 1e3 / 2

@@ -2,6 +2,9 @@
 // All device work is enqueued on the ctx stream; there is no CPU fallback anywhere in this file.
 #include <algorithm>
 #include <atomic>
+#include <chrono>
+#include <condition_variable>
+#include <mutex>
 #include <thread>
 #include <cstdarg>
 #include <cstdio>
@@ -9,8 +12,11 @@
 #include <cstring>
 #include <functional>
 #include <map>
+#include <memory>
 #include <string>
 #include <vector>
+
+#include <immintrin.h>
 
 #include "hcm_device.cuh"
 
@@ -29,6 +35,57 @@ using namespace hcm;
 
 static thread_local std::string g_create_error;
 
+// Persistent host worker threads (the uniform-chunk scan of large uploads): spawning 15 threads per call costs ~0.5 ms.
+struct WorkerPool {
+	std::vector<std::thread> threads;
+	std::mutex mu;
+	std::condition_variable cv, cv_done;
+	std::function<void()> job;
+	uint64_t generation = 0;
+	uint32_t running = 0;
+	bool stop = false;
+	void start(uint32_t n) {
+		for (uint32_t i = 0; i < n; ++i)
+			threads.emplace_back([this]() {
+				uint64_t seen = 0;
+				for (;;) {
+					std::function<void()> f;
+					{
+						std::unique_lock<std::mutex> lk(mu);
+						cv.wait(lk, [&] { return stop || generation != seen; });
+						if (stop)
+							return;
+						seen = generation, f = job;
+					}
+					f();
+					{
+						std::lock_guard<std::mutex> lk(mu);
+						if (--running == 0)
+							cv_done.notify_all();
+					}
+				}
+			});
+	}
+	void launch(std::function<void()> f) {
+		std::lock_guard<std::mutex> lk(mu);
+		job = std::move(f), ++generation, running = (uint32_t)threads.size();
+		cv.notify_all();
+	}
+	void wait() {
+		std::unique_lock<std::mutex> lk(mu);
+		cv_done.wait(lk, [&] { return running == 0; });
+	}
+	~WorkerPool() {
+		{
+			std::lock_guard<std::mutex> lk(mu);
+			stop = true;
+		}
+		cv.notify_all();
+		for (auto &t : threads)
+			t.join();
+	}
+};
+
 struct hcm_ctx {
 	int device = 0;
 	cudaStream_t stream = nullptr;
@@ -43,6 +100,7 @@ struct hcm_ctx {
 	std::vector<int32_t> cell_block; // scratch of hcm_upload_and_mesh
 	bool use_batch_copy = true;
 	uint32_t upload_block = 2048, min_sub_batch = 512; // pipeline granularity (env HCM_UPLOAD_BLOCK, HCM_MIN_SUB_BATCH: test knobs)
+	std::unique_ptr<WorkerPool> pool;
 	uint32_t host_threads = 0; // scan threads of hcm_upload_chunks (env HCM_HOST_THREADS; 0 = hardware_concurrency - 1, at most 15)
 	DevWorld w{};
 	size_t n_cells = 0; // window chunks
@@ -134,10 +192,27 @@ bool in_window(const hcm_ctx *c, const int16_t *pos, int *cx, int *cy, int *cz) 
 size_t cell(const hcm_ctx *c, int cx, int cy, int cz) { return ((size_t)cy * c->w.wz + cz) * c->w.wx + cx; }
 
 // true when all 32768 voxels hold the same Block value (period-4 array whose first four elements are equal)
-inline bool chunk_is_uniform(const uint16_t *b) {
+inline bool chunk_is_uniform_generic(const uint16_t *b) {
 	const uint16_t v = b[0];
 	return b[1] == v && b[2] == v && b[3] == v && memcmp(b, b + 4, (HCM_CHUNK_VOXELS - 4) * 2) == 0;
 }
+// one aligned-or-not 32-byte load per 16 voxels, early exit every 256 bytes (terrain chunks differ within the first rows)
+__attribute__((target("avx2"))) bool chunk_is_uniform_avx2(const uint16_t *b) {
+	const __m256i v = _mm256_set1_epi16((short)b[0]);
+	const __m256i *p = reinterpret_cast<const __m256i *>(b);
+	for (int i = 0; i < HCM_CHUNK_VOXELS / 16; i += 8) {
+		__m256i a0 = _mm256_xor_si256(_mm256_loadu_si256(p + i), v), a1 = _mm256_xor_si256(_mm256_loadu_si256(p + i + 1), v);
+		__m256i a2 = _mm256_xor_si256(_mm256_loadu_si256(p + i + 2), v), a3 = _mm256_xor_si256(_mm256_loadu_si256(p + i + 3), v);
+		a0 = _mm256_or_si256(a0, _mm256_xor_si256(_mm256_loadu_si256(p + i + 4), v)), a1 = _mm256_or_si256(a1, _mm256_xor_si256(_mm256_loadu_si256(p + i + 5), v));
+		a2 = _mm256_or_si256(a2, _mm256_xor_si256(_mm256_loadu_si256(p + i + 6), v)), a3 = _mm256_or_si256(a3, _mm256_xor_si256(_mm256_loadu_si256(p + i + 7), v));
+		const __m256i a = _mm256_or_si256(_mm256_or_si256(a0, a1), _mm256_or_si256(a2, a3));
+		if (!_mm256_testz_si256(a, a))
+			return false;
+	}
+	return true;
+}
+const bool g_have_avx2 = __builtin_cpu_supports("avx2");
+inline bool chunk_is_uniform(const uint16_t *b) { return g_have_avx2 ? chunk_is_uniform_avx2(b) : chunk_is_uniform_generic(b); }
 
 constexpr uint32_t kUploadBlock = 2048; // default chunks per pipeline stage (128 MB of Block data); hcm_ctx::upload_block
 constexpr uint32_t kScanGrain = 32;     // chunks per work item of the scan threads
@@ -624,6 +699,53 @@ static int upload_impl(hcm_ctx *c, uint32_t n, const int16_t *pos, const uint16_
 	if (n > c->max_chunks)
 		return fail(c, HCM_ERR_CAPACITY, "upload of %u chunks exceeds max_chunks %u", n, c->max_chunks);
 	CU(cudaSetDevice(c->device));
+	// Uniform chunks (all air / all stone: most of a load sphere) cross the bus as one Block value instead of 64 KB.
+	// Pipeline per block of upload_block chunks: host threads scan block b+1 (early exit at the first difference) while
+	// the copy engine moves block b and the derive kernel runs on block b-1.  The scan starts before anything else: it
+	// only reads the caller's arrays, and it is the longest stage of a large upload.
+	const uint32_t n_items = (n + kScanGrain - 1) / kScanGrain;
+	std::vector<std::atomic<uint8_t>> item_done(n_items);
+	for (auto &d : item_done)
+		d.store(0, std::memory_order_relaxed);
+	std::vector<int32_t> uniform_value(n); // Block value of a uniform chunk, else -1; written by the scan before item_done
+	std::atomic<uint32_t> next{0};
+	std::atomic<bool> abort_scan{false};
+	int32_t *uni = uniform_value.data();
+	auto scan_work = [&item_done, &next, &abort_scan, uni, n, n_items, blocks]() {
+		for (;;) {
+			const uint32_t it = next.fetch_add(1);
+			if (it >= n_items || abort_scan.load(std::memory_order_relaxed))
+				break;
+			const uint32_t lo = it * kScanGrain, hi = std::min(n, lo + kScanGrain);
+			for (uint32_t i = lo; i < hi; ++i) {
+				const uint16_t *b = blocks + (size_t)i * HCM_CHUNK_VOXELS;
+				uni[i] = chunk_is_uniform(b) ? (int32_t)b[0] : -1;
+			}
+			item_done[it].store(1, std::memory_order_release);
+		}
+	};
+	const unsigned hw = std::max(2u, std::thread::hardware_concurrency());
+	const uint32_t want_threads = c->host_threads ? c->host_threads : std::min<uint32_t>(hw - 1, 15);
+	const bool threaded = n >= 256 && want_threads > 0;
+	if (threaded) {
+		if (!c->pool || c->pool->threads.size() != want_threads) {
+			c->pool.reset(new WorkerPool);
+			c->pool->start(want_threads);
+		}
+		c->pool->launch(scan_work);
+	}
+	struct ScanGuard { // the workers reference this frame: never leave it while they run
+		hcm_ctx *c;
+		bool active;
+		std::atomic<bool> &abort_scan;
+		~ScanGuard() {
+			if (active) {
+				abort_scan.store(true);
+				c->pool->wait();
+			}
+		}
+	} scan_guard{c, threaded, abort_scan};
+
 	std::vector<UploadEntry> entries(n);
 	std::vector<int32_t> fresh; // slots taken in this call (rolled back on error)
 	auto roll_back = [&]() {
@@ -669,48 +791,13 @@ static int upload_impl(hcm_ctx *c, uint32_t n, const int16_t *pos, const uint16_
 	cudaStream_t st = c->stream, cs = c->copy_stream;
 	CU(cudaEventRecord(c->ev[EV_UP0], st));
 	CU(cudaStreamWaitEvent(cs, c->ev[EV_UP0], 0)); // earlier kernels may still read the raw slots
-	// Uniform chunks (all air / all stone: most of a load sphere) cross the bus as one Block value instead of 64 KB.
-	// Pipeline per block of kUploadBlock chunks: host threads scan block b+1 (memcmp, early exit at the first difference)
-	// while the copy engine moves block b and the derive kernel runs on block b-1.
 	while (c->block_events.size() < n_blocks) {
 		cudaEvent_t e;
 		CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
 		c->block_events.push_back(e);
 	}
-	const uint32_t n_items = (n + kScanGrain - 1) / kScanGrain;
-	std::vector<std::atomic<uint8_t>> item_done(n_items);
-	for (auto &d : item_done)
-		d.store(0, std::memory_order_relaxed);
-	std::atomic<uint32_t> next{0};
 	UploadEntry *ent = entries.data();
-	auto scan_work = [&]() {
-		for (;;) {
-			const uint32_t it = next.fetch_add(1);
-			if (it >= n_items)
-				break;
-			const uint32_t lo = it * kScanGrain, hi = std::min(n, lo + kScanGrain);
-			for (uint32_t i = lo; i < hi; ++i) {
-				const uint16_t *b = blocks + (size_t)i * HCM_CHUNK_VOXELS;
-				if (chunk_is_uniform(b))
-					ent[i].flags |= UE_UNIFORM, ent[i].value = b[0];
-			}
-			item_done[it].store(1, std::memory_order_release);
-		}
-	};
-	const unsigned hw = std::max(2u, std::thread::hardware_concurrency());
-	const size_t want_threads = c->host_threads ? c->host_threads : std::min<size_t>(hw - 1, 15);
-	const uint32_t n_threads = n < 256 ? 0u : (uint32_t)std::min<size_t>(want_threads, (size_t)n_items);
-	std::vector<std::thread> scanners;
-	for (uint32_t t = 0; t < n_threads; ++t)
-		scanners.emplace_back(scan_work);
-	struct Joiner {
-		std::vector<std::thread> &ts;
-		~Joiner() {
-			for (auto &t : ts)
-				t.join();
-		}
-	} joiner{scanners};
-	if (n_threads == 0)
+	if (!threaded)
 		scan_work();
 
 	uint64_t copied = 0;
@@ -721,6 +808,9 @@ static int upload_impl(hcm_ctx *c, uint32_t n, const int16_t *pos, const uint16_
 		for (uint32_t it = lo / kScanGrain; it < (hi + kScanGrain - 1) / kScanGrain; ++it) // upload_block is a multiple of kScanGrain
 			while (!item_done[it].load(std::memory_order_acquire))
 				std::this_thread::yield();
+		for (uint32_t i = lo; i < hi; ++i)
+			if (uni[i] >= 0)
+				ent[i].flags |= UE_UNIFORM, ent[i].value = (uint16_t)uni[i];
 		// heights for every chunk, blocks for the non-uniform ones; one copy per run of consecutive slots, all runs of the
 		// block submitted with ONE cudaMemcpyBatchAsync (thousands of single calls would cost more than the transfer)
 		cp_dst.clear(), cp_src.clear(), cp_size.clear();
@@ -1061,6 +1151,11 @@ int hcm_upload_and_mesh(hcm_ctx *c, uint32_t n_chunks, const int16_t *pos, const
 		return HCM_OK;
 	};
 
+	const bool trace = getenv("HCM_TRACE") != nullptr; // host-side timeline of the pipeline on stderr
+	const auto T0 = std::chrono::steady_clock::now();
+	auto ms_now = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - T0).count(); };
+	double t_assigned = 0, t_enqueued = 0, t_kernels = 0;
+
 	UploadHooks hooks;
 	hooks.assigned = [&](const std::vector<UploadEntry> &entries, uint32_t n_blocks) -> int {
 		// every neighbour of every task must be resident once this upload is through (ChunkMeshTask.cpp:18-34)
@@ -1123,6 +1218,7 @@ int hcm_upload_and_mesh(hcm_ctx *c, uint32_t n_chunks, const int16_t *pos, const
 			CU(cudaMemcpyAsync(c->d_tasks, c->tasks.data(), (size_t)n_tasks * sizeof(TaskIn), cudaMemcpyHostToDevice, st));
 		CU(cudaMemsetAsync(c->d_heads, 0, sizeof(BatchHeads), st));
 		c->stats.h2d_bytes += (uint64_t)n_tasks * sizeof(TaskIn);
+		t_assigned = ms_now();
 		return HCM_OK;
 	};
 	hooks.block_enqueued = [&](uint32_t blk, uint32_t n_blocks) -> int {
@@ -1147,9 +1243,14 @@ int hcm_upload_and_mesh(hcm_ctx *c, uint32_t n_chunks, const int16_t *pos, const
 		cudaStreamSynchronize(st), cudaStreamSynchronize(fs);
 		return rc;
 	}
+	t_enqueued = ms_now();
 	if (int rc = fetch_completed(true))
 		return rc;
+	t_kernels = ms_now();
 	CU(cudaStreamSynchronize(fs));
+	if (trace)
+		fprintf(stderr, "[hcm] upload_and_mesh: %u chunks, %u tasks, %u sub-batches | tasks sorted %.2f ms, uploads enqueued %.2f, last kernel done %.2f, last copy done %.2f\n",
+		        n_chunks, n_tasks, n_sub, t_assigned, t_enqueued, t_kernels, ms_now());
 	if (overflow) { // rare: grow the arenas like hcm_mesh_wait does and take the plain path; every chunk is resident by now
 		CU(cudaStreamSynchronize(st));
 		const uint64_t need_v = std::max<uint64_t>(prev.vtx, prev.idx / 6 * 4);
