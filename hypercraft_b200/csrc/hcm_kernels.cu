@@ -749,106 +749,139 @@ __device__ __forceinline__ u32 pack_geo(u32 u, u32 v, u32 w, u32 h, bool tr, u32
 	return u | (v << 5) | ((w - 1) << 10) | ((h - 1) << 15) | ((tr ? 1u : 0u) << 20) | (rank << 21);
 }
 
-// Lane = column v.  A set-up pass turns the mask into three words per lane -- fcol (bit u: cell (u,v) is a face),
-// eql (bit u: same key as the face to its left) and eqd (bit u: same key as the face below) -- with all key loads
-// independent of each other; the sequential part then runs on registers only:
-//   run starts   = ballot(active && !(left active && eql))           (width,  BlockMeshAlgo.hpp:364-368)
-//   run height   = 1 + redux.min over the run of the number of consecutive eqd bits from row u   (:371-379)
-//   consumption  = each lane sets bits u..u+height-1 of its own `cons` word                        (:462-466)
-// A cell below an unconsumed cell can only be consumed by the very quad that starts at that cell, so the height test
-// needs no activity check.  Records overwrite the mask's (already read) key slots in emission order.
+// State lives in registers with lane = ROW: Frow (bit v: cell (u,v) is a face), EL (bit v: same key as the face to its
+// left), ED (bit v: same key as the face below) and C (consumed cells).  Three passes:
+//  1. set-up, lane = column: coalesced key loads, one ballot per EL/ED word, four rows in flight;
+//  2. the sequential scan, one row per iteration, every lane doing the same word arithmetic on broadcast row words:
+//       active cells   A = F[u] & ~C[u]
+//       run starts     S = A & ~((A << 1) & EL[u])                                    (width,  BlockMeshAlgo.hpp:364-368)
+//       run height     lane v owns the run that starts at column v; it stays alive at row r while ED[r-1] covers its
+//                      cells; the union of the live runs (redux.or) is what row r loses        (:371-379, :462-466)
+//     A cell below an unconsumed cell can only be consumed by the very quad that starts at that cell, so the height
+//     test needs no activity check.  A warp issues one instruction every ~7 cycles here, so this pass is kept to the
+//     bare recurrence: it only leaves (u, v, width, height) per quad, in emission order;
+//  3. lane = quad: fetch the key of the quad's first cell, split into the opaque / transparent streams (ranks by
+//     ballot) and finish the records.  Records overwrite the mask's (already read) key slots in emission order.
 __device__ void merge_mask(Small &S, const u32 *F, u64 *keys, u32 *geo, int m, int g0, int lane) {
-	const u32 lt = lanemask_lt();
-	const u32 Frow = F[m * kFS + lane]; // lane = row for these two
+	const u32 lt = (1u << lane) - 1u;
+	const u32 Frow = F[m * kFS + lane];
 	const u32 pre = warp_excl_scan(__popc(Frow), lane);
 	const u32 base = S.fcpre[m] - S.fcpre[g0];
-	u32 fcol = 0, eql = 0, eqd = 0;
+	const u32 rows = __ballot_sync(FULL, Frow != 0);
+	u32 EL = 0, ED = 0;
 #ifdef HCM_PHASE_TIMING
 	const long long tms0_ = clock64();
 #endif
 	{
+		// a face key is never 0 (its texture code is not 0), so k == 0 stands for "no face here"
 		u64 kprev = 0;
-		bool fprev = false;
-		u32 rows = __ballot_sync(FULL, Frow != 0);
 		int uprev = -2;
-		while (rows) {
-			const int u = __ffs(rows) - 1;
-			rows &= rows - 1;
-			const u32 Fu = __shfl_sync(FULL, Frow, u), pu = __shfl_sync(FULL, pre, u);
-			const bool f = (Fu >> lane) & 1;
-			const u64 k = f ? keys[base + pu + __popc(Fu & lt)] : 0ull;
-			const u64 kl = __shfl_up_sync(FULL, k, 1);
-			const bool fl = lane > 0 && ((Fu >> (lane - 1)) & 1);
-			fcol |= (f ? 1u : 0u) << u;
-			eql |= ((f && fl && kl == k) ? 1u : 0u) << u;
-			if (uprev == u - 1)
-				eqd |= ((f && fprev && kprev == k) ? 1u : 0u) << (u - 1);
-			kprev = k, fprev = f, uprev = u;
+		u32 rr = rows;
+		while (rr) {
+			int u[4];
+			u32 Fu[4], pu[4];
+			u64 k[4];
+#pragma unroll
+			for (int j = 0; j < 4; ++j) {
+				u[j] = rr ? __ffs(rr) - 1 : 32;
+				rr &= rr - 1;
+			}
+#pragma unroll
+			for (int j = 0; j < 4; ++j) {
+				Fu[j] = __shfl_sync(FULL, Frow, u[j] & 31) & (u[j] < 32 ? 0xffffffffu : 0u);
+				pu[j] = __shfl_sync(FULL, pre, u[j] & 31);
+			}
+#pragma unroll
+			for (int j = 0; j < 4; ++j)
+				k[j] = ((Fu[j] >> lane) & 1) ? keys[base + pu[j] + __popc(Fu[j] & lt)] : 0ull;
+#pragma unroll
+			for (int j = 0; j < 4; ++j) {
+				u64 kl = __shfl_up_sync(FULL, k[j], 1);
+				if (lane == 0)
+					kl = 0;
+				const u64 kup = j == 0 ? kprev : k[j ? j - 1 : 0];
+				const int uup = j == 0 ? uprev : u[j ? j - 1 : 0];
+				const u32 el = __ballot_sync(FULL, k[j] != 0 && k[j] == kl);
+				const u32 ed = __ballot_sync(FULL, k[j] != 0 && k[j] == kup);
+				if (lane == u[j])
+					EL = el;
+				if (uup == u[j] - 1 && lane == uup)
+					ED = ed;
+			}
+			kprev = k[3], uprev = u[3];
 		}
 	}
 #ifdef HCM_PHASE_TIMING
 	const long long tms1_ = clock64();
-	u32 iters_ = 0;
+	u32 iters_ = 0, hsteps_ = 0;
 #endif
-	u32 cons = 0, nq = 0, nqt = 0;
-	for (;;) {
+	u32 C = 0, nq = 0;
+	const u32 right = ~((2u << lane) - 1u); // columns right of this lane
+	u32 rr = rows;
+	while (rr) {
+		const int u = __ffs(rr) - 1;
+		rr &= rr - 1;
+		const u32 Fu = __shfl_sync(FULL, Frow, u), ELu = __shfl_sync(FULL, EL, u);
+		const u32 A = Fu & ~__shfl_sync(FULL, C, u);
+		if (!A)
+			continue;
 #ifdef HCM_PHASE_TIMING
 		++iters_;
 #endif
-		const u32 mine = fcol & ~cons;
-		const int u = (int)__reduce_min_sync(FULL, mine ? (u32)(__ffs(mine) - 1) : 32u); // rows above are fully consumed
-		if (u >= 32)
-			break;
-		const bool active = (mine >> u) & 1;
-		const u32 rowbits = __ballot_sync(FULL, active);
-		const u32 eqlrow = __ballot_sync(FULL, (eql >> u) & 1);
-		const u32 startmask = rowbits & ~((rowbits << 1) & eqlrow); // unconsumed, and not continuing an equal unconsumed left neighbour
-		const u32 brk = startmask | ~rowbits;                       // run boundaries
-		u32 val = active ? (u32)(__ffs(~(eqd >> u)) - 1) : 31u;     // equal faces straight below (bit 31 of eqd is never set)
-		u32 hmin;
-		if ((startmask & (startmask - 1)) == 0) { // one run in this row
-			hmin = __reduce_min_sync(FULL, val);
-		} else { // segmented suffix-min: a lane joins lane+d when no run boundary lies in (lane, lane+d]
-#pragma unroll
-			for (int d = 1; d < 32; d <<= 1) {
-				const u32 other = __shfl_down_sync(FULL, val, d);
-				if ((((u64)brk >> (lane + 1)) & ((1u << d) - 1u)) == 0)
-					val = min(val, other);
-			}
-			const int s = 31 - __clz(startmask & (lt | (1u << lane))); // leader of my run (meaningful for active lanes)
-			hmin = __shfl_sync(FULL, val, s & 31);
-		}
-		const u32 height = hmin + 1;
-		if (active)
-			cons |= (height == 32 ? 0xffffffffu : ((1u << height) - 1u)) << u;
+		const u32 startmask = A & ~((A << 1) & ELu); // unconsumed, and not continuing an equal unconsumed left neighbour
+		const u32 nb = (startmask | ~A) & right;     // run boundaries right of this lane
+		const u32 low = nb & (0u - nb);
 		const bool start = (startmask >> lane) & 1;
-		const u32 Fu = __shfl_sync(FULL, Frow, u), pu = __shfl_sync(FULL, pre, u);
+		const u32 rm = start ? ((low - 1u) & ~lt) : 0u; // cells of the run that starts here
+		u32 height = 1, alive = rm;
+		for (int r = u + 1;; ++r) { // ED[31] == 0 ends every run
+#ifdef HCM_PHASE_TIMING
+			++hsteps_;
+#endif
+			const u32 e = __shfl_sync(FULL, ED, (r - 1) & 31);
+			alive = (e & alive) == alive ? alive : 0u;
+			const u32 un = __reduce_or_sync(FULL, alive);
+			if (!un)
+				break;
+			height += alive != 0;
+			if (lane == r)
+				C |= un;
+		}
+		if (start)
+			geo[base + nq + __popc(startmask & lt)] = (u32)u | ((u32)lane << 5) | ((u32)(__popc(rm) - 1) << 10) | ((height - 1) << 15);
+		nq += __popc(startmask);
+	}
+#ifdef HCM_PHASE_TIMING
+	const long long tms2_ = clock64();
+#endif
+	u32 nqt = 0;
+	for (u32 i0 = 0; i0 < nq; i0 += 32) {
+		const u32 i = i0 + lane;
+		const bool valid = i < nq;
+		const u32 g = valid ? geo[base + i] : 0u;
+		const u32 Fr = __shfl_sync(FULL, Frow, g & 31), pr = __shfl_sync(FULL, pre, g & 31);
 		u64 key = 0;
 		bool tr = false;
-		u32 width = 0;
-		if (start) {
-			key = keys[base + pu + __popc(Fu & lt)];
+		if (valid) {
+			key = keys[base + pr + __popc(Fr & ((1u << ((g >> 5) & 31)) - 1u))];
 			tr = S.tab.texflags[key >> 56] & HCM_TEX_TRANS_PASS; // UseTransparentPass, BlockMeshAlgo.hpp:394
-			const u64 rest = (u64)brk >> (lane + 1);
-			width = rest ? (u32)__ffsll((long long)rest) : 32u - lane;
 		}
-		const u32 trmask = __ballot_sync(FULL, tr);
+		const u32 trm = __ballot_sync(FULL, tr);
 		__syncwarp();
-		if (start) {
-			const u32 slot = base + nq + __popc(startmask & lt);
-			const u32 rank = tr ? nqt + __popc(trmask & lt) : (nq - nqt) + __popc(startmask & ~trmask & lt);
-			keys[slot] = key;
-			geo[slot] = pack_geo((u32)u, (u32)lane, width, height, tr, rank);
+		if (valid) { // slot i <= position of the quad's first cell < position of any later quad's first cell
+			const u32 tb = nqt + __popc(trm & lt);
+			keys[base + i] = key;
+			geo[base + i] = g | ((tr ? 1u : 0u) << 20) | ((tr ? tb : i - tb) << 21);
 		}
-		nq += __popc(startmask);
-		nqt += __popc(trmask);
-		__syncwarp();
+		nqt += __popc(trm);
 	}
 #ifdef HCM_PHASE_TIMING
 	if (lane == 0) {
 		PHASE_COUNT(37, tms1_ - tms0_);       // set-up loop cycles
-		PHASE_COUNT(38, clock64() - tms1_);   // main loop cycles
+		PHASE_COUNT(38, tms2_ - tms1_);       // main loop cycles
 		PHASE_COUNT(39, iters_);              // main loop iterations
+		PHASE_COUNT(55, hsteps_);             // height steps
+		PHASE_COUNT(56, clock64() - tms2_);   // record pass cycles
 	}
 #endif
 	if (lane == 0)
