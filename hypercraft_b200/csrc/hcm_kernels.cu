@@ -1160,9 +1160,55 @@ __global__ void __launch_bounds__(kThreads, 1) mesh_kernel(const __grid_constant
 						cfo |= p.w.cflags[((size_t)(ti.cy + dy) * p.w.wz + (ti.cz + dz)) * p.w.wx + (ti.cx + dx)];
 			S.any_torch = (cfo & CF_HAS_TORCH) ? 1u : 0u;
 		}
+		PHASE_MARK(1); // task set-up
+		// ---- light first: the flood reads the y-packed planes in global memory, not the voxel box, so it runs while the TMA
+		// box of this task is still in flight (a task without any face pays for a flood it does not need: classify_kernel
+		// leaves next to none of those) --------------------------------------------------------------------------------
+		const bool want_light = p.debug_light != nullptr;
+		__syncthreads(); // S.any_torch
+		{
+			u64 *sbuf = reinterpret_cast<u64 *>(region + RG_SBUF);
+			for (int i = tid; i < 2 * kSB * kSB; i += kThreads)
+				sbuf[i] = 0; // both buffers: zero border and interior
+			ColInfo ci;
+			ci.X = (u32)p.w.X;
+			ci.g0 = (u32)(((size_t)(ti.cy - 1) * p.w.Z + (size_t)(ti.cz * 32 - 15)) * p.w.X + (size_t)(ti.cx * 32 - 15));
+			u64 P[kColsPerThread];
+			const size_t plane_stride = (size_t)p.w.Z * p.w.X;
+#pragma unroll
+			for (int k = 0; k < kColsPerThread; ++k) {
+				int x = 0, z = 0; // domain coords: world x = x - 15
+				bool ok = slot_column(tid, k, x, z);
+				const int dx = x < 14 ? 14 - x : (x > 47 ? x - 47 : 0), dz = z < 14 ? 14 - z : (z > 47 ? z - 47 : 0);
+				ok = ok && dx + dz <= 14; // farther columns can never reach the inner square
+				if (ok) {
+					ci.c[k] = ((z + 1) * kSB + (x + 1)) | ((14 - dx - dz) << 16);
+					const u32 gk = ci.g(k);
+					P[k] = combine3(p.w.pass[gk], p.w.pass[gk + plane_stride], p.w.pass[gk + 2 * plane_stride]);
+				} else {
+					ci.c[k] = -1, P[k] = 0;
+				}
+			}
+			__syncthreads();
+			PHASE_MARK(6); // flood setup (plane loads)
+			flood_channel<false>(p, ci, P, sbuf, light, tid);
+			if (S.any_torch && p.w.n_levels > 0) {
+				for (int i = tid; i < 2 * kSB * kSB; i += kThreads)
+					sbuf[i] = 0;
+				__syncthreads();
+				flood_channel<true>(p, ci, P, sbuf, light, tid);
+			}
+			if (want_light) // canonical order (x fastest, then z, then y) for hcm_debug_light
+				for (int i = tid; i < kLightBytes; i += kThreads) {
+					const int x = i % kLS - 1, z = (i / kLS) % kLS - 1, y = i / (kLS * kLS) - 1;
+					p.debug_light[(size_t)task * kLightBytes + i] = light[lvol_index(x, y, z)];
+				}
+		}
+
+		PHASE_MARK(7); // flood + unpack
 		mbar_wait(&S.bar, phase);
 		phase ^= 1;
-		PHASE_MARK(1); // TMA + zeroing
+		PHASE_MARK(17); // TMA wait
 
 		// ---- phase 1: class bit planes (bit x+1 of row (y,z)); one lane builds one row from three 16-byte loads -------
 		{
@@ -1348,54 +1394,12 @@ __global__ void __launch_bounds__(kThreads, 1) mesh_kernel(const __grid_constant
 		PHASE_MARK(5); // face counts + prefix
 		const u32 n_faces = S.fcpre[kMasks];
 		const u32 n_custom = S.n_custom;
-		const bool want_light = p.debug_light != nullptr;
 		if (n_faces == 0 && n_custom == 0 && !want_light) {
 			if (tid == 0)
 				p.task_out[task] = hcm_task_result{0u, 0u};
 			continue;
 		}
 
-		// ---- phase 4: light ---------------------------------------------------------------------------------------------
-		{
-			u64 *sbuf = reinterpret_cast<u64 *>(region + RG_SBUF);
-			for (int i = tid; i < 2 * kSB * kSB; i += kThreads)
-				sbuf[i] = 0; // both buffers: zero border and interior
-			ColInfo ci;
-			ci.X = (u32)p.w.X;
-			ci.g0 = (u32)(((size_t)(ti.cy - 1) * p.w.Z + (size_t)(ti.cz * 32 - 15)) * p.w.X + (size_t)(ti.cx * 32 - 15));
-			u64 P[kColsPerThread];
-			const size_t plane_stride = (size_t)p.w.Z * p.w.X;
-#pragma unroll
-			for (int k = 0; k < kColsPerThread; ++k) {
-				int x = 0, z = 0; // domain coords: world x = x - 15
-				bool ok = slot_column(tid, k, x, z);
-				const int dx = x < 14 ? 14 - x : (x > 47 ? x - 47 : 0), dz = z < 14 ? 14 - z : (z > 47 ? z - 47 : 0);
-				ok = ok && dx + dz <= 14; // farther columns can never reach the inner square
-				if (ok) {
-					ci.c[k] = ((z + 1) * kSB + (x + 1)) | ((14 - dx - dz) << 16);
-					const u32 gk = ci.g(k);
-					P[k] = combine3(p.w.pass[gk], p.w.pass[gk + plane_stride], p.w.pass[gk + 2 * plane_stride]);
-				} else {
-					ci.c[k] = -1, P[k] = 0;
-				}
-			}
-			__syncthreads();
-			PHASE_MARK(6); // flood setup (plane loads)
-			flood_channel<false>(p, ci, P, sbuf, light, tid);
-			if (S.any_torch && p.w.n_levels > 0) {
-				for (int i = tid; i < 2 * kSB * kSB; i += kThreads)
-					sbuf[i] = 0;
-				__syncthreads();
-				flood_channel<true>(p, ci, P, sbuf, light, tid);
-			}
-			if (want_light) // canonical order (x fastest, then z, then y) for hcm_debug_light
-				for (int i = tid; i < kLightBytes; i += kThreads) {
-					const int x = i % kLS - 1, z = (i / kLS) % kLS - 1, y = i / (kLS * kLS) - 1;
-					p.debug_light[(size_t)task * kLightBytes + i] = light[lvol_index(x, y, z)];
-				}
-		}
-
-		PHASE_MARK(7); // flood + unpack
 		// ---- phase 5: custom faces per row and stream (count), exclusive prefix in (y,z) row order -------------------
 		if (n_custom) {
 			constexpr int kRPT = 1024 / kThreads; // (y,z) rows per thread

@@ -26,9 +26,9 @@ out = (ctypes.c_ulonglong * 64)()
 L.hcm_debug_phase_cycles(out, 1)
 m.mesh_async(meshed); c = m.wait(); st = m.stats()
 L.hcm_debug_phase_cycles(out, 0)
-names = ["task fetch", "TMA+zero", "planes", "liquid", "faces", "counts+prefix", "flood setup", "flood+unpack", "custom count", "fill", "keys", "merge",
-         "scan", "alloc", "emit", "custom emit", "descriptors"]
-tot = sum(out[:17]); n = c["n_worked"]
+names = ["task fetch", "task set-up", "planes", "liquid", "faces", "counts+prefix", "flood setup", "flood+unpack", "custom count", "fill", "keys", "merge",
+         "scan", "alloc", "emit", "custom emit", "descriptors", "TMA wait"]
+tot = sum(out[:18]); n = c["n_worked"]
 print(f"r={R}: {n} worked tasks, mesh_ms {st['mesh_ms']:.3f}, cycles/task {tot / n:.0f}")
 print(f"  per task: masks merged {out[20]/n:.1f}, faces {out[21]/n:.0f}, non-empty rows {out[22]/n:.0f}, quads {out[23]/n:.0f}")
 print("  masks per task by face count (<=8,<=16,<=32,<=64,<=128,>128):", [round(out[40+i]/n,1) for i in range(6)], " rows:", [round(out[48+i]/n,1) for i in range(6)])
