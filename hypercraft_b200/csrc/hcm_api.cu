@@ -626,8 +626,19 @@ int hcm_create(const hcm_registry *registry, const hcm_config *cfg, hcm_ctx **ou
 
 	CUB(dev_alloc(c, &c->d_tables, 1));
 	CUB(cudaMemcpyAsync(c->d_tables, &tables, sizeof(tables), cudaMemcpyHostToDevice, c->stream));
-	CUB(dev_alloc(c, &c->d_prop_index, 65536));
+	// prop_index[65536] followed by the derive kernel's per-id shortcut: u32[256] indexed by the block id (low byte of a
+	// Block): property row | PF flags << 8 | light level << 16 when every meta value maps to the same row, else bit 31
+	uint32_t idinfo[256];
+	for (uint32_t id = 0; id < 256; ++id) {
+		const uint8_t p0 = registry->prop_index[id];
+		bool varies = false;
+		for (uint32_t meta = 1; meta < 256 && !varies; ++meta)
+			varies = registry->prop_index[id | (meta << 8)] != p0;
+		idinfo[id] = varies ? 0x80000000u : (uint32_t)p0 | ((uint32_t)tables.pflags[p0] << 8) | ((uint32_t)(tables.pmisc[p0] >> 4) << 16);
+	}
+	CUB(dev_alloc(c, &c->d_prop_index, 65536 + sizeof(idinfo)));
 	CUB(cudaMemcpyAsync(c->d_prop_index, registry->prop_index, 65536, cudaMemcpyHostToDevice, c->stream));
+	CUB(cudaMemcpyAsync(c->d_prop_index + 65536, idinfo, sizeof(idinfo), cudaMemcpyHostToDevice, c->stream));
 	CUB(dev_alloc(c, &c->d_meshes, std::max<size_t>(registry->n_meshes, 1)));
 	CUB(dev_alloc(c, &c->d_mesh_info, std::max<size_t>(registry->n_meshes, 1)));
 	if (registry->n_meshes) {

@@ -101,10 +101,11 @@ __device__ unsigned long long g_phase_cycles[64];
 // ================================================================================================================
 // derive kernel: one CTA per uploaded chunk, 256 threads; thread t owns columns x4..x4+3 of row z
 // ================================================================================================================
-__global__ void __launch_bounds__(256) derive_kernel(DevWorld w, const UploadEntry *__restrict__ entries, const uint8_t *__restrict__ prop_index,
+__global__ void __launch_bounds__(256, 3) derive_kernel(DevWorld w, const UploadEntry *__restrict__ entries, const uint8_t *__restrict__ prop_index,
                                                      const DevTables *__restrict__ tables, const int8_t *__restrict__ raw_heights) {
 	extern __shared__ __align__(128) uint8_t derive_smem[]; // the chunk's 64 KB of Block data, one TMA bulk copy
 	__shared__ uint16_t s_pinfo[256];                       // pflags | light level << 8
+	__shared__ u32 s_idinfo[256];                           // by block id: row | pflags << 8 | level << 16, bit 31: the row depends on meta
 	__shared__ u32 s_and, s_or;
 	__shared__ __align__(8) u64 s_bar;
 	const int tid = threadIdx.x;
@@ -115,6 +116,7 @@ __global__ void __launch_bounds__(256) derive_kernel(DevWorld w, const UploadEnt
 		s_and = 0xffffffffu, s_or = 0;
 	}
 	s_pinfo[tid] = (uint16_t)(tables->pflags[tid] | ((tables->pmisc[tid] >> 4) << 8));
+	s_idinfo[tid] = reinterpret_cast<const u32 *>(prop_index + 65536)[tid];
 	__syncthreads();
 	if (tid == 0 && !host_uniform) {
 		mbar_expect_tx(&s_bar, HCM_CHUNK_VOXELS * 2);
@@ -162,10 +164,12 @@ __global__ void __launch_bounds__(256) derive_kernel(DevWorld w, const UploadEnt
 			*reinterpret_cast<u32 *>(prow + y * pstride) = p4;
 		const u32 pw = (fl & PF_INDIRECT) ? 0xffffffffu : 0u;
 		*reinterpret_cast<uint4 *>(w.pass + col) = make_uint4(pw, pw, pw, pw);
-		for (int l = 0; l < w.n_levels; ++l) {
-			const u32 tw = (lvl && w.levels[l] == lvl) ? 0xffffffffu : 0u;
-			*reinterpret_cast<uint4 *>(w.torch + l * plane + col) = make_uint4(tw, tw, tw, tw);
-		}
+#pragma unroll
+		for (int l = 0; l < kMaxLightLevels; ++l)
+			if (l < w.n_levels) {
+				const u32 tw = (lvl && w.levels[l] == lvl) ? 0xffffffffu : 0u;
+				*reinterpret_cast<uint4 *>(w.torch + l * plane + col) = make_uint4(tw, tw, tw, tw);
+			}
 		if (tid == 0) {
 			u32 cf = CF_RESIDENT;
 			if (fl & PF_EMPTY)
@@ -185,50 +189,77 @@ __global__ void __launch_bounds__(256) derive_kernel(DevWorld w, const UploadEnt
 	}
 
 	// ---- general chunk -----------------------------------------------------------------------------------------------
-	u32 pass[4] = {0, 0, 0, 0};
-	u32 torch[kMaxLightLevels][4];
-#pragma unroll
-	for (int l = 0; l < kMaxLightLevels; ++l)
-		torch[l][0] = torch[l][1] = torch[l][2] = torch[l][3] = 0;
-	u32 f_and = 0xffu, f_or = 0;              // PF_* accumulated over the thread's voxels (bit 8 of f_or: some voxel emits light)
-	u32 face_solid = 0x3f, face_empty = 0x3f; // per boundary side: every voxel of that layer seen by this thread is class O / E
-	// boundary layers: side 0 +x (x=31), 1 -x (x=0), 2 +y, 3 -y, 4 +z, 5 -z
-	const u32 on_z = (z == 31 ? 16u : 0u) | (z == 0 ? 32u : 0u);
-	const u32 on_x[4] = {on_z | (x4 == 0 ? 2u : 0u), on_z, on_z, on_z | (x4 == 28 ? 1u : 0u)};
+	// Per voxel: one shared-memory lookup by block id (the 64 K table in global memory only for ids whose row depends on
+	// meta), then bit inserts into the column words: pass (indirect light), sol / emp (class O / E).  The boundary-layer
+	// summaries come out of those words after the loop.
+	u32 pass[4] = {0, 0, 0, 0}, sol[4] = {0, 0, 0, 0}, emp[4] = {0, 0, 0, 0};
+	u32 f_and = 0xffffffffu, f_or = 0; // info words accumulated over the thread's voxels: flags in bits 8..15, light level from bit 16
+#pragma unroll 8
 	for (int y = 0; y < 32; ++y) {
 		const uint2 r = *reinterpret_cast<const uint2 *>(sraw + x4 + (y * 32 + z) * 32);
 		const u32 d[4] = {r.x & 0xffffu, r.x >> 16, r.y & 0xffffu, r.y >> 16};
-		const u32 on_y = (y == 31 ? 4u : 0u) | (y == 0 ? 8u : 0u);
-		u32 pr[4];
+		u32 info[4];
 #pragma unroll
 		for (int i = 0; i < 4; ++i)
-			pr[i] = __ldg(prop_index + d[i]);
+			info[i] = s_idinfo[d[i] & 0xffu];
 #pragma unroll
 		for (int i = 0; i < 4; ++i) {
-			const u32 info = s_pinfo[pr[i]], fl = info & 0xffu, lvl = info >> 8;
-			pass[i] |= (fl & PF_INDIRECT) << y; // PF_INDIRECT == 1
-			if (lvl) {
-				f_or |= 0x100u;
-#pragma unroll
-				for (int l = 0; l < kMaxLightLevels; ++l)
-					if (l < w.n_levels && w.levels[l] == lvl)
-						torch[l][i] |= 1u << y;
+			if (info[i] >> 31) {
+				const u32 pr = __ldg(prop_index + d[i]);
+				info[i] = pr | ((u32)s_pinfo[pr] << 8);
 			}
-			f_and &= fl;
-			f_or |= fl;
-			const u32 on = on_x[i] | on_y;
-			face_solid &= ~(on & (((fl >> 2) & 1u) - 1u)); // PF_SOLID == 4
-			face_empty &= ~(on & (((fl >> 3) & 1u) - 1u)); // PF_EMPTY == 8
+			pass[i] |= ((info[i] >> 8) & 1u) << y;  // PF_INDIRECT == 1
+			sol[i] |= ((info[i] >> 10) & 1u) << y;  // PF_SOLID == 4
+			emp[i] |= ((info[i] >> 11) & 1u) << y;  // PF_EMPTY == 8
+			f_and &= info[i], f_or |= info[i];
 		}
-		*reinterpret_cast<u32 *>(prow + y * pstride) = pr[0] | (pr[1] << 8) | (pr[2] << 16) | (pr[3] << 24);
+		*reinterpret_cast<u32 *>(prow + y * pstride) = (info[0] & 0xffu) | ((info[1] & 0xffu) << 8) | ((info[2] & 0xffu) << 16) | (info[3] << 24);
 	}
 	*reinterpret_cast<uint4 *>(w.pass + col) = make_uint4(pass[0], pass[1], pass[2], pass[3]);
-	for (int l = 0; l < w.n_levels; ++l)
-		*reinterpret_cast<uint4 *>(w.torch + l * plane + col) = make_uint4(torch[l][0], torch[l][1], torch[l][2], torch[l][3]);
+	// light sources are rare: their column words are built in a second walk, only by the threads that saw one
+#pragma unroll 1
+	for (int l = 0; l < w.n_levels; ++l) {
+		u32 t[4] = {0, 0, 0, 0};
+		if (f_or >> 16) {
+			const u32 want = l == 0 ? w.levels[0] : (l == 1 ? w.levels[1] : (l == 2 ? w.levels[2] : w.levels[3]));
+#pragma unroll 1
+			for (int y = 0; y < 32; ++y) {
+				const uint2 r = *reinterpret_cast<const uint2 *>(sraw + x4 + (y * 32 + z) * 32);
+				const u32 d[4] = {r.x & 0xffffu, r.x >> 16, r.y & 0xffffu, r.y >> 16};
+#pragma unroll
+				for (int i = 0; i < 4; ++i) {
+					u32 info = s_idinfo[d[i] & 0xffu];
+					if (info >> 31)
+						info = (u32)s_pinfo[__ldg(prop_index + d[i])] << 8;
+					t[i] |= ((info >> 16) == want ? 1u : 0u) << y;
+				}
+			}
+		}
+		*reinterpret_cast<uint4 *>(w.torch + l * plane + col) = make_uint4(t[0], t[1], t[2], t[3]);
+	}
+	// boundary layers: side 0 +x (x=31), 1 -x (x=0), 2 +y, 3 -y, 4 +z, 5 -z: is every voxel of the layer this thread sees class O / E?
+	auto sides = [&](const u32 (&c)[4]) -> u32 {
+		const u32 all = c[0] & c[1] & c[2] & c[3];
+		u32 f = 0x3fu;
+		if (x4 == 28 && c[3] != 0xffffffffu)
+			f &= ~1u;
+		if (x4 == 0 && c[0] != 0xffffffffu)
+			f &= ~2u;
+		if (!(all >> 31))
+			f &= ~4u;
+		if (!(all & 1u))
+			f &= ~8u;
+		if (z == 31 && all != 0xffffffffu)
+			f &= ~16u;
+		if (z == 0 && all != 0xffffffffu)
+			f &= ~32u;
+		return f;
+	};
+	const u32 face_solid = sides(sol), face_empty = sides(emp);
 
 	// block-wide AND / OR of the per-thread summaries
-	u32 a = (f_and & 0xffu) | (face_solid << 8) | (face_empty << 16);
-	u32 o = f_or;
+	u32 a = ((f_and >> 8) & 0xffu) | (face_solid << 8) | (face_empty << 16);
+	u32 o = ((f_or >> 8) & 0xffu) | ((f_or >> 16) ? 0x100u : 0u); // bit 8: some voxel emits light
 	a = __reduce_and_sync(FULL, a);
 	o = __reduce_or_sync(FULL, o);
 	if ((tid & 31) == 0) {
