@@ -115,13 +115,13 @@ __global__ void __launch_bounds__(256, 3) derive_kernel(DevWorld w, const Upload
 		mbar_init(&s_bar, 1);
 		s_and = 0xffffffffu, s_or = 0;
 	}
-	s_pinfo[tid] = (uint16_t)(tables->pflags[tid] | ((tables->pmisc[tid] >> 4) << 8));
-	s_idinfo[tid] = reinterpret_cast<const u32 *>(prop_index + 65536)[tid];
-	__syncthreads();
-	if (tid == 0 && !host_uniform) {
+	if (tid == 0 && !host_uniform) { // the copy first, the tables while it is in flight
 		mbar_expect_tx(&s_bar, HCM_CHUNK_VOXELS * 2);
 		tma_load_1d(derive_smem, w.raw + (size_t)e.slot * HCM_CHUNK_VOXELS, HCM_CHUNK_VOXELS * 2, &s_bar);
 	}
+	s_pinfo[tid] = (uint16_t)(tables->pflags[tid] | ((tables->pmisc[tid] >> 4) << 8));
+	s_idinfo[tid] = reinterpret_cast<const u32 *>(prop_index + 65536)[tid];
+	__syncthreads();
 	const uint16_t *sraw = reinterpret_cast<const uint16_t *>(derive_smem);
 
 	const int z = tid >> 3, x4 = (tid & 7) << 2;
