@@ -24,6 +24,8 @@ namespace hcm {
 void launch_derive(const DevWorld &w, const UploadEntry *entries, uint32_t n, const uint8_t *prop_index, const DevTables *tables,
                    const int8_t *raw_heights, cudaStream_t st);
 void launch_clear(const DevWorld &w, const UploadEntry *entries, uint32_t n, cudaStream_t st);
+void launch_edit(const DevWorld &w, const hcm_block_edit *edits, uint32_t n, const uint2 *columns, uint32_t n_columns, uint32_t *result, const uint8_t *prop_index,
+                 const DevTables *tables, int8_t *raw_heights, hcm_sunlight_change *changes, uint32_t *n_changes, uint32_t cap, cudaStream_t st);
 void launch_classify(const DevWorld &w, const TaskIn *tasks, uint32_t n, uint32_t *worklist, BatchHeads *heads, hcm_task_result *task_out, int force_all,
                      cudaStream_t st);
 cudaError_t mesh_kernel_prepare();
@@ -98,6 +100,14 @@ struct hcm_ctx {
 	hcm_task_result *h_task_stage = nullptr; // pinned: task results in sub-batch order
 	uint64_t h_task_stage_cap = 0;
 	std::vector<int32_t> cell_block; // scratch of hcm_upload_and_mesh
+	// hcm_set_blocks
+	hcm_block_edit *d_edits = nullptr;
+	uint2 *d_edit_columns = nullptr;
+	uint32_t *d_edit_result = nullptr; // [cap] result words, then the change counter
+	hcm_sunlight_change *d_sun_changes = nullptr;
+	uint32_t edit_cap = 0, sun_cap = 0;
+	std::vector<hcm_sunlight_change> edit_sunlight;
+	std::vector<int16_t> edit_remesh;
 	bool use_batch_copy = true;
 	uint32_t upload_block = 2048, min_sub_batch = 512; // pipeline granularity (env HCM_UPLOAD_BLOCK, HCM_MIN_SUB_BATCH: test knobs)
 	std::unique_ptr<WorkerPool> pool;
@@ -333,7 +343,7 @@ int build_tables(hcm_ctx *c, const hcm_registry *reg, DevTables &t, std::vector<
 			fl |= PF_LIQ_FLOW;
 		t.pflags[i] = fl;
 		t.pmesh[i] = p.custom_mesh;
-		t.pmisc[i] = (uint8_t)((p.liquid_obstacle ? 1 : 0) | (p.light_level << 4));
+		t.pmisc[i] = (uint8_t)((p.liquid_obstacle ? 1 : 0) | (p.transparency == 2 ? 2 : 0) | (p.light_level << 4)); // bit1: GetVerticalLightPass, Block.hpp:70
 		if (p.light_level && std::find(levels.begin(), levels.end(), p.light_level) == levels.end())
 			levels.push_back(p.light_level);
 	}
@@ -511,7 +521,7 @@ void hcm_destroy(hcm_ctx *c) {
 	if (c->stream)
 		cudaStreamSynchronize(c->stream);
 	void *dev[] = {c->w.prop8, c->w.pass, c->w.torch, c->w.height, c->w.cflags, c->w.slot, c->d_tables, c->d_prop_index, c->d_meshes, c->d_mesh_info, c->d_raw,
-	               c->d_rawh, c->d_entries, c->d_all_entries, c->d_tasks, c->d_worklist, c->d_heads, c->d_task_out, c->d_mesh_out, c->d_vtx, c->d_idx, c->d_dyn, c->d_debug_light};
+	               c->d_rawh, c->d_entries, c->d_all_entries, c->d_tasks, c->d_worklist, c->d_heads, c->d_task_out, c->d_mesh_out, c->d_vtx, c->d_idx, c->d_dyn, c->d_debug_light, c->d_edits, c->d_edit_columns, c->d_edit_result, c->d_sun_changes};
 	for (void *p : dev)
 		if (p)
 			cudaFree(p);
@@ -978,6 +988,172 @@ int hcm_rederive_chunks(hcm_ctx *c, uint32_t n, const int16_t *pos) {
 	CU(cudaEventRecord(c->ev[EV_UP2], st));
 	c->stats.kernel_launches += 1;
 	c->ev_upload = true;
+	return HCM_OK;
+}
+
+// ChunkShouldRemesh (client/include/client/ChunkMeshTask.inl:9-15): a block at `rel` (relative to a chunk's origin) can
+// reach that chunk's mesh iff its L1 distance to the box [-1,33]^3 is below 15 (IsBorderLightInterfere at level 15)
+static bool chunk_should_remesh(const int rel[3]) {
+	int dist = 0;
+	for (int a = 0; a < 3; ++a) {
+		if (rel[a] < -1)
+			dist += -1 - rel[a];
+		else if (rel[a] >= HCM_CHUNK_SIZE + 1)
+			dist += rel[a] - (HCM_CHUNK_SIZE + 1);
+	}
+	return 15 > dist;
+}
+
+int hcm_set_blocks(hcm_ctx *c, uint32_t n, const hcm_block_edit *edits, hcm_edit_result *out) {
+	if (!c || !out)
+		return HCM_ERR_INVALID;
+	memset(out, 0, sizeof(*out));
+	if (n == 0)
+		return HCM_OK;
+	if (!edits)
+		return fail(c, HCM_ERR_INVALID, "null edits");
+	CU(cudaSetDevice(c->device));
+	for (uint32_t i = 0; i < n; ++i) {
+		int cx, cy, cz;
+		if (!in_window(c, edits[i].chunk, &cx, &cy, &cz))
+			return fail(c, HCM_ERR_OUT_OF_WINDOW, "edit %u: chunk (%d,%d,%d) is outside the window", i, edits[i].chunk[0], edits[i].chunk[1], edits[i].chunk[2]);
+		if (c->slot_of[cell(c, cx, cy, cz)] < 0)
+			return fail(c, HCM_ERR_NOT_RESIDENT, "edit %u: chunk (%d,%d,%d) is not resident", i, edits[i].chunk[0], edits[i].chunk[1], edits[i].chunk[2]);
+		if (edits[i].index >= HCM_CHUNK_VOXELS)
+			return fail(c, HCM_ERR_INVALID, "edit %u: block index %u out of range", i, edits[i].index);
+	}
+	// order: world column (chunk x, chunk z, x, z), highest chunk first; one entry per voxel, the last one given wins
+	// (the reference keeps one pending update per block index, ChunkTaskPool's set-block map)
+	std::vector<uint32_t> order(n);
+	for (uint32_t i = 0; i < n; ++i)
+		order[i] = i;
+	auto key_of = [](const hcm_block_edit &e) {
+		return ((uint64_t)(uint16_t)e.chunk[0] << 32) | ((uint64_t)(uint16_t)e.chunk[2] << 16) | (uint64_t)((((e.index >> 5) & 31u) << 5) | (e.index & 31u));
+	};
+	std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
+		const uint64_t ka = key_of(edits[a]), kb = key_of(edits[b]);
+		if (ka != kb)
+			return ka < kb;
+		if (edits[a].chunk[1] != edits[b].chunk[1])
+			return edits[a].chunk[1] > edits[b].chunk[1];
+		if (edits[a].index != edits[b].index)
+			return edits[a].index > edits[b].index;
+		return a < b;
+	});
+	std::vector<hcm_block_edit> sorted;
+	std::vector<uint2> columns; // per world column: first edit, number of edits
+	sorted.reserve(n);
+	for (uint32_t k = 0; k < n; ++k) {
+		const hcm_block_edit &e = edits[order[k]];
+		if (k + 1 < n) { // the same voxel again, later in the caller's order: that one wins
+			const hcm_block_edit &f = edits[order[k + 1]];
+			if (key_of(e) == key_of(f) && e.chunk[1] == f.chunk[1] && e.index == f.index)
+				continue;
+		}
+		if (sorted.empty() || key_of(sorted.back()) != key_of(e))
+			columns.push_back(make_uint2((unsigned)sorted.size(), 0u));
+		sorted.push_back(e);
+		columns.back().y++;
+	}
+	const uint32_t m = (uint32_t)sorted.size(), ncol = (uint32_t)columns.size();
+	if (m > c->edit_cap) {
+		for (void *p : {(void *)c->d_edits, (void *)c->d_edit_columns, (void *)c->d_edit_result})
+			if (p)
+				cudaFree(p);
+		c->d_edits = nullptr, c->d_edit_columns = nullptr, c->d_edit_result = nullptr;
+		const uint32_t cap = std::max(1024u, m + m / 2);
+		CU(cudaMalloc((void **)&c->d_edits, (size_t)cap * sizeof(hcm_block_edit)));
+		CU(cudaMalloc((void **)&c->d_edit_columns, (size_t)cap * sizeof(uint2)));
+		CU(cudaMalloc((void **)&c->d_edit_result, ((size_t)cap + 1) * sizeof(uint32_t)));
+		c->edit_cap = cap;
+	}
+	const uint32_t sun_need = m * (uint32_t)c->w.wy; // a chain visits each chunk of a column at most once per edit
+	if (sun_need > c->sun_cap) {
+		if (c->d_sun_changes)
+			cudaFree(c->d_sun_changes);
+		c->d_sun_changes = nullptr;
+		CU(cudaMalloc((void **)&c->d_sun_changes, (size_t)sun_need * sizeof(hcm_sunlight_change)));
+		c->sun_cap = sun_need;
+	}
+	cudaStream_t st = c->stream;
+	uint32_t *d_count = c->d_edit_result + c->edit_cap;
+	CU(cudaMemcpyAsync(c->d_edits, sorted.data(), (size_t)m * sizeof(hcm_block_edit), cudaMemcpyHostToDevice, st));
+	CU(cudaMemcpyAsync(c->d_edit_columns, columns.data(), (size_t)ncol * sizeof(uint2), cudaMemcpyHostToDevice, st));
+	CU(cudaMemsetAsync(d_count, 0, sizeof(uint32_t), st));
+	launch_edit(c->w, c->d_edits, m, c->d_edit_columns, ncol, c->d_edit_result, c->d_prop_index, c->d_tables, c->d_rawh, c->d_sun_changes, d_count, c->sun_cap, st);
+	CU(cudaGetLastError());
+	c->stats.kernel_launches += 2;
+	std::vector<uint32_t> result(m);
+	uint32_t n_changes = 0;
+	CU(cudaMemcpyAsync(result.data(), c->d_edit_result, (size_t)m * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+	CU(cudaMemcpyAsync(&n_changes, d_count, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+	CU(cudaStreamSynchronize(st));
+	if (n_changes > c->sun_cap)
+		return fail(c, HCM_ERR_STATE, "internal: sunlight change list overflow");
+	c->edit_sunlight.resize(n_changes);
+	if (n_changes)
+		CU(cudaMemcpy(c->edit_sunlight.data(), c->d_sun_changes, (size_t)n_changes * sizeof(hcm_sunlight_change), cudaMemcpyDeviceToHost));
+	c->stats.h2d_bytes += (uint64_t)m * sizeof(hcm_block_edit) + (uint64_t)ncol * sizeof(uint2);
+	c->stats.d2h_bytes += (uint64_t)m * 4 + 4 + (uint64_t)n_changes * sizeof(hcm_sunlight_change);
+
+	// fan-out on the host: which chunks to derive again, which mesh tasks the reference pushes
+	std::vector<uint8_t> mark(c->n_cells, 0); // bit0: derive again, bit1: remesh
+	auto mark_remesh = [&](int x, int y, int z) {
+		if (x >= 0 && y >= 0 && z >= 0 && x < c->w.wx && y < c->w.wy && z < c->w.wz)
+			mark[cell(c, x, y, z)] |= 2;
+		else
+			out->n_pending++;
+	};
+	for (uint32_t k = 0; k < m; ++k) {
+		if (!((result[k] >> 16) & 1u))
+			continue;
+		out->n_changed_blocks++;
+		const hcm_block_edit &e = sorted[k];
+		const int cx = e.chunk[0] - c->w.ox, cy = e.chunk[1] - c->w.oy, cz = e.chunk[2] - c->w.oz;
+		const int bp[3] = {(int)(e.index & 31u), (int)(e.index >> 10), (int)((e.index >> 5) & 31u)};
+		mark[cell(c, cx, cy, cz)] |= 3;
+		for (int dy = -1; dy <= 1; ++dy)
+			for (int dz = -1; dz <= 1; ++dz)
+				for (int dx = -1; dx <= 1; ++dx) {
+					if (!dx && !dy && !dz)
+						continue;
+					const int rel[3] = {bp[0] - dx * HCM_CHUNK_SIZE, bp[1] - dy * HCM_CHUNK_SIZE, bp[2] - dz * HCM_CHUNK_SIZE};
+					if (chunk_should_remesh(rel)) // ChunkSetBlockTask.cpp:100-107
+						mark_remesh(cx + dx, cy + dy, cz + dz);
+				}
+	}
+	for (const hcm_sunlight_change &s : c->edit_sunlight) {
+		const int cx = s.chunk[0] - c->w.ox, cy = s.chunk[1] - c->w.oy, cz = s.chunk[2] - c->w.oz;
+		mark[cell(c, cx, cy, cz)] |= 1;
+		for (int dy = -1; dy <= 1; ++dy) // ChunkSetSunlightTask.cpp:66-78: the test is against the chunk itself for every neighbour
+			for (int dz = -1; dz <= 1; ++dz)
+				for (int dx = -1; dx <= 1; ++dx)
+					mark_remesh(cx + dx, cy + dy, cz + dz);
+	}
+	std::vector<int16_t> derive_pos;
+	c->edit_remesh.clear();
+	for (int y = 0; y < c->w.wy; ++y)
+		for (int z = 0; z < c->w.wz; ++z)
+			for (int x = 0; x < c->w.wx; ++x) {
+				const uint8_t f = mark[cell(c, x, y, z)];
+				if (!f)
+					continue;
+				const int16_t p[3] = {(int16_t)(x + c->w.ox), (int16_t)(y + c->w.oy), (int16_t)(z + c->w.oz)};
+				if (f & 1)
+					derive_pos.insert(derive_pos.end(), p, p + 3);
+				if (f & 2) {
+					const bool interior = x >= 1 && y >= 1 && z >= 1 && x <= c->w.wx - 2 && y <= c->w.wy - 2 && z <= c->w.wz - 2;
+					if (interior && c->nbr_count[cell(c, x, y, z)] == 27)
+						c->edit_remesh.insert(c->edit_remesh.end(), p, p + 3);
+					else
+						out->n_pending++;
+				}
+			}
+	if (!derive_pos.empty())
+		if (int rc = hcm_rederive_chunks(c, (uint32_t)(derive_pos.size() / 3), derive_pos.data()))
+			return rc;
+	out->n_sunlight = n_changes, out->sunlight = c->edit_sunlight.data();
+	out->n_remesh = (uint32_t)(c->edit_remesh.size() / 3), out->remesh_pos = c->edit_remesh.data();
 	return HCM_OK;
 }
 

@@ -308,6 +308,80 @@ __global__ void __launch_bounds__(256) clear_kernel(DevWorld w, const UploadEntr
 }
 
 // ================================================================================================================
+// block edits: Chunk::SetBlock on the resident Block data, then the sunlight-height chain of the edited columns
+// ================================================================================================================
+// result word per edit: old block | changed << 16 | not resident << 17
+__global__ void __launch_bounds__(128) edit_blocks_kernel(DevWorld w, const hcm_block_edit *__restrict__ edits, u32 n, u32 *__restrict__ result) {
+	const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n)
+		return;
+	const hcm_block_edit e = edits[i];
+	const int cx = e.chunk[0] - w.ox, cy = e.chunk[1] - w.oy, cz = e.chunk[2] - w.oz;
+	const int slot = w.slot[((size_t)cy * w.wz + cz) * w.wx + cx];
+	if (slot < 0) {
+		result[i] = 1u << 17;
+		return;
+	}
+	uint16_t *raw = const_cast<uint16_t *>(w.raw) + (size_t)slot * HCM_CHUNK_VOXELS;
+	const u32 old = raw[e.index & (HCM_CHUNK_VOXELS - 1)];
+	const bool changed = old != e.block; // ChunkSetBlockTask.cpp:89-92
+	if (changed)
+		raw[e.index & (HCM_CHUNK_VOXELS - 1)] = e.block;
+	result[i] = old | ((changed ? 1u : 0u) << 16);
+}
+
+// One thread per edited world column (cx, cz, x, z).  The host sorts the edits by column, highest chunk first, so the
+// thread runs the chain of every changed edit of its column from top to bottom, one after the other: kFloodSunlight
+// (ChunkFloodSunlightTask.cpp:41-57) gives the new height of a chunk's column, kSetSunlight (ChunkSetSunlightTask.cpp:
+// 55-63) stores it and, if it changed, floods the chunk below.  Columns are independent of each other.
+__global__ void __launch_bounds__(128) sunlight_chain_kernel(DevWorld w, const hcm_block_edit *__restrict__ edits, const uint2 *__restrict__ columns,
+                                                             u32 n_columns, const u32 *__restrict__ result, const uint8_t *__restrict__ prop_index,
+                                                             const DevTables *__restrict__ tables, int8_t *__restrict__ raw_heights,
+                                                             hcm_sunlight_change *__restrict__ changes, u32 *__restrict__ n_changes, u32 cap) {
+	const u32 c = blockIdx.x * blockDim.x + threadIdx.x;
+	if (c >= n_columns)
+		return;
+	const uint2 seg = columns[c]; // first edit, number of edits
+	int visited_down_to = 0x7fffffff; // a chain that ran through a chunk already settled it
+	for (u32 i = seg.x; i < seg.x + seg.y; ++i) {
+		if (!((result[i] >> 16) & 1u))
+			continue; // ChunkSetBlockTask.cpp:89-90: an unchanged block floods nothing
+		const hcm_block_edit e = edits[i];
+		const int cx = e.chunk[0] - w.ox, cz = e.chunk[2] - w.oz;
+		const u32 x = e.index & 31u, z = (e.index >> 5) & 31u, xz = x + z * 32u;
+		int cy = e.chunk[1] - w.oy;
+		if (cy >= visited_down_to)
+			continue;
+		for (; cy >= 0 && cy + 1 < w.wy; --cy) {
+			const int slot = w.slot[((size_t)cy * w.wz + cz) * w.wx + cx], up = w.slot[((size_t)(cy + 1) * w.wz + cz) * w.wx + cx];
+			if (slot < 0 || up < 0)
+				break; // Pop needs both chunks (ChunkFloodSunlightTask.cpp:20-23)
+			int nh = HCM_CHUNK_SIZE;
+			if (raw_heights[(size_t)up * HCM_CHUNK_COLUMNS + xz] <= 0) {
+				const uint16_t *raw = w.raw + (size_t)slot * HCM_CHUNK_VOXELS;
+				int y = HCM_CHUNK_SIZE - 1;
+				while (y >= 0 && (tables->pmisc[prop_index[raw[x + (y * 32 + z) * 32]]] & 2u))
+					--y;
+				nh = y + 1;
+			}
+			int8_t *hp = raw_heights + (size_t)slot * HCM_CHUNK_COLUMNS + xz;
+			const int old = *hp;
+			visited_down_to = cy;
+			if (nh == old)
+				break;
+			*hp = (int8_t)nh;
+			const u32 k = atomicAdd(n_changes, 1u);
+			if (k < cap) {
+				hcm_sunlight_change ch{};
+				ch.chunk[0] = e.chunk[0], ch.chunk[1] = (int16_t)(cy + w.oy), ch.chunk[2] = e.chunk[2];
+				ch.index = (uint16_t)xz, ch.old_height = (int8_t)old, ch.new_height = (int8_t)nh;
+				changes[k] = ch;
+			}
+		}
+	}
+}
+
+// ================================================================================================================
 // classify kernel: thread per task
 // ================================================================================================================
 __global__ void __launch_bounds__(256)
@@ -1749,6 +1823,13 @@ void launch_derive(const DevWorld &w, const UploadEntry *entries, u32 n, const u
 void launch_clear(const DevWorld &w, const UploadEntry *entries, u32 n, cudaStream_t st) {
 	if (n)
 		clear_kernel<<<n, 256, 0, st>>>(w, entries);
+}
+void launch_edit(const DevWorld &w, const hcm_block_edit *edits, u32 n, const uint2 *columns, u32 n_columns, u32 *result, const uint8_t *prop_index,
+                 const DevTables *tables, int8_t *raw_heights, hcm_sunlight_change *changes, u32 *n_changes, u32 cap, cudaStream_t st) {
+	if (!n)
+		return;
+	edit_blocks_kernel<<<(n + 127) / 128, 128, 0, st>>>(w, edits, n, result);
+	sunlight_chain_kernel<<<(n_columns + 127) / 128, 128, 0, st>>>(w, edits, columns, n_columns, result, prop_index, tables, raw_heights, changes, n_changes, cap);
 }
 void launch_classify(const DevWorld &w, const TaskIn *tasks, u32 n, u32 *worklist, BatchHeads *heads, hcm_task_result *task_out, int force_all,
                      cudaStream_t st) {

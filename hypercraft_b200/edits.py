@@ -49,3 +49,53 @@ def column_sunlight_height(blocks: np.ndarray, x: int, z: int, up_height: int, v
     while y >= 0 and vertical_pass[int(col[y])]:
         y -= 1
     return y + 1
+
+
+def apply_block_edits(chunks: dict, edit_list, vertical_pass: np.ndarray):
+    """Host restatement of what ``hcm_set_blocks`` does on the device: the reference's kSetBlock -> kFloodSunlight ->
+    kSetSunlight -> kFloodSunlight(below) chain (client/src/ChunkSetBlockTask.cpp:78-107, ChunkFloodSunlightTask.cpp:41-57,
+    ChunkSetSunlightTask.cpp:42-78) run to its settled state on ``chunks`` = {(cx,cy,cz): (blocks u16[32768], heights i8[1024])},
+    which is modified in place.  ``edit_list`` = [((cx,cy,cz), index, block), ...]; one pending update per voxel, the last
+    one given wins.  Returns (n_changed_blocks, sunlight_changes, remesh_positions):
+      sunlight_changes = {((cx,cy,cz), xz): (old, new)}; remesh_positions = set of chunk positions, NOT filtered by residency.
+    """
+    pending = {}
+    for cpos, index, block in edit_list:
+        pending[(tuple(int(v) for v in cpos), int(index))] = int(block)
+    changed = []
+    for (cpos, index), block in pending.items():
+        b, _ = chunks[cpos]
+        if int(b[index]) == block:  # ChunkSetBlockTask.cpp:89-90
+            continue
+        b[index] = block
+        changed.append((cpos, index))
+    remesh = set()
+    for cpos, index in changed:
+        bp = (index & 31, index >> 10, (index >> 5) & 31)
+        for d in remesh_offsets(bp):
+            remesh.add((cpos[0] + d[0], cpos[1] + d[1], cpos[2] + d[2]))
+    sun = {}
+    # columns top-down: a chain settles every chunk it walks through
+    for cpos, index in sorted(changed, key=lambda t: -t[0][1]):
+        x, z = index & 31, (index >> 5) & 31
+        xz = x + z * 32
+        c = cpos
+        while True:
+            up = (c[0], c[1] + 1, c[2])
+            if c not in chunks or up not in chunks:  # Pop needs both chunks, ChunkFloodSunlightTask.cpp:20-23
+                break
+            b, h = chunks[c]
+            nh = column_sunlight_height(b, x, z, int(chunks[up][1][xz]), vertical_pass)
+            old = int(h[xz])
+            if nh == old:
+                break
+            h[xz] = nh
+            key = (c, xz)
+            sun[key] = (sun[key][0] if key in sun else old, nh)
+            for dx in (-1, 0, 1):  # ChunkSetSunlightTask.cpp:66-78: every neighbour, the test never depends on i
+                for dy in (-1, 0, 1):
+                    for dz in (-1, 0, 1):
+                        remesh.add((c[0] + dx, c[1] + dy, c[2] + dz))
+            c = (c[0], c[1] - 1, c[2])
+    sun = {k: v for k, v in sun.items() if v[0] != v[1]}
+    return len(changed), sun, remesh

@@ -45,6 +45,16 @@ class _BatchCounts(ctypes.Structure):
                 ("n_worked", ctypes.c_uint32), ("_pad", ctypes.c_uint32)]
 
 
+class _EditResult(ctypes.Structure):
+    _fields_ = [("n_changed_blocks", ctypes.c_uint32), ("n_sunlight", ctypes.c_uint32), ("n_remesh", ctypes.c_uint32), ("n_pending", ctypes.c_uint32),
+                ("sunlight", _vp), ("remesh_pos", _vp)]
+
+
+BLOCK_EDIT_DTYPE = np.dtype([("chunk", np.int16, 3), ("index", np.uint16), ("block", np.uint16), ("_pad", np.uint16)])
+SUNLIGHT_CHANGE_DTYPE = np.dtype([("chunk", np.int16, 3), ("index", np.uint16), ("old_height", np.int8), ("new_height", np.int8), ("_pad", np.uint16)])
+assert BLOCK_EDIT_DTYPE.itemsize == 12 and SUNLIGHT_CHANGE_DTYPE.itemsize == 12
+
+
 class _Stats(ctypes.Structure):
     _fields_ = [("upload_copy_ms", ctypes.c_float), ("derive_ms", ctypes.c_float), ("classify_ms", ctypes.c_float), ("mesh_ms", ctypes.c_float),
                 ("fetch_copy_ms", ctypes.c_float), ("kernel_launches", ctypes.c_uint32), ("h2d_bytes", ctypes.c_uint64),
@@ -58,7 +68,7 @@ assert MESH_DESC_DTYPE.itemsize == 56
 
 EXPORTS = ["hcm_registry_from_blob", "hcm_create", "hcm_destroy", "hcm_last_error", "hcm_status_string", "hcm_host_alloc", "hcm_host_free",
            "hcm_upload_chunks", "hcm_remove_chunks", "hcm_rederive_chunks", "hcm_is_resident", "hcm_sync", "hcm_mesh_batch", "hcm_mesh_fetch", "hcm_mesh_wait",
-           "hcm_upload_and_mesh", "hcm_get_stats", "hcm_stream", "hcm_debug_light"]
+           "hcm_upload_and_mesh", "hcm_set_blocks", "hcm_get_stats", "hcm_stream", "hcm_debug_light"]
 
 _lib = None
 
@@ -98,6 +108,7 @@ def load_library():
         L.hcm_mesh_fetch.argtypes = [_vp, ctypes.POINTER(_BatchView)]
         L.hcm_mesh_wait.argtypes = [_vp, ctypes.POINTER(_BatchCounts)]
         L.hcm_upload_and_mesh.argtypes = [_vp, ctypes.c_uint32, _vp, _vp, _vp, ctypes.c_uint32, _vp, ctypes.POINTER(_BatchView)]
+        L.hcm_set_blocks.argtypes = [_vp, ctypes.c_uint32, _vp, ctypes.POINTER(_EditResult)]
         L.hcm_get_stats.argtypes = [_vp, ctypes.POINTER(_Stats)]
         L.hcm_debug_light.argtypes = [_vp, _vp, _vp]
         _lib = L
@@ -226,6 +237,28 @@ class Mesher:
         else:
             pos = np.ascontiguousarray(positions, dtype=np.int16).reshape(-1, 3)
             self._check(self.L.hcm_rederive_chunks(self.ctx, len(pos), _ptr(pos)))
+
+    def set_blocks(self, edit_list) -> dict:
+        """Block edits on the resident world (hcm_set_blocks).  ``edit_list`` = [((cx,cy,cz), index, block), ...] or a
+        BLOCK_EDIT_DTYPE array.  Returns n_changed_blocks, n_pending, ``sunlight`` (SUNLIGHT_CHANGE_DTYPE copies) and
+        ``remesh`` (int16[n,3]: the mesh tasks to submit)."""
+        if isinstance(edit_list, np.ndarray) and edit_list.dtype == BLOCK_EDIT_DTYPE:
+            e = np.ascontiguousarray(edit_list)
+        else:
+            e = np.zeros(len(edit_list), dtype=BLOCK_EDIT_DTYPE)
+            for i, (cpos, index, block) in enumerate(edit_list):
+                e[i]["chunk"], e[i]["index"], e[i]["block"] = cpos, index, block
+        r = _EditResult()
+        self._check(self.L.hcm_set_blocks(self.ctx, len(e), _ptr(e) if len(e) else None, ctypes.byref(r)))
+
+        def copy(ptr, count, dtype):
+            if not count:
+                return np.zeros(0, dtype=dtype)
+            buf = (ctypes.c_uint8 * (count * np.dtype(dtype).itemsize)).from_address(ptr)
+            return np.frombuffer(buf, dtype=dtype, count=count).copy()
+
+        return dict(n_changed_blocks=r.n_changed_blocks, n_pending=r.n_pending, sunlight=copy(r.sunlight, r.n_sunlight, SUNLIGHT_CHANGE_DTYPE),
+                    remesh=copy(r.remesh_pos, r.n_remesh * 3, np.int16).reshape(-1, 3))
 
     def is_resident(self, pos) -> bool:
         p = np.ascontiguousarray(pos, dtype=np.int16)

@@ -162,6 +162,50 @@ int hcm_remove_chunks(hcm_ctx *ctx, uint32_t n, const int16_t *pos /* n x 3 */);
  * hcm_rederive_chunks(ctx, 0, NULL) followed by hcm_mesh_batch. */
 int hcm_rederive_chunks(hcm_ctx *ctx, uint32_t n, const int16_t *pos /* n x 3 */);
 int hcm_is_resident(const hcm_ctx *ctx, const int16_t pos[3]); /* 1 / 0 */
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Block edits on the device-resident world: what the reference does in three task types,
+ *   kSetBlock      ChunkTaskRunner<kSetBlock>::Run      client/src/ChunkSetBlockTask.cpp:38-129
+ *   kFloodSunlight ChunkTaskRunner<kFloodSunlight>::Run client/src/ChunkFloodSunlightTask.cpp:33-66
+ *   kSetSunlight   ChunkTaskRunner<kSetSunlight>::Run   client/src/ChunkSetSunlightTask.cpp:28-90
+ * for ChunkSetBlockEntry deltas (common/include/common/Data.hpp:11-14), without a 64 KB re-upload per touched chunk:
+ *   1. Chunk::SetBlock for every entry whose block differs from the resident one;
+ *   2. the sunlight height of each edited column is re-derived in its chunk (32 if the chunk above is not lit down to
+ *      its floor in that column, else one above the highest voxel without vertical light pass) and, while it changes,
+ *      in the chunks below -- the kFloodSunlight -> kSetSunlight -> kFloodSunlight(below) chain, which stops where the
+ *      chunk above a chunk is not resident (the reference keeps that task queued);
+ *   3. the touched chunks go through the derivation kernel again;
+ *   4. the mesh tasks the reference pushes are returned: per changed block the chunk itself and every neighbour i with
+ *      ChunkShouldRemesh(block_pos - offset_i * 32) (ChunkSetBlockTask.cpp:100-107); per changed height the chunk and
+ *      all 26 neighbours (ChunkSetSunlightTask.cpp:66-78 tests the column against the chunk itself for every i, which
+ *      is always true).  Deduplicated; positions whose 27 chunks are not all resident are counted in n_pending instead.
+ * The caller applies `sunlight` to its own Chunk objects (Chunk::SetSunlightHeight) and passes `remesh_pos` to
+ * hcm_mesh_batch.  Pointers in the result belong to the ctx and stay valid until its next call.
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct hcm_block_edit {
+	int16_t chunk[3]; /* ChunkPos3 */
+	uint16_t index;   /* InnerIndex3: x + (y*32 + z)*32 */
+	uint16_t block;   /* Block::GetData() */
+	uint16_t _pad;
+} hcm_block_edit; /* 12 bytes */
+
+typedef struct hcm_sunlight_change {
+	int16_t chunk[3];
+	uint16_t index; /* InnerIndex2: x + z*32 */
+	int8_t old_height, new_height;
+	uint16_t _pad;
+} hcm_sunlight_change; /* 12 bytes */
+
+typedef struct hcm_edit_result {
+	uint32_t n_changed_blocks; /* entries whose block differed from the resident one */
+	uint32_t n_sunlight;
+	uint32_t n_remesh;
+	uint32_t n_pending;
+	const hcm_sunlight_change *sunlight; /* [n_sunlight], each (chunk, column) at most once */
+	const int16_t *remesh_pos;           /* [n_remesh x 3] */
+} hcm_edit_result;
+
+int hcm_set_blocks(hcm_ctx *ctx, uint32_t n, const hcm_block_edit *edits, hcm_edit_result *out);
 int hcm_sync(hcm_ctx *ctx);
 
 /* ------------------------------------------------------------------------------------------------------------

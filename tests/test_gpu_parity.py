@@ -359,3 +359,66 @@ def test_pipelined_world_load_equals_plain_calls(monkeypatch):
     res = m.upload_and_mesh(resident[perm], blocks[perm], heights[perm], meshed)  # everything resident already, re-uploaded shuffled
     assert all(res.serialise(t).tobytes() == want[t] for t in range(len(meshed)))
     m.close()
+
+
+def test_set_blocks_on_device_matches_host_chain(port):
+    """hcm_set_blocks (device-resident edits + sunlight heights on the GPU) against the host restatement of the
+    reference's kSetBlock / kFloodSunlight / kSetSunlight chain: changed-block count, every sunlight change, the mesh tasks
+    pushed, and -- the state that matters -- the meshes of ALL interior chunks afterwards against the oracle on the
+    host-edited world."""
+    from hypercraft_b200 import edits, mesher as M, registry, worldgen
+
+    reg = registry.load()
+    vpass = reg.props["transparency"][reg.prop_index] == 2
+    allpos = np.array([[x, y, z] for x in range(-2, 3) for y in range(-2, 3) for z in range(-2, 3)], dtype=np.int16)
+    chunks = {}
+    for p in allpos:
+        b, h = worldgen.synth_terrain_chunk(78, p)
+        chunks[tuple(int(c) for c in p)] = (b.copy(), h.copy())
+    m = M.Mesher(origin=(-2, -2, -2), extent=(5, 5, 5))
+    m.upload(allpos, np.stack([chunks[tuple(int(c) for c in p)][0] for p in allpos]), np.stack([chunks[tuple(int(c) for c in p)][1] for p in allpos]))
+    interior = np.array([[x, y, z] for x in (-1, 0, 1) for y in (-1, 0, 1) for z in (-1, 0, 1)], dtype=np.int16)
+    rng = np.random.default_rng(21)
+    palette = [0, 1, 24, 14, worldgen.make_block(worldgen.FLOWING_WATER, 5), 9, worldgen.make_block(worldgen.LEAVES, 2), 20, 5]
+
+    def run(batch, what):
+        want_n, want_sun, want_remesh = edits.apply_block_edits(chunks, batch, vpass)
+        r = m.set_blocks(batch)
+        assert r["n_changed_blocks"] == want_n, what
+        got_sun = {(tuple(int(v) for v in s["chunk"]), int(s["index"])): (int(s["old_height"]), int(s["new_height"])) for s in r["sunlight"]}
+        assert got_sun == want_sun, what
+        meshable = {p for p in want_remesh if all(abs(v) <= 1 for v in p)}  # the 27 chunks around must be inside the 5^3 window
+        assert {tuple(int(v) for v in p) for p in r["remesh"]} == meshable, what
+        res = m.mesh(interior)  # every chunk that could have changed, and the ones that must not have
+        for t, p in enumerate(interior):
+            got, want = res.serialise(t), port.mesh(chunks, p)
+            assert got.size == want.size and (got == want).all(), f"{what}: chunk {p}\n" + describe_diff(got, want)
+
+    # 1. a shaft dug from the sky down through two chunks in ONE batch (the chain has to run top-down), then closed again
+    x, z = 9, 20
+    col = [((0, cy, 0), x + (y * 32 + z) * 32, 0) for cy in (1, 0) for y in range(32)]
+    run(col, "shaft")
+    run([((0, 1, 0), x + (31 * 32 + z) * 32, 1)], "lid")
+    # 2. random batches around the terrain surface: duplicates, no-ops, several edits per column, neighbours across chunk borders
+    for it in range(6):
+        batch = []
+        for _ in range(int(rng.integers(1, 40))):
+            cpos = (int(rng.integers(-1, 2)), int(rng.integers(-1, 2)), int(rng.integers(-1, 2)))
+            bx, bz = int(rng.integers(0, 32)), int(rng.integers(0, 32))
+            h = int(chunks[cpos][1][bx + bz * 32])
+            by = int(np.clip(h + int(rng.integers(-4, 3)), 0, 31)) if rng.integers(0, 3) else int(rng.integers(0, 32))
+            batch.append((cpos, bx + (by * 32 + bz) * 32, palette[int(rng.integers(0, len(palette)))]))
+            if rng.integers(0, 5) == 0:
+                batch.append(batch[-1][:2] + (palette[int(rng.integers(0, len(palette)))],))  # same voxel twice: the last one wins
+            if rng.integers(0, 4) == 0:  # another edit in the same world column, other chunk
+                batch.append(((cpos[0], int(rng.integers(-1, 2)), cpos[2]), bx + (int(rng.integers(0, 32)) * 32 + bz) * 32, 0))
+        run(batch, f"random batch {it}")
+    # 3. errors: chunk outside the window, chunk not resident
+    with pytest.raises(M.HcmError) as e:
+        m.set_blocks([((9, 0, 0), 0, 1)])
+    assert e.value.status == -5
+    m.remove(np.array([[2, 2, 2]], dtype=np.int16))
+    with pytest.raises(M.HcmError) as e:
+        m.set_blocks([((2, 2, 2), 0, 1)])
+    assert e.value.status == -4
+    m.close()

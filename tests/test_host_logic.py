@@ -155,3 +155,37 @@ def test_column_sunlight_height_rule():
     b[3 + (20 * 32 + 4) * 32] = 14  # water (semi-transparent) at y = 20 blocks vertical light too
     assert edits.column_sunlight_height(b, 3, 4, 0, vpass) == 21
     assert edits.column_sunlight_height(b, 3, 4, 5, vpass) == 32
+
+
+def test_apply_block_edits_chain():
+    """The settled state of kSetBlock -> kFloodSunlight -> kSetSunlight -> kFloodSunlight(below): opening and closing a
+    shaft through three stacked chunks, no-op edits, last-update-wins, and the remesh fan-out of a height change."""
+    from hypercraft_b200 import edits, registry
+
+    reg = registry.load()
+    vpass = reg.props["transparency"][reg.prop_index] == 2
+    chunks = {}
+    for cy in range(-1, 3):  # column of chunks at cx = cz = 0; y = 2 is open sky, the others solid stone
+        b = np.full(32768, 0 if cy == 2 else 1, dtype=np.uint16)
+        h = np.full(1024, 0 if cy == 2 else 32, dtype=np.int8)
+        chunks[(0, cy, 0)] = (b, h)
+    x, z = 5, 7
+    xz = x + z * 32
+    idx = lambda y: x + (y * 32 + z) * 32
+    # no-op: stone over stone changes nothing and floods nothing
+    n, sun, remesh = edits.apply_block_edits(chunks, [((0, 1, 0), idx(31), 1)], vpass)
+    assert n == 0 and not sun and not remesh
+    # dig the whole column of chunk y=1 and the top 5 voxels of chunk y=0 in one batch
+    batch = [((0, 1, 0), idx(y), 0) for y in range(32)] + [((0, 0, 0), idx(y), 0) for y in range(27, 32)]
+    batch.append(((0, 0, 0), idx(27), 1))  # the same voxel again: the later update wins, y = 27 stays stone
+    n, sun, remesh = edits.apply_block_edits(chunks, batch, vpass)
+    assert n == 32 + 4
+    assert sun == {((0, 1, 0), xz): (32, 0), ((0, 0, 0), xz): (32, 28)}
+    assert int(chunks[(0, 1, 0)][1][xz]) == 0 and int(chunks[(0, 0, 0)][1][xz]) == 28 and int(chunks[(0, -1, 0)][1][xz]) == 32
+    assert (1, 2, 1) in remesh and (-1, -1, -1) in remesh and (0, -2, 0) not in remesh  # 27 around both changed chunks
+    # close the shaft at the very top: both chunks below fall back to "not lit from above"
+    n, sun, remesh = edits.apply_block_edits(chunks, [((0, 1, 0), idx(31), 1)], vpass)
+    assert n == 1 and sun == {((0, 1, 0), xz): (0, 32), ((0, 0, 0), xz): (28, 32)}
+    # the top chunk has nothing above it in the map: its chain cannot start (Pop needs the chunk above)
+    n, sun, remesh = edits.apply_block_edits(chunks, [((0, 2, 0), idx(3), 1)], vpass)
+    assert n == 1 and not sun and (0, 2, 0) in remesh
