@@ -102,6 +102,39 @@ public:
 
 	size_t Pending() const { return m_tasks.size(); }
 
+	// ChunkSetBlockEntry deltas (common/include/common/Data.hpp:11-14) for chunks that are already on the device -- the
+	// work of ChunkTaskRunner<kSetBlock>::Run and of the kFloodSunlight / kSetSunlight chain it starts
+	// (client/src/ChunkSetBlockTask.cpp:78-129, ChunkFloodSunlightTask.cpp:41-57, ChunkSetSunlightTask.cpp:42-90) without
+	// re-uploading 64 KB per touched chunk.  The caller has already applied (or now applies) the same blocks to its own
+	// Chunk objects with Chunk::SetBlock; `on_sunlight(const SunlightChange&)` is where it calls Chunk::SetSunlightHeight,
+	// `on_remesh(const ChunkPos3&)` where it would Push<kMesh> -- typically Submit(the 27 chunks around that position).
+	struct SetBlock {
+		ChunkPos3 chunk;
+		uint16_t index; // InnerIndex3: x + (y*32 + z)*32
+		uint16_t block; // Block::GetData()
+	};
+	struct SunlightChange {
+		ChunkPos3 chunk;
+		uint16_t index; // InnerIndex2: x + z*32
+		int8_t old_height, new_height;
+	};
+	template <typename OnSunlight, typename OnRemesh> uint32_t SetBlocks(const std::vector<SetBlock> &edits, OnSunlight &&on_sunlight, OnRemesh &&on_remesh) {
+		std::vector<hcm_block_edit> e(edits.size());
+		for (size_t i = 0; i < edits.size(); ++i) {
+			e[i].chunk[0] = edits[i].chunk.x, e[i].chunk[1] = edits[i].chunk.y, e[i].chunk[2] = edits[i].chunk.z;
+			e[i].index = edits[i].index, e[i].block = edits[i].block, e[i]._pad = 0;
+		}
+		hcm_edit_result r{};
+		check(hcm_set_blocks(m_ctx, (uint32_t)e.size(), e.data(), &r));
+		for (uint32_t i = 0; i < r.n_sunlight; ++i) {
+			const hcm_sunlight_change &s = r.sunlight[i];
+			on_sunlight(SunlightChange{ChunkPos3{s.chunk[0], s.chunk[1], s.chunk[2]}, s.index, s.old_height, s.new_height});
+		}
+		for (uint32_t i = 0; i < r.n_remesh; ++i)
+			on_remesh(ChunkPos3{r.remesh_pos[3 * i], r.remesh_pos[3 * i + 1], r.remesh_pos[3 * i + 2]});
+		return r.n_changed_blocks;
+	}
+
 	// Runs the batch and calls sink(const ChunkPos3&, std::vector<BlockMesh>&&) once per submitted task, in submission
 	// order -- the place where Run() calls WorldRenderer::PushChunkMesh.  Zero meshes is a valid result and is pushed too
 	// (it clears the chunk's old handles, WorldRenderer.hpp:81-86).

@@ -123,6 +123,28 @@ int main(int argc, char **argv) {
 	disp.Submit(gather(0, 0, 0));
 	disp.Submit(gather(1, 0, 0));
 	disp.Flush(sink);
+	// device-side edits: dig a shaft through the terrain of chunk (0,0,0) and drop a lamp and some water next to it; the
+	// host chunks are edited in place (same objects: nothing is uploaded again), the sunlight heights come back from the
+	// device, and the remesh set it returns is meshed and compared with the oracle on the host's world
+	{
+		using D = hcm_host::MeshTaskDispatcher<Chunk>;
+		std::vector<D::SetBlock> edits;
+		for (int y = 0; y < 32; ++y)
+			edits.push_back({{0, 0, 0}, (uint16_t)(7 + (y * 32 + 9) * 32), 0});
+		edits.push_back({{0, 0, 0}, (uint16_t)(8 + (3 * 32 + 9) * 32), 24});
+		edits.push_back({{0, -1, 0}, (uint16_t)(7 + (31 * 32 + 9) * 32), 14});
+		edits.push_back({{1, 0, -1}, (uint16_t)(0 + (12 * 32 + 31) * 32), 1});
+		for (auto &e : edits)
+			world[{e.chunk.x, e.chunk.y, e.chunk.z}]->blocks[e.index] = e.block;
+		int n_sun = 0, n_remesh = 0;
+		const uint32_t changed = disp.SetBlocks(
+		    edits, [&](const D::SunlightChange &s) { world[{s.chunk.x, s.chunk.y, s.chunk.z}]->heights[s.index] = s.new_height, ++n_sun; },
+		    [&](const hcm_host::ChunkPos3 &p) { disp.Submit(gather(p.x, p.y, p.z)), ++n_remesh; });
+		disp.Flush(sink);
+		printf("device edits: %u blocks changed, %d sunlight heights changed, %d chunks remeshed\n", changed, n_sun, n_remesh);
+		if (!changed || !n_remesh)
+			++bad;
+	}
 	printf("%s: %d tasks pushed, %zu vertices, %d mismatches\n", bad ? "FAIL" : "PASS", pushed, verts, bad);
 	return bad ? 1 : 0;
 }

@@ -76,4 +76,28 @@ for batch in (1, 8, 64, 512):
                               "latency_ms_p99": float(np.percentile(lat, 99)), "remeshed_chunks_per_s": float(np.mean(ntasks[1:]) / np.mean(lat) * 1e3),
                               "includes": "host edit bookkeeping (python), upload of dirty chunks, mesh kernel, fetch of the meshes"}
 out["config5_edits"] = cfg5
+
+# ---- config 5 through hcm_set_blocks: the edit, the sunlight chain and the fan-out happen on the device-resident world ----
+cfg5d = {}
+for batch in (1, 8, 64, 512):
+    lat, ntasks, nsun = [], [], []
+    for rep in range(12 if batch <= 64 else 5):
+        batch_edits = np.zeros(batch, dtype=M.BLOCK_EDIT_DTYPE)
+        for e in range(batch):
+            cpos = surface[int(rng.integers(0, len(surface)))]
+            i = index[cpos]
+            bx, bz = int(rng.integers(0, 32)), int(rng.integers(0, 32))
+            by = int(np.clip(int(heights[i][bx + bz * 32]) + int(rng.integers(-2, 2)), 0, 31))
+            batch_edits[e]["chunk"], batch_edits[e]["index"], batch_edits[e]["block"] = cpos, bx + (by * 32 + bz) * 32, [0, 1, 24, 14][int(rng.integers(0, 4))]
+        t0 = time.perf_counter()
+        r = m.set_blocks(batch_edits)
+        res = m.mesh(r["remesh"])
+        lat.append((time.perf_counter() - t0) * 1e3); ntasks.append(len(r["remesh"])); nsun.append(len(r["sunlight"]))
+    lat = np.array(lat[1:])
+    cfg5d[f"batch_{batch}"] = {"edits": batch, "remeshed_chunks_mean": float(np.mean(ntasks)), "sunlight_changes_mean": float(np.mean(nsun)),
+                               "latency_ms_p50": float(np.percentile(lat, 50)), "latency_ms_p99": float(np.percentile(lat, 99)),
+                               "remeshed_chunks_per_s": float(np.mean(ntasks[1:]) / np.mean(lat) * 1e3),
+                               "includes": "hcm_set_blocks (edit + sunlight chain kernels, host fan-out, derive of touched chunks), mesh kernel, fetch of the meshes; "
+                                           "the remesh set is the reference's (27 chunks around every changed sunlight height)"}
+out["config5_edits_on_device"] = cfg5d
 print(json.dumps(out))
