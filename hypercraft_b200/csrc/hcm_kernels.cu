@@ -1212,6 +1212,22 @@ __device__ void emit_custom_voxel(const MeshParams &p, Small &S, const uint8_t *
 	}
 }
 
+// The chunk's totals are known: claim its vertex, index and descriptor ranges.  One thread issues the three atomics back
+// to back and only then looks at the results, so their round trips to the L2 overlap (three lanes with one atomic each
+// measured slower: the divergent paths wait one after the other).
+__device__ __forceinline__ void claim_output(const MeshParams &p, Small &S, int tid) {
+	if (tid == 0) {
+		S.Qo = S.run_o, S.Qt = S.run_t;
+		const u64 nv = 4ull * (S.Qo + S.Qt), ni = 6ull * (S.Qo + S.Qt);
+		const u32 nm = (S.Qo + kQuadsPerMesh - 1) / kQuadsPerMesh + (S.Qt + kQuadsPerMesh - 1) / kQuadsPerMesh;
+		const u64 voff = atomicAdd(&p.heads->vtx, nv), ioff = atomicAdd(&p.heads->idx, ni);
+		const u32 moff = atomicAdd(&p.heads->meshes, nm);
+		S.voff = voff, S.ioff = ioff, S.moff = moff;
+		if (voff + nv > p.vtx_cap || ioff + ni > p.idx_cap || moff + nm > p.mesh_cap)
+			S.overflow = 1, atomicExch(&p.heads->overflow, 1u);
+	}
+}
+
 __global__ void __launch_bounds__(kThreads, 1) mesh_kernel(const __grid_constant__ CUtensorMap tmap, const MeshParams p) {
 	extern __shared__ __align__(128) uint8_t smem[];
 	uint8_t *vox = smem + SM_VOX;
@@ -1235,15 +1251,19 @@ __global__ void __launch_bounds__(kThreads, 1) mesh_kernel(const __grid_constant
 	DynRec *dyn = p.dyn_scratch + (size_t)blockIdx.x * kLightBytes;
 	const u32 n_work = p.heads->n_work;
 
+	if (tid == 0)
+		S.work_item = atomicAdd(&p.heads->cursor, 1u);
 	for (;;) {
-		__syncthreads(); // previous task fully retired (smem reuse, S.work_item)
-		if (tid == 0)
-			S.work_item = atomicAdd(&p.heads->cursor, 1u);
-		__syncthreads();
+		__syncthreads(); // previous task fully retired (smem reuse); S.work_item holds this CTA's next work item
 		const u32 wi = S.work_item;
 		PHASE_MARK(0); // task fetch
 		if (wi >= n_work)
 			break;
+		// thread 0 claims the work item after this one now; the atomic's round trip hides behind the task set-up, and the
+		// result is published behind the next barrier, when everybody has read the current one
+		u32 wi_next = 0;
+		if (tid == 0)
+			wi_next = atomicAdd(&p.heads->cursor, 1u);
 		const u32 task = p.worklist[wi];
 		const TaskIn ti = p.tasks[task];
 
@@ -1271,6 +1291,8 @@ __global__ void __launch_bounds__(kThreads, 1) mesh_kernel(const __grid_constant
 		// leaves next to none of those) --------------------------------------------------------------------------------
 		const bool want_light = p.debug_light != nullptr;
 		__syncthreads(); // S.any_torch
+		if (tid == 0)
+			S.work_item = wi_next;
 		{
 			u64 *sbuf = reinterpret_cast<u64 *>(region + RG_SBUF);
 			for (int i = tid; i < 2 * kSB * kSB; i += kThreads)
@@ -1703,16 +1725,7 @@ __global__ void __launch_bounds__(kThreads, 1) mesh_kernel(const __grid_constant
 				}
 				if (single) {
 					// totals are known after the only group: allocate now
-					if (tid == 0) {
-						S.Qo = S.run_o, S.Qt = S.run_t;
-						const u64 nv = 4ull * (S.Qo + S.Qt), ni = 6ull * (S.Qo + S.Qt);
-						const u32 nm = (S.Qo + kQuadsPerMesh - 1) / kQuadsPerMesh + (S.Qt + kQuadsPerMesh - 1) / kQuadsPerMesh;
-						S.voff = atomicAdd(&p.heads->vtx, nv);
-						S.ioff = atomicAdd(&p.heads->idx, ni);
-						S.moff = atomicAdd(&p.heads->meshes, nm);
-						if (S.voff + nv > p.vtx_cap || S.ioff + ni > p.idx_cap || S.moff + nm > p.mesh_cap)
-							S.overflow = 1, atomicExch(&p.heads->overflow, 1u);
-					}
+					claim_output(p, S, tid);
 					__syncthreads();
 				}
 				PHASE_MARK(13); // alloc
@@ -1722,16 +1735,7 @@ __global__ void __launch_bounds__(kThreads, 1) mesh_kernel(const __grid_constant
 				g0 = g1;
 			}
 			if (!single && pass == 0) {
-				if (tid == 0) {
-					S.Qo = S.run_o, S.Qt = S.run_t;
-					const u64 nv = 4ull * (S.Qo + S.Qt), ni = 6ull * (S.Qo + S.Qt);
-					const u32 nm = (S.Qo + kQuadsPerMesh - 1) / kQuadsPerMesh + (S.Qt + kQuadsPerMesh - 1) / kQuadsPerMesh;
-					S.voff = atomicAdd(&p.heads->vtx, nv);
-					S.ioff = atomicAdd(&p.heads->idx, ni);
-					S.moff = atomicAdd(&p.heads->meshes, nm);
-					if (S.voff + nv > p.vtx_cap || S.ioff + ni > p.idx_cap || S.moff + nm > p.mesh_cap)
-						S.overflow = 1, atomicExch(&p.heads->overflow, 1u);
-				}
+				claim_output(p, S, tid);
 				__syncthreads();
 			}
 		}
