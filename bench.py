@@ -118,6 +118,10 @@ def build_world(radius: int, centre, threads: int):
     return meshed, resident, pb, ph, label, ref
 
 
+def workload_name(radius: int) -> str:
+    return f"full load-radius remesh r={radius} (misc/load_radius.cpp; kWorldMaxLoadRadius) per GPU"
+
+
 def run_reference(args, rank, world):
     """The reference's own CPU implementation of the path (unmodified ChunkTaskRunner<kMesh>::Run, all host threads)."""
     if rank != 0:
@@ -155,8 +159,8 @@ def run_reference(args, rank, world):
     out = {"impl": "reference", "metric": "chunks meshed/sec", "value": value, "unit": "chunks/s", "n_gpus": args.gpus, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/u16 integer",
            "data": f"synthetic: reference DefaultTerrain(seed {SEED})",
-           "config": {"workload": f"load-radius remesh r={radius} (misc/load_radius.cpp, kWorldMaxLoadRadius), bounded sample", "radius": radius,
-                      "chunks_per_step": len(sample)},
+           "config": {"workload": workload_name(radius), "radius": radius, "chunks_per_step": len(sample),
+                      "note": "each step meshes a bounded sample of the workload's task list (cpu_baseline.sample)"},
            "quads_per_s": quads / (ms / 1e3),
            "cpu_baseline": {"value": value, "unit": "chunks/s", "cores": threads, "kind": "reference", "sample": sample_txt},
            "e2e": {"value": value, "unit": "chunks/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -315,7 +319,7 @@ def main():
             "metric": "chunks meshed/sec", "value": value, "unit": "chunks/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/u16 integer",
             "data": data_label,
-            "config": {"workload": f"full load-radius remesh r={radius} (misc/load_radius.cpp; kWorldMaxLoadRadius) per GPU", "radius": radius,
+            "config": {"workload": workload_name(radius), "radius": radius,
                        "chunks_meshed_per_gpu": int(len(meshed)), "chunks_resident_per_gpu": int(len(resident)),
                        "tasks_through_full_kernel_per_gpu": int(counts["n_worked"]), "parallelism": f"{world} independent spheres (no collective)",
                        "l2": f"inputs ({m.stats()['device_bytes'] / 1e9:.1f} GB of device-resident world per GPU) larger than L2; no flush needed",
