@@ -761,13 +761,7 @@ __device__ __forceinline__ void flood_channel(const MeshParams &p, const ColInfo
 				}
 				if (inject) { // sources of level 15 - step
 					if (!kTorch) {
-						u32 sl[3];
-#pragma unroll
-						for (int d = 0; d < 3; ++d) {
-							const int h = p.w.height[ci.g(k) + d * plane_stride];
-							sl[d] = h >= 32 ? 0u : (h <= 0 ? 0xffffffffu : (0xffffffffu << h)); // sunlit: y >= height, Chunk.hpp:73-76
-						}
-						add |= combine3(sl[0], sl[1], sl[2]) & ~g;
+						add |= rd[c] & ~g; // sunlit cells, left there by the set-up pass (step 0: rd is the buffer nobody writes)
 					} else {
 						const u32 *src = p.w.torch + (size_t)level_plane * p.w.wy * plane_stride;
 						const u32 gk = ci.g(k);
@@ -1300,7 +1294,7 @@ __global__ void __launch_bounds__(kThreads, 1) mesh_kernel(const __grid_constant
 			ColInfo ci;
 			ci.X = (u32)p.w.X;
 			ci.g0 = (u32)(((size_t)(ti.cy - 1) * p.w.Z + (size_t)(ti.cz * 32 - 15)) * p.w.X + (size_t)(ti.cx * 32 - 15));
-			u64 P[kColsPerThread];
+			u64 P[kColsPerThread], sun0[kColsPerThread]; // passable cells; sunlit cells (the sources of the sunlight flood)
 			const size_t plane_stride = (size_t)p.w.Z * p.w.X;
 #pragma unroll
 			for (int k = 0; k < kColsPerThread; ++k) {
@@ -1311,12 +1305,26 @@ __global__ void __launch_bounds__(kThreads, 1) mesh_kernel(const __grid_constant
 				if (ok) {
 					ci.c[k] = ((z + 1) * kSB + (x + 1)) | ((14 - dx - dz) << 16);
 					const u32 gk = ci.g(k);
+					// the three height loads ride in the same memory round trip as the three plane loads
+					u32 sl[3];
+#pragma unroll
+					for (int d = 0; d < 3; ++d) {
+						const int h = p.w.height[gk + d * plane_stride];
+						sl[d] = h >= 32 ? 0u : (h <= 0 ? 0xffffffffu : (0xffffffffu << h)); // sunlit: y >= height, Chunk.hpp:73-76
+					}
 					P[k] = combine3(p.w.pass[gk], p.w.pass[gk + plane_stride], p.w.pass[gk + 2 * plane_stride]);
+					sun0[k] = combine3(sl[0], sl[1], sl[2]);
 				} else {
-					ci.c[k] = -1, P[k] = 0;
+					ci.c[k] = -1, P[k] = 0, sun0[k] = 0;
 				}
 			}
 			__syncthreads();
+			// Step 0 of the sunlight flood reads its sources from the buffer it does not write (its own entry only).  The
+			// word is what the column holds after step 0 anyway, so the double-buffer protocol is not disturbed.
+#pragma unroll
+			for (int k = 0; k < kColsPerThread; ++k)
+				if (ci.c[k] >= 0)
+					sbuf[kSB * kSB + ci.idx(k)] = sun0[k];
 			PHASE_MARK(6); // flood setup (plane loads)
 			flood_channel<false>(p, ci, P, sbuf, light, tid);
 			if (S.any_torch && p.w.n_levels > 0) {
