@@ -24,6 +24,7 @@ namespace hcm {
 void launch_derive(const DevWorld &w, const UploadEntry *entries, uint32_t n, const uint8_t *prop_index, const DevTables *tables,
                    const int8_t *raw_heights, cudaStream_t st);
 void launch_clear(const DevWorld &w, const UploadEntry *entries, uint32_t n, cudaStream_t st);
+void launch_flood_slots(uint4 *out, cudaStream_t st);
 void launch_edit(const DevWorld &w, const hcm_block_edit *edits, uint32_t n, const uint2 *columns, uint32_t n_columns, uint32_t *result, const uint8_t *prop_index,
                  const DevTables *tables, int8_t *raw_heights, hcm_sunlight_change *changes, uint32_t *n_changes, uint32_t cap, cudaStream_t st);
 void launch_classify(const DevWorld &w, const TaskIn *tasks, uint32_t n, uint32_t *worklist, BatchHeads *heads, hcm_task_result *task_out, int force_all,
@@ -142,6 +143,7 @@ struct hcm_ctx {
 	uint64_t vtx_cap = 0, idx_cap = 0;
 	uint32_t mesh_cap = 0;
 	DynRec *d_dyn = nullptr;
+	uint4 *d_flood_slots = nullptr; // per-thread flood columns of the mesh kernel
 	uint8_t *d_debug_light = nullptr;
 	int grid = 0;
 
@@ -404,6 +406,7 @@ MeshParams mesh_params(const hcm_ctx *c, uint32_t first_task) {
 	p.task_out = c->d_task_out + first_task, p.mesh_out = c->d_mesh_out, p.vtx = c->d_vtx, p.idx = c->d_idx;
 	p.vtx_cap = c->vtx_cap, p.idx_cap = c->idx_cap, p.mesh_cap = c->mesh_cap;
 	p.dyn_scratch = c->d_dyn, p.debug_light = c->d_debug_light;
+	p.flood_slots = c->d_flood_slots;
 	return p;
 }
 
@@ -521,7 +524,7 @@ void hcm_destroy(hcm_ctx *c) {
 	if (c->stream)
 		cudaStreamSynchronize(c->stream);
 	void *dev[] = {c->w.prop8, c->w.pass, c->w.torch, c->w.height, c->w.cflags, c->w.slot, c->d_tables, c->d_prop_index, c->d_meshes, c->d_mesh_info, c->d_raw,
-	               c->d_rawh, c->d_entries, c->d_all_entries, c->d_tasks, c->d_worklist, c->d_heads, c->d_task_out, c->d_mesh_out, c->d_vtx, c->d_idx, c->d_dyn, c->d_debug_light, c->d_edits, c->d_edit_columns, c->d_edit_result, c->d_sun_changes};
+	               c->d_rawh, c->d_entries, c->d_all_entries, c->d_tasks, c->d_worklist, c->d_heads, c->d_task_out, c->d_mesh_out, c->d_vtx, c->d_idx, c->d_dyn, c->d_flood_slots, c->d_debug_light, c->d_edits, c->d_edit_columns, c->d_edit_result, c->d_sun_changes};
 	for (void *p : dev)
 		if (p)
 			cudaFree(p);
@@ -675,6 +678,9 @@ int hcm_create(const hcm_registry *registry, const hcm_config *cfg, hcm_ctx **ou
 	CUB(mesh_kernel_prepare());
 	c->grid = prop.multiProcessorCount; // one persistent CTA per SM (shared-memory bound)
 	CUB(dev_alloc(c, &c->d_dyn, (size_t)c->grid * kLightBytes));
+	CUB(dev_alloc(c, &c->d_flood_slots, (size_t)kThreads));
+	launch_flood_slots(c->d_flood_slots, c->stream);
+	CUB(cudaGetLastError());
 
 	// TMA descriptor over the dense property grid: dims (x, z, y), box 48 x 36 x 34, out-of-window reads give 0 (= air)
 	{

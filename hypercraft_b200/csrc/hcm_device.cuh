@@ -166,6 +166,7 @@ struct MeshParams {
 	unsigned long long vtx_cap, idx_cap;
 	unsigned int mesh_cap;
 	DynRec *dyn_scratch;   // [gridDim.x][34^3]
+	const uint4 *flood_slots; // [kThreads] the flood columns of each thread, eight 16-bit words: sbuf index | last relevant step << 12, 0xffff = none
 	uint8_t *debug_light;  // optional [n_tasks][39304]
 };
 

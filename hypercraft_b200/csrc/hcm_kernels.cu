@@ -1206,6 +1206,24 @@ __device__ void emit_custom_voxel(const MeshParams &p, Small &S, const uint8_t *
 	}
 }
 
+// The flood columns of each thread depend on nothing but the thread index: they are computed once per context (the
+// divisions by 34, 62 and 28 of slot_column cost ~600 instructions per warp and chunk when done in the mesh kernel).
+__global__ void flood_slots_kernel(uint4 *out) {
+	const int tid = threadIdx.x;
+	u32 v[8] = {0xffffu, 0xffffu, 0xffffu, 0xffffu, 0xffffu, 0xffffu, 0xffffu, 0xffffu};
+	static_assert(kColsPerThread <= 8, "flood slot table holds eight columns per thread");
+	for (int k = 0; k < kColsPerThread; ++k) {
+		int x = 0, z = 0; // domain coords: world x = x - 15
+		bool ok = slot_column(tid, k, x, z);
+		const int dx = x < 14 ? 14 - x : (x > 47 ? x - 47 : 0), dz = z < 14 ? 14 - z : (z > 47 ? z - 47 : 0);
+		ok = ok && dx + dz <= 14; // farther columns can never reach the inner square
+		if (ok)
+			v[k] = (u32)((z + 1) * kSB + (x + 1)) | ((u32)(14 - dx - dz) << 12);
+	}
+	out[tid] = make_uint4(v[0] | (v[1] << 16), v[2] | (v[3] << 16), v[4] | (v[5] << 16), v[6] | (v[7] << 16));
+}
+void launch_flood_slots(uint4 *out, cudaStream_t st) { flood_slots_kernel<<<1, kThreads, 0, st>>>(out); }
+
 // The chunk's totals are known: claim its vertex, index and descriptor ranges.  One thread issues the three atomics back
 // to back and only then looks at the results, so their round trips to the L2 overlap (three lanes with one atomic each
 // measured slower: the divergent paths wait one after the other).
@@ -1284,41 +1302,71 @@ __global__ void __launch_bounds__(kThreads, 1) mesh_kernel(const __grid_constant
 		// box of this task is still in flight (a task without any face pays for a flood it does not need: classify_kernel
 		// leaves next to none of those) --------------------------------------------------------------------------------
 		const bool want_light = p.debug_light != nullptr;
+#ifdef HCM_PHASE_TIMING
+		const long long tq0_ = clock64();
+#endif
 		__syncthreads(); // S.any_torch
+#ifdef HCM_PHASE_TIMING
+		const long long tq1_ = clock64();
+#endif
 		if (tid == 0)
 			S.work_item = wi_next;
 		{
 			u64 *sbuf = reinterpret_cast<u64 *>(region + RG_SBUF);
 			for (int i = tid; i < 2 * kSB * kSB; i += kThreads)
 				sbuf[i] = 0; // both buffers: zero border and interior
+#ifdef HCM_PHASE_TIMING
+			const long long tq2_ = clock64();
+#endif
 			ColInfo ci;
 			ci.X = (u32)p.w.X;
 			ci.g0 = (u32)(((size_t)(ti.cy - 1) * p.w.Z + (size_t)(ti.cz * 32 - 15)) * p.w.X + (size_t)(ti.cx * 32 - 15));
 			u64 P[kColsPerThread], sun0[kColsPerThread]; // passable cells; sunlit cells (the sources of the sunlight flood)
 			const size_t plane_stride = (size_t)p.w.Z * p.w.X;
+			// All loads of a thread's columns are issued before the first one is used (unconditionally, from a safe address for
+			// slots without a column): one memory round trip per thread instead of one per column.
+			u32 gidx[kColsPerThread];
+			const uint4 slots = __ldg(p.flood_slots + tid);
 #pragma unroll
 			for (int k = 0; k < kColsPerThread; ++k) {
-				int x = 0, z = 0; // domain coords: world x = x - 15
-				bool ok = slot_column(tid, k, x, z);
-				const int dx = x < 14 ? 14 - x : (x > 47 ? x - 47 : 0), dz = z < 14 ? 14 - z : (z > 47 ? z - 47 : 0);
-				ok = ok && dx + dz <= 14; // farther columns can never reach the inner square
-				if (ok) {
-					ci.c[k] = ((z + 1) * kSB + (x + 1)) | ((14 - dx - dz) << 16);
-					const u32 gk = ci.g(k);
-					// the three height loads ride in the same memory round trip as the three plane loads
-					u32 sl[3];
-#pragma unroll
-					for (int d = 0; d < 3; ++d) {
-						const int h = p.w.height[gk + d * plane_stride];
-						sl[d] = h >= 32 ? 0u : (h <= 0 ? 0xffffffffu : (0xffffffffu << h)); // sunlit: y >= height, Chunk.hpp:73-76
-					}
-					P[k] = combine3(p.w.pass[gk], p.w.pass[gk + plane_stride], p.w.pass[gk + 2 * plane_stride]);
-					sun0[k] = combine3(sl[0], sl[1], sl[2]);
-				} else {
-					ci.c[k] = -1, P[k] = 0, sun0[k] = 0;
-				}
+				const u32 v = ((k < 2 ? slots.x : (k < 4 ? slots.y : (k < 6 ? slots.z : slots.w))) >> (16 * (k & 1))) & 0xffffu;
+				const bool ok = v != 0xffffu;
+				ci.c[k] = ok ? (int)((v & 0xfffu) | ((v >> 12) << 16)) : -1;
+				gidx[k] = ok ? ci.g(k) : ci.g0;
 			}
+			u32 pw[kColsPerThread][3];
+			int hw[kColsPerThread][3];
+#pragma unroll
+			for (int k = 0; k < kColsPerThread; ++k)
+#pragma unroll
+				for (int d = 0; d < 3; ++d) {
+					pw[k][d] = __ldg(p.w.pass + gidx[k] + d * plane_stride);
+					hw[k][d] = __ldg(p.w.height + gidx[k] + d * plane_stride);
+				}
+#pragma unroll
+			for (int k = 0; k < kColsPerThread; ++k) {
+				u32 sl[3];
+#pragma unroll
+				for (int d = 0; d < 3; ++d) {
+					const int h = hw[k][d];
+					sl[d] = h >= 32 ? 0u : (h <= 0 ? 0xffffffffu : (0xffffffffu << h)); // sunlit: y >= height, Chunk.hpp:73-76
+				}
+				const bool ok = ci.c[k] >= 0;
+				P[k] = ok ? combine3(pw[k][0], pw[k][1], pw[k][2]) : 0ull;
+				sun0[k] = ok ? combine3(sl[0], sl[1], sl[2]) : 0ull;
+			}
+#ifdef HCM_PHASE_TIMING
+			const long long tq3_ = clock64();
+#endif
 			__syncthreads();
+#ifdef HCM_PHASE_TIMING
+			if (tid == 64) {
+				PHASE_COUNT(61, tq1_ - tq0_);        // wait at the set-up barrier (thread 0's flag loads)
+				PHASE_COUNT(62, tq2_ - tq1_);        // zeroing
+				PHASE_COUNT(63, tq3_ - tq2_);        // plane + height loads
+				PHASE_COUNT(60, clock64() - tq3_);   // wait at the barrier after the loads
+			}
+#endif
 			// Step 0 of the sunlight flood reads its sources from the buffer it does not write (its own entry only).  The
 			// word is what the column holds after step 0 anyway, so the double-buffer protocol is not disturbed.
 #pragma unroll

@@ -41,6 +41,7 @@ print(f"  exact Show() candidate pairs per task: {out[26]/n:.0f}")
 print(f"  warp-level merges: {out[20]/n:.1f} masks/task, {out[22]/n:.0f} rows/task, {out[24]/max(out[22],1):.0f} cycles/row, longest single mask {out[33]} cycles")
 print(f"  warp merge: set-up {out[37]/max(out[20],1):.0f} cyc/mask, main loop {out[38]/max(out[39],1):.0f} cyc/iteration, {out[39]/n:.0f} iterations/task")
 print(f"  warp merge: height steps {out[55]/max(out[39],1):.1f} per iteration, record pass {out[56]/max(out[20],1):.0f} cyc/mask")
+print(f"  flood set-up (thread 64): wait for task set-up {out[61]/n:.0f}, zeroing {out[62]/n:.0f}, loads {out[63]/n:.0f}, barrier after loads {out[60]/n:.0f} cycles/task")
 print(f"  tiny-mask warps: {out[36]/n:.2f} per task, {out[35]/max(out[36],1):.0f} cycles each; merge section per-warp mean {out[34]/n/32:.0f} cycles")
 for i, nm in enumerate(names):
     print(f"  {nm:14s} {out[i] / n:9.0f} cyc/task  {100 * out[i] / tot:5.1f}%")
