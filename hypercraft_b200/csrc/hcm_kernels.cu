@@ -954,6 +954,7 @@ __device__ void merge_mask(Small &S, const u32 *F, u64 *keys, u32 *geo, int m, i
 	const long long tms2_ = clock64();
 #endif
 	u32 nqt = 0;
+	__syncwarp(); // pass 2 wrote the geometry words lane by lane; pass 3 reads them quad by quad
 	for (u32 i0 = 0; i0 < nq; i0 += 32) {
 		const u32 i = i0 + lane;
 		const bool valid = i < nq;
