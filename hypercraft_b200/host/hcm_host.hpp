@@ -141,8 +141,8 @@ public:
 	template <typename Sink> void Flush(Sink &&sink) {
 		if (m_tasks.empty())
 			return;
-		if (!m_upload.empty()) {
-			const size_t n = m_upload.size();
+		const size_t n = m_upload.size();
+		if (n) {
 			m_pos.resize(n * 3), m_blocks.resize(n * HCM_CHUNK_VOXELS), m_heights.resize(n * HCM_CHUNK_COLUMNS);
 			for (size_t i = 0; i < n; ++i) {
 				const auto p = m_upload[i]->GetPosition();
@@ -151,14 +151,14 @@ public:
 				for (uint32_t k = 0; k < HCM_CHUNK_COLUMNS; ++k)
 					m_heights[i * HCM_CHUNK_COLUMNS + k] = (int8_t)m_upload[i]->GetSunlightHeight(k);
 			}
-			check(hcm_upload_chunks(m_ctx, (uint32_t)n, m_pos.data(), m_blocks.data(), m_heights.data()));
 		}
 		std::vector<int16_t> tp(m_tasks.size() * 3);
 		for (size_t i = 0; i < m_tasks.size(); ++i)
 			tp[3 * i] = m_tasks[i].x, tp[3 * i + 1] = m_tasks[i].y, tp[3 * i + 2] = m_tasks[i].z;
-		check(hcm_mesh_batch(m_ctx, (uint32_t)m_tasks.size(), tp.data()));
+		// one call: new chunks go up, every task is meshed as soon as the last of its 27 chunks is on the device, finished
+		// meshes come back while later chunks are still uploading (with nothing to upload it is batch + fetch)
 		hcm_batch_view v{};
-		check(hcm_mesh_fetch(m_ctx, &v));
+		check(hcm_upload_and_mesh(m_ctx, (uint32_t)n, m_pos.data(), m_blocks.data(), m_heights.data(), (uint32_t)m_tasks.size(), tp.data(), &v));
 		for (uint32_t t = 0; t < v.n_tasks; ++t) {
 			std::vector<BlockMesh> meshes(v.tasks[t].n_meshes);
 			for (uint32_t k = 0; k < v.tasks[t].n_meshes; ++k) {
