@@ -8,25 +8,35 @@ from __future__ import annotations
 import numpy as np
 
 
-def slab_bounds(positions: np.ndarray, world: int) -> list[tuple[int, int]]:
-    """Per rank [x_lo, x_hi) such that the slabs tile the x-range and hold balanced task counts."""
+def slab_bounds(positions: np.ndarray, world: int, weights=None) -> list[tuple[int, int]]:
+    """Per rank [x_lo, x_hi) such that the slabs tile the x-range and hold balanced task counts -- or, with ``weights``
+    (one per position), balanced total weight: most chunks of a load sphere are all air or all stone and cost next to
+    nothing, so SURVEY 8e asks for a balance by estimated surface chunks."""
     pos = np.asarray(positions, dtype=np.int64).reshape(-1, 3)
     if len(pos) == 0:
         return [(0, 0)] * world
-    xs = np.sort(pos[:, 0])
-    x_min, x_max = int(xs[0]), int(xs[-1]) + 1
+    w = np.ones(len(pos)) if weights is None else np.asarray(weights, dtype=np.float64).reshape(-1)
+    x_min, x_max = int(pos[:, 0].min()), int(pos[:, 0].max()) + 1
+    plane = np.bincount(pos[:, 0] - x_min, weights=w, minlength=x_max - x_min)  # weight of each x-plane
+    before = np.concatenate([[0.0], np.cumsum(plane)])                            # weight left of boundary x_min + i
     cuts = [x_min]
     for r in range(1, world):
-        target = (len(xs) * r) // world
-        c = int(xs[min(target, len(xs) - 1)])
-        cuts.append(max(c, cuts[-1]))
+        i = int(np.argmin(np.abs(before - before[-1] * r / world)))               # the plane boundary nearest to the target
+        cuts.append(max(x_min + i, cuts[-1]))
     cuts.append(x_max)
     return [(cuts[r], cuts[r + 1]) for r in range(world)]
 
 
-def shard_tasks(positions: np.ndarray, world: int, rank: int) -> np.ndarray:
+def surface_weights(positions: np.ndarray, band: int = 3, factor: float = 8.0) -> np.ndarray:
+    """Cost estimate per task for terrain worlds: chunks within ``band`` chunk layers of y = 0 hold the surface and go
+    through the full light + mesh kernel (about ``factor`` times the cost of a chunk that is classified away)."""
+    pos = np.asarray(positions, dtype=np.int64).reshape(-1, 3)
+    return 1.0 + factor * (np.abs(pos[:, 1]) <= band)
+
+
+def shard_tasks(positions: np.ndarray, world: int, rank: int, weights=None) -> np.ndarray:
     pos = np.asarray(positions, dtype=np.int16).reshape(-1, 3)
-    lo, hi = slab_bounds(pos, world)[rank]
+    lo, hi = slab_bounds(pos, world, weights)[rank]
     sel = (pos[:, 0] >= lo) & (pos[:, 0] < hi)
     return pos[sel]
 
