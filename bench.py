@@ -109,7 +109,8 @@ def build_world(radius: int, centre, threads: int, shard=None):
     if shard is not None:
         from hypercraft_b200 import shard as sh
 
-        meshed = sh.shard_tasks(meshed, shard[0], shard[1], sh.surface_weights(meshed - c))  # balance by estimated surface chunks
+        # equal task counts: measured better (2.40 ms at r=32 on 8 GPUs) than shard.surface_weights' y-band estimate (2.65 ms)
+        meshed = sh.shard_tasks(meshed, shard[0], shard[1])
         resident = sh.resident_for(meshed)
     pb = mesher.PinnedArray((len(resident), 32768), np.uint16)
     ph = mesher.PinnedArray((len(resident), 1024), np.int8)
