@@ -441,6 +441,7 @@ struct Small {
 	u32 n_quads, n_cand, cand_overflow;
 	uint8_t order[3][kMasks + 2]; // non-empty masks of the current group: [0] heavy, [1] medium (dynamic warp scheduling), [2] tiny (one thread each)
 	u32 n_order[3], next_mask;
+	u32 rowmask[kMasks + 2]; // bit u: row u of the mask holds a face
 	u32 crow_o[1024], crow_t[1024]; // custom faces per (y,z) row and stream -> exclusive prefix
 	u32 aabb[2][kMaxSplits][6];
 	u32 split_other[2][kMaxSplits];
@@ -997,7 +998,8 @@ __device__ void merge_mask_thread(Small &S, const u32 *F, u64 *keys, u32 *geo, i
 	const u32 *Fm = F + m * kFS;
 	const u32 base = S.fcpre[m] - S.fcpre[g0];
 	u32 nq = 0, nqt = 0, rowslot = base;
-	for (int u = 0; u < 32; ++u) {
+	for (u32 rr = S.rowmask[m]; rr; rr &= rr - 1) { // non-empty rows only: a tiny mask has three of them on average
+		const int u = __ffs(rr) - 1;
 		const u32 Fu = Fm[u];
 		u32 bits = Fu;
 		while (bits) {
@@ -1664,6 +1666,9 @@ __global__ void __launch_bounds__(kThreads, 1) mesh_kernel(const __grid_constant
 						if (!S.fc[m])
 							continue;
 						u32 fw = F[m * kFS + lane];
+						const u32 rows = __ballot_sync(FULL, fw != 0);
+						if (lane == 0)
+							S.rowmask[m] = rows;
 						u32 at = S.fcpre[m] - S.fcpre[g0] + warp_excl_scan(__popc(fw), lane);
 						while (fw) {
 							const u32 v = __ffs(fw) - 1;
