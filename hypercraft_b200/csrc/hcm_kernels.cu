@@ -992,8 +992,14 @@ __device__ void merge_mask(Small &S, const u32 *F, u64 *keys, u32 *geo, int m, i
 // The same scan done by ONE thread, for masks with a handful of faces (4 out of 5 masks of a terrain chunk have at most
 // 16): 32 such masks run side by side in one warp.  Consumed cells are marked in place with a key no face can have.
 constexpr u64 kConsumedKey = ~0ull; // sun field 63 > 60
-constexpr u32 kThreadMergeMax = 12; // faces
-constexpr int kTinyPerWarp = 8;     // tiny masks per warp: fewer lanes per warp = less divergence, and spare warps are plentiful here
+#ifndef HCM_THREAD_MERGE_MAX
+#define HCM_THREAD_MERGE_MAX 12
+#endif
+#ifndef HCM_TINY_PER_WARP
+#define HCM_TINY_PER_WARP 8
+#endif
+constexpr u32 kThreadMergeMax = HCM_THREAD_MERGE_MAX; // faces
+constexpr int kTinyPerWarp = HCM_TINY_PER_WARP;     // tiny masks per warp: fewer lanes per warp = less divergence, and spare warps are plentiful here
 __device__ void merge_mask_thread(Small &S, const u32 *F, u64 *keys, u32 *geo, int m, int g0) {
 	const u32 *Fm = F + m * kFS;
 	const u32 base = S.fcpre[m] - S.fcpre[g0];

@@ -4,7 +4,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle"))
 csrc = os.path.join(ROOT, "hypercraft_b200", "csrc")
-so = os.path.join(csrc, "libhcm_timing.so")
+so = os.environ.get("HCM_TIMING_SO") or os.path.join(csrc, "libhcm_timing.so")
 if "--build" in sys.argv or not os.path.exists(so):
     subprocess.run(["nvcc", "-O3", "-std=c++17", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC,-fvisibility=hidden",
                     "-DHCM_PHASE_TIMING", "-shared", "-o", so, os.path.join(csrc, "hcm_api.cu"), os.path.join(csrc, "hcm_kernels.cu")], check=True)
