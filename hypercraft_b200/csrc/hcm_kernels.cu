@@ -1411,18 +1411,22 @@ __global__ void __launch_bounds__(kThreads, 1) mesh_kernel(const __grid_constant
 				const uint4 *r = reinterpret_cast<const uint4 *>(vox + (yy * kVZ + zz + 1) * kVX);
 				const uint4 q0 = r[0], q1 = r[1], q2 = r[2];
 				const u32 w[12] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w};
-				u32 lo[4] = {0, 0, 0, 0}, hi[4] = {0, 0, 0, 0};
+				// Eight voxels at a time: the four class bits of a voxel are spread to bit 0 of the four bytes of a word
+				// (spread4) and shifted to the voxel's place, so that byte k of the group's word is class k of its 8 voxels --
+				// four instructions per voxel instead of two per voxel AND class; byte permutes assemble the row words.
+				u32 acc[5] = {0, 0, 0, 0, 0};
 #pragma unroll
 				for (int i = 0; i < 34; ++i) { // stored byte i + 3 <-> world x = i - 1 <-> plane bit i
 					const u32 pr = (w[(i + 3) >> 2] >> (8 * ((i + 3) & 3))) & 0xffu;
-					const u32 cls = (u32)S.tab.pflags[pr] >> 2; // bit0 O, bit1 E, bit2 C, bit3 D
+					const u32 cls = ((u32)S.tab.pflags[pr] >> 2) & 15u; // bit0 O, bit1 E, bit2 C, bit3 D
+					acc[i >> 3] += spread4(cls) << (i & 7);
+				}
+				u32 lo[4], hi[4];
 #pragma unroll
-					for (int k = 0; k < 4; ++k) {
-						if (i < 32)
-							lo[k] |= ((cls >> k) & 1u) << i;
-						else
-							hi[k] |= ((cls >> k) & 1u) << (i - 32);
-					}
+				for (int k = 0; k < 4; ++k) {
+					const u32 pick = (u32)(k | ((4 + k) << 4)); // byte k of the first operand, byte k of the second
+					lo[k] = __byte_perm(__byte_perm(acc[0], acc[1], pick), __byte_perm(acc[2], acc[3], pick), 0x5410u);
+					hi[k] = (acc[4] >> (8 * k)) & 0xffu;
 				}
 				Opl[row] = ((u64)hi[0] << 32) | lo[0], Epl[row] = ((u64)hi[1] << 32) | lo[1];
 				Cpl[row] = ((u64)hi[2] << 32) | lo[2], Dpl[row] = ((u64)hi[3] << 32) | lo[3];
