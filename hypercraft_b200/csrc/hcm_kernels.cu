@@ -403,8 +403,14 @@ __global__ void __launch_bounds__(256)
 	if (trivial && !force_all) {
 		task_out[t] = hcm_task_result{0u, 0u};
 	} else {
+		// bit 31 of the work item: some chunk of the 27 emits light (the mesh kernel then runs the torch flood as well)
+		u32 any = 0;
+		for (int dy = -1; dy <= 1; ++dy)
+			for (int dz = -1; dz <= 1; ++dz)
+				for (int dx = -1; dx <= 1; ++dx)
+					any |= cf(dx, dy, dz);
 		const u32 i = atomicAdd(&heads->n_work, 1u);
-		worklist[i] = t;
+		worklist[i] = t | ((any & CF_HAS_TORCH) ? 0x80000000u : 0u);
 	}
 }
 
@@ -447,7 +453,7 @@ struct Small {
 	u32 split_other[2][kMaxSplits];
 	u32 wtmp[2][kWarps + 1];
 	u64 bar;
-	u32 work_item, n_custom, any_dyn, any_torch, Co, Ct, run_o, run_t, Qo, Qt, overflow, moff;
+	u32 work_item, n_custom, any_dyn, Co, Ct, run_o, run_t, Qo, Qt, overflow, moff;
 	u64 voff, ioff;
 };
 constexpr int kSmemBytes = SM_SMALL + (int)sizeof(Small);
@@ -1285,7 +1291,9 @@ __global__ void __launch_bounds__(kThreads, 1) mesh_kernel(const __grid_constant
 		u32 wi_next = 0;
 		if (tid == 0)
 			wi_next = atomicAdd(&p.heads->cursor, 1u);
-		const u32 task = p.worklist[wi];
+		const u32 item = p.worklist[wi]; // task index | torch sources among the 27 chunks << 31 (classify_kernel)
+		const u32 task = item & 0x7fffffffu;
+		const bool any_torch = item >> 31;
 		const TaskIn ti = p.tasks[task];
 
 		// ---- phase 0: halo gather -- one TMA box of the dense property grid ---------------------------------------
@@ -1299,12 +1307,6 @@ __global__ void __launch_bounds__(kThreads, 1) mesh_kernel(const __grid_constant
 			(&S.aabb[0][0][0])[i] = (i % 6) < 3 ? 0xffffffffu : 0u; // dep/AABB.hpp:11
 		if (tid == 0) {
 			S.n_custom = 0, S.any_dyn = 0, S.overflow = 0, S.n_cand = 0, S.cand_overflow = 0;
-			u32 cfo = 0; // torch sources anywhere in the 27 chunks?
-			for (int dy = -1; dy <= 1; ++dy)
-				for (int dz = -1; dz <= 1; ++dz)
-					for (int dx = -1; dx <= 1; ++dx)
-						cfo |= p.w.cflags[((size_t)(ti.cy + dy) * p.w.wz + (ti.cz + dz)) * p.w.wx + (ti.cx + dx)];
-			S.any_torch = (cfo & CF_HAS_TORCH) ? 1u : 0u;
 		}
 		PHASE_MARK(1); // task set-up
 		// ---- light first: the flood reads the y-packed planes in global memory, not the voxel box, so it runs while the TMA
@@ -1314,7 +1316,7 @@ __global__ void __launch_bounds__(kThreads, 1) mesh_kernel(const __grid_constant
 #ifdef HCM_PHASE_TIMING
 		const long long tq0_ = clock64();
 #endif
-		__syncthreads(); // S.any_torch
+		__syncthreads(); // the per-task fields of S are reset, S.work_item has been read by everybody
 #ifdef HCM_PHASE_TIMING
 		const long long tq1_ = clock64();
 #endif
@@ -1384,7 +1386,7 @@ __global__ void __launch_bounds__(kThreads, 1) mesh_kernel(const __grid_constant
 					sbuf[kSB * kSB + ci.idx(k)] = sun0[k];
 			PHASE_MARK(6); // flood setup (plane loads)
 			flood_channel<false>(p, ci, P, sbuf, light, tid);
-			if (S.any_torch && p.w.n_levels > 0) {
+			if (any_torch && p.w.n_levels > 0) {
 				for (int i = tid; i < 2 * kSB * kSB; i += kThreads)
 					sbuf[i] = 0;
 				__syncthreads();
