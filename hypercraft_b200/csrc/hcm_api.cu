@@ -345,7 +345,11 @@ int build_tables(hcm_ctx *c, const hcm_registry *reg, DevTables &t, std::vector<
 			fl |= PF_LIQ_FLOW;
 		t.pflags[i] = fl;
 		t.pmesh[i] = p.custom_mesh;
-		t.pmisc[i] = (uint8_t)((p.liquid_obstacle ? 1 : 0) | (p.transparency == 2 ? 2 : 0) | (p.light_level << 4)); // bit1: GetVerticalLightPass, Block.hpp:70
+		bool one_texture = !dynamic;
+		for (int f = 1; f < 6; ++f)
+			one_texture = one_texture && p.tex[f] == p.tex[0];
+		t.pmisc[i] = (uint8_t)((p.liquid_obstacle ? 1 : 0) | (p.transparency == 2 ? 2 : 0) | (one_texture ? 4 : 0) |
+		                       (p.light_level << 4)); // bit1: GetVerticalLightPass, Block.hpp:70
 		if (p.light_level && std::find(levels.begin(), levels.end(), p.light_level) == levels.end())
 			levels.push_back(p.light_level);
 	}

@@ -74,7 +74,8 @@ struct DevTables {
 	uint8_t ptex[256][8];  // property row -> texture code per face (codes index tex16/texflags; 0 = BlockTexture{} )
 	uint8_t pflags[256];   // PF_*
 	uint8_t pmesh[256];    // custom mesh index + 1, 0 = none
-	uint8_t pmisc[256];    // bit0: liquid obstacle, bit1: vertical light pass (transparency == transparent), bits 4..7: light level
+	uint8_t pmisc[256];    // bit0: liquid obstacle, bit1: vertical light pass (transparency == transparent), bit2: the six face
+	                       // textures are one and the same and the mesh is not dynamic, bits 4..7: light level
 	uint16_t tex16[256];   // code -> BlockTexture::GetData()
 	uint8_t texflags[256]; // code -> HCM_TEX_* | TF_EMPTY
 };

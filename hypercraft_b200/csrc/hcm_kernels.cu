@@ -1478,6 +1478,11 @@ __global__ void __launch_bounds__(kThreads, 1) mesh_kernel(const __grid_constant
 				const int axis = ent >> 16, xa = (ent >> 10) & 63, u = (ent >> 5) & 31, v = ent & 31;
 				const int ax = axis == 0 ? xa - 1 : v, ay = axis == 1 ? xa - 1 : u, az = axis == 2 ? xa - 1 : (axis == 0 ? v : u);
 				const int bx = axis == 0 ? xa : v, by = axis == 1 ? xa : u, bz = axis == 2 ? xa : (axis == 0 ? v : u);
+				// two voxels of the same property whose six textures are one texture (water, leaves, glass ...): Show() sees
+				// a == b on both sides and shows nothing -- most candidate pairs of an ocean or a tree crown end here
+				const u32 pa = vox[vox_index(ax, ay, az)];
+				if (pa == vox[vox_index(bx, by, bz)] && (S.tab.pmisc[pa] & 4u))
+					return;
 				const u32 ta = tex_code(S, vox, dyn, ax, ay, az, axis * 2), tb = tex_code(S, vox, dyn, bx, by, bz, axis * 2 + 1);
 				if (xa != 0 && tex_show(tf, ta, tb))
 					atomicOr(&F[mask_id(axis, xa, 0) * kFS + u], 1u << v);
