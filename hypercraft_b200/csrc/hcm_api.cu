@@ -31,7 +31,7 @@ void launch_classify(const DevWorld &w, const TaskIn *tasks, uint32_t n, uint32_
                      cudaStream_t st);
 cudaError_t mesh_kernel_prepare();
 int mesh_kernel_smem_bytes();
-void launch_mesh(const CUtensorMap &tmap, const MeshParams &p, int grid, cudaStream_t st);
+void launch_mesh(const MeshMaps &maps, const MeshParams &p, int grid, cudaStream_t st);
 } // namespace hcm
 
 using namespace hcm;
@@ -124,7 +124,7 @@ struct hcm_ctx {
 	uint16_t *d_raw = nullptr;
 	int8_t *d_rawh = nullptr;
 	UploadEntry *d_entries = nullptr;
-	CUtensorMap tmap{};
+	MeshMaps maps{}; // TMA descriptors: property grid (halo box), indirect-light-pass planes and sunlight heights (flood inputs)
 
 	std::vector<int32_t> slot_of; // host mirror of DevWorld::slot
 	std::vector<uint8_t> nbr_count; // per cell: resident chunks in its 3x3x3 neighbourhood (27 = a mesh task is possible)
@@ -437,7 +437,7 @@ int launch_batch(hcm_ctx *c) {
 	CU(cudaMemsetAsync(c->d_heads, 0, sizeof(BatchHeads), st));
 	launch_classify(c->w, c->d_tasks, c->batch_n, c->d_worklist, c->d_heads, c->d_task_out, c->force_all, st);
 	CU(cudaEventRecord(c->ev[EV_B1], st));
-	launch_mesh(c->tmap, mesh_params(c, 0), c->grid, st);
+	launch_mesh(c->maps, mesh_params(c, 0), c->grid, st);
 	CU(cudaGetLastError());
 	CU(cudaEventRecord(c->ev[EV_B2], st));
 	c->stats.kernel_launches += 2;
@@ -699,8 +699,20 @@ int hcm_create(const hcm_registry *registry, const hcm_config *cfg, hcm_ctx **ou
 		const cuuint64_t strides[2] = {(cuuint64_t)w.XP, (cuuint64_t)w.XP * w.Z};
 		const cuuint32_t box[3] = {(cuuint32_t)kVX, (cuuint32_t)kVZ, (cuuint32_t)kVY};
 		const cuuint32_t estr[3] = {1, 1, 1};
-		CUresult r = ((PFN_encodeTiled)fn)(&c->tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, w.prop8, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+		CUresult r = ((PFN_encodeTiled)fn)(&c->maps.vox, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, w.prop8, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
 		                                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+		// flood inputs: the 62 x 62 columns of a task's light domain over three chunk layers, widened to 64 columns so that the box
+		// starts on a 16-byte boundary (x = 32 cx - 16); dims (x, z, chunk layer)
+		const cuuint64_t fdims[3] = {(cuuint64_t)w.X, (cuuint64_t)w.Z, (cuuint64_t)w.wy};
+		const cuuint32_t fbox[3] = {(cuuint32_t)kFloodBoxX, (cuuint32_t)kFD, 3u};
+		const cuuint64_t pstr[2] = {(cuuint64_t)w.X * 4, (cuuint64_t)w.X * w.Z * 4};
+		const cuuint64_t hstr[2] = {(cuuint64_t)w.X, (cuuint64_t)w.X * w.Z};
+		if (r == CUDA_SUCCESS)
+			r = ((PFN_encodeTiled)fn)(&c->maps.pass, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, w.pass, fdims, pstr, fbox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+			                          CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+		if (r == CUDA_SUCCESS)
+			r = ((PFN_encodeTiled)fn)(&c->maps.height, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, w.height, fdims, hstr, fbox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+			                          CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
 		if (r != CUDA_SUCCESS) {
 			fail(c, HCM_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
 			return bail(HCM_ERR_CUDA);
@@ -1425,7 +1437,7 @@ int hcm_upload_and_mesh(hcm_ctx *c, uint32_t n_chunks, const int16_t *pos, const
 			const uint32_t t0 = submitted, t1 = ready;
 			CU(cudaMemsetAsync(&c->d_heads->n_work, 0, 2 * sizeof(unsigned int), st)); // n_work and cursor; the allocation heads keep counting
 			launch_classify(c->w, c->d_tasks + t0, t1 - t0, c->d_worklist, c->d_heads, c->d_task_out + t0, 0, st);
-			launch_mesh(c->tmap, mesh_params(c, t0), c->grid, st);
+			launch_mesh(c->maps, mesh_params(c, t0), c->grid, st);
 			CU(cudaGetLastError());
 			CU(cudaMemcpyAsync(c->h_heads_ring + n_sub, c->d_heads, sizeof(BatchHeads), cudaMemcpyDeviceToHost, st));
 			CU(cudaEventRecord(c->sub_events[n_sub], st));

@@ -51,6 +51,16 @@ constexpr int kOuterSlots = (2688 + kThreads - 1) / kThreads; // outer columns p
 constexpr int kColsPerThread = kInnerSlots + kOuterSlots;
 constexpr int kInner = 34;              // columns x,z in [-1,32] carry the result
 constexpr int kInnerCols = kInner * kInner;
+// The flood's inputs (pass words, sunlight heights) of a task arrive as two TMA boxes of 64 x 62 columns x 3 chunk layers:
+// box column 0 is world x = 32 cx - 16 (16-byte aligned for both element sizes), domain column x sits at box column x + 1.
+constexpr int kFloodBoxX = 64;
+constexpr int kFloodBoxCols = kFloodBoxX * kFD;              // 3968 columns per chunk layer
+constexpr int kFloodPassBytes = kFloodBoxCols * 3 * 4;       // 47616
+constexpr int kFloodHeightBytes = kFloodBoxCols * 3;         // 11904
+
+struct MeshMaps {
+	CUtensorMap vox, pass, height;
+};
 
 constexpr uint32_t kQuadsPerMesh = HCM_MESH_MAX_VERTICES / 4; // 16383 quads fill a BlockMesh (BlockMeshAlgo.hpp:397-403)
 constexpr int kMaxSplits = 40;                                 // >= ceil(622592 / 16383) meshes per stream

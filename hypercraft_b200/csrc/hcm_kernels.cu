@@ -426,6 +426,10 @@ constexpr int SM_CPLANE = SM_F + kMasks * kFS * 4;
 constexpr int SM_REGION = SM_CPLANE + kInnerCols * 8; // 132656
 constexpr int kRegionBytes = kGroupCap * 12;          // 73728
 constexpr int SM_SMALL = SM_REGION + kRegionBytes;    // 206384
+// flood inputs are staged by TMA over the light volume and the head of F: neither is written before the flood has read them
+constexpr int SM_FPASS = SM_LIGHT, SM_FHEIGHT = SM_FPASS + kFloodPassBytes;
+static_assert(SM_FPASS % 128 == 0 && SM_FHEIGHT % 128 == 0, "TMA destinations");
+static_assert(SM_FHEIGHT + kFloodHeightBytes <= SM_REGION, "flood input staging must end before the phase region (the flood's own buffers)");
 
 // region views
 constexpr int RG_O = 0, RG_E = kInnerCols * 8, RG_D = 2 * kInnerCols * 8; // planes phase
@@ -452,7 +456,7 @@ struct Small {
 	u32 aabb[2][kMaxSplits][6];
 	u32 split_other[2][kMaxSplits];
 	u32 wtmp[2][kWarps + 1];
-	u64 bar;
+	u64 bar, bar_flood;
 	u32 work_item, n_custom, any_dyn, Co, Ct, run_o, run_t, Qo, Qt, overflow, moff;
 	u64 voff, ioff;
 };
@@ -1255,7 +1259,7 @@ __device__ __forceinline__ void claim_output(const MeshParams &p, Small &S, int 
 	}
 }
 
-__global__ void __launch_bounds__(kThreads, 1) mesh_kernel(const __grid_constant__ CUtensorMap tmap, const MeshParams p) {
+__global__ void __launch_bounds__(kThreads, 1) mesh_kernel(const __grid_constant__ MeshMaps maps, const MeshParams p) {
 	extern __shared__ __align__(128) uint8_t smem[];
 	uint8_t *vox = smem + SM_VOX;
 	uint8_t *light = smem + SM_LIGHT;
@@ -1268,8 +1272,10 @@ __global__ void __launch_bounds__(kThreads, 1) mesh_kernel(const __grid_constant
 
 	for (int i = tid; i < (int)(sizeof(DevTables) / 4); i += kThreads)
 		reinterpret_cast<u32 *>(&S.tab)[i] = reinterpret_cast<const u32 *>(p.tables)[i];
-	if (tid == 0)
+	if (tid == 0) {
 		mbar_init(&S.bar, 1);
+		mbar_init(&S.bar_flood, 1);
+	}
 	__syncthreads();
 	u32 phase = 0;
 #ifdef HCM_PHASE_TIMING
@@ -1297,12 +1303,16 @@ __global__ void __launch_bounds__(kThreads, 1) mesh_kernel(const __grid_constant
 		const TaskIn ti = p.tasks[task];
 
 		// ---- phase 0: halo gather -- one TMA box of the dense property grid ---------------------------------------
+		// plus the flood's inputs: two boxes (pass words, sunlight heights) of the 62 x 62 columns x 3 chunk layers around the
+		// task, parked over the light volume / F until the flood's set-up has read them (the flood runs before the box is used)
 		if (tid == 0) {
+			asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // the previous task's generic writes to these bytes come first
+			mbar_expect_tx(&S.bar_flood, kFloodPassBytes + kFloodHeightBytes);
+			tma_load_3d(smem + SM_FPASS, &maps.pass, ti.cx * 32 - 16, ti.cz * 32 - 15, ti.cy - 1, &S.bar_flood);
+			tma_load_3d(smem + SM_FHEIGHT, &maps.height, ti.cx * 32 - 16, ti.cz * 32 - 15, ti.cy - 1, &S.bar_flood);
 			mbar_expect_tx(&S.bar, kVoxBytes);
-			tma_load_3d(vox, &tmap, ti.cx * 32, ti.cz * 32 - 2, ti.cy * 32 - 1, &S.bar); // stored column = x + kXMargin
+			tma_load_3d(vox, &maps.vox, ti.cx * 32, ti.cz * 32 - 2, ti.cy * 32 - 1, &S.bar); // stored column = x + kXMargin
 		}
-		for (int i = tid; i < 66 * kFS; i += kThreads)
-			F[i] = 0; // axis-0 masks are filled with atomicOr; the others are overwritten
 		for (int i = tid; i < 2 * kMaxSplits * 6; i += kThreads)
 			(&S.aabb[0][0][0])[i] = (i % 6) < 3 ? 0xffffffffu : 0u; // dep/AABB.hpp:11
 		if (tid == 0) {
@@ -1333,26 +1343,29 @@ __global__ void __launch_bounds__(kThreads, 1) mesh_kernel(const __grid_constant
 			ci.X = (u32)p.w.X;
 			ci.g0 = (u32)(((size_t)(ti.cy - 1) * p.w.Z + (size_t)(ti.cz * 32 - 15)) * p.w.X + (size_t)(ti.cx * 32 - 15));
 			u64 P[kColsPerThread], sun0[kColsPerThread]; // passable cells; sunlit cells (the sources of the sunlight flood)
-			const size_t plane_stride = (size_t)p.w.Z * p.w.X;
-			// All loads of a thread's columns are issued before the first one is used (unconditionally, from a safe address for
-			// slots without a column): one memory round trip per thread instead of one per column.
-			u32 gidx[kColsPerThread];
+			// The columns' pass words and heights were fetched by the two TMA boxes issued with the halo box; slots without a
+			// column read box entry 0.
 			const uint4 slots = __ldg(p.flood_slots + tid);
+			u32 bidx[kColsPerThread];
 #pragma unroll
 			for (int k = 0; k < kColsPerThread; ++k) {
 				const u32 v = ((k < 2 ? slots.x : (k < 4 ? slots.y : (k < 6 ? slots.z : slots.w))) >> (16 * (k & 1))) & 0xffffu;
 				const bool ok = v != 0xffffu;
 				ci.c[k] = ok ? (int)((v & 0xfffu) | ((v >> 12) << 16)) : -1;
-				gidx[k] = ok ? ci.g(k) : ci.g0;
+				bidx[k] = ok ? (u32)(ci.idx(k) - kSB) : 0u; // sbuf index (z+1)*64 + (x+1) -> box index z*64 + (x+1)
 			}
+			static_assert(kSB == kFloodBoxX, "the flood buffers and the TMA boxes share their row pitch");
+			const u32 *fpass = reinterpret_cast<const u32 *>(smem + SM_FPASS);
+			const int8_t *fheight = reinterpret_cast<const int8_t *>(smem + SM_FHEIGHT);
+			mbar_wait(&S.bar_flood, phase);
 			u32 pw[kColsPerThread][3];
 			int hw[kColsPerThread][3];
 #pragma unroll
 			for (int k = 0; k < kColsPerThread; ++k)
 #pragma unroll
 				for (int d = 0; d < 3; ++d) {
-					pw[k][d] = __ldg(p.w.pass + gidx[k] + d * plane_stride);
-					hw[k][d] = __ldg(p.w.height + gidx[k] + d * plane_stride);
+					pw[k][d] = fpass[bidx[k] + d * kFloodBoxCols];
+					hw[k][d] = fheight[bidx[k] + d * kFloodBoxCols];
 				}
 #pragma unroll
 			for (int k = 0; k < kColsPerThread; ++k) {
@@ -1403,6 +1416,8 @@ __global__ void __launch_bounds__(kThreads, 1) mesh_kernel(const __grid_constant
 		mbar_wait(&S.bar, phase);
 		phase ^= 1;
 		PHASE_MARK(17); // TMA wait
+		for (int i = tid; i < 66 * kFS; i += kThreads)
+			F[i] = 0; // axis-0 masks are filled with atomicOr; the others are overwritten (the flood inputs were parked here until now)
 
 		// ---- phase 1: class bit planes (bit x+1 of row (y,z)); one lane builds one row from three 16-byte loads -------
 		{
@@ -1936,6 +1951,6 @@ cudaError_t mesh_kernel_prepare() {
 	return cudaFuncSetAttribute(mesh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
 }
 int mesh_kernel_smem_bytes() { return kSmemBytes; }
-void launch_mesh(const CUtensorMap &tmap, const MeshParams &p, int grid, cudaStream_t st) { mesh_kernel<<<grid, kThreads, kSmemBytes, st>>>(tmap, p); }
+void launch_mesh(const MeshMaps &maps, const MeshParams &p, int grid, cudaStream_t st) { mesh_kernel<<<grid, kThreads, kSmemBytes, st>>>(maps, p); }
 
 } // namespace hcm
