@@ -426,10 +426,14 @@ constexpr int SM_CPLANE = SM_F + kMasks * kFS * 4;
 constexpr int SM_REGION = SM_CPLANE + kInnerCols * 8; // 132656
 constexpr int kRegionBytes = kGroupCap * 12;          // 73728
 constexpr int SM_SMALL = SM_REGION + kRegionBytes;    // 206384
-// flood inputs are staged by TMA over the light volume and the head of F: neither is written before the flood has read them
-constexpr int SM_FPASS = SM_LIGHT, SM_FHEIGHT = SM_FPASS + kFloodPassBytes;
-static_assert(SM_FPASS % 128 == 0 && SM_FHEIGHT % 128 == 0, "TMA destinations");
-static_assert(SM_FHEIGHT + kFloodHeightBytes <= SM_REGION, "flood input staging must end before the phase region (the flood's own buffers)");
+// The flood's inputs are staged by TMA in the phase region, which is idle from the end of a task's quad emission to the next
+// task's plane phase: the boxes of task k+1 are fetched while task k emits its custom faces and descriptors.  The sunlight
+// flood's own double buffer lies over the light volume, F and the custom-face plane (all written after the flood); the rarer
+// torch flood, which must not touch the finished sunlight values, takes the phase region once the staged inputs are in registers.
+constexpr int SM_FPASS = (SM_REGION + 127) / 128 * 128, SM_FHEIGHT = SM_FPASS + kFloodPassBytes;
+static_assert(SM_FHEIGHT % 128 == 0, "TMA destinations");
+static_assert(SM_FHEIGHT + kFloodHeightBytes <= SM_REGION + kRegionBytes, "flood input staging must fit the phase region");
+constexpr int SM_SUNBUF = SM_LIGHT;
 
 // region views
 constexpr int RG_O = 0, RG_E = kInnerCols * 8, RG_D = 2 * kInnerCols * 8; // planes phase
@@ -457,9 +461,12 @@ struct Small {
 	u32 split_other[2][kMaxSplits];
 	u32 wtmp[2][kWarps + 1];
 	u64 bar, bar_flood;
-	u32 work_item, n_custom, any_dyn, Co, Ct, run_o, run_t, Qo, Qt, overflow, moff;
+	TaskIn next_task; // work item S.work_item: coordinates and worklist word, published by thread 0 a task ahead
+	u32 next_item;
+	u32 work_item, work_next, n_custom, any_dyn, Co, Ct, run_o, run_t, Qo, Qt, overflow, moff;
 	u64 voff, ioff;
 };
+static_assert(SM_SUNBUF % 8 == 0 && SM_SUNBUF + 2 * kSB * kSB * 8 <= SM_REGION, "sunlight flood buffers end before the phase region");
 constexpr int kSmemBytes = SM_SMALL + (int)sizeof(Small);
 static_assert(kSmemBytes <= 232448, "shared memory budget (227 KB per CTA)");
 
@@ -1284,32 +1291,52 @@ __global__ void __launch_bounds__(kThreads, 1) mesh_kernel(const __grid_constant
 	DynRec *dyn = p.dyn_scratch + (size_t)blockIdx.x * kLightBytes;
 	const u32 n_work = p.heads->n_work;
 
-	if (tid == 0)
-		S.work_item = atomicAdd(&p.heads->cursor, 1u);
+	// the two TMA boxes with the flood inputs of a task (thread 0)
+	auto fetch_flood_inputs = [&](const TaskIn &t) {
+		asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // generic accesses to these bytes come first
+		mbar_expect_tx(&S.bar_flood, kFloodPassBytes + kFloodHeightBytes);
+		tma_load_3d(smem + SM_FPASS, &maps.pass, t.cx * 32 - 16, t.cz * 32 - 15, t.cy - 1, &S.bar_flood);
+		tma_load_3d(smem + SM_FHEIGHT, &maps.height, t.cx * 32 - 16, t.cz * 32 - 15, t.cy - 1, &S.bar_flood);
+	};
+	// The work cursor runs two items ahead: S.work_item is the current task, S.work_next the one after it, whose coordinates
+	// thread 0 loads during the current task so that it can fetch that task's flood inputs before the current one has ended.
+	if (tid == 0) {
+		const u32 w0 = atomicAdd(&p.heads->cursor, 1u);
+		S.work_item = w0, S.work_next = atomicAdd(&p.heads->cursor, 1u);
+		if (w0 < n_work) {
+			S.next_item = p.worklist[w0];
+			S.next_task = p.tasks[S.next_item & 0x7fffffffu];
+			fetch_flood_inputs(S.next_task);
+		}
+	}
 	for (;;) {
 		__syncthreads(); // previous task fully retired (smem reuse); S.work_item holds this CTA's next work item
 		const u32 wi = S.work_item;
 		PHASE_MARK(0); // task fetch
 		if (wi >= n_work)
 			break;
-		// thread 0 claims the work item after this one now; the atomic's round trip hides behind the task set-up, and the
-		// result is published behind the next barrier, when everybody has read the current one
-		u32 wi_next = 0;
-		if (tid == 0)
-			wi_next = atomicAdd(&p.heads->cursor, 1u);
-		const u32 item = p.worklist[wi]; // task index | torch sources among the 27 chunks << 31 (classify_kernel)
+		// thread 0 claims the work item two after this one now and loads the next one's coordinates; the round trips hide behind
+		// the task, and the cursor values are published behind the next barrier, when everybody has read the current one
+		u32 wi_next = 0, wi_next2 = 0, item_next = 0;
+		TaskIn ti_next{};
+		if (tid == 0) {
+			wi_next = S.work_next;
+			wi_next2 = atomicAdd(&p.heads->cursor, 1u);
+			if (wi_next < n_work) {
+				item_next = p.worklist[wi_next];
+				ti_next = p.tasks[item_next & 0x7fffffffu];
+			}
+		}
+		const u32 item = S.next_item; // task index | torch sources among the 27 chunks << 31 (classify_kernel)
 		const u32 task = item & 0x7fffffffu;
 		const bool any_torch = item >> 31;
-		const TaskIn ti = p.tasks[task];
+		const TaskIn ti = S.next_task;
 
 		// ---- phase 0: halo gather -- one TMA box of the dense property grid ---------------------------------------
-		// plus the flood's inputs: two boxes (pass words, sunlight heights) of the 62 x 62 columns x 3 chunk layers around the
-		// task, parked over the light volume / F until the flood's set-up has read them (the flood runs before the box is used)
+		// (the flood's inputs -- pass words and sunlight heights of the 62 x 62 columns x 3 chunk layers around the task -- are
+		// two more boxes, already on their way: fetch_flood_inputs)
 		if (tid == 0) {
-			asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // the previous task's generic writes to these bytes come first
-			mbar_expect_tx(&S.bar_flood, kFloodPassBytes + kFloodHeightBytes);
-			tma_load_3d(smem + SM_FPASS, &maps.pass, ti.cx * 32 - 16, ti.cz * 32 - 15, ti.cy - 1, &S.bar_flood);
-			tma_load_3d(smem + SM_FHEIGHT, &maps.height, ti.cx * 32 - 16, ti.cz * 32 - 15, ti.cy - 1, &S.bar_flood);
+			asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 			mbar_expect_tx(&S.bar, kVoxBytes);
 			tma_load_3d(vox, &maps.vox, ti.cx * 32, ti.cz * 32 - 2, ti.cy * 32 - 1, &S.bar); // stored column = x + kXMargin
 		}
@@ -1331,9 +1358,9 @@ __global__ void __launch_bounds__(kThreads, 1) mesh_kernel(const __grid_constant
 		const long long tq1_ = clock64();
 #endif
 		if (tid == 0)
-			S.work_item = wi_next;
+			S.work_item = wi_next, S.work_next = wi_next2, S.next_task = ti_next, S.next_item = item_next; // loaded a task set-up ago: no long-lived registers
 		{
-			u64 *sbuf = reinterpret_cast<u64 *>(region + RG_SBUF);
+			u64 *sbuf = reinterpret_cast<u64 *>(smem + SM_SUNBUF);
 			for (int i = tid; i < 2 * kSB * kSB; i += kThreads)
 				sbuf[i] = 0; // both buffers: zero border and interior
 #ifdef HCM_PHASE_TIMING
@@ -1400,10 +1427,11 @@ __global__ void __launch_bounds__(kThreads, 1) mesh_kernel(const __grid_constant
 			PHASE_MARK(6); // flood setup (plane loads)
 			flood_channel<false>(p, ci, P, sbuf, light, tid);
 			if (any_torch && p.w.n_levels > 0) {
+				u64 *tbuf = reinterpret_cast<u64 *>(region + RG_SBUF); // the staged inputs are in registers by now
 				for (int i = tid; i < 2 * kSB * kSB; i += kThreads)
-					sbuf[i] = 0;
+					tbuf[i] = 0;
 				__syncthreads();
-				flood_channel<true>(p, ci, P, sbuf, light, tid);
+				flood_channel<true>(p, ci, P, tbuf, light, tid);
 			}
 			if (want_light) // canonical order (x fastest, then z, then y) for hcm_debug_light
 				for (int i = tid; i < kLightBytes; i += kThreads) {
@@ -1613,8 +1641,11 @@ __global__ void __launch_bounds__(kThreads, 1) mesh_kernel(const __grid_constant
 		const u32 n_faces = S.fcpre[kMasks];
 		const u32 n_custom = S.n_custom;
 		if (n_faces == 0 && n_custom == 0 && !want_light) {
-			if (tid == 0)
+			if (tid == 0) {
 				p.task_out[task] = hcm_task_result{0u, 0u};
+				if (S.work_item < n_work)
+					fetch_flood_inputs(S.next_task); // the phase region was last read before the barrier above
+			}
 			continue;
 		}
 
@@ -1834,6 +1865,8 @@ __global__ void __launch_bounds__(kThreads, 1) mesh_kernel(const __grid_constant
 			}
 		}
 
+		if (tid == 0 && S.work_item < n_work)
+			fetch_flood_inputs(S.next_task); // the phase region is idle from here on (every pass ends in a barrier)
 		PHASE_MARK(14); // emit
 		// ---- custom / dynamic faces: warp per (y,z) row, lane per voxel --------------------------------------------------
 		if (n_custom && !S.overflow) {
