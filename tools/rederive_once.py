@@ -9,6 +9,7 @@ meshed, resident = worldgen.load_radius_positions(R)
 ref = hcoracle.RefWorld(); ref.generate(resident)
 b, h = ref.get_chunks(resident)
 ext = 2 * R + 3
+if os.environ.get("HCM_SO"): M.LIB_PATH = os.environ["HCM_SO"]
 m = M.Mesher(origin=(-R - 1,) * 3, extent=(ext,) * 3, max_chunks=len(resident), max_tasks=len(meshed))
 m.upload(resident, b, h); m.sync()
 for _ in range(3):
