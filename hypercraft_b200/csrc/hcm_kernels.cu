@@ -700,7 +700,7 @@ struct ColInfo {
 };
 
 __device__ __forceinline__ u64 combine3(u32 lo, u32 mid, u32 hi) { // chunk words y-1, y, y+1 -> bits of y in [-15,46]
-	return (u64)(lo >> 17) | ((u64)mid << 15) | ((u64)(hi & 0x7fffu) << 47);
+	return (u64)__funnelshift_r(lo, mid, 17) | ((u64)__funnelshift_r(mid, hi & 0x7fffu, 17) << 32); // two funnel shifts and a mask
 }
 
 // slot k of thread tid -> domain column (x,z) in [0,62)^2, or false
@@ -1400,7 +1400,7 @@ __global__ void __launch_bounds__(kThreads, 1) mesh_kernel(const __grid_constant
 #pragma unroll
 				for (int d = 0; d < 3; ++d) {
 					const int h = hw[k][d];
-					sl[d] = h >= 32 ? 0u : (h <= 0 ? 0xffffffffu : (0xffffffffu << h)); // sunlit: y >= height, Chunk.hpp:73-76
+					sl[d] = __funnelshift_lc(0u, 0xffffffffu, (u32)max(h, 0)); // sunlit: y >= height (all for h <= 0, none for h >= 32), Chunk.hpp:73-76
 				}
 				const bool ok = ci.c[k] >= 0;
 				P[k] = ok ? combine3(pw[k][0], pw[k][1], pw[k][2]) : 0ull;
