@@ -110,7 +110,9 @@ struct hcm_ctx {
 	std::vector<hcm_sunlight_change> edit_sunlight;
 	std::vector<int16_t> edit_remesh;
 	bool use_batch_copy = true;
-	uint32_t upload_block = 2048, min_sub_batch = 512; // pipeline granularity (env HCM_UPLOAD_BLOCK, HCM_MIN_SUB_BATCH: test knobs)
+	// pipeline granularity (env HCM_UPLOAD_BLOCK, HCM_MIN_SUB_BATCH: test knobs): chunks per pipeline stage (2048 = 128 MB of Block
+	// data); ready sets smaller than min_sub_batch wait for the next upload block
+	uint32_t upload_block = 2048, min_sub_batch = 512;
 	std::unique_ptr<WorkerPool> pool;
 	uint32_t host_threads = 0; // scan threads of hcm_upload_chunks (env HCM_HOST_THREADS; 0 = hardware_concurrency - 1, at most 15)
 	DevWorld w{};
@@ -226,7 +228,6 @@ __attribute__((target("avx2"))) bool chunk_is_uniform_avx2(const uint16_t *b) {
 const bool g_have_avx2 = __builtin_cpu_supports("avx2");
 inline bool chunk_is_uniform(const uint16_t *b) { return g_have_avx2 ? chunk_is_uniform_avx2(b) : chunk_is_uniform_generic(b); }
 
-constexpr uint32_t kUploadBlock = 2048; // default chunks per pipeline stage (128 MB of Block data); hcm_ctx::upload_block
 constexpr uint32_t kScanGrain = 32;     // chunks per work item of the scan threads
 
 // a chunk became resident (+1) or was removed (-1): update the 27 cells that see it as a neighbour
@@ -1282,7 +1283,6 @@ int hcm_mesh_fetch(hcm_ctx *c, hcm_batch_view *out) {
 // The three stages of a world (re)load overlap: while the copy engine moves upload block b+1 to the device, the mesh
 // kernel works on the tasks whose 27 chunks arrived with blocks <= b, and the second copy engine returns the meshes of
 // earlier sub-batches.  Same kernels, same arenas (the allocation heads simply keep counting across sub-batches).
-constexpr uint32_t kMinSubBatch = 512; // default hcm_ctx::min_sub_batch: smaller ready sets wait for the next upload block
 
 int hcm_upload_and_mesh(hcm_ctx *c, uint32_t n_chunks, const int16_t *pos, const uint16_t *blocks, const int8_t *heights, uint32_t n_tasks,
                         const int16_t *task_pos, hcm_batch_view *out) {
