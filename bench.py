@@ -97,7 +97,7 @@ class ClockSampler:
 
 
 def build_world(radius: int, centre, threads: int, shard=None):
-    """(meshed positions, resident positions, pinned blocks, pinned heights, data label, RefWorld or None).
+    """(meshed positions, resident positions, pinned blocks, pinned heights, data label, CPU arm: RefWorld or PortArm).
     shard = (world, rank): only this rank's x-slab of the task list and its one-chunk dilation (hypercraft_b200/shard.py)."""
     import hcoracle
     from hypercraft_b200 import mesher, worldgen
@@ -115,7 +115,7 @@ def build_world(radius: int, centre, threads: int, shard=None):
     pb = mesher.PinnedArray((len(resident), 32768), np.uint16)
     ph = mesher.PinnedArray((len(resident), 1024), np.int8)
     ref = None
-    if hcoracle.have_ref():
+    if use_reference_build():
         ref = hcoracle.RefWorld()
         ref.generate(resident, seed=SEED, threads=threads)
         ref.get_chunks(resident, pb.array, ph.array)
@@ -123,6 +123,7 @@ def build_world(radius: int, centre, threads: int, shard=None):
     else:
         for i, p in enumerate(resident):
             pb.array[i], ph.array[i] = worldgen.synth_terrain_chunk(SEED, p)
+        ref = PortArm({tuple(int(c) for c in p): (pb.array[i], ph.array[i]) for i, p in enumerate(resident)})
         label = "synthetic: repo height-field terrain (oracle/_ref terrain generator not available)"
     return meshed, resident, pb, ph, label, ref
 
@@ -133,30 +134,66 @@ def workload_name(radius: int, strong: bool = False) -> str:
     return f"full load-radius remesh r={radius} (misc/load_radius.cpp; kWorldMaxLoadRadius) per GPU"
 
 
+class PortArm:
+    """The CPU arm when oracle/_ref is absent: this repo's restatement (oracle/hc_oracle.cpp, kind "port") behind the two
+    calls bench.py makes on a RefWorld -- mesh_batch and mesh -- over chunks held in a dict."""
+    kind = "port"
+    what = "oracle/hc_oracle.cpp (CPU restatement of ChunkTaskRunner<kMesh>::Run), one call stream per thread"
+
+    def __init__(self, chunks: dict):
+        import hcoracle
+        from hypercraft_b200 import registry
+
+        self.port = hcoracle.PortOracle(registry.load().blob)
+        self.chunks = chunks
+
+    def mesh_batch(self, positions, threads=1, per_chunk=False):
+        st, per, _ = self.port.mesh_batch(self.chunks, positions, threads=threads)
+        return st, (per if per_chunk else None)
+
+    def mesh(self, pos):
+        return self.port.mesh(self.chunks, tuple(int(c) for c in pos))
+
+
+def use_reference_build() -> bool:
+    """oracle/_ref when it was compiled (it travels to the GPU box); HCM_BENCH_FORCE_PORT=1 selects the port (test knob)."""
+    import hcoracle
+
+    return hcoracle.have_ref() and not os.environ.get("HCM_BENCH_FORCE_PORT")
+
+
 def run_reference(args, rank, world):
-    """The reference's own CPU implementation of the path (unmodified ChunkTaskRunner<kMesh>::Run, all host threads)."""
+    """The reference's own CPU implementation of the path (unmodified ChunkTaskRunner<kMesh>::Run from oracle/_ref, all host
+    threads); the oracle port (cpu_baseline.kind "port") where oracle/_ref was not built."""
     if rank != 0:
         return
     import hcoracle
     from hypercraft_b200 import worldgen
 
-    if not hcoracle.have_ref():
-        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libhcref.so not built (needs /root/reference at build time)"}))
-        return
     threads = os.cpu_count() or 1
     radius = args.radius
     meshed, resident = worldgen.load_radius_positions(radius)
-    # bounded sample: a contiguous-in-list stride of the task list, neighbours generated on demand
-    ref = hcoracle.RefWorld()
+    if use_reference_build():
+        ref, kind, data = hcoracle.RefWorld(), "reference", f"synthetic: reference DefaultTerrain(seed {SEED})"
+
+        def provide(need):  # neighbours generated on demand
+            ref.generate(need, seed=SEED, threads=threads)
+    else:  # the reference did not compile here: its restatement, on the terrain the b200 arm falls back to as well
+        ref, kind, data = PortArm({}), "port", "synthetic: repo height-field terrain (oracle/_ref terrain generator not available)"
+
+        def provide(need):
+            for q in need:
+                key = tuple(int(c) for c in q)
+                if key not in ref.chunks:
+                    ref.chunks[key] = worldgen.synth_terrain_chunk(SEED, q)
+    # bounded sample: a stride of the task list
     probe = meshed[:: max(1, len(meshed) // 256)][:256]
-    need = np.unique(np.concatenate([worldgen.neighbourhood(p) for p in probe]), axis=0)
-    ref.generate(need, seed=SEED, threads=threads)
+    provide(np.unique(np.concatenate([worldgen.neighbourhood(p) for p in probe]), axis=0))
     st, _ = ref.mesh_batch(probe, threads=threads)
     rate = st["chunks"] / max(st["seconds"], 1e-6)
     per_step = int(min(len(meshed), max(256, rate * args.cpu_seconds / max(1, args.steps + args.warmup) * 2)))
     sample = meshed[:: max(1, len(meshed) // per_step)][:per_step]
-    need = np.unique(np.concatenate([worldgen.neighbourhood(p) for p in sample]), axis=0)
-    ref.generate(need, seed=SEED, threads=threads)
+    provide(np.unique(np.concatenate([worldgen.neighbourhood(p) for p in sample]), axis=0))
     for _ in range(args.warmup):
         ref.mesh_batch(sample, threads=threads)
     secs, quads = 0.0, 0
@@ -169,11 +206,11 @@ def run_reference(args, rank, world):
     sample_txt = f"{len(sample)} of the {len(meshed)} chunks of the r={radius} load sphere (every {max(1, len(meshed) // per_step)}th), per step"
     out = {"impl": "reference", "metric": "chunks meshed/sec", "value": value, "unit": "chunks/s", "n_gpus": args.gpus, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/u16 integer",
-           "data": f"synthetic: reference DefaultTerrain(seed {SEED})",
+           "data": data,
            "config": {"workload": workload_name(radius), "radius": radius, "chunks_per_step": len(sample),
                       "note": "each step meshes a bounded sample of the workload's task list (cpu_baseline.sample)"},
            "quads_per_s": quads / (ms / 1e3),
-           "cpu_baseline": {"value": value, "unit": "chunks/s", "cores": threads, "kind": "reference", "sample": sample_txt},
+           "cpu_baseline": {"value": value, "unit": "chunks/s", "cores": threads, "kind": kind, "sample": sample_txt},
            "e2e": {"value": value, "unit": "chunks/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out))
 
@@ -299,10 +336,10 @@ def main():
         stride = max(1, len(meshed) // n_s)
         idx = np.arange(0, len(meshed), stride)[:n_s]
         st, per = ref.mesh_batch(meshed[idx], threads=cpu_threads, per_chunk=True)
-        cpu_baseline = {"value": st["chunks"] / st["seconds"], "unit": "chunks/s", "cores": cpu_threads, "kind": "reference",
+        cpu_baseline = {"value": st["chunks"] / st["seconds"], "unit": "chunks/s", "cores": cpu_threads, "kind": getattr(ref, "kind", "reference"),
                         "quads_per_s": st["vertices"] / 4 / st["seconds"],
-                        "sample": f"{len(idx)} of {len(meshed)} chunks (every {stride}th of the r={radius} task list), unmodified "
-                                  f"ChunkTaskRunner<kMesh>::Run, one runner per thread"}
+                        "sample": f"{len(idx)} of {len(meshed)} chunks (every {stride}th of the r={radius} task list), "
+                                  + getattr(ref, "what", "unmodified ChunkTaskRunner<kMesh>::Run, one runner per thread")}
         # parity: mesh/vertex/index counts of every sampled chunk + full bytes of the heaviest ones against the reference
         got_m = res.tasks["n_meshes"][idx].astype(np.uint64)
         first = res.tasks["first_mesh"][idx]

@@ -217,6 +217,39 @@ class PortOracle:
         self.L.hco_light34(self.o, bp, hp, _ptr(out))
         return out
 
+    def mesh_batch(self, chunks: dict, positions, threads: int = 1, keep: bool = False):
+        """Mesh many chunks on `threads` host threads (hco_mesh holds no state between calls and ctypes releases the GIL).
+        -> ({"chunks", "seconds", "vertices"}, per-chunk [n_meshes, vertices, indices] u64, serialised buffers or None).
+        The timed region holds the mesher calls only, like RefWorld.mesh_batch."""
+        import time
+        from concurrent.futures import ThreadPoolExecutor
+
+        positions = [tuple(int(c) for c in p) for p in positions]
+        args = [self._arrays(chunks, p) for p in positions]
+        per = np.zeros((len(positions), 3), dtype=np.uint64)
+        bufs = [None] * len(positions)
+
+        def work(first):
+            buf = np.zeros(1 << 22, dtype=np.uint8)
+            for i in range(first, len(positions), threads):  # interleaved: heavy chunks are neighbours in the task list
+                bp, hp, _ = args[i]
+                n = self.L.hco_mesh(self.o, bp, hp, _ptr(buf), ctypes.c_uint64(buf.size))
+                if n > buf.size:
+                    buf = np.zeros(int(n), dtype=np.uint8)
+                    self.L.hco_mesh(self.o, bp, hp, _ptr(buf), ctypes.c_uint64(buf.size))
+                k = int(buf[:4].view(np.uint32)[0])
+                hdr = buf[4:4 + 36 * k].view(np.uint32).reshape(k, 9)
+                per[i] = (k, int(hdr[:, 7].sum()), int(hdr[:, 8].sum()))
+                if keep:
+                    bufs[i] = buf[:n].copy()
+
+        threads = max(1, min(threads, len(positions)))
+        t0 = time.perf_counter()
+        with ThreadPoolExecutor(threads) as ex:
+            list(ex.map(work, range(threads)))
+        secs = time.perf_counter() - t0
+        return {"chunks": len(positions), "seconds": secs, "vertices": int(per[:, 1].sum())}, per, (bufs if keep else None)
+
     def dynamic_mesh_eval(self, block: int, neighbours: np.ndarray):
         nb = np.ascontiguousarray(neighbours, dtype=np.uint16)
         faces = np.zeros(16 * 24, dtype=np.uint8)

@@ -207,3 +207,40 @@ def test_apply_block_edits_chain():
     # the top chunk has nothing above it in the map: its chain cannot start (Pop needs the chunk above)
     n, sun, remesh = edits.apply_block_edits(chunks, [((0, 2, 0), idx(3), 1)], vpass)
     assert n == 1 and not sun and (0, 2, 0) in remesh
+
+
+@pytest.mark.parametrize("force_port", [False, True])
+def test_bench_reference_arm_prints_the_contract_line(force_port):
+    """`bench.py --impl reference` on a small sphere: oracle/_ref when it is built, the oracle port otherwise
+    (HCM_BENCH_FORCE_PORT selects the port to cover that leg where _ref exists).  Needs no GPU."""
+    import json
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ)
+    env.pop("HCM_BENCH_FORCE_PORT", None)
+    if force_port:
+        env["HCM_BENCH_FORCE_PORT"] = "1"
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--radius", "3", "--steps", "1", "--warmup", "0",
+                          "--cpu-seconds", "1"], env=env, capture_output=True, text=True, timeout=300, check=True).stdout
+    line = json.loads(out.strip().splitlines()[-1])
+    have_ref = os.path.exists(os.path.join(root, "oracle", "_ref", "libhcref.so"))
+    assert line["impl"] == "reference" and line["metric"] == "chunks meshed/sec" and line["unit"] == "chunks/s"
+    assert line["cpu_baseline"]["kind"] == ("reference" if have_ref and not force_port else "port")
+    assert line["value"] > 0 and line["cpu_baseline"]["value"] == line["value"] == line["e2e"]["value"]
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+    assert line["config"]["chunks_per_step"] == 123  # the whole r=3 sphere (misc/load_radius.cpp counts)
+
+
+def test_port_oracle_batch_equals_single_calls(port):
+    """PortOracle.mesh_batch (bench.py's "port" CPU arm) returns what one mesh() call per chunk returns."""
+    from hypercraft_b200 import worldgen
+
+    meshed, resident = worldgen.load_radius_positions(1)
+    chunks = {tuple(int(c) for c in p): worldgen.synth_terrain_chunk(7, p) for p in resident}
+    st, per, bufs = port.mesh_batch(chunks, meshed, threads=3, keep=True)
+    assert st["chunks"] == len(meshed) and st["vertices"] == int(per[:, 1].sum()) > 0
+    for i, p in enumerate(meshed):
+        want = port.mesh(chunks, p)
+        assert bufs[i].size == want.size and (bufs[i] == want).all()
