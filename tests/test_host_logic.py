@@ -244,3 +244,22 @@ def test_port_oracle_batch_equals_single_calls(port):
     for i, p in enumerate(meshed):
         want = port.mesh(chunks, p)
         assert bufs[i].size == want.size and (bufs[i] == want).all()
+
+
+def test_cpp_host_mirror_compiles_and_fails_loudly_without_gpu(tmp_path):
+    """hypercraft_b200/host/hcm_host.hpp compiles warning-free as C++20 against include/hcm.h (what a HyperCraft build does) and,
+    on a machine without a GPU, MeshTaskDispatcher's constructor throws hcm_host::Error -- it never meshes on the CPU."""
+    import subprocess
+
+    import torch
+
+    exe = str(tmp_path / "test_dispatcher")
+    lib = os.path.join(ROOT, "hypercraft_b200", "csrc")
+    r = subprocess.run(["g++", "-std=c++20", "-O1", "-Wall", "-Wextra", "-Werror", "-o", exe, os.path.join(ROOT, "tests", "cpp", "test_dispatcher.cpp"),
+                        f"-L{lib}", "-lhcm", "-ldl", f"-Wl,-rpath,{lib}"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present: the run itself is tests/test_gpu_parity.py::test_cpp_host_mirror_dispatcher")
+    r = subprocess.run([exe, os.path.join(ROOT, "hypercraft_b200", "data", "registry.bin"), os.path.join(ROOT, "oracle", "libhcoracle.so")],
+                       capture_output=True, text=True)
+    assert r.returncode != 0 and "no CPU fallback" in r.stderr and "PASS" not in r.stdout
