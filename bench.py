@@ -134,6 +134,15 @@ def workload_name(radius: int, strong: bool = False) -> str:
     return f"full load-radius remesh r={radius} (misc/load_radius.cpp; kWorldMaxLoadRadius) per GPU"
 
 
+def algorithmic_bytes(n_chunks: int, n_vertices: int, n_meshes: int) -> dict:
+    """SURVEY 8d, per mesh_kernel launch: the canonical figure roofline.achieved uses (34^3 halo blocks 2 B + light 1 B per chunk, 8 B
+    per vertex written) and the two secondary ones -- "full": what the reference task really touches (62^3 blocks + 3 x 62^2 heights,
+    light re-derived from raw blocks); "min": every chunk read once from HBM with perfect halo reuse, vertices + indices + mesh infos."""
+    return {"canonical": n_chunks * H_BYTES + 8 * n_vertices,
+            "full": n_chunks * (62 ** 3 * 2 + 62 * 62 * 3) + 8 * n_vertices,
+            "min": n_chunks * 66560 + 11 * n_vertices + 40 * n_meshes}
+
+
 class PortArm:
     """The CPU arm when oracle/_ref is absent: this repo's restatement (oracle/hc_oracle.cpp, kind "port") behind the two
     calls bench.py makes on a RefWorld -- mesh_batch and mesh -- over chunks held in a dict."""
@@ -271,7 +280,8 @@ def main():
     for _ in range(max(args.warmup, 3)):
         counts = step_resident()
     n_quads = counts["n_vertices"] // 4
-    algo_bytes = len(meshed) * H_BYTES + 8 * counts["n_vertices"]
+    algo = algorithmic_bytes(len(meshed), int(counts["n_vertices"]), int(counts["n_meshes"]))
+    algo_bytes = algo["canonical"]
 
     # ---- timed: K steps, device timed on the ctx stream, max over ranks --------------------------------------------
     barrier()
@@ -340,6 +350,11 @@ def main():
                         "quads_per_s": st["vertices"] / 4 / st["seconds"],
                         "sample": f"{len(idx)} of {len(meshed)} chunks (every {stride}th of the r={radius} task list), "
                                   + getattr(ref, "what", "unmodified ChunkTaskRunner<kMesh>::Run, one runner per thread")}
+        # the reference's own worker count (Application.cpp:248: hardware_concurrency() * 3 / 4), same sample
+        pool_threads = max(1, cpu_threads * 3 // 4)
+        st34, _ = ref.mesh_batch(meshed[idx], threads=pool_threads)
+        cpu_baseline["reference_pool_threads"] = {"cores": pool_threads, "value": st34["chunks"] / st34["seconds"], "unit": "chunks/s",
+                                                  "note": "hardware_concurrency()*3/4 workers, the reference client's choice (Application.cpp:248)"}
         # parity: mesh/vertex/index counts of every sampled chunk + full bytes of the heaviest ones against the reference
         got_m = res.tasks["n_meshes"][idx].astype(np.uint64)
         first = res.tasks["first_mesh"][idx]
@@ -386,7 +401,11 @@ def main():
             "kernel_ms": {"derive": float(np.mean(derive_ms)), "classify": float(np.mean(classify_ms)), "mesh": k_ms},
             "roofline": {"bound": "hbm", "kernel": "hcm::mesh_kernel", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
                          "traffic": traffic, "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": int(algo_bytes), "formula": "sum over chunks of 34^3*3 + 8*vertices (SURVEY 8d)"},
+                         "algorithmic_bytes_per_launch": int(algo_bytes), "formula": "sum over chunks of 34^3*3 + 8*vertices (SURVEY 8d)",
+                         "secondary": {k: {"algorithmic_bytes_per_launch": int(algo[k]), "achieved": algo[k] / (k_ms / 1e3) / 1e9,
+                                           "frac": algo[k] / (k_ms / 1e3) / 1e9 / peak_gbs} for k in ("full", "min")},
+                         "secondary_formulas": {"full": "62^3*2 + 62*62*3 + 8*V per chunk (what the reference task touches)",
+                                                "min": "66560 + 11*V + 40*M per chunk (each chunk read once, vertices + indices + mesh infos)"}},
             "cpu_baseline": cpu_baseline, "parity": parity, "clocks": clocks,
         }
         print(json.dumps(out))

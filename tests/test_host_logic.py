@@ -263,3 +263,16 @@ def test_cpp_host_mirror_compiles_and_fails_loudly_without_gpu(tmp_path):
     r = subprocess.run([exe, os.path.join(ROOT, "hypercraft_b200", "data", "registry.bin"), os.path.join(ROOT, "oracle", "libhcoracle.so")],
                        capture_output=True, text=True)
     assert r.returncode != 0 and "no CPU fallback" in r.stderr and "PASS" not in r.stdout
+
+
+def test_bench_algorithmic_byte_figures():
+    """canonical 34^3*3 + 8V per chunk, "full" 488 188 + 8V, "min" 66 560 + 11V + 40M."""
+    import sys
+
+    sys.path.insert(0, ROOT)
+    import bench
+
+    a = bench.algorithmic_bytes(1, 655, 2)
+    assert a == {"canonical": 117912 + 8 * 655, "full": 488188 + 8 * 655, "min": 66560 + 11 * 655 + 80}
+    # the r = 20 sphere of profiles/r01_head_bench_r20_n1.json
+    assert bench.algorithmic_bytes(33401, 32818052, 0)["canonical"] == 4200923128
