@@ -134,6 +134,16 @@ def workload_name(radius: int, strong: bool = False) -> str:
     return f"full load-radius remesh r={radius} (misc/load_radius.cpp; kWorldMaxLoadRadius) per GPU"
 
 
+def cpu_model() -> str:
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
 def algorithmic_bytes(n_chunks: int, n_vertices: int, n_meshes: int) -> dict:
     """SURVEY 8d, per mesh_kernel launch: the canonical figure roofline.achieved uses (34^3 halo blocks 2 B + light 1 B per chunk, 8 B
     per vertex written) and the two secondary ones -- "full": what the reference task really touches (62^3 blocks + 3 x 62^2 heights,
@@ -219,7 +229,7 @@ def run_reference(args, rank, world):
            "config": {"workload": workload_name(radius), "radius": radius, "chunks_per_step": len(sample),
                       "note": "each step meshes a bounded sample of the workload's task list (cpu_baseline.sample)"},
            "quads_per_s": quads / (ms / 1e3),
-           "cpu_baseline": {"value": value, "unit": "chunks/s", "cores": threads, "kind": kind, "sample": sample_txt},
+           "cpu_baseline": {"value": value, "unit": "chunks/s", "cores": threads, "kind": kind, "sample": sample_txt, "cpu_model": cpu_model()},
            "e2e": {"value": value, "unit": "chunks/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out))
 
@@ -347,7 +357,7 @@ def main():
         idx = np.arange(0, len(meshed), stride)[:n_s]
         st, per = ref.mesh_batch(meshed[idx], threads=cpu_threads, per_chunk=True)
         cpu_baseline = {"value": st["chunks"] / st["seconds"], "unit": "chunks/s", "cores": cpu_threads, "kind": getattr(ref, "kind", "reference"),
-                        "quads_per_s": st["vertices"] / 4 / st["seconds"],
+                        "quads_per_s": st["vertices"] / 4 / st["seconds"], "cpu_model": cpu_model(),
                         "sample": f"{len(idx)} of {len(meshed)} chunks (every {stride}th of the r={radius} task list), "
                                   + getattr(ref, "what", "unmodified ChunkTaskRunner<kMesh>::Run, one runner per thread")}
         # the reference's own worker count (Application.cpp:248: hardware_concurrency() * 3 / 4), same sample
