@@ -153,6 +153,22 @@ def algorithmic_bytes(n_chunks: int, n_vertices: int, n_meshes: int) -> dict:
             "min": n_chunks * 66560 + 11 * n_vertices + 40 * n_meshes}
 
 
+def roofline_secondary(algo: dict, kernel_ms: float, peak_gbs: float) -> dict:
+    """The two secondary byte models of SURVEY 8d against the same launch time and peak as roofline.achieved."""
+    return {"secondary": {k: {"algorithmic_bytes_per_launch": int(algo[k]), "achieved": algo[k] / (kernel_ms / 1e3) / 1e9,
+                              "frac": algo[k] / (kernel_ms / 1e3) / 1e9 / peak_gbs} for k in ("full", "min")},
+            "secondary_formulas": {"full": "62^3*2 + 62*62*3 + 8*V per chunk (what the reference task touches)",
+                                   "min": "66560 + 11*V + 40*M per chunk (each chunk read once, vertices + indices + mesh infos)"}}
+
+
+def pool_baseline(ref, positions, cpu_threads: int) -> dict:
+    """The CPU arm at the reference client's own worker count (Application.cpp:248: hardware_concurrency() * 3 / 4), same sample."""
+    pool_threads = max(1, cpu_threads * 3 // 4)
+    st, _ = ref.mesh_batch(positions, threads=pool_threads)
+    return {"cores": pool_threads, "value": st["chunks"] / st["seconds"], "unit": "chunks/s",
+            "note": "hardware_concurrency()*3/4 workers, the reference client's choice (Application.cpp:248)"}
+
+
 class PortArm:
     """The CPU arm when oracle/_ref is absent: this repo's restatement (oracle/hc_oracle.cpp, kind "port") behind the two
     calls bench.py makes on a RefWorld -- mesh_batch and mesh -- over chunks held in a dict."""
@@ -361,10 +377,7 @@ def main():
                         "sample": f"{len(idx)} of {len(meshed)} chunks (every {stride}th of the r={radius} task list), "
                                   + getattr(ref, "what", "unmodified ChunkTaskRunner<kMesh>::Run, one runner per thread")}
         # the reference's own worker count (Application.cpp:248: hardware_concurrency() * 3 / 4), same sample
-        pool_threads = max(1, cpu_threads * 3 // 4)
-        st34, _ = ref.mesh_batch(meshed[idx], threads=pool_threads)
-        cpu_baseline["reference_pool_threads"] = {"cores": pool_threads, "value": st34["chunks"] / st34["seconds"], "unit": "chunks/s",
-                                                  "note": "hardware_concurrency()*3/4 workers, the reference client's choice (Application.cpp:248)"}
+        cpu_baseline["reference_pool_threads"] = pool_baseline(ref, meshed[idx], cpu_threads)
         # parity: mesh/vertex/index counts of every sampled chunk + full bytes of the heaviest ones against the reference
         got_m = res.tasks["n_meshes"][idx].astype(np.uint64)
         first = res.tasks["first_mesh"][idx]
@@ -412,10 +425,7 @@ def main():
             "roofline": {"bound": "hbm", "kernel": "hcm::mesh_kernel", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
                          "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": int(algo_bytes), "formula": "sum over chunks of 34^3*3 + 8*vertices (SURVEY 8d)",
-                         "secondary": {k: {"algorithmic_bytes_per_launch": int(algo[k]), "achieved": algo[k] / (k_ms / 1e3) / 1e9,
-                                           "frac": algo[k] / (k_ms / 1e3) / 1e9 / peak_gbs} for k in ("full", "min")},
-                         "secondary_formulas": {"full": "62^3*2 + 62*62*3 + 8*V per chunk (what the reference task touches)",
-                                                "min": "66560 + 11*V + 40*M per chunk (each chunk read once, vertices + indices + mesh infos)"}},
+                         **roofline_secondary(algo, k_ms, peak_gbs)},
             "cpu_baseline": cpu_baseline, "parity": parity, "clocks": clocks,
         }
         print(json.dumps(out))

@@ -276,3 +276,32 @@ def test_bench_algorithmic_byte_figures():
     assert a == {"canonical": 117912 + 8 * 655, "full": 488188 + 8 * 655, "min": 66560 + 11 * 655 + 80}
     # the r = 20 sphere of profiles/r01_head_bench_r20_n1.json
     assert bench.algorithmic_bytes(33401, 32818052, 0)["canonical"] == 4200923128
+
+
+def test_bench_cpu_side_helpers(have_ref):
+    """The pieces of bench.py's b200 arm that need no GPU: secondary roofline figures, the CPU arm at the reference's worker count
+    (on oracle/_ref when present and on the port), JSON-serialisable as they stand."""
+    import json
+    import sys
+
+    sys.path.insert(0, ROOT)
+    import bench
+    from hypercraft_b200 import worldgen
+
+    sec = bench.roofline_secondary(bench.algorithmic_bytes(33401, 32818052, 11000), 2.488064, 6541.8)
+    assert abs(sec["secondary"]["full"]["frac"] - 1.018) < 2e-3 and abs(sec["secondary"]["min"]["achieved"] - 1039) < 2
+    meshed, resident = worldgen.load_radius_positions(1)
+    arms = [bench.PortArm({tuple(int(c) for c in p): worldgen.synth_terrain_chunk(3, p) for p in resident})]
+    if have_ref:
+        import hcoracle
+
+        ref = hcoracle.RefWorld()
+        ref.generate(resident)
+        arms.append(ref)
+    for arm in arms:
+        st, per = arm.mesh_batch(meshed, threads=2, per_chunk=True)
+        assert st["chunks"] == len(meshed) and per.shape[0] == len(meshed) and per.shape[1] >= 3
+        assert arm.mesh(meshed[0]).dtype == np.uint8
+        pb = bench.pool_baseline(arm, meshed, 8)
+        assert pb["cores"] == 6 and pb["value"] > 0
+        json.dumps({**sec, "pool": pb, "algo": bench.algorithmic_bytes(3, 4, 5)})
