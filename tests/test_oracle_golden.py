@@ -44,6 +44,25 @@ def test_port_matches_reference_golden_mixed(port, i):
     _check(port, chunks, GOLDEN["mixed"][i])
 
 
+TERRAIN = [(12314524, (0, 0, 0)), (12314524, (0, 1, 2)), (12314524, (2, -1, 1)), (7, (-2, 0, -1)), (7, (0, 0, 1)), (7, (-1, -1, -2))]
+
+
+@pytest.mark.parametrize("i", range(len(TERRAIN)))
+def test_port_matches_reference_golden_terrain(port, i):
+    """Surface chunks of the repo's integer-hash height-field terrain (oceans, plants, lamps; sunlight heights below the
+    chunk top): the reference's digests for six centres."""
+    import hcoracle
+    from hypercraft_b200 import worldgen
+
+    seed, centre = TERRAIN[i]
+    chunks = {tuple(int(c) for c in p): worldgen.synth_terrain_chunk(seed, p) for p in worldgen.neighbourhood(centre)}
+    want = GOLDEN["terrain"][i]
+    buf = port.mesh(chunks, centre)
+    assert [[m["transparent"], len(m["vertices"]), len(m["indices"])] for m in hcoracle.parse_meshes(buf)] == want["meshes"]
+    assert hashlib.sha256(buf.tobytes()).hexdigest() == want["mesh_sha256"]
+    assert hashlib.sha256(port.light34(chunks, centre).tobytes()).hexdigest() == want["light_sha256"]
+
+
 def test_known_structure_checkerboard(port):
     """3-D checkerboard: 98 304 quads = 393 216 vertices, cut every 65 532 vertices, first index quad of every
     continuation mesh carries the stale cur_vertex 65532..65535 (BlockMeshAlgo.hpp:397-403 then :440-459)."""
