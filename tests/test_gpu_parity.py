@@ -1,14 +1,22 @@
 """GPU parity: the CUDA mesher (through the C ABI) against the CPU oracle, byte for byte.
 
 Bar (BASELINE.json north_star): bit-exact per chunk on mesh count, transparent flags, AABBs, vertex bytes and index
-bytes.  Inputs are seeded synthetic chunks (machine independent) and, where oracle/_ref is present, terrain from the
-reference's own generator meshed by the unmodified reference mesher."""
+bytes.  Inputs are seeded synthetic chunks (machine independent: their meshes and light volumes are also held to the
+digests the UNMODIFIED reference produced, tests/golden/synth_golden.json) and, where oracle/_ref is present, terrain
+from the reference's own generator meshed by the unmodified reference mesher."""
+import hashlib
+import json
+import os
+
 import numpy as np
 import pytest
 
 from util import describe_diff, synth_world
 
 pytestmark = pytest.mark.gpu
+
+# digests of the UNMODIFIED reference's output on the same synthetic inputs (tests/golden/make_golden.py)
+GOLDEN = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "synth_golden.json")))
 
 KINDS = ["air", "stone", "checker", "transparent", "mix", "rawmeta", "caves", "flow"]
 
@@ -31,6 +39,7 @@ def test_light_stage_matches_oracle(mesher, port, kind, seed):
     want = port.light34(chunks, (0, 0, 0))
     bad = np.nonzero(got != want)[0]
     assert len(bad) == 0, f"{len(bad)} light bytes differ, first at {bad[0]}: {got[bad[0]]:#x} vs {want[bad[0]]:#x}"
+    assert hashlib.sha256(got.tobytes()).hexdigest() == GOLDEN["cases"][f"{kind}/{seed}"]["light_sha256"]  # the reference's own bytes
 
 
 @pytest.mark.parametrize("kind", KINDS)
@@ -42,6 +51,7 @@ def test_mesh_matches_oracle(mesher, port, kind, seed):
     got = res.serialise(0)
     want = port.mesh(chunks, (0, 0, 0))
     assert got.size == want.size and (got == want).all(), describe_diff(got, want)
+    assert hashlib.sha256(got.tobytes()).hexdigest() == GOLDEN["cases"][f"{kind}/{seed}"]["mesh_sha256"]  # the reference's own bytes
 
 
 def test_mixed_neighbourhood(mesher, port):
