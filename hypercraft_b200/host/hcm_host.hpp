@@ -15,6 +15,7 @@
 #pragma once
 
 #include <array>
+#include <cstddef>
 #include <cstdint>
 #include <cstring>
 #include <memory>
@@ -61,6 +62,68 @@ public:
 	Error(int s, const std::string &what) : std::runtime_error(what), status(s) {}
 };
 
+// The pending mesh requests of the world, one per chunk position -- what the per-chunk `ChunkTaskData<kMesh>` flags are in
+// the reference: `Push(high_priority)` sets `m_queued` and ORs `m_high_priority` (ChunkMeshTask.inl:38-41), so a chunk asked
+// for twice before it runs is meshed once, and an edit (`Push<kMesh>(pos, true)`, ChunkSetBlockTask.cpp:119) overtakes the
+// streaming requests (`ChunkGenerateTask.cpp:38`, low).  `Pop(n)` is the producer's pick of a round
+// (ChunkTaskPool.cpp:16-85): high priority first, each class in the order of first request.  No GPU involved.
+class MeshRequestQueue {
+public:
+	// true if the position was not pending yet
+	bool Push(const ChunkPos3 &pos, bool high_priority = false) {
+		auto it = m_index.find(pos);
+		if (it == m_index.end()) {
+			m_index.emplace(pos, m_entries.size());
+			m_entries.push_back(Entry{pos, high_priority, true});
+			++m_live;
+			return true;
+		}
+		m_entries[it->second].high |= high_priority;
+		return false;
+	}
+	// ChunkTaskData<kMesh>::OnUnload (ChunkMeshTask.inl:48): the chunk left the world, its request with it
+	bool Drop(const ChunkPos3 &pos) {
+		auto it = m_index.find(pos);
+		if (it == m_index.end())
+			return false;
+		m_entries[it->second].live = false;
+		m_index.erase(it);
+		--m_live;
+		return true;
+	}
+	bool IsQueued(const ChunkPos3 &pos) const { return m_index.count(pos) != 0; }
+	size_t Size() const { return m_live; }
+	// at most max_tasks positions, removed from the queue
+	std::vector<ChunkPos3> Pop(size_t max_tasks = SIZE_MAX) {
+		std::vector<ChunkPos3> out;
+		for (int want_high = 1; want_high >= 0; --want_high)
+			for (Entry &e : m_entries)
+				if (e.live && e.high == (want_high != 0) && out.size() < max_tasks) {
+					out.push_back(e.pos);
+					e.live = false;
+					m_index.erase(e.pos);
+				}
+		m_live -= out.size();
+		std::vector<Entry> rest; // compact, keeping the order of first request
+		for (const Entry &e : m_entries)
+			if (e.live) {
+				m_index[e.pos] = rest.size();
+				rest.push_back(e);
+			}
+		m_entries.swap(rest);
+		return out;
+	}
+
+private:
+	struct Entry {
+		ChunkPos3 pos;
+		bool high, live;
+	};
+	std::vector<Entry> m_entries;
+	std::unordered_map<ChunkPos3, size_t, ChunkPos3Hash> m_index;
+	size_t m_live{0};
+};
+
 template <typename ChunkT> class MeshTaskDispatcher {
 public:
 	// registry_blob: the serialised hcm_registry (INTEGRATION.md shows the exporter); window: chunks the device may hold
@@ -85,7 +148,9 @@ public:
 
 	// Same input as ChunkTaskRunnerData<kMesh> (ChunkMeshTask.inl:17-29).  Like Run(), the chunks are read-only snapshots
 	// held by shared_ptr until Flush() returns.
-	void Submit(const std::array<std::shared_ptr<ChunkT>, 27> &chunks) {
+	// A position submitted again before it was flushed stays ONE task (the later snapshot wins, the priority is sticky):
+	// MeshRequestQueue above.  high_priority = the `true` of Push<kMesh>(pos, true) that edits use.
+	void Submit(const std::array<std::shared_ptr<ChunkT>, 27> &chunks, bool high_priority = false) {
 		for (const auto &c : chunks) {
 			const auto p = c->GetPosition();
 			ChunkPos3 pos{(int16_t)p.x, (int16_t)p.y, (int16_t)p.z};
@@ -96,11 +161,12 @@ public:
 			}
 		}
 		const auto p = chunks[26]->GetPosition();
-		m_tasks.push_back(ChunkPos3{(int16_t)p.x, (int16_t)p.y, (int16_t)p.z});
-		m_keepalive.insert(m_keepalive.end(), chunks.begin(), chunks.end());
+		const ChunkPos3 centre{(int16_t)p.x, (int16_t)p.y, (int16_t)p.z};
+		m_queue.Push(centre, high_priority);
+		m_snapshot[centre] = chunks;
 	}
 
-	size_t Pending() const { return m_tasks.size(); }
+	size_t Pending() const { return m_queue.Size(); }
 
 	// ChunkSetBlockEntry deltas (common/include/common/Data.hpp:11-14) for chunks that are already on the device -- the
 	// work of ChunkTaskRunner<kSetBlock>::Run and of the kFloodSunlight / kSetSunlight chain it starts
@@ -138,8 +204,11 @@ public:
 	// Runs the batch and calls sink(const ChunkPos3&, std::vector<BlockMesh>&&) once per submitted task, in submission
 	// order -- the place where Run() calls WorldRenderer::PushChunkMesh.  Zero meshes is a valid result and is pushed too
 	// (it clears the chunk's old handles, WorldRenderer.hpp:81-86).
-	template <typename Sink> void Flush(Sink &&sink) {
-		if (m_tasks.empty())
+	// max_tasks: the budget of one round (the reference producer hands out at most 256 tasks per round,
+	// ChunkTaskPool.cpp:16-85); what does not fit stays pending, high priority goes first.
+	template <typename Sink> void Flush(Sink &&sink, size_t max_tasks = SIZE_MAX) {
+		const std::vector<ChunkPos3> tasks = m_queue.Pop(max_tasks);
+		if (tasks.empty())
 			return;
 		const size_t n = m_upload.size();
 		if (n) {
@@ -152,13 +221,13 @@ public:
 					m_heights[i * HCM_CHUNK_COLUMNS + k] = (int8_t)m_upload[i]->GetSunlightHeight(k);
 			}
 		}
-		std::vector<int16_t> tp(m_tasks.size() * 3);
-		for (size_t i = 0; i < m_tasks.size(); ++i)
-			tp[3 * i] = m_tasks[i].x, tp[3 * i + 1] = m_tasks[i].y, tp[3 * i + 2] = m_tasks[i].z;
+		std::vector<int16_t> tp(tasks.size() * 3);
+		for (size_t i = 0; i < tasks.size(); ++i)
+			tp[3 * i] = tasks[i].x, tp[3 * i + 1] = tasks[i].y, tp[3 * i + 2] = tasks[i].z;
 		// one call: new chunks go up, every task is meshed as soon as the last of its 27 chunks is on the device, finished
 		// meshes come back while later chunks are still uploading (with nothing to upload it is batch + fetch)
 		hcm_batch_view v{};
-		check(hcm_upload_and_mesh(m_ctx, (uint32_t)n, m_pos.data(), m_blocks.data(), m_heights.data(), (uint32_t)m_tasks.size(), tp.data(), &v));
+		check(hcm_upload_and_mesh(m_ctx, (uint32_t)n, m_pos.data(), m_blocks.data(), m_heights.data(), (uint32_t)tasks.size(), tp.data(), &v));
 		for (uint32_t t = 0; t < v.n_tasks; ++t) {
 			std::vector<BlockMesh> meshes(v.tasks[t].n_meshes);
 			for (uint32_t k = 0; k < v.tasks[t].n_meshes; ++k) {
@@ -170,9 +239,11 @@ public:
 				std::memcpy(m.aabb.min, d.aabb_min, 12), std::memcpy(m.aabb.max, d.aabb_max, 12);
 				m.transparent = d.transparent != 0;
 			}
-			sink(m_tasks[t], std::move(meshes));
+			sink(tasks[t], std::move(meshes));
 		}
-		m_tasks.clear(), m_upload.clear(), m_keepalive.clear();
+		m_upload.clear();
+		for (const ChunkPos3 &t : tasks)
+			m_snapshot.erase(t);
 	}
 
 	hcm_ctx *Context() { return m_ctx; }
@@ -184,8 +255,9 @@ private:
 	}
 	hcm_ctx *m_ctx{};
 	std::unordered_map<ChunkPos3, const ChunkT *, ChunkPos3Hash> m_resident;
-	std::vector<std::shared_ptr<ChunkT>> m_upload, m_keepalive;
-	std::vector<ChunkPos3> m_tasks;
+	std::vector<std::shared_ptr<ChunkT>> m_upload;
+	MeshRequestQueue m_queue;
+	std::unordered_map<ChunkPos3, std::array<std::shared_ptr<ChunkT>, 27>, ChunkPos3Hash> m_snapshot; // held until the task is flushed
 	std::vector<int16_t> m_pos;
 	std::vector<uint16_t> m_blocks;
 	std::vector<int8_t> m_heights;

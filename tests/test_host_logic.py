@@ -305,3 +305,18 @@ def test_bench_cpu_side_helpers(have_ref):
         pb = bench.pool_baseline(arm, meshed, 8)
         assert pb["cores"] == 6 and pb["value"] > 0
         json.dumps({**sec, "pool": pb, "algo": bench.algorithmic_bytes(3, 4, 5)})
+
+
+@pytest.mark.parametrize("name", ["test_request_queue", "test_dispatcher_logic"])
+def test_cpp_host_mirror_logic(tmp_path, name):
+    """The C++ host mirror's own logic, no GPU and no libhcm.so: the request queue's dedupe / priority rules
+    (ChunkMeshTask.inl:38-48) and MeshTaskDispatcher against a recording fake of the C ABI (which chunks cross the
+    boundary, one task per position, high priority first, task budget, task -> sink mapping)."""
+    import subprocess
+
+    exe = str(tmp_path / name)
+    r = subprocess.run(["g++", "-std=c++20", "-O1", "-Wall", "-Wextra", "-Werror", "-o", exe, os.path.join(ROOT, "tests", "cpp", name + ".cpp")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.strip().splitlines()[-1].startswith("PASS"), r.stdout + r.stderr
