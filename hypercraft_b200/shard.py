@@ -62,3 +62,63 @@ def window_for(resident: np.ndarray) -> tuple[tuple[int, int, int], tuple[int, i
     r = np.asarray(resident, dtype=np.int32).reshape(-1, 3)
     lo, hi = r.min(axis=0), r.max(axis=0)
     return tuple(int(v) for v in lo), tuple(int(v) for v in (hi - lo + 1))
+
+
+# ---- edits on a sharded world (last sentence; BASELINE config 5 on N GPUs) -----------------------
+# An edit belongs to the rank whose slab holds the edited chunk.  With resident_for_slab() that rank has the chunk's whole
+# column of the world, i.e. exactly what the single-GPU world gives the sunlight chain (the chain walks along y, a slab is
+# cut along x), so its hcm_set_blocks result -- changed heights and remesh fan-out -- is the undivided world's.  A rank that holds a touched chunk only as halo does NOT run the chain (the chunk above may be outside its
+# dilation): it takes the owner's chunk as data (hcm_upload_chunks of that one chunk) before it meshes.  Remesh tasks go
+# to the rank that owns their position.  All of it is host-side bookkeeping of a few bytes per edit; no collective.
+
+def resident_for_slab(world_resident: np.ndarray, bounds, rank: int) -> np.ndarray:
+    """Residency of a rank that also takes edits: every chunk of the undivided world's resident set in the x-planes
+    [x_lo - 1, x_hi] -- a superset of resident_for(its tasks) by the fringe chunks that only a neighbouring slab's taller
+    columns bring in.  With it the owner of a chunk holds that chunk's whole column of the world, so the sunlight chain
+    stops on it exactly where it stops on one GPU, and "holds chunk c as halo" is a statement about c's x alone."""
+    r = np.asarray(world_resident, dtype=np.int16).reshape(-1, 3)
+    lo, hi = bounds[rank]
+    if hi <= lo:
+        return r[:0]
+    return r[(r[:, 0] >= lo - 1) & (r[:, 0] <= hi)]
+
+
+def owner_rank(chunk_pos, bounds) -> int:
+    """Rank whose [x_lo, x_hi) holds the chunk (positions left / right of all slabs go to the first / last rank)."""
+    x = int(chunk_pos[0])
+    for r, (lo, hi) in enumerate(bounds):
+        if x < hi and (x >= lo or r == 0):
+            return r
+    return len(bounds) - 1
+
+
+def halo_ranks(chunk_pos, bounds) -> list[int]:
+    """Ranks other than the owner whose slab, dilated by one chunk, reaches the chunk's x-plane."""
+    x, own = int(chunk_pos[0]), owner_rank(chunk_pos, bounds)
+    return [r for r, (lo, hi) in enumerate(bounds) if r != own and hi > lo and lo - 1 <= x <= hi]
+
+
+def route_edits(edit_list, bounds) -> list[list]:
+    """edit_list = [((cx,cy,cz), index, block), ...] -> per rank, the edits it applies with hcm_set_blocks (owner only)."""
+    out = [[] for _ in bounds]
+    for e in edit_list:
+        out[owner_rank(e[0], bounds)].append(e)
+    return out
+
+
+def mirror_plan(touched_chunks, bounds) -> list[list[tuple[int, int, int]]]:
+    """touched_chunks = chunk positions whose blocks or sunlight heights an owner changed -> per rank, the chunks it holds
+    as halo and must take from the owner (re-upload) before its next mesh batch."""
+    out = [[] for _ in bounds]
+    for c in sorted({tuple(int(v) for v in c) for c in touched_chunks}):
+        for r in halo_ranks(c, bounds):
+            out[r].append(c)
+    return out
+
+
+def split_tasks(positions, bounds) -> list[list[tuple[int, int, int]]]:
+    """Remesh positions reported by the owners -> per rank, the ones it meshes (its own slab)."""
+    out = [[] for _ in bounds]
+    for p in sorted({tuple(int(v) for v in p) for p in positions}):
+        out[owner_rank(p, bounds)].append(p)
+    return out

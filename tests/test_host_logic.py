@@ -320,3 +320,73 @@ def test_cpp_host_mirror_logic(tmp_path, name):
     assert r.returncode == 0, r.stderr
     r = subprocess.run([exe], capture_output=True, text=True)
     assert r.returncode == 0 and r.stdout.strip().splitlines()[-1].startswith("PASS"), r.stdout + r.stderr
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_edit_round_equals_the_undivided_world(port, world):
+    """SURVEY 8e / config 5 on N ranks, host logic only (apply_block_edits stands in for hcm_set_blocks, the CPU oracle
+    for the mesh kernel): edits go to the slab owner, touched chunks are mirrored to the ranks that hold them as halo,
+    remesh tasks go to the rank that owns their position -- block changes, sunlight changes, remesh set and every
+    remeshed chunk's bytes equal those of one world taking the same edits."""
+    import hashlib
+
+    from hypercraft_b200 import edits, shard, worldgen
+
+    meshed, resident = worldgen.load_radius_positions(3)
+    vpass = worldgen._vertical_pass_table()
+    bounds = shard.slab_bounds(meshed, world)
+    base = {tuple(int(c) for c in p): worldgen.synth_terrain_chunk(5, p) for p in resident}
+
+    def clone(keys):
+        return {k: (base[k][0].copy(), base[k][1].copy()) for k in keys}
+
+    # seeded edits in task chunks on both sides of every cut and in the middle: dig, build towers (sunlight), lamps, water
+    rng = np.random.default_rng(42)
+    task_set = {tuple(int(c) for c in p) for p in meshed}
+    cut_planes = sorted({b[0] for b in bounds[1:]} | {b[0] - 1 for b in bounds[1:]} | {0})
+    cands = [t for t in sorted(task_set) if t[0] in cut_planes and abs(t[1]) <= 1]
+    edit_list = []
+    for k in range(60):
+        c = cands[int(rng.integers(0, len(cands)))]
+        x, y, z = (int(v) for v in rng.integers(0, 32, 3))
+        if k % 4 == 0:
+            x = int(rng.choice([0, 1, 30, 31]))  # next to the slab face: the fan-out crosses the cut
+        block = [worldgen.AIR, worldgen.STONE, worldgen.GLOWSTONE, worldgen.WATER][k % 4]
+        edit_list.append((c, x + (y * 32 + z) * 32, block))
+
+    one = clone(base)
+    n1, sun1, remesh1 = edits.apply_block_edits(one, edit_list, vpass)
+    remesh1 = {p for p in remesh1 if p in task_set}
+    assert n1 > 30 and len(sun1) > 5 and len(remesh1) > 10
+
+    res = [shard.resident_for_slab(resident, bounds, r) for r in range(world)]
+    for r in range(world):  # a superset of the bench's minimal residency, inside the world
+        mine = {tuple(int(c) for c in p) for p in res[r]}
+        assert {tuple(int(c) for c in p) for p in shard.resident_for(shard.shard_tasks(meshed, world, r))} <= mine <= set(base)
+    worlds = [clone(tuple(int(c) for c in p) for p in res[r]) for r in range(world)]
+    blind = [clone(tuple(int(c) for c in p) for p in res[r]) for r in range(world)]  # control: owners edit, nobody mirrors
+    n_sum, sun_all, remesh_all, mirrored = 0, {}, set(), 0
+    for r, mine in enumerate(shard.route_edits(edit_list, bounds)):
+        edits.apply_block_edits(blind[r], mine, vpass)
+        n, sun, remesh = edits.apply_block_edits(worlds[r], mine, vpass)
+        n_sum += n
+        assert not set(sun) & set(sun_all)
+        sun_all.update(sun)
+        remesh_all |= remesh
+        touched = {e[0] for e in mine} | {c for c, _ in sun}
+        for h, chunks in enumerate(shard.mirror_plan(touched, bounds)):
+            for c in chunks:  # the halo holder takes the owner's chunk as data
+                assert h != r and c in worlds[h]
+                worlds[h][c] = (worlds[r][c][0].copy(), worlds[r][c][1].copy())
+                mirrored += 1
+    assert n_sum == n1 and sun_all == sun1 and {p for p in remesh_all if p in task_set} == remesh1
+    stale = 0
+    for r, tasks in enumerate(shard.split_tasks(remesh1, bounds)):
+        lo, hi = bounds[r]
+        for t in tasks:
+            assert lo <= t[0] < hi
+            a, b = port.mesh(worlds[r], t), port.mesh(one, t)
+            assert hashlib.sha256(a.tobytes()).digest() == hashlib.sha256(b.tobytes()).digest(), (r, t)
+            c = port.mesh(blind[r], t)
+            stale += not (c.size == b.size and (c == b).all())
+    assert mirrored > 0 and stale > 0  # the cuts were really crossed: without the mirror step some meshes come out stale
