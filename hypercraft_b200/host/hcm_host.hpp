@@ -19,6 +19,7 @@
 #include <cstdint>
 #include <cstring>
 #include <memory>
+#include <mutex>
 #include <stdexcept>
 #include <string>
 #include <unordered_map>
@@ -94,12 +95,16 @@ public:
 	bool IsQueued(const ChunkPos3 &pos) const { return m_index.count(pos) != 0; }
 	size_t Size() const { return m_live; }
 	// at most max_tasks positions, removed from the queue
-	std::vector<ChunkPos3> Pop(size_t max_tasks = SIZE_MAX) {
+	std::vector<ChunkPos3> Pop(size_t max_tasks = SIZE_MAX, std::vector<bool> *high = nullptr) {
 		std::vector<ChunkPos3> out;
+		if (high)
+			high->clear();
 		for (int want_high = 1; want_high >= 0; --want_high)
 			for (Entry &e : m_entries)
 				if (e.live && e.high == (want_high != 0) && out.size() < max_tasks) {
 					out.push_back(e.pos);
+					if (high)
+						high->push_back(e.high);
 					e.live = false;
 					m_index.erase(e.pos);
 				}
@@ -144,13 +149,19 @@ public:
 
 	// A chunk whose blocks or sunlight heights changed since it was last seen (the SetBlock / SetSunlight tasks that
 	// `Push<kMesh>`, ChunkSetBlockTask.cpp:119, ChunkSetSunlightTask.cpp:84) must be re-uploaded before its remesh.
-	void MarkDirty(const ChunkPos3 &pos) { m_resident.erase(pos); }
+	void MarkDirty(const ChunkPos3 &pos) {
+		std::lock_guard<std::mutex> g(m_mutex);
+		m_resident.erase(pos);
+	}
 
 	// Same input as ChunkTaskRunnerData<kMesh> (ChunkMeshTask.inl:17-29).  Like Run(), the chunks are read-only snapshots
 	// held by shared_ptr until Flush() returns.
 	// A position submitted again before it was flushed stays ONE task (the later snapshot wins, the priority is sticky):
 	// MeshRequestQueue above.  high_priority = the `true` of Push<kMesh>(pos, true) that edits use.
+	// Thread-safe like Run(): the reference calls it from N worker threads (ChunkTaskPool.cpp:119-129); Submit / MarkDirty only
+	// touch the bookkeeping, the calls into the ctx (Flush, SetBlocks) are serialised among themselves.
 	void Submit(const std::array<std::shared_ptr<ChunkT>, 27> &chunks, bool high_priority = false) {
+		std::lock_guard<std::mutex> g(m_mutex);
 		for (const auto &c : chunks) {
 			const auto p = c->GetPosition();
 			ChunkPos3 pos{(int16_t)p.x, (int16_t)p.y, (int16_t)p.z};
@@ -166,14 +177,18 @@ public:
 		m_snapshot[centre] = chunks;
 	}
 
-	size_t Pending() const { return m_queue.Size(); }
+	size_t Pending() const {
+		std::lock_guard<std::mutex> g(m_mutex);
+		return m_queue.Size();
+	}
 
 	// ChunkSetBlockEntry deltas (common/include/common/Data.hpp:11-14) for chunks that are already on the device -- the
 	// work of ChunkTaskRunner<kSetBlock>::Run and of the kFloodSunlight / kSetSunlight chain it starts
 	// (client/src/ChunkSetBlockTask.cpp:78-129, ChunkFloodSunlightTask.cpp:41-57, ChunkSetSunlightTask.cpp:42-90) without
 	// re-uploading 64 KB per touched chunk.  The caller has already applied (or now applies) the same blocks to its own
 	// Chunk objects with Chunk::SetBlock; `on_sunlight(const SunlightChange&)` is where it calls Chunk::SetSunlightHeight,
-	// `on_remesh(const ChunkPos3&)` where it would Push<kMesh> -- typically Submit(the 27 chunks around that position).
+	// `on_remesh(const ChunkPos3&)` where it would Push<kMesh> -- typically Submit(the 27 chunks around that position, true);
+	// the callbacks run inside the ctx's critical section: Submit / MarkDirty are fine there, Flush / SetBlocks are not.
 	struct SetBlock {
 		ChunkPos3 chunk;
 		uint16_t index; // InnerIndex3: x + (y*32 + z)*32
@@ -190,6 +205,7 @@ public:
 			e[i].chunk[0] = edits[i].chunk.x, e[i].chunk[1] = edits[i].chunk.y, e[i].chunk[2] = edits[i].chunk.z;
 			e[i].index = edits[i].index, e[i].block = edits[i].block, e[i]._pad = 0;
 		}
+		std::lock_guard<std::mutex> ctx_lock(m_ctx_mutex); // the result's pointers belong to the ctx until its next call
 		hcm_edit_result r{};
 		check(hcm_set_blocks(m_ctx, (uint32_t)e.size(), e.data(), &r));
 		for (uint32_t i = 0; i < r.n_sunlight; ++i) {
@@ -207,18 +223,32 @@ public:
 	// max_tasks: the budget of one round (the reference producer hands out at most 256 tasks per round,
 	// ChunkTaskPool.cpp:16-85); what does not fit stays pending, high priority goes first.
 	template <typename Sink> void Flush(Sink &&sink, size_t max_tasks = SIZE_MAX) {
-		const std::vector<ChunkPos3> tasks = m_queue.Pop(max_tasks);
-		if (tasks.empty())
-			return;
-		const size_t n = m_upload.size();
+		std::lock_guard<std::mutex> ctx_lock(m_ctx_mutex); // one call into the ctx at a time; Submit stays open meanwhile
+		std::vector<ChunkPos3> tasks;
+		std::vector<bool> high;
+		std::vector<std::shared_ptr<ChunkT>> upload;
+		std::vector<std::array<std::shared_ptr<ChunkT>, 27>> snapshots; // read-only inputs, held until the sink has run
+		{
+			std::lock_guard<std::mutex> g(m_mutex);
+			tasks = m_queue.Pop(max_tasks, &high);
+			if (tasks.empty())
+				return;
+			upload.swap(m_upload);
+			for (const ChunkPos3 &t : tasks) {
+				auto it = m_snapshot.find(t);
+				snapshots.push_back(std::move(it->second));
+				m_snapshot.erase(it);
+			}
+		}
+		const size_t n = upload.size();
 		if (n) {
 			m_pos.resize(n * 3), m_blocks.resize(n * HCM_CHUNK_VOXELS), m_heights.resize(n * HCM_CHUNK_COLUMNS);
 			for (size_t i = 0; i < n; ++i) {
-				const auto p = m_upload[i]->GetPosition();
+				const auto p = upload[i]->GetPosition();
 				m_pos[3 * i] = (int16_t)p.x, m_pos[3 * i + 1] = (int16_t)p.y, m_pos[3 * i + 2] = (int16_t)p.z;
-				std::memcpy(m_blocks.data() + i * HCM_CHUNK_VOXELS, m_upload[i]->GetBlockData(), HCM_CHUNK_VOXELS * 2);
+				std::memcpy(m_blocks.data() + i * HCM_CHUNK_VOXELS, upload[i]->GetBlockData(), HCM_CHUNK_VOXELS * 2);
 				for (uint32_t k = 0; k < HCM_CHUNK_COLUMNS; ++k)
-					m_heights[i * HCM_CHUNK_COLUMNS + k] = (int8_t)m_upload[i]->GetSunlightHeight(k);
+					m_heights[i * HCM_CHUNK_COLUMNS + k] = (int8_t)upload[i]->GetSunlightHeight(k);
 			}
 		}
 		std::vector<int16_t> tp(tasks.size() * 3);
@@ -227,7 +257,16 @@ public:
 		// one call: new chunks go up, every task is meshed as soon as the last of its 27 chunks is on the device, finished
 		// meshes come back while later chunks are still uploading (with nothing to upload it is batch + fetch)
 		hcm_batch_view v{};
-		check(hcm_upload_and_mesh(m_ctx, (uint32_t)n, m_pos.data(), m_blocks.data(), m_heights.data(), (uint32_t)tasks.size(), tp.data(), &v));
+		if (int rc = hcm_upload_and_mesh(m_ctx, (uint32_t)n, m_pos.data(), m_blocks.data(), m_heights.data(), (uint32_t)tasks.size(), tp.data(), &v)) {
+			// nothing was pushed: the round goes back to pending, behind the requests that arrived meanwhile
+			std::lock_guard<std::mutex> g(m_mutex);
+			m_upload.insert(m_upload.begin(), upload.begin(), upload.end());
+			for (size_t i = 0; i < tasks.size(); ++i) {
+				m_queue.Push(tasks[i], high[i]);
+				m_snapshot.emplace(tasks[i], std::move(snapshots[i])); // a newer snapshot, if one came in, wins
+			}
+			throw Error(rc, hcm_last_error(m_ctx));
+		}
 		for (uint32_t t = 0; t < v.n_tasks; ++t) {
 			std::vector<BlockMesh> meshes(v.tasks[t].n_meshes);
 			for (uint32_t k = 0; k < v.tasks[t].n_meshes; ++k) {
@@ -241,9 +280,6 @@ public:
 			}
 			sink(tasks[t], std::move(meshes));
 		}
-		m_upload.clear();
-		for (const ChunkPos3 &t : tasks)
-			m_snapshot.erase(t);
 	}
 
 	hcm_ctx *Context() { return m_ctx; }
@@ -254,6 +290,8 @@ private:
 			throw Error(rc, hcm_last_error(m_ctx));
 	}
 	hcm_ctx *m_ctx{};
+	mutable std::mutex m_mutex; // m_resident, m_upload, m_queue, m_snapshot
+	std::mutex m_ctx_mutex;     // calls into m_ctx and the staging vectors below
 	std::unordered_map<ChunkPos3, const ChunkT *, ChunkPos3Hash> m_resident;
 	std::vector<std::shared_ptr<ChunkT>> m_upload;
 	MeshRequestQueue m_queue;

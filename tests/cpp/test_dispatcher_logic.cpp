@@ -2,10 +2,13 @@
 // of the six C-ABI calls it makes -- test infrastructure only, linked instead of libhcm.so, it meshes nothing.  Checked:
 // which chunks cross the boundary (once per chunk object, again after MarkDirty or when the object changed), that a
 // position submitted twice is one task, that high-priority tasks go first, that a task budget leaves the rest pending,
-// and that every sink call receives the meshes of its own task.
+// that every sink call receives the meshes of its own task, that a failed boundary call leaves the round pending, and
+// that Submit may be called from many threads while the owner flushes (also clean under -fsanitize=thread).
+#include <atomic>
 #include <cstdio>
 #include <map>
 #include <set>
+#include <thread>
 
 #include "../../hypercraft_b200/host/hcm_host.hpp"
 
@@ -18,6 +21,7 @@ std::vector<hcm_task_result> tasks;
 std::vector<hcm_mesh_desc> meshes;
 std::vector<uint64_t> vertices;
 std::vector<uint16_t> indices;
+bool fail_next = false;
 uint32_t tag(int x, int y, int z) { return (uint32_t)((x + 50) * 10000 + (y + 50) * 100 + (z + 50)); }
 } // namespace fake
 
@@ -33,6 +37,8 @@ int hcm_set_blocks(hcm_ctx *, uint32_t, const hcm_block_edit *, hcm_edit_result 
 // one mesh per task: 4 vertices whose first word is the task position's tag, 6 indices, aabb_min[0] = tag
 int hcm_upload_and_mesh(hcm_ctx *, uint32_t n_chunks, const int16_t *pos, const uint16_t *blocks, const int8_t *heights, uint32_t n_tasks,
                         const int16_t *task_pos, hcm_batch_view *out) {
+	if (fake::fail_next)
+		return fake::fail_next = false, HCM_ERR_CUDA;
 	fake::Call c;
 	for (uint32_t i = 0; i < n_chunks; ++i) {
 		c.uploaded.push_back({pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]});
@@ -96,8 +102,8 @@ int main() {
 			for (int dy = -1; dy <= 1; ++dy)
 				for (int dz = -1; dz <= 1; ++dz)
 					if (dx || dy || dz)
-						a[i++] = world[{x + dx, y + dy, z + dz}];
-		a[26] = world[{x, y, z}];
+						a[i++] = world.at({x + dx, y + dy, z + dz});
+		a[26] = world.at({x, y, z});
 		return a;
 	};
 	const char blob[4] = {};
@@ -152,6 +158,67 @@ int main() {
 	disp.Flush(sink, 2);
 	CHECK(sunk.size() == 3 && sunk[2] == (ChunkPos3{0, 0, 1}) && disp.Pending() == 0);
 	CHECK(fake::calls.size() == 5 && fake::calls[4].uploaded.empty()); // its chunks went up with the first of the two flushes
+
+	// round 5: the boundary call fails -- Flush throws, nothing is pushed, the round (tasks, priorities, uploads) is pending again
+	sunk.clear();
+	disp.MarkDirty({0, 0, 0});
+	disp.Submit(gather(0, 0, 0));
+	disp.Submit(gather(1, 0, 0), true);
+	fake::fail_next = true;
+	bool threw = false;
+	try {
+		disp.Flush(sink);
+	} catch (const hcm_host::Error &e) {
+		threw = e.status == HCM_ERR_CUDA;
+	}
+	CHECK(threw && sunk.empty() && disp.Pending() == 2 && fake::calls.size() == 5);
+	disp.Flush(sink);
+	CHECK(fake::calls.size() == 6 && fake::calls[5].uploaded.size() == 1 && fake::calls[5].uploaded[0] == (std::array<int, 3>{0, 0, 0}));
+	CHECK(sunk.size() == 2 && sunk[0] == (ChunkPos3{1, 0, 0}) && sunk[1] == (ChunkPos3{0, 0, 0}) && disp.Pending() == 0);
+
+	// round 6: Submit from eight threads (the reference calls Run() from its worker pool) while the owner thread flushes
+	{
+		sunk.clear();
+		const size_t calls_before = fake::calls.size();
+		std::set<std::array<int, 3>> uploaded_before;
+		for (const auto &c : fake::calls)
+			uploaded_before.insert(c.uploaded.begin(), c.uploaded.end());
+		for (int x = -2; x <= 2; ++x) // brand-new chunk objects everywhere: each must cross the boundary exactly once more
+			for (int y = -2; y <= 2; ++y)
+				for (int z = -2; z <= 2; ++z)
+					world[{x, y, z}] = std::make_shared<Chunk>(Pos{x, y, z});
+		std::atomic<int> running{8};
+		std::vector<std::thread> workers;
+		for (int w = 0; w < 8; ++w)
+			workers.emplace_back([&, w] {
+				for (int rep = 0; rep < 20; ++rep)
+					for (int i = w; i < 27; i += 4) // every position from two threads, twenty times each
+						disp.Submit(gather(i % 3 - 1, i / 3 % 3 - 1, i / 9 - 1), (i + rep) % 5 == 0);
+				--running;
+			});
+		while (running.load())
+			disp.Flush(sink, 5);
+		for (auto &t : workers)
+			t.join();
+		while (disp.Pending())
+			disp.Flush(sink, 5);
+		std::map<std::array<int, 3>, int> up;
+		size_t n_tasks = 0;
+		for (size_t i = calls_before; i < fake::calls.size(); ++i) {
+			for (const auto &c : fake::calls[i].uploaded)
+				++up[c];
+			n_tasks += fake::calls[i].tasks.size();
+			CHECK(fake::calls[i].tasks.size() <= 5);
+		}
+		bool once = up.size() == 125;
+		for (const auto &kv : up)
+			once &= kv.second == 1;
+		CHECK(once); // 125 new chunk objects, each uploaded once although 27 neighbourhoods x 40 submissions named them
+		std::set<std::array<int, 3>> meshed;
+		for (const ChunkPos3 &p : sunk)
+			meshed.insert({p.x, p.y, p.z});
+		CHECK(meshed.size() == 27 && sunk.size() == n_tasks && n_tasks >= 27 && n_tasks < 27 * 40);
+	}
 
 	printf("%s: %zu boundary calls\n", fails ? "FAIL" : "PASS", fake::calls.size());
 	return fails != 0;

@@ -315,7 +315,7 @@ def test_cpp_host_mirror_logic(tmp_path, name):
     import subprocess
 
     exe = str(tmp_path / name)
-    r = subprocess.run(["g++", "-std=c++20", "-O1", "-Wall", "-Wextra", "-Werror", "-o", exe, os.path.join(ROOT, "tests", "cpp", name + ".cpp")],
+    r = subprocess.run(["g++", "-std=c++20", "-O1", "-Wall", "-Wextra", "-Werror", "-pthread", "-o", exe, os.path.join(ROOT, "tests", "cpp", name + ".cpp")],
                        capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     r = subprocess.run([exe], capture_output=True, text=True)
