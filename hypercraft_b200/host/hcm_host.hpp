@@ -158,6 +158,29 @@ public:
 	// held by shared_ptr until Flush() returns.
 	// A position submitted again before it was flushed stays ONE task (the later snapshot wins, the priority is sticky):
 	// MeshRequestQueue above.  high_priority = the `true` of Push<kMesh>(pos, true) that edits use.
+	// The chunk left the world (ChunkPool::Update evicts it, client/src/ChunkPool.cpp:9-33, and the task pool calls
+	// ChunkTaskData<kMesh>::OnUnload, ChunkMeshTask.inl:48): its device slot is freed, its pending request and its not yet
+	// uploaded copy are dropped.  Requests of its neighbours stay; like Pop() in the reference they fail (NOT_RESIDENT)
+	// unless the chunk comes back before they are flushed.
+	void Unload(const ChunkPos3 &pos) {
+		{
+			std::lock_guard<std::mutex> g(m_mutex);
+			m_resident.erase(pos);
+			m_queue.Drop(pos);
+			m_snapshot.erase(pos);
+			for (size_t i = 0; i < m_upload.size();) {
+				const auto p = m_upload[i]->GetPosition();
+				if (ChunkPos3{(int16_t)p.x, (int16_t)p.y, (int16_t)p.z} == pos)
+					m_upload.erase(m_upload.begin() + (std::ptrdiff_t)i);
+				else
+					++i;
+			}
+		}
+		std::lock_guard<std::mutex> ctx_lock(m_ctx_mutex);
+		const int16_t p[3] = {pos.x, pos.y, pos.z};
+		check(hcm_remove_chunks(m_ctx, 1, p));
+	}
+
 	// Thread-safe like Run(): the reference calls it from N worker threads (ChunkTaskPool.cpp:119-129); Submit / MarkDirty only
 	// touch the bookkeeping, the calls into the ctx (Flush, SetBlocks) are serialised among themselves.
 	void Submit(const std::array<std::shared_ptr<ChunkT>, 27> &chunks, bool high_priority = false) {

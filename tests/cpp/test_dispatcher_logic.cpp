@@ -1,5 +1,5 @@
 // CPU test of the host logic of hcm_host::MeshTaskDispatcher (hypercraft_b200/host/hcm_host.hpp) against a RECORDING FAKE
-// of the six C-ABI calls it makes -- test infrastructure only, linked instead of libhcm.so, it meshes nothing.  Checked:
+// of the seven C-ABI calls it makes -- test infrastructure only, linked instead of libhcm.so, it meshes nothing.  Checked:
 // which chunks cross the boundary (once per chunk object, again after MarkDirty or when the object changed), that a
 // position submitted twice is one task, that high-priority tasks go first, that a task budget leaves the rest pending,
 // that every sink call receives the meshes of its own task, that a failed boundary call leaves the round pending, and
@@ -22,6 +22,7 @@ std::vector<hcm_mesh_desc> meshes;
 std::vector<uint64_t> vertices;
 std::vector<uint16_t> indices;
 bool fail_next = false;
+std::vector<std::array<int, 3>> removed;
 uint32_t tag(int x, int y, int z) { return (uint32_t)((x + 50) * 10000 + (y + 50) * 100 + (z + 50)); }
 } // namespace fake
 
@@ -33,6 +34,11 @@ int hcm_registry_from_blob(const void *, size_t, hcm_registry *out) { return *ou
 int hcm_create(const hcm_registry *, const hcm_config *, hcm_ctx **out) { return *out = new hcm_ctx{}, HCM_OK; }
 void hcm_destroy(hcm_ctx *c) { delete c; }
 const char *hcm_last_error(const hcm_ctx *) { return "fake"; }
+int hcm_remove_chunks(hcm_ctx *, uint32_t n, const int16_t *pos) {
+	for (uint32_t i = 0; i < n; ++i)
+		fake::removed.push_back({pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]});
+	return HCM_OK;
+}
 int hcm_set_blocks(hcm_ctx *, uint32_t, const hcm_block_edit *, hcm_edit_result *out) { return *out = hcm_edit_result{}, HCM_OK; }
 // one mesh per task: 4 vertices whose first word is the task position's tag, 6 indices, aabb_min[0] = tag
 int hcm_upload_and_mesh(hcm_ctx *, uint32_t n_chunks, const int16_t *pos, const uint16_t *blocks, const int8_t *heights, uint32_t n_tasks,
@@ -175,6 +181,18 @@ int main() {
 	disp.Flush(sink);
 	CHECK(fake::calls.size() == 6 && fake::calls[5].uploaded.size() == 1 && fake::calls[5].uploaded[0] == (std::array<int, 3>{0, 0, 0}));
 	CHECK(sunk.size() == 2 && sunk[0] == (ChunkPos3{1, 0, 0}) && sunk[1] == (ChunkPos3{0, 0, 0}) && disp.Pending() == 0);
+
+	// round 5b: a chunk is unloaded -- its slot is freed on the device, its own request is dropped, and when it comes back
+	// (same object) it crosses the boundary again
+	sunk.clear();
+	disp.Submit(gather(1, 0, 0));
+	disp.Submit(gather(0, 0, 0));
+	disp.Unload({1, 0, 0});
+	CHECK(fake::removed.size() == 1 && fake::removed[0] == (std::array<int, 3>{1, 0, 0}) && disp.Pending() == 1);
+	disp.Submit(gather(0, 0, 0)); // the neighbour is back in the world before the flush
+	disp.Flush(sink);
+	CHECK(sunk.size() == 1 && sunk[0] == (ChunkPos3{0, 0, 0}));
+	CHECK(fake::calls.back().uploaded.size() == 1 && fake::calls.back().uploaded[0] == (std::array<int, 3>{1, 0, 0}));
 
 	// round 6: Submit from eight threads (the reference calls Run() from its worker pool) while the owner thread flushes
 	{
