@@ -148,7 +148,7 @@ def test_cpp_host_mirror_dispatcher():
     exe = os.path.join(root, "tests", "cpp", "test_dispatcher")
     src = exe + ".cpp"
     lib = os.path.join(root, "hypercraft_b200", "csrc")
-    subprocess.run(["g++", "-std=c++20", "-O2", "-o", exe, src, f"-L{lib}", "-lhcm", "-ldl", f"-Wl,-rpath,{lib}"], check=True)
+    subprocess.run(["g++", "-std=c++20", "-O2", "-pthread", "-o", exe, src, f"-L{lib}", "-lhcm", "-ldl", f"-Wl,-rpath,{lib}"], check=True)
     import hcoracle
 
     hcoracle.build(ref=False, port=True)

@@ -255,7 +255,7 @@ def test_cpp_host_mirror_compiles_and_fails_loudly_without_gpu(tmp_path):
 
     exe = str(tmp_path / "test_dispatcher")
     lib = os.path.join(ROOT, "hypercraft_b200", "csrc")
-    r = subprocess.run(["g++", "-std=c++20", "-O1", "-Wall", "-Wextra", "-Werror", "-o", exe, os.path.join(ROOT, "tests", "cpp", "test_dispatcher.cpp"),
+    r = subprocess.run(["g++", "-std=c++20", "-O1", "-Wall", "-Wextra", "-Werror", "-pthread", "-o", exe, os.path.join(ROOT, "tests", "cpp", "test_dispatcher.cpp"),
                         f"-L{lib}", "-lhcm", "-ldl", f"-Wl,-rpath,{lib}"], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     if torch.cuda.is_available():
