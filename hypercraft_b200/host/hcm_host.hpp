@@ -23,6 +23,7 @@
 #include <stdexcept>
 #include <string>
 #include <unordered_map>
+#include <unordered_set>
 #include <vector>
 
 #include "../../include/hcm.h"
@@ -322,6 +323,159 @@ private:
 	std::vector<int16_t> m_pos;
 	std::vector<uint16_t> m_blocks;
 	std::vector<int8_t> m_heights;
+};
+
+// One MeshTaskDispatcher per GPU over x-slabs of the world: chunks are independent given their halo, so
+// the GPUs never exchange anything -- a task runs on the GPU whose slab [x_lo, x_hi) holds its position, and that GPU's
+// window spans the planes x_lo - 1 .. x_hi, i.e. the boundary planes live on both neighbours.  The host's Chunk objects
+// are the authority: a chunk that changes is marked dirty on every GPU that can hold it and goes up again with the next
+// task that reads it.  Edits (SetBlocks) run on the owner of the edited chunk, whose column of the world is complete
+// (the sunlight chain walks along y, the cut is along x); GPUs holding a touched chunk as halo do not run the chain, they
+// take the chunk as data.  hypercraft_b200/shard.py is the same bookkeeping for the Python benchmark.
+template <typename ChunkT> class ShardedMeshDispatcher {
+public:
+	using Shard = MeshTaskDispatcher<ChunkT>;
+	struct Slab {
+		int device;        // CUDA ordinal
+		int16_t x_lo, x_hi; // tasks with x_lo <= x < x_hi
+	};
+	// world window: origin / extent in y and z are shared, x comes from the slabs (which must tile an x-range, in order)
+	ShardedMeshDispatcher(const void *registry_blob, size_t blob_size, const std::vector<Slab> &slabs, int16_t origin_y, int16_t origin_z,
+	                      uint16_t extent_y, uint16_t extent_z)
+	    : m_slabs(slabs) {
+		if (slabs.empty())
+			throw Error(HCM_ERR_INVALID, "no slabs");
+		for (size_t r = 0; r < slabs.size(); ++r) {
+			if (slabs[r].x_hi <= slabs[r].x_lo || (r && slabs[r].x_lo != slabs[r - 1].x_hi))
+				throw Error(HCM_ERR_INVALID, "slabs must be non-empty and tile the x-range in order");
+			m_shards.push_back(std::make_unique<Shard>(registry_blob, blob_size, slabs[r].device, ChunkPos3{(int16_t)(slabs[r].x_lo - 1), origin_y, origin_z},
+			                                           std::array<uint16_t, 3>{(uint16_t)(slabs[r].x_hi - slabs[r].x_lo + 2), extent_y, extent_z}));
+		}
+	}
+
+	size_t Ranks() const { return m_shards.size(); }
+	Shard &Rank(size_t r) { return *m_shards[r]; }
+	// rank whose slab holds x; -1 outside all slabs
+	int Owner(int x) const {
+		for (size_t r = 0; r < m_slabs.size(); ++r)
+			if (x >= m_slabs[r].x_lo && x < m_slabs[r].x_hi)
+				return (int)r;
+		return -1;
+	}
+	// ranks whose window (slab dilated by one plane) reaches the x-plane, the owner included
+	std::vector<int> Holders(int x) const {
+		std::vector<int> out;
+		for (size_t r = 0; r < m_slabs.size(); ++r)
+			if (x >= m_slabs[r].x_lo - 1 && x <= m_slabs[r].x_hi)
+				out.push_back((int)r);
+		return out;
+	}
+
+	void Submit(const std::array<std::shared_ptr<ChunkT>, 27> &chunks, bool high_priority = false) {
+		m_shards[owner_or_throw((int)chunks[26]->GetPosition().x)]->Submit(chunks, high_priority);
+	}
+	void MarkDirty(const ChunkPos3 &pos) {
+		for (int r : Holders(pos.x))
+			m_shards[r]->MarkDirty(pos);
+	}
+	void Unload(const ChunkPos3 &pos) {
+		for (int r : Holders(pos.x))
+			m_shards[r]->Unload(pos);
+	}
+	size_t Pending() const {
+		size_t n = 0;
+		for (const auto &s : m_shards)
+			n += s->Pending();
+		return n;
+	}
+
+	// ChunkShouldRemesh (client/include/client/ChunkMeshTask.inl:9-15): a block at `rel` (relative to a chunk's origin) can change
+	// that chunk's mesh iff its L1 distance to the box [-1,33]^3 is below 15 (BlockLightAlgo.hpp:32-42 with level 15)
+	static bool ShouldRemesh(int rx, int ry, int rz) {
+		int dist = 0;
+		for (int c : {rx, ry, rz})
+			dist += c < -1 ? -1 - c : (c >= HCM_CHUNK_SIZE + 1 ? c - (HCM_CHUNK_SIZE + 1) : 0);
+		return dist < 15;
+	}
+
+	// Edits go to the owner of their chunk; its heights and its remesh fan-out are the undivided world's for every position it
+	// can see whole.  A fan-out position in ANOTHER slab is not reported by the owner's ctx (one of its 27 chunks lies outside
+	// that window), so those are derived here from the reference's rules: per edit the neighbours passing ChunkShouldRemesh
+	// (ChunkSetBlockTask.cpp:100-107; every edit is taken as a change -- a superset by the no-op edits), per changed height
+	// the 26 neighbours (ChunkSetSunlightTask.cpp:66-78).  `on_sunlight` / `on_remesh` as in MeshTaskDispatcher::SetBlocks: the
+	// caller updates its Chunk objects in on_sunlight and answers on_remesh -- for positions whose 27 chunks exist, the test
+	// Pop() makes in the reference -- with Submit(the 27 chunks, true), which lands on the rank that owns the position.  Every
+	// touched chunk is marked dirty on the ranks that hold it as halo: the next task there that reads it uploads the host's
+	// (by then current) copy.  on_remesh runs after every owner has applied its edits.
+	using SetBlock = typename Shard::SetBlock;
+	using SunlightChange = typename Shard::SunlightChange;
+	template <typename OnSunlight, typename OnRemesh> uint32_t SetBlocks(const std::vector<SetBlock> &edits, OnSunlight &&on_sunlight, OnRemesh &&on_remesh) {
+		std::vector<std::vector<SetBlock>> by_rank(m_shards.size());
+		for (const SetBlock &e : edits)
+			by_rank[owner_or_throw(e.chunk.x)].push_back(e);
+		uint32_t changed = 0;
+		std::vector<ChunkPos3> remesh;
+		std::unordered_set<ChunkPos3, ChunkPos3Hash> seen;
+		auto add = [&](const ChunkPos3 &p) {
+			if (seen.insert(p).second)
+				remesh.push_back(p);
+		};
+		for (size_t r = 0; r < m_shards.size(); ++r) {
+			if (by_rank[r].empty())
+				continue;
+			auto add_foreign = [&](const ChunkPos3 &c, int dx, int dy, int dz) { // a fan-out position the owner's ctx cannot report
+				const ChunkPos3 q{(int16_t)(c.x + dx), (int16_t)(c.y + dy), (int16_t)(c.z + dz)};
+				const int o = Owner(q.x);
+				if (o >= 0 && o != (int)r)
+					add(q);
+			};
+			std::vector<ChunkPos3> touched;
+			for (const SetBlock &e : by_rank[r]) {
+				touched.push_back(e.chunk);
+				const int bx = e.index & 31, by = e.index >> 10, bz = (e.index >> 5) & 31; // InnerIndex3: x + (y*32 + z)*32
+				for (int dx = -1; dx <= 1; dx += 2) // only a step in x leaves the slab
+					for (int dy = -1; dy <= 1; ++dy)
+						for (int dz = -1; dz <= 1; ++dz)
+							if (ShouldRemesh(bx - dx * HCM_CHUNK_SIZE, by - dy * HCM_CHUNK_SIZE, bz - dz * HCM_CHUNK_SIZE))
+								add_foreign(e.chunk, dx, dy, dz);
+			}
+			changed += m_shards[r]->SetBlocks(
+			    by_rank[r],
+			    [&](const SunlightChange &s) {
+				    touched.push_back(s.chunk);
+				    for (int dx = -1; dx <= 1; dx += 2)
+					    for (int dy = -1; dy <= 1; ++dy)
+						    for (int dz = -1; dz <= 1; ++dz)
+							    add_foreign(s.chunk, dx, dy, dz);
+				    on_sunlight(s);
+			    },
+			    [&](const ChunkPos3 &p) { add(p); });
+			for (const ChunkPos3 &c : touched)
+				for (int h : Holders(c.x))
+					if (h != (int)r)
+						m_shards[h]->MarkDirty(c);
+		}
+		for (const ChunkPos3 &p : remesh)
+			on_remesh(p);
+		return changed;
+	}
+
+	// Every rank's round, one after the other on the calling thread (a HyperCraft build would give each rank its own thread:
+	// the shards share nothing).  max_tasks is per rank.
+	template <typename Sink> void Flush(Sink &&sink, size_t max_tasks = SIZE_MAX) {
+		for (auto &s : m_shards)
+			s->Flush(sink, max_tasks);
+	}
+
+private:
+	size_t owner_or_throw(int x) const {
+		const int r = Owner(x);
+		if (r < 0)
+			throw Error(HCM_ERR_OUT_OF_WINDOW, "position outside every slab");
+		return (size_t)r;
+	}
+	std::vector<Slab> m_slabs;
+	std::vector<std::unique_ptr<Shard>> m_shards;
 };
 
 } // namespace hcm_host

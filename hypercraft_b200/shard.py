@@ -69,7 +69,7 @@ def window_for(resident: np.ndarray) -> tuple[tuple[int, int, int], tuple[int, i
 # column of the world, i.e. exactly what the single-GPU world gives the sunlight chain (the chain walks along y, a slab is
 # cut along x), so its hcm_set_blocks result -- changed heights and remesh fan-out -- is the undivided world's.  A rank that holds a touched chunk only as halo does NOT run the chain (the chunk above may be outside its
 # dilation): it takes the owner's chunk as data (hcm_upload_chunks of that one chunk) before it meshes.  Remesh tasks go
-# to the rank that owns their position.  All of it is host-side bookkeeping of a few bytes per edit; no collective.
+# to the rank that owns their position; the owner's ctx reports those inside its slab, foreign_fanout() the rest.  All of it is host-side bookkeeping of a few bytes per edit; no collective.
 
 def resident_for_slab(world_resident: np.ndarray, bounds, rank: int) -> np.ndarray:
     """Residency of a rank that also takes edits: every chunk of the undivided world's resident set in the x-planes
@@ -113,6 +113,31 @@ def mirror_plan(touched_chunks, bounds) -> list[list[tuple[int, int, int]]]:
     for c in sorted({tuple(int(v) for v in c) for c in touched_chunks}):
         for r in halo_ranks(c, bounds):
             out[r].append(c)
+    return out
+
+
+def foreign_fanout(edit_list, sunlight_chunks, bounds, rank: int) -> set:
+    """Remesh positions in OTHER ranks' slabs caused by `rank`'s edits.  Its hcm_set_blocks cannot report them -- one of their
+    27 chunks lies outside its window, so the device counts them as pending -- hence they follow from the reference's rules on
+    the host: per edit the neighbours passing ChunkShouldRemesh (ChunkSetBlockTask.cpp:100-107; every edit counts as a change,
+    a superset by the no-op edits), per chunk with a changed sunlight height all 26 neighbours (ChunkSetSunlightTask.cpp:66-78).
+    Same rule as hcm_host::ShardedMeshDispatcher::SetBlocks."""
+    from . import edits as _edits
+
+    out = set()
+    for cpos, index, _ in edit_list:
+        bp = (int(index) & 31, int(index) >> 10, (int(index) >> 5) & 31)
+        for d in _edits.remesh_offsets(bp):
+            q = (int(cpos[0]) + d[0], int(cpos[1]) + d[1], int(cpos[2]) + d[2])
+            if owner_rank(q, bounds) != rank:
+                out.add(q)
+    for c in sunlight_chunks:
+        for dx in (-1, 1):
+            for dy in (-1, 0, 1):
+                for dz in (-1, 0, 1):
+                    q = (int(c[0]) + dx, int(c[1]) + dy, int(c[2]) + dz)
+                    if owner_rank(q, bounds) != rank:
+                        out.add(q)
     return out
 
 

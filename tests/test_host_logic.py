@@ -307,11 +307,12 @@ def test_bench_cpu_side_helpers(have_ref):
         json.dumps({**sec, "pool": pb, "algo": bench.algorithmic_bytes(3, 4, 5)})
 
 
-@pytest.mark.parametrize("name", ["test_request_queue", "test_dispatcher_logic"])
+@pytest.mark.parametrize("name", ["test_request_queue", "test_dispatcher_logic", "test_sharded_dispatcher"])
 def test_cpp_host_mirror_logic(tmp_path, name):
     """The C++ host mirror's own logic, no GPU and no libhcm.so: the request queue's dedupe / priority rules
     (ChunkMeshTask.inl:38-48) and MeshTaskDispatcher against a recording fake of the C ABI (which chunks cross the
-    boundary, one task per position, high priority first, task budget, task -> sink mapping)."""
+    boundary, one task per position, high priority first, task budget, task -> sink mapping), and ShardedMeshDispatcher
+    against one fake ctx per GPU (tasks on the slab owner, boundary planes on both GPUs, edits next to a cut)."""
     import subprocess
 
     exe = str(tmp_path / name)
@@ -372,16 +373,20 @@ def test_sharded_edit_round_equals_the_undivided_world(port, world):
         n_sum += n
         assert not set(sun) & set(sun_all)
         sun_all.update(sun)
-        remesh_all |= remesh
+        lo, hi = bounds[r]
+        # what the owner's ctx can report (positions it sees whole: its own slab) + the host-derived fan-out into other slabs
+        remesh_all |= {p for p in remesh if lo <= p[0] < hi} | shard.foreign_fanout(mine, {c for c, _ in sun}, bounds, r)
         touched = {e[0] for e in mine} | {c for c, _ in sun}
         for h, chunks in enumerate(shard.mirror_plan(touched, bounds)):
             for c in chunks:  # the halo holder takes the owner's chunk as data
                 assert h != r and c in worlds[h]
                 worlds[h][c] = (worlds[r][c][0].copy(), worlds[r][c][1].copy())
                 mirrored += 1
-    assert n_sum == n1 and sun_all == sun1 and {p for p in remesh_all if p in task_set} == remesh1
+    remesh_all = {p for p in remesh_all if p in task_set}
+    assert n_sum == n1 and sun_all == sun1 and remesh1 <= remesh_all  # a superset only by edits that changed nothing
+    assert any(shard.owner_rank(p, bounds) != shard.owner_rank(e[0], bounds) for e in edit_list for p in [tuple(np.add(e[0], d)) for d in edits.remesh_offsets((e[1] & 31, e[1] >> 10, (e[1] >> 5) & 31))])
     stale = 0
-    for r, tasks in enumerate(shard.split_tasks(remesh1, bounds)):
+    for r, tasks in enumerate(shard.split_tasks(remesh_all, bounds)):
         lo, hi = bounds[r]
         for t in tasks:
             assert lo <= t[0] < hi
