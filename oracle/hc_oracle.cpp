@@ -8,7 +8,7 @@
 //
 // PARITY PINNING: the reference holds no tests or golden vectors for this path, so this
 // restatement is pinned against the reference itself, compiled unmodified into oracle/_ref/libhcref.so:
-// tests/test_oracle_vs_reference.py compares serialised meshes byte for byte on reference-terrain chunks and on
+// tests/test_oracle_golden.py compares serialised meshes byte for byte on reference-terrain chunks and on
 // synthetic stress chunks, and tests/golden/ holds hashes recorded from the reference for the synthetic
 // (machine-independent) inputs.
 //
