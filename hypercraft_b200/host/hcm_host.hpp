@@ -18,10 +18,12 @@
 #include <cstddef>
 #include <cstdint>
 #include <cstring>
+#include <exception>
 #include <memory>
 #include <mutex>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <unordered_map>
 #include <unordered_set>
 #include <vector>
@@ -465,6 +467,28 @@ public:
 	template <typename Sink> void Flush(Sink &&sink, size_t max_tasks = SIZE_MAX) {
 		for (auto &s : m_shards)
 			s->Flush(sink, max_tasks);
+	}
+
+	// The same with one host thread per GPU, so that the GPUs work at the same time.  `sink` is called from those threads
+	// concurrently -- as WorldRenderer::PushChunkMesh is in the reference, where every worker pushes its own result (it is
+	// thread-safe: cuckoo map + MPMC queue, WorldRenderer.hpp:69-87).  The first error of any rank is rethrown after all ranks
+	// have finished; the other ranks' rounds are not affected (a failed round stays pending on its rank).
+	template <typename Sink> void FlushParallel(Sink &&sink, size_t max_tasks = SIZE_MAX) {
+		std::vector<std::thread> threads;
+		std::vector<std::exception_ptr> errors(m_shards.size());
+		for (size_t r = 0; r < m_shards.size(); ++r)
+			threads.emplace_back([&, r] {
+				try {
+					m_shards[r]->Flush(sink, max_tasks);
+				} catch (...) {
+					errors[r] = std::current_exception();
+				}
+			});
+		for (auto &t : threads)
+			t.join();
+		for (auto &e : errors)
+			if (e)
+				std::rethrow_exception(e);
 	}
 
 private:

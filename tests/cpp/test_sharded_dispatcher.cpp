@@ -5,6 +5,7 @@
 // both neighbours, an edit next to a cut is applied by the owner alone, remeshes the tasks across the cut as well, and makes
 // the other GPU take the edited chunk again.
 #include <algorithm>
+#include <atomic>
 #include <cstdio>
 #include <map>
 #include <set>
@@ -27,7 +28,7 @@ struct hcm_ctx {
 };
 }
 static std::vector<hcm_ctx *> g_ctx;
-static int g_violations = 0;
+static std::atomic<int> g_violations{0};
 
 extern "C" {
 int hcm_registry_from_blob(const void *, size_t, hcm_registry *out) { return *out = hcm_registry{}, HCM_OK; }
@@ -232,6 +233,24 @@ int main() {
 	disp.Flush(sink);
 	CHECK(g_ctx[0]->tasks.size() == 3 && g_ctx[0]->tasks[2].size() == 9 && g_ctx[0]->uploads[2].size() == 1 && g_ctx[0]->uploads[2][0] == (P3{0, 0, 0}));
 	CHECK(g_ctx[1]->tasks.size() == 4 && g_ctx[1]->tasks[3].size() == 18 && g_ctx[1]->uploads[3].empty() && sunk.size() == 27 && g_violations == 0);
+
+	// both GPUs' rounds on their own host threads: the sink is called concurrently, every task exactly once
+	{
+		for (int x = -3; x <= 2; ++x)
+			for (int y = -1; y <= 1; ++y)
+				for (int z = -1; z <= 1; ++z)
+					disp.Submit(gather(x, y, z));
+		std::atomic<int> pushed{0}, wrong_rank{0};
+		std::mutex mu;
+		std::set<P3> seen;
+		disp.FlushParallel([&](const ChunkPos3 &p, std::vector<hcm_host::BlockMesh> &&) {
+			++pushed;
+			std::lock_guard<std::mutex> g(mu);
+			wrong_rank += !seen.insert({p.x, p.y, p.z}).second;
+		});
+		CHECK(pushed == 54 && wrong_rank == 0 && seen.size() == 54 && disp.Pending() == 0 && g_violations == 0);
+		CHECK(g_ctx[0]->tasks.back().size() == 27 && g_ctx[1]->tasks.back().size() == 27 && g_ctx[0]->uploads.back().empty() && g_ctx[1]->uploads.back().empty());
+	}
 
 	printf("%s\n", fails ? "FAIL" : "PASS");
 	return fails != 0;
