@@ -266,6 +266,16 @@ public:
 				m_snapshot.erase(it);
 			}
 		}
+		if (upload.size() > 1) { // a chunk that was replaced while its first copy was still waiting: only the latest object goes up
+			std::unordered_set<ChunkPos3, ChunkPos3Hash> seen;
+			std::vector<std::shared_ptr<ChunkT>> latest;
+			for (size_t i = upload.size(); i-- > 0;) {
+				const auto p = upload[i]->GetPosition();
+				if (seen.insert(ChunkPos3{(int16_t)p.x, (int16_t)p.y, (int16_t)p.z}).second)
+					latest.push_back(std::move(upload[i]));
+			}
+			upload.assign(latest.rbegin(), latest.rend());
+		}
 		const size_t n = upload.size();
 		if (n) {
 			m_pos.resize(n * 3), m_blocks.resize(n * HCM_CHUNK_VOXELS), m_heights.resize(n * HCM_CHUNK_COLUMNS);

@@ -15,6 +15,7 @@
 namespace fake {
 struct Call {
 	std::vector<std::array<int, 3>> uploaded, tasks;
+	std::vector<uint16_t> version; // blocks[1] of every uploaded chunk
 };
 std::vector<Call> calls;
 std::vector<hcm_task_result> tasks;
@@ -48,6 +49,7 @@ int hcm_upload_and_mesh(hcm_ctx *, uint32_t n_chunks, const int16_t *pos, const 
 	fake::Call c;
 	for (uint32_t i = 0; i < n_chunks; ++i) {
 		c.uploaded.push_back({pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]});
+		c.version.push_back(blocks[(size_t)i * HCM_CHUNK_VOXELS + 1]);
 		// the marshalled arrays carry the chunk's own data (block 0 = its tag, height 0 = its x)
 		if (blocks[(size_t)i * HCM_CHUNK_VOXELS] != (uint16_t)fake::tag(pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]) || heights[(size_t)i * HCM_CHUNK_COLUMNS] != (int8_t)pos[3 * i])
 			return HCM_ERR_INVALID;
@@ -193,6 +195,18 @@ int main() {
 	disp.Flush(sink);
 	CHECK(sunk.size() == 1 && sunk[0] == (ChunkPos3{0, 0, 0}));
 	CHECK(fake::calls.back().uploaded.size() == 1 && fake::calls.back().uploaded[0] == (std::array<int, 3>{1, 0, 0}));
+
+	// round 5c: a chunk object is replaced twice while a task that reads it is waiting -- one copy goes up, the latest
+	sunk.clear();
+	for (uint16_t version : {7, 8}) {
+		world[{0, 1, 0}] = std::make_shared<Chunk>(*world.at({0, 1, 0}));
+		world.at({0, 1, 0})->blocks[1] = version;
+		disp.MarkDirty({0, 1, 0});
+		disp.Submit(gather(0, 0, 0));
+	}
+	disp.Flush(sink);
+	CHECK(sunk.size() == 1 && fake::calls.back().uploaded.size() == 1 && fake::calls.back().uploaded[0] == (std::array<int, 3>{0, 1, 0}) &&
+	      fake::calls.back().version[0] == 8);
 
 	// round 6: Submit from eight threads (the reference calls Run() from its worker pool) while the owner thread flushes
 	{
