@@ -151,6 +151,8 @@ void hcm_host_free(void *p);
  *   pos    : Chunk::GetPosition() (ChunkPos3 = i16vec3)
  * The call enqueues the host->device copy and the derivation kernel on the ctx stream and returns; the host
  * arrays must stay valid until hcm_sync / hcm_mesh_fetch.  Re-uploading a position replaces it (block edits).
+ * Positions must be distinct within one call: both copies of a repeated position would target one device slot and
+ * which one stays is undefined (hcm_host::MeshTaskDispatcher sends the latest object only).
  * Large uploads scan the host arrays for uniform chunks on worker threads (environment HCM_HOST_THREADS, default
  * min(15, cores - 1)); set it when several processes share one host, one ctx per GPU.
  * ---------------------------------------------------------------------------------------------------------- */
