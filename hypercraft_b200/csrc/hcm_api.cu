@@ -210,11 +210,18 @@ inline bool chunk_is_uniform_generic(const uint16_t *b) {
 	const uint16_t v = b[0];
 	return b[1] == v && b[2] == v && b[3] == v && memcmp(b, b + 4, (HCM_CHUNK_VOXELS - 4) * 2) == 0;
 }
-// one aligned-or-not 32-byte load per 16 voxels, early exit every 256 bytes (terrain chunks differ within the first rows)
+// one aligned-or-not 32-byte load per 16 voxels, early exit every 256 bytes (terrain chunks differ within the first rows).
+// The scan of a uniform chunk is a pure DRAM stream over 4 KB pages, where the hardware prefetchers stop at every page
+// boundary: software prefetches 4 KB ahead (into the next chunk at the end; a prefetch never faults) measured +10..20 % per
+// thread and at 8 threads on the build host (11 -> 12.5 GB/s, 78 -> 88 GB/s).
+constexpr int kScanPrefetchAhead = 4096;
 __attribute__((target("avx2"))) bool chunk_is_uniform_avx2(const uint16_t *b) {
 	const __m256i v = _mm256_set1_epi16((short)b[0]);
 	const __m256i *p = reinterpret_cast<const __m256i *>(b);
+	const char *ahead = reinterpret_cast<const char *>(b) + kScanPrefetchAhead;
 	for (int i = 0; i < HCM_CHUNK_VOXELS / 16; i += 8) {
+		_mm_prefetch(ahead + i * 32, _MM_HINT_T0), _mm_prefetch(ahead + i * 32 + 64, _MM_HINT_T0);
+		_mm_prefetch(ahead + i * 32 + 128, _MM_HINT_T0), _mm_prefetch(ahead + i * 32 + 192, _MM_HINT_T0);
 		__m256i a0 = _mm256_xor_si256(_mm256_loadu_si256(p + i), v), a1 = _mm256_xor_si256(_mm256_loadu_si256(p + i + 1), v);
 		__m256i a2 = _mm256_xor_si256(_mm256_loadu_si256(p + i + 2), v), a3 = _mm256_xor_si256(_mm256_loadu_si256(p + i + 3), v);
 		a0 = _mm256_or_si256(a0, _mm256_xor_si256(_mm256_loadu_si256(p + i + 4), v)), a1 = _mm256_or_si256(a1, _mm256_xor_si256(_mm256_loadu_si256(p + i + 5), v));
