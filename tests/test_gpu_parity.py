@@ -54,6 +54,35 @@ def test_mesh_matches_oracle(mesher, port, kind, seed):
     assert hashlib.sha256(got.tobytes()).hexdigest() == GOLDEN["cases"][f"{kind}/{seed}"]["mesh_sha256"]  # the reference's own bytes
 
 
+TERRAIN = [(12314524, (0, 0, 0)), (12314524, (0, 1, 2)), (12314524, (2, -1, 1)), (7, (-2, 0, -1)), (7, (0, 0, 1)), (7, (-1, -1, -2))]
+
+
+@pytest.mark.parametrize("i", range(len(TERRAIN)))
+def test_terrain_goldens(port, i):
+    """Surface chunks of the repo's integer-hash height-field terrain (oceans, plants, lamps): CUDA mesh and light volume
+    against the oracle and against the digests the unmodified reference produced for the same inputs."""
+    from hypercraft_b200 import mesher as M
+    from hypercraft_b200 import worldgen
+
+    seed, centre = TERRAIN[i]
+    pos = worldgen.neighbourhood(centre)
+    data = [worldgen.synth_terrain_chunk(seed, p) for p in pos]
+    blocks, heights = np.stack([d[0] for d in data]), np.stack([d[1] for d in data])
+    chunks = {tuple(int(c) for c in p): d for p, d in zip(pos, data)}
+    m = M.Mesher(origin=tuple(c - 2 for c in centre), extent=(5, 5, 5))
+    try:
+        m.upload(pos, blocks, heights)
+        got = m.mesh(np.array([centre], dtype=np.int16)).serialise(0)
+        light = m.debug_light(centre)
+    finally:
+        m.close()
+    want = port.mesh(chunks, centre)
+    assert got.size == want.size and (got == want).all(), describe_diff(got, want)
+    assert (light == port.light34(chunks, centre)).all()
+    assert hashlib.sha256(got.tobytes()).hexdigest() == GOLDEN["terrain"][i]["mesh_sha256"]
+    assert hashlib.sha256(light.tobytes()).hexdigest() == GOLDEN["terrain"][i]["light_sha256"]
+
+
 def test_mixed_neighbourhood(mesher, port):
     """Centre of one kind, neighbours of others: halo faces, halo flowing water, halo light sources."""
     combos = [("stone", {(1, 0, 0): "air", (0, 1, 0): "mix", (0, 0, -1): "flow"}),
