@@ -13,7 +13,13 @@ kWorldMaxLoadRadius (client/include/client/Config.hpp:14), terrain from the refe
                                                   = hcm_upload_chunks + hcm_mesh_batch + hcm_mesh_fetch, overlapped)
 Multi-GPU (--gpus N under torchrun): chunks are independent given their halo, so every rank meshes its own sphere
 (centre shifted by 3r chunks per rank) with no collective on the data path -> weak scaling; value = total chunks of
-all ranks / max-over-ranks time.
+all ranks / max-over-ranks time.  For N > 1 the line also carries `config4`: ONE r = 32 sphere (BASELINE.json
+configs[3]) cut into x-slabs balanced by estimated worked chunks, one slab (dilated by a chunk) per GPU, kernel-only and
+end to end.  For N = 1 it carries `secondary_configs`: configs[2] (worst-case chunks) and configs[4] (edit-driven remesh).
+
+Parity gate: EVERY chunk meshed in the last end-to-end step of EVERY rank is compared with the reference CPU mesher through
+a digest of its serialised meshes (mesh count, flags, AABBs, vertex bytes, index bytes); the mismatch count is summed over
+the ranks.  `parity.byte_compared_chunks == parity.chunks_meshed` is the bar.
 
 Prints ONE JSON line on rank 0.
 """
@@ -35,6 +41,8 @@ sys.path.insert(0, os.path.join(ROOT, "oracle"))
 
 SEED = 12314524  # client/src/LocalClient.cpp:37
 H_BYTES = 34 ** 3 * 3  # blocks (2 B) + light (1 B) on [-1,32]^3: SURVEY.md section 8d
+# derive_kernel per chunk: reads Block data + heights, writes property bytes, pass / torch words, heights
+DERIVE_READ, DERIVE_WRITE_FIXED, DERIVE_WRITE_PER_LEVEL = 65536 + 1024, 32768 + 4096 + 1024, 4096
 
 
 def parse_args():
@@ -45,9 +53,11 @@ def parse_args():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--radius", type=int, default=20)
     ap.add_argument("--strong", action="store_true",
-                    help="BASELINE config 4: ONE load sphere cut into x-slabs of equal task count, one slab (dilated by a chunk) per GPU")
-    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU work of the cpu_baseline sample")
-    ap.add_argument("--no-cpu-baseline", action="store_true")
+                    help="make BASELINE config 4 the headline: ONE load sphere cut into x-slabs, one slab (dilated by a chunk) per GPU")
+    ap.add_argument("--config4-radius", type=int, default=32, help="radius of the config4 block printed for --gpus N > 1 (0 = skip it)")
+    ap.add_argument("--no-secondary", action="store_true", help="skip secondary_configs (configs 3 and 5) at N = 1")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU work per step of the --impl reference arm")
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU leg (parity gate and cpu_baseline): profiling runs only")
     return ap.parse_args()
 
 
@@ -96,36 +106,42 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
 
 
-def build_world(radius: int, centre, threads: int, shard=None):
-    """(meshed positions, resident positions, pinned blocks, pinned heights, data label, CPU arm: RefWorld or PortArm).
-    shard = (world, rank): only this rank's x-slab of the task list and its one-chunk dilation (hypercraft_b200/shard.py)."""
+def make_cpu_arm(threads: int):
+    """(arm, provide(positions), data label): the CPU side of the bench -- input generator, parity checker and CPU baseline.  The
+    unmodified reference from oracle/_ref when it was built, else this repo's port on its own integer-hash terrain."""
     import hcoracle
-    from hypercraft_b200 import mesher, worldgen
+    from hypercraft_b200 import worldgen
 
-    meshed, resident = worldgen.load_radius_positions(radius)
-    c = np.asarray(centre, dtype=np.int16)
-    meshed = (meshed + c).astype(np.int16)
-    resident = (resident + c).astype(np.int16)
-    if shard is not None:
-        from hypercraft_b200 import shard as sh
-
-        # equal task counts: measured better (2.40 ms at r=32 on 8 GPUs) than shard.surface_weights' y-band estimate (2.65 ms)
-        meshed = sh.shard_tasks(meshed, shard[0], shard[1])
-        resident = sh.resident_for(meshed)
-    pb = mesher.PinnedArray((len(resident), 32768), np.uint16)
-    ph = mesher.PinnedArray((len(resident), 1024), np.int8)
-    ref = None
     if use_reference_build():
         ref = hcoracle.RefWorld()
-        ref.generate(resident, seed=SEED, threads=threads)
-        ref.get_chunks(resident, pb.array, ph.array)
-        label = f"synthetic: reference DefaultTerrain(seed {SEED}) run on this host via oracle/_ref (no dataset)"
-    else:
+
+        def provide(need):
+            ref.generate(need, seed=SEED, threads=threads)
+
+        return ref, provide, f"synthetic: reference DefaultTerrain(seed {SEED}) run on this host via oracle/_ref (no dataset)"
+    arm = PortArm({})
+
+    def provide(need):
+        for q in need:
+            key = tuple(int(c) for c in q)
+            if key not in arm.chunks:
+                arm.chunks[key] = worldgen.synth_terrain_chunk(SEED, q)
+
+    return arm, provide, "synthetic: repo height-field terrain (oracle/_ref terrain generator not available)"
+
+
+def fill_pinned(arm, resident):
+    """Pinned host arrays (blocks, heights) of `resident` from the CPU arm's world."""
+    from hypercraft_b200 import mesher
+
+    pb = mesher.PinnedArray((len(resident), 32768), np.uint16)
+    ph = mesher.PinnedArray((len(resident), 1024), np.int8)
+    if isinstance(arm, PortArm):
         for i, p in enumerate(resident):
-            pb.array[i], ph.array[i] = worldgen.synth_terrain_chunk(SEED, p)
-        ref = PortArm({tuple(int(c) for c in p): (pb.array[i], ph.array[i]) for i, p in enumerate(resident)})
-        label = "synthetic: repo height-field terrain (oracle/_ref terrain generator not available)"
-    return meshed, resident, pb, ph, label, ref
+            pb.array[i], ph.array[i] = arm.chunks[tuple(int(c) for c in p)]
+    else:
+        arm.get_chunks(resident, pb.array, ph.array)
+    return pb, ph
 
 
 def workload_name(radius: int, strong: bool = False) -> str:
@@ -145,9 +161,10 @@ def cpu_model() -> str:
 
 
 def algorithmic_bytes(n_chunks: int, n_vertices: int, n_meshes: int) -> dict:
-    """SURVEY 8d, per mesh_kernel launch: the canonical figure roofline.achieved uses (34^3 halo blocks 2 B + light 1 B per chunk, 8 B
-    per vertex written) and the two secondary ones -- "full": what the reference task really touches (62^3 blocks + 3 x 62^2 heights,
-    light re-derived from raw blocks); "min": every chunk read once from HBM with perfect halo reuse, vertices + indices + mesh infos."""
+    """SURVEY 8d for `n_chunks` chunks that emit `n_vertices` vertices: the canonical figure roofline.achieved uses (34^3 halo blocks
+    2 B + light 1 B per chunk, 8 B per vertex written) and the two secondary ones -- "full": what the reference task really touches
+    (62^3 blocks + 3 x 62^2 heights, light re-derived from raw blocks); "min": every chunk read once from HBM with perfect halo reuse,
+    vertices + indices + mesh infos."""
     return {"canonical": n_chunks * H_BYTES + 8 * n_vertices,
             "full": n_chunks * (62 ** 3 * 2 + 62 * 62 * 3) + 8 * n_vertices,
             "min": n_chunks * 66560 + 11 * n_vertices + 40 * n_meshes}
@@ -159,6 +176,37 @@ def roofline_secondary(algo: dict, kernel_ms: float, peak_gbs: float) -> dict:
                               "frac": algo[k] / (kernel_ms / 1e3) / 1e9 / peak_gbs} for k in ("full", "min")},
             "secondary_formulas": {"full": "62^3*2 + 62*62*3 + 8*V per chunk (what the reference task touches)",
                                    "min": "66560 + 11*V + 40*M per chunk (each chunk read once, vertices + indices + mesh infos)"}}
+
+
+def derive_bytes(n_chunks: int, n_levels: int = 1) -> int:
+    """derive_kernel's algorithmic bytes for one launch over n_chunks resident chunks."""
+    return n_chunks * (DERIVE_READ + DERIVE_WRITE_FIXED + DERIVE_WRITE_PER_LEVEL * n_levels)
+
+
+def roofline_block(n_meshed: int, n_worked: int, n_resident: int, n_vertices: int, n_meshes: int, kernel_ms: dict, ms_per_step: float, peak_gbs: float,
+                   peak_src: str, traffic: dict | None) -> dict:
+    """The `roofline` object of the bench line.  The dominant kernel is mesh_kernel, and ONE launch of it processes the `n_worked`
+    chunks classify_kernel did not answer from the chunk flags -- those are its units (every emitted vertex belongs to one of
+    them).  `step_frac` is the whole step (derive + classify + mesh) against the canonical bytes of ALL meshed chunks."""
+    k_ms = kernel_ms["mesh"]
+    algo = algorithmic_bytes(n_worked, n_vertices, n_meshes)
+    achieved = algo["canonical"] / (k_ms / 1e3) / 1e9
+    all_bytes = algorithmic_bytes(n_meshed, n_vertices, n_meshes)["canonical"]
+    d_bytes = derive_bytes(n_resident)
+    d_ach = d_bytes / (kernel_ms["derive"] / 1e3) / 1e9
+    t = traffic or {}
+    return {"bound": "hbm", "kernel": "hcm::mesh_kernel", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
+            "traffic": t.get("mesh_kernel_dram_bytes_per_launch"), "traffic_source": t.get("source"), "peak_source": peak_src,
+            "units_per_launch": int(n_worked), "unit_name": "chunks through the full light + mesh path (classify_kernel answers the others from chunk flags)",
+            "algorithmic_bytes_per_launch": int(algo["canonical"]), "formula": "sum over the launch's worked chunks of 34^3*3 + 8*vertices (SURVEY 8d)",
+            "kernel_ms": k_ms,
+            "step_frac": all_bytes / (ms_per_step / 1e3) / 1e9 / peak_gbs,
+            "step_formula": "sum over ALL meshed chunks of 34^3*3 + 8*vertices, over ms_per_step (derive + classify + mesh)",
+            "derive_kernel": {"kernel": "hcm::derive_kernel", "units_per_launch": int(n_resident), "algorithmic_bytes_per_launch": int(d_bytes),
+                              "formula": "per resident chunk: 66560 read + 41984 written (property bytes, pass + torch words, heights)",
+                              "kernel_ms": kernel_ms["derive"], "achieved": d_ach, "frac": d_ach / peak_gbs,
+                              "traffic": t.get("derive_kernel_dram_bytes_per_launch")},
+            **roofline_secondary(algo, k_ms, peak_gbs)}
 
 
 def pool_baseline(ref, positions, cpu_threads: int) -> dict:
@@ -197,30 +245,32 @@ def use_reference_build() -> bool:
     return hcoracle.have_ref() and not os.environ.get("HCM_BENCH_FORCE_PORT")
 
 
+def compare_all_chunks(res, arm, meshed, threads: int) -> tuple[dict, dict]:
+    """The parity gate: every task of the fetched batch `res` against the CPU arm, digest for digest (hcoracle.digest_batch serialises
+    each task's meshes exactly like oracle/ref_shim.cpp does for the reference and hashes the bytes).  -> (parity dict, CPU stats)."""
+    import hcoracle
+
+    st, per = arm.mesh_batch(meshed, threads=threads, per_chunk=True)
+    got = hcoracle.digest_batch(res, threads)
+    count_bad = int((got[:, :3] != per[:, :3]).any(axis=1).sum())
+    byte_bad = int((got[:, :4] != per[:, :4]).any(axis=1).sum())
+    return ({"chunks_meshed": int(len(meshed)), "byte_compared_chunks": int(len(meshed)), "count_mismatches": count_bad, "byte_mismatches": byte_bad,
+             "how": "FNV-1a of each chunk's serialised meshes (mesh count, flags, AABBs, vertex bytes, index bytes) vs the CPU arm's digest of the same chunk"},
+            st)
+
+
 def run_reference(args, rank, world):
     """The reference's own CPU implementation of the path (unmodified ChunkTaskRunner<kMesh>::Run from oracle/_ref, all host
     threads); the oracle port (cpu_baseline.kind "port") where oracle/_ref was not built."""
     if rank != 0:
         return
-    import hcoracle
     from hypercraft_b200 import worldgen
 
     threads = os.cpu_count() or 1
     radius = args.radius
     meshed, resident = worldgen.load_radius_positions(radius)
-    if use_reference_build():
-        ref, kind, data = hcoracle.RefWorld(), "reference", f"synthetic: reference DefaultTerrain(seed {SEED})"
-
-        def provide(need):  # neighbours generated on demand
-            ref.generate(need, seed=SEED, threads=threads)
-    else:  # the reference did not compile here: its restatement, on the terrain the b200 arm falls back to as well
-        ref, kind, data = PortArm({}), "port", "synthetic: repo height-field terrain (oracle/_ref terrain generator not available)"
-
-        def provide(need):
-            for q in need:
-                key = tuple(int(c) for c in q)
-                if key not in ref.chunks:
-                    ref.chunks[key] = worldgen.synth_terrain_chunk(SEED, q)
+    ref, provide, data = make_cpu_arm(threads)
+    kind = getattr(ref, "kind", "reference")
     # bounded sample: a stride of the task list
     probe = meshed[:: max(1, len(meshed) // 256)][:256]
     provide(np.unique(np.concatenate([worldgen.neighbourhood(p) for p in probe]), axis=0))
@@ -250,91 +300,82 @@ def run_reference(args, rank, world):
     print(json.dumps(out))
 
 
-def main():
-    args = parse_args()
-    rank, world, local = dist_env()
-    if args.impl == "reference":
-        run_reference(args, rank, world)
-        return
+class Dist:
+    """torch.distributed plumbing of the bench: barrier and small reductions only -- nothing of the data path."""
 
+    def __init__(self, world: int, local: int):
+        import torch
+
+        self.torch, self.world = torch, world
+        if world > 1:
+            import torch.distributed as dist
+
+            self.dist = dist
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def reduce(self, values, op: str = "sum") -> list:
+        t = self.torch.tensor([float(v) for v in values], dtype=self.torch.float64, device="cuda")
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX if op == "max" else self.dist.ReduceOp.SUM)
+        return [float(x) for x in t.tolist()]
+
+    def gather(self, value: float) -> list:
+        t = self.torch.zeros(self.world, dtype=self.torch.float64, device="cuda")
+        t[int(os.environ.get("RANK", "0"))] = float(value)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return [float(x) for x in t.tolist()]
+
+    def close(self):
+        if self.world > 1:
+            self.dist.destroy_process_group()
+
+
+def measure(D: Dist, local: int, meshed, resident, pb, ph, origin, extent, steps: int, warmup: int, arm, cpu_threads: int, check: bool) -> dict:
+    """One workload on this rank's GPU: `steps` device-timed steps with the inputs resident in HBM, `steps` end-to-end steps from
+    pinned host buffers, then the parity gate over every chunk of the last end-to-end result.  Times are max over ranks, counts are
+    sums over ranks."""
     import torch
-    import torch.distributed as dist
-
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device -- the mesher has no CPU path (use --impl reference for the CPU baseline)")
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     from hypercraft_b200 import mesher as M
 
-    radius = args.radius
-    threads = max(1, (os.cpu_count() or 1) // world)
-    os.environ.setdefault("HCM_HOST_THREADS", str(max(1, min(15, threads - 1))))  # upload scan threads of this rank's hcm_ctx
-    centre = (0, 0, 0) if args.strong else (3 * radius * rank, 0, 0)
-    t_setup = time.time()
-    meshed, resident, pb, ph, data_label, ref = build_world(radius, centre, threads, (world, rank) if args.strong else None)
-    if args.strong:
-        from hypercraft_b200 import shard as sh
-
-        origin, extent = sh.window_for(resident)
-    else:
-        ext = 2 * radius + 3
-        origin, extent = (centre[0] - radius - 1, -radius - 1, -radius - 1), (ext, ext, ext)
     m = M.Mesher(origin=origin, extent=extent, device=local, max_chunks=len(resident), max_tasks=len(meshed))
     m.upload(resident, pb.array, ph.array)
     m.sync()
-    setup_s = time.time() - t_setup
-
     stream = torch.cuda.ExternalStream(m.stream_ptr(), device=torch.device("cuda", local))
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
 
     def step_resident():
         m.rederive()
         m.mesh_async(meshed)
         return m.wait()
 
-    sampler = ClockSampler(local)
-    sampler.start()
-    # ---- warm-up (also sizes the output arenas) -------------------------------------------------------------------
     counts = None
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(max(warmup, 3)):  # warm-up (also sizes the output arenas)
         counts = step_resident()
-    n_quads = counts["n_vertices"] // 4
-    algo = algorithmic_bytes(len(meshed), int(counts["n_vertices"]), int(counts["n_meshes"]))
-    algo_bytes = algo["canonical"]
-
     # ---- timed: K steps, device timed on the ctx stream, max over ranks --------------------------------------------
-    barrier()
+    D.barrier()
     launches0 = m.stats()["kernel_launches"]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     mesh_ms, derive_ms, classify_ms = [], [], []
     e0.record(stream)
-    for _ in range(args.steps):
+    for _ in range(steps):
         step_resident()
         s = m.stats()
         mesh_ms.append(s["mesh_ms"]), derive_ms.append(s["derive_ms"]), classify_ms.append(s["classify_ms"])
     e1.record(stream)
-    barrier()
+    D.barrier()
     launches = m.stats()["kernel_launches"] - launches0
-    ms_total = e0.elapsed_time(e1)
-    t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
-    tot = torch.tensor([len(meshed), int(n_quads), int(launches)], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-    ms_per_step = float(t.item()) / args.steps
-    total_chunks, total_quads, total_launches = (float(x) for x in tot.tolist())
-    value = total_chunks / (ms_per_step / 1e3)
+    ms_per_step = D.reduce([e0.elapsed_time(e1)], "max")[0] / steps
+    tot_chunks, tot_quads, tot_launches, tot_worked = D.reduce([len(meshed), counts["n_vertices"] // 4, launches, counts["n_worked"]])
 
     # ---- end to end: host buffers in, host meshes out, every step ---------------------------------------------------
-    res = None
-    barrier()
+    D.barrier()
     for it in range(3):  # the three calls one after the other (first pass: warm-up of the pinned result buffers)
         if it == 1:
             t0 = time.perf_counter()
@@ -343,53 +384,175 @@ def main():
     e2e_serial_ms = (time.perf_counter() - t0) * 1e3 / 2
     res = m.upload_and_mesh(resident, pb.array, ph.array, meshed)
     d2h0, h2d0 = m.stats()["d2h_bytes"], m.stats()["h2d_bytes"]
-    barrier()
+    D.barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(steps):
         res = m.upload_and_mesh(resident, pb.array, ph.array, meshed)  # same three stages, overlapped
     torch.cuda.synchronize()
-    e2e_ms = (time.perf_counter() - t0) * 1e3
-    t = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_ms_step = float(t.item()) / args.steps
+    e2e_local = (time.perf_counter() - t0) * 1e3 / steps
+    e2e_ms_step = D.reduce([e2e_local], "max")[0]
     s = m.stats()
-    h2d_step = (s["h2d_bytes"] - h2d0) // args.steps
-    d2h_step = (s["d2h_bytes"] - d2h0) // args.steps
-    e2e_value = total_chunks / (e2e_ms_step / 1e3)
+    out = {"ms_per_step": ms_per_step, "value": tot_chunks / (ms_per_step / 1e3), "quads_per_s": tot_quads / (ms_per_step / 1e3),
+           "total_chunks": tot_chunks, "total_quads": tot_quads, "total_launches": tot_launches, "total_worked": tot_worked,
+           "counts": counts, "kernel_ms": {"derive": float(np.mean(derive_ms)), "classify": float(np.mean(classify_ms)), "mesh": float(np.mean(mesh_ms))},
+           "e2e_ms_per_step": e2e_ms_step, "e2e_value": tot_chunks / (e2e_ms_step / 1e3), "e2e_serial_ms": e2e_serial_ms,
+           "e2e_ms_per_rank": D.gather(e2e_local), "worked_per_rank": D.gather(counts["n_worked"]), "tasks_per_rank": D.gather(len(meshed)),
+           "h2d_step": (s["h2d_bytes"] - h2d0) // steps, "d2h_step": (s["d2h_bytes"] - d2h0) // steps, "device_bytes": s["device_bytes"],
+           "parity": None, "cpu_stats": None}
+    if check:
+        parity, st = compare_all_chunks(res, arm, meshed, cpu_threads)
+        bad = D.reduce([parity["chunks_meshed"], parity["byte_compared_chunks"], parity["count_mismatches"], parity["byte_mismatches"]])
+        parity.update(chunks_meshed=int(bad[0]), byte_compared_chunks=int(bad[1]), count_mismatches=int(bad[2]), byte_mismatches=int(bad[3]),
+                      ranks=D.world)
+        out["parity"], out["cpu_stats"] = parity, st
+    m.close()
+    return out
+
+
+def config4_block(D: Dist, args, rank: int, world: int, local: int, threads: int) -> dict:
+    """BASELINE.json configs[3]: ONE r = 32 load sphere, its task list cut into `world` x-slabs, each GPU holding its slab dilated by one
+    chunk (hypercraft_b200/shard.py; no collective on the data path).  The cut balances ESTIMATED WORK, not task counts: most chunks of
+    a sphere are all air or all stone and never reach the mesh kernel, so every rank generates a thin sample of the world (its share
+    of the x-planes, every 4th z-column), counts the non-uniform chunks per plane, and the per-plane estimates are summed over the
+    ranks -- a few hundred bytes of host bookkeeping.  Reference: misc/load_radius.cpp:17-35 (the list), SURVEY 8e (the partition)."""
+    from hypercraft_b200 import shard as sh
+    from hypercraft_b200 import worldgen
+
+    radius = args.config4_radius
+    t0 = time.time()
+    meshed_all, _ = worldgen.load_radius_positions(radius)
+    arm, provide, _ = make_cpu_arm(threads)
+    # -- work estimate per x-plane from a sample of the terrain -------------------------------------------------------------------
+    x_min = int(meshed_all[:, 0].min())
+    n_planes = int(meshed_all[:, 0].max()) - x_min + 1
+    zstride = 4
+    mine = ((meshed_all[:, 0].astype(np.int32) - x_min) % world == rank) & ((meshed_all[:, 2].astype(np.int32) - x_min) % zstride == 0)
+    sample = meshed_all[mine]
+    provide(sample)
+    est = np.zeros(n_planes)
+    if len(sample):
+        sb = np.empty((len(sample), 32768), dtype=np.uint16)
+        shh = np.empty((len(sample), 1024), dtype=np.int8)
+        if isinstance(arm, PortArm):
+            for i, p in enumerate(sample):
+                sb[i], shh[i] = arm.chunks[tuple(int(c) for c in p)]
+        else:
+            arm.get_chunks(sample, sb, shh)
+        nonuniform = (sb != sb[:, :1]).any(axis=1)
+        np.add.at(est, sample[:, 0].astype(np.int32) - x_min, nonuniform * float(zstride))
+        del sb, shh
+    est = np.array(D.reduce(est.tolist()))
+    tasks_per_plane = np.bincount(meshed_all[:, 0].astype(np.int32) - x_min, minlength=n_planes).astype(np.float64)
+    # SM-time per unit (measured at r = 20): ~41 us per worked chunk in mesh_kernel, ~4.7 us per resident chunk in derive_kernel
+    frac_worked = np.divide(est, tasks_per_plane, out=np.zeros_like(est), where=tasks_per_plane > 0)
+    weights = 4.7 + 41.0 * frac_worked[meshed_all[:, 0].astype(np.int32) - x_min]
+    bounds = sh.slab_bounds(meshed_all, world, weights)
+    meshed = sh.shard_tasks(meshed_all, world, rank, weights)
+    resident = sh.resident_for(meshed)
+    provide(resident)
+    pb, ph = fill_pinned(arm, resident)
+    origin, extent = sh.window_for(resident)
+    setup_s = time.time() - t0
+    r = measure(D, local, meshed, resident, pb, ph, origin, extent, args.steps, args.warmup, arm, threads, not args.no_cpu_baseline)
+    pb.free(), ph.free()
+    worked = r["worked_per_rank"]
+    return {"workload": workload_name(radius, True), "radius": radius, "scaling": "strong", "chunks_meshed": int(r["total_chunks"]),
+            "value": r["value"], "unit": "chunks/s", "ms_per_step": r["ms_per_step"], "quads_per_s": r["quads_per_s"],
+            "e2e": {"value": r["e2e_value"], "unit": "chunks/s", "ms_per_step": r["e2e_ms_per_step"], "ms_per_rank": r["e2e_ms_per_rank"],
+                    "h2d_bytes_per_step_rank0": int(r["h2d_step"]), "d2h_bytes_per_step_rank0": int(r["d2h_step"])},
+            "kernel_ms_rank0": r["kernel_ms"], "slab_x_bounds": [[int(a), int(b)] for a, b in bounds],
+            "tasks_per_rank": [int(v) for v in r["tasks_per_rank"]], "worked_chunks_per_rank": [int(v) for v in worked],
+            "worked_imbalance_max_over_mean": float(max(worked) / max(np.mean(worked), 1.0)),
+            "balance": "x-slabs balanced on estimated work per x-plane: 41 us x (sampled non-uniform chunks) + 4.7 us x tasks; the sample is every "
+                       "4th z-column of the terrain, generated by the ranks in turn and summed (host bookkeeping, no data-path collective)",
+            "halo": "each slab's boundary chunk planes are uploaded from the host to both neighbours (no peer copies): the chunks live in host Chunk "
+                    "objects anyway and a world load moves every chunk over PCIe once per holder",
+            "parity": r["parity"], "setup_seconds": setup_s}
+
+
+def secondary_configs(local: int, threads: int) -> dict:
+    """BASELINE.json configs[2] (worst-case face density) and configs[4] (edit-driven remesh), small and bounded; each result is
+    compared with the CPU arm chunk for chunk.  See tools/bench_configs.py."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import bench_configs
+
+    out = {}
+    try:
+        out["config3_worst_case"] = bench_configs.config3(local, threads)
+        out["config5_edits_on_device"] = bench_configs.config5_device(local, threads)
+    except Exception as e:  # secondary figures never take the headline down
+        out["error"] = f"{type(e).__name__}: {e}"
+    return out
+
+
+def main():
+    args = parse_args()
+    rank, world, local = dist_env()
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the mesher has no CPU path (use --impl reference for the CPU baseline)")
+    torch.cuda.set_device(local)
+    D = Dist(world, local)
+
+    from hypercraft_b200 import shard as sh
+    from hypercraft_b200 import worldgen
+
+    radius = args.radius
+    threads = max(1, (os.cpu_count() or 1) // world)
+    os.environ.setdefault("HCM_HOST_THREADS", str(max(1, min(15, threads - 1))))  # upload scan threads of this rank's hcm_ctx
+    check = not args.no_cpu_baseline
+    sampler = ClockSampler(local)
+    sampler.start()
+
+    if args.strong:  # config 4 as the headline
+        args.config4_radius = radius
+        c4 = config4_block(D, args, rank, world, local, threads)
+        clocks = sampler.stop()
+        if rank == 0:
+            print(json.dumps({"metric": "chunks meshed/sec", "value": c4["value"], "unit": "chunks/s", "n_gpus": world, "steps": args.steps,
+                              "warmup": max(args.warmup, 3), "ms_per_step": c4["ms_per_step"], "higher_is_better": True, "scaling": "strong",
+                              "vs_baseline": None, "dtype": "u8/u16 integer", "data": f"synthetic: DefaultTerrain(seed {SEED}) or repo terrain, see config4",
+                              "config": {"workload": c4["workload"], "radius": radius}, "quads_per_s": c4["quads_per_s"],
+                              "e2e": c4["e2e"], "config4": c4, "parity": c4["parity"], "clocks": clocks}))
+        D.close()
+        return
+
+    centre = (3 * radius * rank, 0, 0)
+    t_setup = time.time()
+    meshed, resident = worldgen.load_radius_positions(radius)
+    c = np.asarray(centre, dtype=np.int16)
+    meshed, resident = (meshed + c).astype(np.int16), (resident + c).astype(np.int16)
+    arm, provide, data_label = make_cpu_arm(threads)
+    provide(resident)
+    pb, ph = fill_pinned(arm, resident)
+    ext = 2 * radius + 3
+    origin, extent = (centre[0] - radius - 1, -radius - 1, -radius - 1), (ext, ext, ext)
+    setup_s = time.time() - t_setup
+    r = measure(D, local, meshed, resident, pb, ph, origin, extent, args.steps, args.warmup, arm, threads, check)
     clocks = sampler.stop()  # sampled from the first warm-up step to the last end-to-end step
+    pb.free(), ph.free()
 
-    # ---- parity gate + CPU baseline on rank 0 (bounded sample of the same workload) -----------------------------------
-    cpu_baseline, parity = None, None
-    if rank == 0 and ref is not None and not args.no_cpu_baseline:
-        import hcoracle
-
-        cpu_threads = os.cpu_count() or 1
-        probe = meshed[:: max(1, len(meshed) // 128)][:128]
-        st, _ = ref.mesh_batch(probe, threads=cpu_threads)
-        rate = st["chunks"] / max(st["seconds"], 1e-6)
-        n_s = int(min(len(meshed), max(128, rate * args.cpu_seconds)))
-        stride = max(1, len(meshed) // n_s)
-        idx = np.arange(0, len(meshed), stride)[:n_s]
-        st, per = ref.mesh_batch(meshed[idx], threads=cpu_threads, per_chunk=True)
-        cpu_baseline = {"value": st["chunks"] / st["seconds"], "unit": "chunks/s", "cores": cpu_threads, "kind": getattr(ref, "kind", "reference"),
+    cpu_baseline = None
+    if rank == 0 and world == 1 and check:  # the CPU baseline is reported at N = 1 only; the same call was the parity gate's checker
+        st = r["cpu_stats"]
+        cpu_baseline = {"value": st["chunks"] / st["seconds"], "unit": "chunks/s", "cores": threads, "kind": getattr(arm, "kind", "reference"),
                         "quads_per_s": st["vertices"] / 4 / st["seconds"], "cpu_model": cpu_model(),
-                        "sample": f"{len(idx)} of {len(meshed)} chunks (every {stride}th of the r={radius} task list), "
-                                  + getattr(ref, "what", "unmodified ChunkTaskRunner<kMesh>::Run, one runner per thread")}
-        # the reference's own worker count (Application.cpp:248: hardware_concurrency() * 3 / 4), same sample
-        cpu_baseline["reference_pool_threads"] = pool_baseline(ref, meshed[idx], cpu_threads)
-        # parity: mesh/vertex/index counts of every sampled chunk + full bytes of the heaviest ones against the reference
-        got_m = res.tasks["n_meshes"][idx].astype(np.uint64)
-        first = res.tasks["first_mesh"][idx]
-        gv = np.array([int(res.meshes["vertex_count"][f:f + n].sum()) for f, n in zip(first, got_m)], dtype=np.uint64)
-        gi = np.array([int(res.meshes["index_count"][f:f + n].sum()) for f, n in zip(first, got_m)], dtype=np.uint64)
-        count_bad = int(((got_m != per[:, 0]) | (gv != per[:, 1]) | (gi != per[:, 2])).sum())
-        heavy = idx[np.argsort(-per[:, 1].astype(np.int64))[:48]]
-        byte_bad = 0
-        for t_i in heavy:
-            a, b = res.serialise(int(t_i)), ref.mesh(meshed[t_i])
-            byte_bad += not (a.size == b.size and (a == b).all())
-        parity = {"sampled_chunks": int(len(idx)), "count_mismatches": count_bad, "byte_compared_chunks": int(len(heavy)), "byte_mismatches": int(byte_bad)}
+                        "sample": f"{len(meshed)} of {len(meshed)} chunks (the whole r={radius} task list, {st['seconds']:.1f} s), "
+                                  + getattr(arm, "what", "unmodified ChunkTaskRunner<kMesh>::Run, one runner per thread")}
+        cpu_baseline["reference_pool_threads"] = pool_baseline(arm, meshed[:: max(1, len(meshed) // 8192)], threads)
+    del arm
+
+    config4 = None
+    if world > 1 and args.config4_radius > 0:
+        config4 = config4_block(D, args, rank, world, local, threads)
+    secondary = None
+    if world == 1 and rank == 0 and not args.no_secondary and check:
+        secondary = secondary_configs(local, threads)
 
     if rank == 0:
         peaks = {}
@@ -399,39 +562,38 @@ def main():
             pass
         peak_gbs, peak_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json)") if "hbm_gbs" in peaks else (6650.0, "fallback (B200_PROFILING.md)")
         traffic = None
-        if radius == 20:  # the ncu capture is of this workload; other radii have no measured traffic figure
+        if radius == 20:  # the committed ncu launch list is of this workload; other radii have no measured traffic figure
             try:
-                traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_summary.json"))).get("mesh_kernel_dram_bytes_per_launch")
+                traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_summary.json")))
             except Exception:
                 pass
-        k_ms = float(np.mean(mesh_ms))
-        achieved = algo_bytes / (k_ms / 1e3) / 1e9
+        counts = r["counts"]
         out = {
-            "metric": "chunks meshed/sec", "value": value, "unit": "chunks/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if args.strong else "weak", "vs_baseline": None, "dtype": "u8/u16 integer",
+            "metric": "chunks meshed/sec", "value": r["value"], "unit": "chunks/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/u16 integer",
             "data": data_label,
-            "config": {"workload": workload_name(radius, args.strong), "radius": radius,
+            "config": {"workload": workload_name(radius), "radius": radius,
                        "chunks_meshed_per_gpu": int(len(meshed)), "chunks_resident_per_gpu": int(len(resident)),
                        "tasks_through_full_kernel_per_gpu": int(counts["n_worked"]),
-                       "parallelism": (f"{world} x-slabs of one sphere, each dilated by one chunk (no collective); per-GPU figures are rank 0's"
-                                       if args.strong else f"{world} independent spheres (no collective)"),
-                       "l2": f"inputs ({m.stats()['device_bytes'] / 1e9:.1f} GB of device-resident world per GPU) larger than L2; no flush needed",
+                       "parallelism": f"{world} independent spheres (no collective)",
+                       "l2": f"inputs ({r['device_bytes'] / 1e9:.1f} GB of device-resident world per GPU) larger than L2; no flush needed",
                        "setup_seconds": setup_s},
-            "quads_per_s": total_quads / (ms_per_step / 1e3), "quads_per_step": total_quads, "vertices_per_step_per_gpu": int(counts["n_vertices"]),
-            "e2e": {"value": e2e_value, "unit": "chunks/s", "ms_per_step": e2e_ms_step, "h2d_bytes_per_step": int(h2d_step),
-                    "d2h_bytes_per_step": int(d2h_step), "call": "hcm_upload_and_mesh", "unpipelined_ms_per_step": e2e_serial_ms},
-            "gpu_launches": int(total_launches),
-            "kernel_ms": {"derive": float(np.mean(derive_ms)), "classify": float(np.mean(classify_ms)), "mesh": k_ms},
-            "roofline": {"bound": "hbm", "kernel": "hcm::mesh_kernel", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
-                         "traffic": traffic, "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": int(algo_bytes), "formula": "sum over chunks of 34^3*3 + 8*vertices (SURVEY 8d)",
-                         **roofline_secondary(algo, k_ms, peak_gbs)},
-            "cpu_baseline": cpu_baseline, "parity": parity, "clocks": clocks,
+            "quads_per_s": r["quads_per_s"], "quads_per_step": r["total_quads"], "vertices_per_step_per_gpu": int(counts["n_vertices"]),
+            "e2e": {"value": r["e2e_value"], "unit": "chunks/s", "ms_per_step": r["e2e_ms_per_step"], "h2d_bytes_per_step": int(r["h2d_step"]),
+                    "d2h_bytes_per_step": int(r["d2h_step"]), "call": "hcm_upload_and_mesh", "unpipelined_ms_per_step": r["e2e_serial_ms"],
+                    "ms_per_rank": r["e2e_ms_per_rank"]},
+            "gpu_launches": int(r["total_launches"]),
+            "kernel_ms": r["kernel_ms"],
+            "roofline": roofline_block(len(meshed), int(counts["n_worked"]), len(resident), int(counts["n_vertices"]), int(counts["n_meshes"]),
+                                       r["kernel_ms"], r["ms_per_step"], peak_gbs, peak_src, traffic),
+            "cpu_baseline": cpu_baseline, "parity": r["parity"], "clocks": clocks,
         }
+        if config4 is not None:
+            out["config4"] = config4
+        if secondary is not None:
+            out["secondary_configs"] = secondary
         print(json.dumps(out))
-    m.close()
-    if world > 1:
-        dist.destroy_process_group()
+    D.close()
 
 
 if __name__ == "__main__":

@@ -158,6 +158,19 @@ void hcm_host_free(void *p);
  * ---------------------------------------------------------------------------------------------------------- */
 int hcm_upload_chunks(hcm_ctx *ctx, uint32_t n, const int16_t *pos /* n x 3 */, const uint16_t *blocks /* n x 32768 */,
                       const int8_t *heights /* n x 1024 */);
+/* The same with what the caller already knows about each chunk, so that the host-side scan can be skipped (it reads every byte of a
+ * uniform chunk: at r = 20 that is 1.9 GB of host DRAM traffic per full upload, the largest part of a world load's wall time):
+ *   uniform_hint[i] >= 0              : every voxel of chunk i holds this Block value (the generator filled it with one block --
+ *                                       client/src/ChunkGenerateTask.cpp:21-39 runs DefaultTerrain::Generate, which knows when a chunk
+ *                                       is all air or all stone); the 64 KB are NOT read and not copied
+ *   HCM_HINT_UNKNOWN     (-1)         : scan it (what hcm_upload_chunks does for every chunk)
+ *   HCM_HINT_NOT_UNIFORM (-2)         : copy it without scanning
+ * A wrong hint is the caller's bug: a chunk hinted uniform is derived from the hint, whatever its array holds.
+ * uniform_hint == NULL is hcm_upload_chunks. */
+#define HCM_HINT_UNKNOWN (-1)
+#define HCM_HINT_NOT_UNIFORM (-2)
+int hcm_upload_chunks_hinted(hcm_ctx *ctx, uint32_t n, const int16_t *pos /* n x 3 */, const uint16_t *blocks /* n x 32768 */,
+                             const int8_t *heights /* n x 1024 */, const int32_t *uniform_hint /* n, or NULL */);
 int hcm_remove_chunks(hcm_ctx *ctx, uint32_t n, const int16_t *pos /* n x 3 */);
 /* Re-run the derivation kernel on chunks whose Block data is already device resident (n == 0: every resident chunk).
  * This is the device-side half of hcm_upload_chunks; a full remesh "with inputs resident in HBM" is
@@ -222,7 +235,7 @@ int hcm_sync(hcm_ctx *ctx);
  * valid result and must still be pushed (WorldRenderer.hpp:81-86).
  * ---------------------------------------------------------------------------------------------------------- */
 typedef struct hcm_mesh_desc {
-	uint32_t task;         /* index into the batch */
+	uint32_t task;         /* index into the batch (the caller's task order, also after hcm_upload_and_mesh) */
 	uint32_t transparent;  /* BlockMesh::transparent */
 	uint64_t vertex_offset;/* first vertex in hcm_batch_view::vertices */
 	uint64_t index_offset; /* first index in hcm_batch_view::indices */
@@ -260,6 +273,33 @@ typedef struct hcm_batch_counts {
 } hcm_batch_counts;
 int hcm_mesh_wait(hcm_ctx *ctx, hcm_batch_counts *out);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Device-side sink: meshes go straight into caller-owned DEVICE buffers, no vertex or index byte crosses the bus.
+ * The reference renderer gives every BlockMesh a range of a MeshCluster's vertex and index buffer (MeshCluster::try_alloc,
+ * client/include/client/mesh/MeshCluster.hpp:38-67: VMA virtual allocations, alignment sizeof(Vertex) / sizeof(Index)), then builds
+ * two staging buffers per mesh and copies them in (mesh/MeshHandle.hpp:75-87, MeshCluster.hpp:76-118).  With the meshes already in
+ * device memory the staging disappears:
+ *   1. hcm_mesh_batch(ctx, n, pos)
+ *   2. hcm_mesh_counts(ctx, &view)   waits and returns tasks + mesh descriptors (counts, AABBs, transparency) only;
+ *                                    view.vertices and view.indices are NULL, view.n_vertices / n_indices are the totals
+ *   3. the caller allocates a range per mesh, exactly as MeshCluster::try_alloc does, and fills one hcm_mesh_placement per mesh
+ *   4. hcm_mesh_emit_into(...)       one kernel copies every placed mesh's vertices and indices from the ctx's arena to
+ *                                    vertex_base + vertex_offset (in vertices) and index_base + index_offset (in indices).
+ * vertex_base / index_base are device pointers valid on the ctx's device: cudaMalloc'd memory, or a Vulkan buffer imported with
+ * cudaImportExternalMemory + cudaExternalMemoryGetMappedBuffer.  The call returns when the copies
+ * are complete.  Ranges must not overlap; a range that does not fit its capacity is HCM_ERR_INVALID and nothing is written.
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct hcm_mesh_placement {
+	uint32_t mesh;          /* index into hcm_batch_view::meshes of the last batch */
+	uint32_t _pad;
+	uint64_t vertex_offset; /* first vertex of the mesh in the caller's vertex buffer (MeshInfo::m_vertex_offset) */
+	uint64_t index_offset;  /* first index of the mesh in the caller's index buffer (MeshInfo::m_first_index) */
+} hcm_mesh_placement; /* 24 bytes */
+
+int hcm_mesh_counts(hcm_ctx *ctx, hcm_batch_view *out);
+int hcm_mesh_emit_into(hcm_ctx *ctx, uint32_t n, const hcm_mesh_placement *placements, void *dev_vertex_base, uint64_t vertex_capacity /* vertices */,
+                       void *dev_index_base, uint64_t index_capacity /* indices */);
+
 /* World (re)load in one call: hcm_upload_chunks + hcm_mesh_batch + hcm_mesh_fetch with the three stages overlapped.
  * The reference streams in the same way: a mesh task is pushed as soon as the 27 chunks around it exist
  * (client/src/ChunkMeshTask.cpp:18-34, World::update pushes tasks per finished neighbour) and WorldRenderer takes each
@@ -281,6 +321,7 @@ typedef struct hcm_stats {
 	float classify_ms;     /* classify kernel of the last hcm_mesh_batch */
 	float mesh_ms;         /* mesh kernel of the last hcm_mesh_batch */
 	float fetch_copy_ms;   /* device->host copies of the last hcm_mesh_fetch */
+	float sink_ms;         /* scatter kernel of the last hcm_mesh_emit_into */
 	uint32_t kernel_launches; /* kernels launched by this ctx since creation */
 	uint64_t h2d_bytes;    /* cumulative */
 	uint64_t d2h_bytes;    /* cumulative */

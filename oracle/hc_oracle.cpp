@@ -19,6 +19,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <queue>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
@@ -642,6 +643,65 @@ void hco_neighbour_offset(uint32_t idx, int32_t *dxyz) {
 	idx /= 3u;
 	dxyz[1] = kRev[idx % 3u];
 	dxyz[0] = kRev[idx / 3u];
+}
+
+// FNV-1a 64 of a byte range -- the digest oracle/ref_shim.cpp (hcref_mesh_batch, per_chunk[.][3]) takes of a chunk's serialised meshes
+uint64_t hco_fnv1a(const void *data, uint64_t n) {
+	const uint8_t *p = (const uint8_t *)data;
+	uint64_t h = 1469598103934665603ull;
+	for (uint64_t i = 0; i < n; ++i)
+		h = (h ^ p[i]) * 1099511628211ull;
+	return h;
+}
+
+// Checker for whole batches: the arrays of an hcm_batch_view (include/hcm.h) -> per task {n_meshes, n_vertices, n_indices, FNV-1a of the
+// task's meshes in the serialised layout of oracle/ref_shim.cpp}, i.e. the row hcref_mesh_batch writes for the same chunk.  Lets bench.py
+// and the tests compare EVERY chunk of a batch with the reference, not a sample.
+void hco_digest_batch_view(const hcm_task_result *tasks, uint64_t n_tasks, const hcm_mesh_desc *meshes, const uint64_t *vertices,
+                           const uint16_t *indices, uint64_t *out /* n_tasks x 4 */, int n_threads) {
+	auto work = [&](uint64_t lo, uint64_t hi) {
+		std::vector<uint8_t> buf;
+		for (uint64_t t = lo; t < hi; ++t) {
+			const hcm_mesh_desc *ms = meshes + tasks[t].first_mesh;
+			const uint32_t n = tasks[t].n_meshes;
+			size_t size = 4 + (size_t)n * 36;
+			uint64_t nv = 0, ni = 0;
+			for (uint32_t k = 0; k < n; ++k) {
+				size += (size_t)ms[k].vertex_count * 8 + (((size_t)ms[k].index_count * 2 + 3) & ~size_t(3));
+				nv += ms[k].vertex_count, ni += ms[k].index_count;
+			}
+			buf.assign(size, 0);
+			uint8_t *p = buf.data();
+			auto put32 = [&p](uint32_t v) { memcpy(p, &v, 4), p += 4; };
+			put32(n);
+			for (uint32_t k = 0; k < n; ++k) {
+				put32(ms[k].transparent ? 1u : 0u);
+				for (int i = 0; i < 3; ++i)
+					put32(ms[k].aabb_min[i]);
+				for (int i = 0; i < 3; ++i)
+					put32(ms[k].aabb_max[i]);
+				put32(ms[k].vertex_count);
+				put32(ms[k].index_count);
+			}
+			for (uint32_t k = 0; k < n; ++k) {
+				memcpy(p, vertices + ms[k].vertex_offset, (size_t)ms[k].vertex_count * 8), p += (size_t)ms[k].vertex_count * 8;
+				memcpy(p, indices + ms[k].index_offset, (size_t)ms[k].index_count * 2), p += (size_t)ms[k].index_count * 2;
+				while ((p - buf.data()) & 3)
+					*p++ = 0;
+			}
+			out[4 * t + 0] = n, out[4 * t + 1] = nv, out[4 * t + 2] = ni, out[4 * t + 3] = hco_fnv1a(buf.data(), size);
+		}
+	};
+	if (n_threads < 1)
+		n_threads = 1;
+	std::vector<std::thread> ts;
+	const uint64_t per = (n_tasks + n_threads - 1) / n_threads;
+	for (int i = 1; i < n_threads; ++i)
+		if ((uint64_t)i * per < n_tasks)
+			ts.emplace_back(work, (uint64_t)i * per, std::min(n_tasks, (uint64_t)(i + 1) * per));
+	work(0, std::min(n_tasks, per));
+	for (auto &t : ts)
+		t.join();
 }
 
 } // extern "C"

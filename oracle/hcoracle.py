@@ -161,6 +161,43 @@ class RefWorld:
         return n, faces[:max(n, 0) * 24].copy(), tex, dyn.value
 
 
+_port_lib = None
+
+
+def _port():
+    global _port_lib
+    if _port_lib is None:
+        if not os.path.exists(PORT_SO):
+            build(ref=False, port=True)
+        L = ctypes.CDLL(PORT_SO)
+        L.hco_create.restype = _vp
+        L.hco_mesh.restype = ctypes.c_int64
+        L.hco_fnv1a.restype = ctypes.c_uint64
+        L.hco_fnv1a.argtypes = [_vp, ctypes.c_uint64]
+        L.hco_digest_batch_view.argtypes = [_vp, ctypes.c_uint64, _vp, _vp, _vp, _vp, ctypes.c_int]
+        _port_lib = L
+    return _port_lib
+
+
+def fnv1a(buf: np.ndarray) -> int:
+    """FNV-1a 64 of a byte array: the per-chunk digest RefWorld.mesh_batch(per_chunk=True) returns in column 3."""
+    b = np.ascontiguousarray(buf, dtype=np.uint8)
+    return int(_port().hco_fnv1a(_ptr(b), ctypes.c_uint64(b.size)))
+
+
+def digest_batch(result, threads: int = 0) -> np.ndarray:
+    """Checker for whole batches.  ``result`` = a fetched batch (hypercraft_b200.mesher.BatchResult: tasks, meshes, vertices,
+    indices as the C ABI returned them) -> u64[n_tasks, 4] = {n_meshes, n_vertices, n_indices, FNV-1a of the task's serialised
+    meshes}: row for row what RefWorld.mesh_batch(per_chunk=True) / PortOracle.mesh_batch give for the same chunks."""
+    n = len(result.tasks)
+    out = np.zeros((n, 4), dtype=np.uint64)
+    if n:
+        t, m = np.ascontiguousarray(result.tasks), np.ascontiguousarray(result.meshes)
+        v, i = np.ascontiguousarray(result.vertices), np.ascontiguousarray(result.indices)
+        _port().hco_digest_batch_view(_ptr(t), ctypes.c_uint64(n), _ptr(m), _ptr(v), _ptr(i), _ptr(out), ctypes.c_int(threads or (os.cpu_count() or 1)))
+    return out
+
+
 # neighbour order of the 27-array: NeighbourIndex2CmpXYZ, common/include/common/Position.hpp:146-152
 def neighbour_offsets() -> np.ndarray:
     rev = (1, -1, 0)
@@ -171,11 +208,7 @@ class PortOracle:
     """This repo's CPU restatement of the mesh task (oracle/hc_oracle.cpp)."""
 
     def __init__(self, registry_blob: np.ndarray):
-        if not os.path.exists(PORT_SO):
-            build(ref=False, port=True)
-        L = ctypes.CDLL(PORT_SO)
-        L.hco_create.restype = _vp
-        L.hco_mesh.restype = ctypes.c_int64
+        L = _port()
         self.L = L
         self.blob = np.ascontiguousarray(registry_blob, dtype=np.uint8)
         self.o = _vp(L.hco_create(_ptr(self.blob), ctypes.c_uint64(self.blob.size)))
@@ -219,14 +252,15 @@ class PortOracle:
 
     def mesh_batch(self, chunks: dict, positions, threads: int = 1, keep: bool = False):
         """Mesh many chunks on `threads` host threads (hco_mesh holds no state between calls and ctypes releases the GIL).
-        -> ({"chunks", "seconds", "vertices"}, per-chunk [n_meshes, vertices, indices] u64, serialised buffers or None).
+        -> ({"chunks", "seconds", "vertices"}, per-chunk [n_meshes, vertices, indices, FNV-1a of the serialised meshes] u64,
+        serialised buffers or None).
         The timed region holds the mesher calls only, like RefWorld.mesh_batch."""
         import time
         from concurrent.futures import ThreadPoolExecutor
 
         positions = [tuple(int(c) for c in p) for p in positions]
         args = [self._arrays(chunks, p) for p in positions]
-        per = np.zeros((len(positions), 3), dtype=np.uint64)
+        per = np.zeros((len(positions), 4), dtype=np.uint64)
         bufs = [None] * len(positions)
 
         def work(first):
@@ -239,7 +273,7 @@ class PortOracle:
                     self.L.hco_mesh(self.o, bp, hp, _ptr(buf), ctypes.c_uint64(buf.size))
                 k = int(buf[:4].view(np.uint32)[0])
                 hdr = buf[4:4 + 36 * k].view(np.uint32).reshape(k, 9)
-                per[i] = (k, int(hdr[:, 7].sum()), int(hdr[:, 8].sum()))
+                per[i] = (k, int(hdr[:, 7].sum()), int(hdr[:, 8].sum()), int(self.L.hco_fnv1a(_ptr(buf), ctypes.c_uint64(int(n)))))
                 if keep:
                     bufs[i] = buf[:n].copy()
 

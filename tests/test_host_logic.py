@@ -246,6 +246,48 @@ def test_port_oracle_batch_equals_single_calls(port):
         assert bufs[i].size == want.size and (bufs[i] == want).all()
 
 
+def test_digest_batch_is_the_cpu_arms_per_chunk_digest(port, have_ref):
+    """bench.py's parity gate compares EVERY chunk through hcoracle.digest_batch: rows built from an hcm_batch_view must equal the
+    rows the CPU arms produce for the same chunks (port: PortOracle.mesh_batch; reference: hcref_mesh_batch's per_chunk), and a
+    single flipped vertex bit must change exactly that chunk's digest."""
+    import hcoracle
+    from hypercraft_b200 import worldgen
+    from hypercraft_b200.mesher import MESH_DESC_DTYPE, TASK_RESULT_DTYPE, BatchResult
+
+    meshed, resident = worldgen.load_radius_positions(2)
+    chunks = {tuple(int(c) for c in p): worldgen.synth_terrain_chunk(9, p) for p in resident}
+    st, per, bufs = port.mesh_batch(chunks, meshed, threads=3, keep=True)
+    assert per.shape == (len(meshed), 4) and int(per[:, 1].sum()) > 0
+    tasks = np.zeros(len(meshed), dtype=TASK_RESULT_DTYPE)
+    descs, verts, idxs = [], [np.zeros(3, dtype=np.uint64)], [np.zeros(5, dtype=np.uint16)]  # arenas do not start at a task's data
+    nv, ni = 3, 5
+    for t, buf in enumerate(bufs):
+        assert hcoracle.fnv1a(buf) == int(per[t, 3])
+        ms = hcoracle.parse_meshes(buf)
+        tasks[t] = (len(descs), len(ms))
+        for m in ms:
+            d = np.zeros((), dtype=MESH_DESC_DTYPE)
+            d["task"], d["transparent"], d["vertex_offset"], d["index_offset"] = t, m["transparent"], nv, ni
+            d["vertex_count"], d["index_count"], d["aabb_min"], d["aabb_max"] = len(m["vertices"]), len(m["indices"]), m["aabb_min"], m["aabb_max"]
+            descs.append(d)
+            verts.append(m["vertices"]), idxs.append(m["indices"])
+            nv, ni = nv + len(m["vertices"]), ni + len(m["indices"])
+    res = BatchResult(tasks, np.array(descs, dtype=MESH_DESC_DTYPE), np.concatenate(verts), np.concatenate(idxs))
+    got = hcoracle.digest_batch(res, 3)
+    assert (got == per).all()
+    heavy = int(np.argmax(per[:, 1]))
+    res.vertices[int(res.meshes[int(tasks[heavy]["first_mesh"])]["vertex_offset"]) + 1] ^= np.uint64(1 << 40)
+    bad = (hcoracle.digest_batch(res, 1) != per).any(axis=1)
+    assert bad.sum() == 1 and bad[heavy]
+    if have_ref:
+        ref = hcoracle.RefWorld()
+        for p, (b, h) in chunks.items():
+            ref.set_chunk(p, b, h)
+        _, rper = ref.mesh_batch(meshed, threads=2, per_chunk=True)
+        assert (rper == per).all()  # the port is pinned to the reference, digest for digest
+        assert hcoracle.fnv1a(ref.mesh(meshed[heavy])) == int(rper[heavy, 3])
+
+
 def test_cpp_host_mirror_compiles_and_fails_loudly_without_gpu(tmp_path):
     """hypercraft_b200/host/hcm_host.hpp compiles warning-free as C++20 against include/hcm.h (what a HyperCraft build does) and,
     on a machine without a GPU, MeshTaskDispatcher's constructor throws hcm_host::Error -- it never meshes on the CPU."""
