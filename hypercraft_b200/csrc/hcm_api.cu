@@ -32,6 +32,8 @@ void launch_classify(const DevWorld &w, const TaskIn *tasks, uint32_t n, uint32_
 cudaError_t mesh_kernel_prepare();
 int mesh_kernel_smem_bytes();
 void launch_mesh(const MeshMaps &maps, const MeshParams &p, int grid, cudaStream_t st);
+void launch_scatter(const hcm_mesh_placement *placements, uint32_t n, const hcm_mesh_desc *meshes, const unsigned long long *vtx, const uint16_t *idx, void *vdst,
+                    void *idst, int grid, cudaStream_t st);
 } // namespace hcm
 
 using namespace hcm;
@@ -89,7 +91,17 @@ struct WorkerPool {
 	}
 };
 
+// Pipeline stages ("blocks") of one upload: stage 0 holds `first` chunks, every later stage c->upload_block.
+struct BlockLayout {
+	uint32_t n, first, size;
+	uint32_t count() const { return n <= first ? 1u : 1u + (n - first + size - 1) / size; }
+	uint32_t of(uint32_t i) const { return i < first ? 0u : 1u + (i - first) / size; }
+	uint32_t lo(uint32_t b) const { return b == 0 ? 0u : std::min(n, first + (b - 1) * size); }
+	uint32_t hi(uint32_t b) const { return std::min(n, first + b * size); }
+};
+
 struct hcm_ctx {
+	BlockLayout layout{0, 1, 1}; // of the upload in progress (hcm_upload_and_mesh buckets its tasks by stage)
 	int device = 0;
 	cudaStream_t stream = nullptr;
 	cudaStream_t copy_stream = nullptr; // host->device copies of large uploads overlap the host-side scan and the derive kernel
@@ -113,6 +125,13 @@ struct hcm_ctx {
 	// pipeline granularity (env HCM_UPLOAD_BLOCK, HCM_MIN_SUB_BATCH: test knobs): chunks per pipeline stage (2048 = 128 MB of Block
 	// data); ready sets smaller than min_sub_batch wait for the next upload block
 	uint32_t upload_block = 2048, min_sub_batch = 512;
+	// first pipeline stage of a threaded upload (env HCM_UPLOAD_FIRST_BLOCK): small, because it usually crosses the bus unscanned
+	uint32_t first_block = 256;
+	bool adaptive_upload = true; // env HCM_UPLOAD_ADAPTIVE=0: always wait for the scan (the round-1 behaviour)
+	hcm_mesh_placement *d_placements = nullptr; // hcm_mesh_emit_into
+	uint32_t placement_cap = 0;
+	uint32_t sink_meshes = 0;
+	bool counts_valid = false; // h_task_out / h_mesh_out hold the last batch's rows (hcm_mesh_counts, hcm_mesh_fetch, hcm_upload_and_mesh)
 	std::unique_ptr<WorkerPool> pool;
 	uint32_t host_threads = 0; // scan threads of hcm_upload_chunks (env HCM_HOST_THREADS; 0 = hardware_concurrency - 1, at most 15)
 	DevWorld w{};
@@ -163,14 +182,15 @@ struct hcm_ctx {
 	int force_all = 0;
 
 	cudaEvent_t ev[10]{};
-	bool ev_upload = false, ev_batch = false, ev_fetch = false;
+	bool ev_upload = false, ev_batch = false, ev_fetch = false, ev_sink = false;
 	hcm_stats stats{};
 	std::string err;
 };
 
 namespace {
 
-enum { EV_UP0, EV_UP1, EV_UP2, EV_B0, EV_B1, EV_B2, EV_F0, EV_F1, EV_COUNT };
+enum { EV_UP0, EV_UP1, EV_UP2, EV_B0, EV_B1, EV_B2, EV_F0, EV_F1, EV_S0, EV_S1, EV_COUNT };
+static_assert(EV_COUNT <= 10, "hcm_ctx::ev");
 
 int fail(hcm_ctx *c, int status, const char *fmt, ...) {
 	char buf[512];
@@ -536,7 +556,7 @@ void hcm_destroy(hcm_ctx *c) {
 	if (c->stream)
 		cudaStreamSynchronize(c->stream);
 	void *dev[] = {c->w.prop8, c->w.pass, c->w.torch, c->w.height, c->w.cflags, c->w.slot, c->d_tables, c->d_prop_index, c->d_meshes, c->d_mesh_info, c->d_raw,
-	               c->d_rawh, c->d_entries, c->d_all_entries, c->d_tasks, c->d_worklist, c->d_heads, c->d_task_out, c->d_mesh_out, c->d_vtx, c->d_idx, c->d_dyn, c->d_flood_slots, c->d_debug_light, c->d_edits, c->d_edit_columns, c->d_edit_result, c->d_sun_changes};
+	               c->d_rawh, c->d_entries, c->d_all_entries, c->d_tasks, c->d_worklist, c->d_heads, c->d_task_out, c->d_mesh_out, c->d_vtx, c->d_idx, c->d_dyn, c->d_flood_slots, c->d_debug_light, c->d_edits, c->d_edit_columns, c->d_edit_result, c->d_sun_changes, c->d_placements};
 	for (void *p : dev)
 		if (p)
 			cudaFree(p);
@@ -595,6 +615,11 @@ int hcm_create(const hcm_registry *registry, const hcm_config *cfg, hcm_ctx **ou
 		c->upload_block = std::max(32u, (uint32_t)atoi(ub) / 32u * 32u); // a multiple of the scan grain
 	if (const char *ms = getenv("HCM_MIN_SUB_BATCH"))
 		c->min_sub_batch = std::max(1u, (uint32_t)atoi(ms));
+	if (const char *fb = getenv("HCM_UPLOAD_FIRST_BLOCK"))
+		c->first_block = std::max(32u, (uint32_t)atoi(fb) / 32u * 32u);
+	c->first_block = std::min(c->first_block, c->upload_block);
+	if (const char *ad = getenv("HCM_UPLOAD_ADAPTIVE"))
+		c->adaptive_upload = atoi(ad) != 0;
 	DevTables tables;
 	std::vector<DevMeshInfo> minfo;
 	if (int rc = build_tables(c, registry, tables, minfo))
@@ -744,7 +769,8 @@ struct UploadHooks {
 	std::function<int(uint32_t blk, uint32_t n_blocks)> block_enqueued;               // copy + derive of block blk are in the streams
 };
 
-static int upload_impl(hcm_ctx *c, uint32_t n, const int16_t *pos, const uint16_t *blocks, const int8_t *heights, const UploadHooks *hooks) {
+static int upload_impl(hcm_ctx *c, uint32_t n, const int16_t *pos, const uint16_t *blocks, const int8_t *heights, const int32_t *hint,
+                       const UploadHooks *hooks) {
 	if (!pos || !blocks || !heights)
 		return fail(c, HCM_ERR_INVALID, "null upload arrays");
 	if (n > c->max_chunks)
@@ -754,25 +780,49 @@ static int upload_impl(hcm_ctx *c, uint32_t n, const int16_t *pos, const uint16_
 	// Pipeline per block of upload_block chunks: host threads scan block b+1 (early exit at the first difference) while
 	// the copy engine moves block b and the derive kernel runs on block b-1.  The scan starts before anything else: it
 	// only reads the caller's arrays, and it is the longest stage of a large upload.
+	//
+	// The scan and the copy engine balance themselves: a work item (kScanGrain chunks) belongs to whoever claims it first.
+	// Scan threads claim items front to back.  The uploading thread, when it reaches a block whose scan is not complete while
+	// the copy engine has nothing left to do, claims the block's unclaimed items itself and sends them as they are -- the
+	// derive kernel recognises a uniform chunk on the device as well (its AND/OR test), at HBM speed.  With many scan threads
+	// per GPU next to nothing goes unscanned; with 8 GPUs sharing one host's cores (3 scan threads each) most of the world does,
+	// and the upload runs at bus speed instead of at the speed of the scan.
+	// Caller's knowledge (hcm_upload_chunks_hinted) short-cuts both: a chunk hinted uniform is neither read nor copied, a chunk
+	// hinted not-uniform is copied unread.
 	const uint32_t n_items = (n + kScanGrain - 1) / kScanGrain;
-	std::vector<std::atomic<uint8_t>> item_done(n_items);
-	for (auto &d : item_done)
-		d.store(0, std::memory_order_relaxed);
-	std::vector<int32_t> uniform_value(n); // Block value of a uniform chunk, else -1; written by the scan before item_done
+	enum : uint8_t { IT_FREE = 0, IT_BUSY = 1, IT_DONE = 2 };
+	std::vector<std::atomic<uint8_t>> item_state(n_items);
+	for (auto &d : item_state)
+		d.store(IT_FREE, std::memory_order_relaxed);
+	std::vector<int32_t> uniform_value(n); // Block value of a uniform chunk, else -1; written by the item's owner before IT_DONE
 	std::atomic<uint32_t> next{0};
 	std::atomic<bool> abort_scan{false};
 	int32_t *uni = uniform_value.data();
-	auto scan_work = [&item_done, &next, &abort_scan, uni, n, n_items, blocks]() {
+	// resolve one item; `scan` = read the chunks that carry no hint
+	auto resolve_item = [uni, n, blocks, hint](uint32_t it, bool scan) {
+		const uint32_t lo = it * kScanGrain, hi = std::min(n, lo + kScanGrain);
+		for (uint32_t i = lo; i < hi; ++i) {
+			const int32_t h = hint ? hint[i] : HCM_HINT_UNKNOWN;
+			if (h >= 0)
+				uni[i] = h & 0xffff;
+			else if (h == HCM_HINT_NOT_UNIFORM || !scan)
+				uni[i] = -1;
+			else {
+				const uint16_t *b = blocks + (size_t)i * HCM_CHUNK_VOXELS;
+				uni[i] = chunk_is_uniform(b) ? (int32_t)b[0] : -1;
+			}
+		}
+	};
+	auto scan_work = [&item_state, &next, &abort_scan, resolve_item, n_items]() {
 		for (;;) {
 			const uint32_t it = next.fetch_add(1);
 			if (it >= n_items || abort_scan.load(std::memory_order_relaxed))
 				break;
-			const uint32_t lo = it * kScanGrain, hi = std::min(n, lo + kScanGrain);
-			for (uint32_t i = lo; i < hi; ++i) {
-				const uint16_t *b = blocks + (size_t)i * HCM_CHUNK_VOXELS;
-				uni[i] = chunk_is_uniform(b) ? (int32_t)b[0] : -1;
-			}
-			item_done[it].store(1, std::memory_order_release);
+			uint8_t expect = IT_FREE;
+			if (!item_state[it].compare_exchange_strong(expect, IT_BUSY, std::memory_order_acq_rel))
+				continue; // the uploading thread took it unscanned
+			resolve_item(it, true);
+			item_state[it].store(IT_DONE, std::memory_order_release);
 		}
 	};
 	const unsigned hw = std::max(2u, std::thread::hardware_concurrency());
@@ -796,6 +846,7 @@ static int upload_impl(hcm_ctx *c, uint32_t n, const int16_t *pos, const uint16_
 			}
 		}
 	} scan_guard{c, threaded, abort_scan};
+	const bool adaptive = threaded && c->adaptive_upload;
 
 	std::vector<UploadEntry> entries(n);
 	std::vector<int32_t> fresh; // slots taken in this call (rolled back on error)
@@ -833,7 +884,10 @@ static int upload_impl(hcm_ctx *c, uint32_t n, const int16_t *pos, const uint16_
 		}
 		entries[i] = UploadEntry{slot, (int16_t)cx, (int16_t)cy, (int16_t)cz, 0, 0};
 	}
-	const uint32_t n_blocks = (n + c->upload_block - 1) / c->upload_block;
+	// block boundaries are multiples of kScanGrain (upload_block and first_block are)
+	const BlockLayout layout{n, adaptive ? std::min(c->first_block, c->upload_block) : c->upload_block, c->upload_block};
+	c->layout = layout;
+	const uint32_t n_blocks = layout.count();
 	if (hooks && hooks->assigned)
 		if (int rc = hooks->assigned(entries, n_blocks)) {
 			roll_back();
@@ -852,13 +906,30 @@ static int upload_impl(hcm_ctx *c, uint32_t n, const int16_t *pos, const uint16_
 		scan_work();
 
 	uint64_t copied = 0;
+	uint32_t n_unscanned = 0;
 	std::vector<void *> cp_dst, cp_src;
 	std::vector<size_t> cp_size;
 	for (uint32_t blk = 0; blk < n_blocks; ++blk) {
-		const uint32_t lo = blk * c->upload_block, hi = std::min(n, lo + c->upload_block);
-		for (uint32_t it = lo / kScanGrain; it < (hi + kScanGrain - 1) / kScanGrain; ++it) // upload_block is a multiple of kScanGrain
-			while (!item_done[it].load(std::memory_order_acquire))
+		const uint32_t lo = layout.lo(blk), hi = layout.hi(blk);
+		bool engine_idle = false; // the copy stream has finished everything enqueued so far (it never becomes busy again before this block)
+		for (uint32_t it = lo / kScanGrain; it < (hi + kScanGrain - 1) / kScanGrain; ++it)
+			for (;;) {
+				const uint8_t s = item_state[it].load(std::memory_order_acquire);
+				if (s == IT_DONE)
+					break;
+				if (s == IT_FREE && adaptive) {
+					if (!engine_idle)
+						engine_idle = blk == 0 || cudaEventQuery(c->block_events[blk - 1]) == cudaSuccess;
+					uint8_t expect = IT_FREE;
+					if (engine_idle && item_state[it].compare_exchange_strong(expect, IT_BUSY, std::memory_order_acq_rel)) {
+						resolve_item(it, false);
+						item_state[it].store(IT_DONE, std::memory_order_release);
+						n_unscanned += std::min(n, (it + 1) * kScanGrain) - it * kScanGrain;
+						break;
+					}
+				}
 				std::this_thread::yield();
+			}
 		for (uint32_t i = lo; i < hi; ++i)
 			if (uni[i] >= 0)
 				ent[i].flags |= UE_UNIFORM, ent[i].value = (uint16_t)uni[i];
@@ -918,6 +989,7 @@ static int upload_impl(hcm_ctx *c, uint32_t n, const int16_t *pos, const uint16_
 				return rc;
 	}
 	c->stats.h2d_bytes += copied + (uint64_t)n * sizeof(UploadEntry);
+	c->stats.upload_unscanned_chunks = n_unscanned;
 	c->ev_upload = true;
 	return HCM_OK;
 }
@@ -927,7 +999,19 @@ int hcm_upload_chunks(hcm_ctx *c, uint32_t n, const int16_t *pos, const uint16_t
 		return HCM_ERR_INVALID;
 	if (n == 0)
 		return HCM_OK;
-	return upload_impl(c, n, pos, blocks, heights, nullptr);
+	return upload_impl(c, n, pos, blocks, heights, nullptr, nullptr);
+}
+
+int hcm_upload_chunks_hinted(hcm_ctx *c, uint32_t n, const int16_t *pos, const uint16_t *blocks, const int8_t *heights, const int32_t *uniform_hint) {
+	if (!c)
+		return HCM_ERR_INVALID;
+	if (n == 0)
+		return HCM_OK;
+	if (uniform_hint)
+		for (uint32_t i = 0; i < n; ++i)
+			if (uniform_hint[i] > 0xffff || uniform_hint[i] < HCM_HINT_NOT_UNIFORM)
+				return fail(c, HCM_ERR_INVALID, "uniform_hint[%u] = %d is neither a Block value nor HCM_HINT_*", i, uniform_hint[i]);
+	return upload_impl(c, n, pos, blocks, heights, uniform_hint, nullptr);
 }
 
 int hcm_remove_chunks(hcm_ctx *c, uint32_t n, const int16_t *pos) {
@@ -1222,7 +1306,7 @@ static int submit(hcm_ctx *c, uint32_t n, const int16_t *pos, int force_all) {
 		c->tasks[i] = TaskIn{(int16_t)cx, (int16_t)cy, (int16_t)cz, 0};
 	}
 	c->batch_n = n;
-	c->batch_pending = true, c->batch_done = false;
+	c->batch_pending = true, c->batch_done = false, c->counts_valid = false;
 	c->force_all = force_all;
 	if (n)
 		CU(cudaMemcpyAsync(c->d_tasks, c->tasks.data(), n * sizeof(TaskIn), cudaMemcpyHostToDevice, c->stream));
@@ -1283,6 +1367,95 @@ int hcm_mesh_fetch(hcm_ctx *c, hcm_batch_view *out) {
 	c->stats.d2h_bytes += (uint64_t)c->batch_n * sizeof(hcm_task_result) + (uint64_t)h.meshes * sizeof(hcm_mesh_desc) + h.vtx * 8 + h.idx * 2;
 	out->n_tasks = c->batch_n, out->n_meshes = h.meshes, out->n_vertices = h.vtx, out->n_indices = h.idx;
 	out->tasks = c->h_task_out, out->meshes = c->h_mesh_out, out->vertices = c->h_vtx, out->indices = c->h_idx;
+	c->counts_valid = true, c->sink_meshes = h.meshes;
+	return HCM_OK;
+}
+
+// ---- device-side sink ------------------------------------------------------------------------------------------------
+int hcm_mesh_counts(hcm_ctx *c, hcm_batch_view *out) {
+	if (!c || !out)
+		return HCM_ERR_INVALID;
+	CU(cudaSetDevice(c->device));
+	if (int rc = wait_batch(c))
+		return rc;
+	const BatchHeads h = *c->h_heads;
+	uint64_t tcap = c->h_task_cap, mcap = c->h_mesh_cap;
+	if (int rc = host_reserve(c, &c->h_task_out, &tcap, c->batch_n))
+		return rc;
+	if (int rc = host_reserve(c, &c->h_mesh_out, &mcap, h.meshes))
+		return rc;
+	c->h_task_cap = (uint32_t)tcap, c->h_mesh_cap = (uint32_t)mcap;
+	cudaStream_t st = c->stream;
+	if (c->batch_n)
+		CU(cudaMemcpyAsync(c->h_task_out, c->d_task_out, (size_t)c->batch_n * sizeof(hcm_task_result), cudaMemcpyDeviceToHost, st));
+	if (h.meshes)
+		CU(cudaMemcpyAsync(c->h_mesh_out, c->d_mesh_out, (size_t)h.meshes * sizeof(hcm_mesh_desc), cudaMemcpyDeviceToHost, st));
+	CU(cudaStreamSynchronize(st));
+	c->stats.d2h_bytes += (uint64_t)c->batch_n * sizeof(hcm_task_result) + (uint64_t)h.meshes * sizeof(hcm_mesh_desc);
+	out->n_tasks = c->batch_n, out->n_meshes = h.meshes, out->n_vertices = h.vtx, out->n_indices = h.idx;
+	out->tasks = c->h_task_out, out->meshes = c->h_mesh_out, out->vertices = nullptr, out->indices = nullptr;
+	c->counts_valid = true, c->sink_meshes = h.meshes;
+	return HCM_OK;
+}
+
+int hcm_mesh_emit_into(hcm_ctx *c, uint32_t n, const hcm_mesh_placement *placements, void *dev_vertex_base, uint64_t vertex_capacity, void *dev_index_base,
+                       uint64_t index_capacity) {
+	if (!c)
+		return HCM_ERR_INVALID;
+	if (!c->counts_valid)
+		return fail(c, HCM_ERR_STATE, "hcm_mesh_emit_into needs the descriptors of the last batch: call hcm_mesh_counts (or hcm_mesh_fetch) first");
+	if (n == 0)
+		return HCM_OK;
+	if (!placements || !dev_vertex_base || !dev_index_base)
+		return fail(c, HCM_ERR_INVALID, "null placements / device buffers");
+	if (((size_t)dev_vertex_base & 7) || ((size_t)dev_index_base & 1))
+		return fail(c, HCM_ERR_INVALID, "device buffers must be aligned to sizeof(Vertex) = 8 and sizeof(Index) = 2");
+	CU(cudaSetDevice(c->device));
+	const uint32_t n_meshes = c->sink_meshes;
+	// every range inside its buffer, no two ranges overlapping (a mesh placed twice would be legal but is a caller bug more often than not)
+	std::vector<std::pair<uint64_t, uint64_t>> vr(n), ir(n);
+	for (uint32_t i = 0; i < n; ++i) {
+		const hcm_mesh_placement &pl = placements[i];
+		if (pl.mesh >= n_meshes)
+			return fail(c, HCM_ERR_INVALID, "placement %u: mesh %u of %u", i, pl.mesh, n_meshes);
+		const hcm_mesh_desc &d = c->h_mesh_out[pl.mesh];
+		if (pl.vertex_offset > vertex_capacity || d.vertex_count > vertex_capacity - pl.vertex_offset)
+			return fail(c, HCM_ERR_INVALID, "placement %u: %u vertices at %llu do not fit %llu", i, d.vertex_count, (unsigned long long)pl.vertex_offset,
+			            (unsigned long long)vertex_capacity);
+		if (pl.index_offset > index_capacity || d.index_count > index_capacity - pl.index_offset)
+			return fail(c, HCM_ERR_INVALID, "placement %u: %u indices at %llu do not fit %llu", i, d.index_count, (unsigned long long)pl.index_offset,
+			            (unsigned long long)index_capacity);
+		vr[i] = {pl.vertex_offset, pl.vertex_offset + d.vertex_count}, ir[i] = {pl.index_offset, pl.index_offset + d.index_count};
+	}
+	for (auto *r : {&vr, &ir}) {
+		std::sort(r->begin(), r->end());
+		for (uint32_t i = 1; i < n; ++i)
+			if ((*r)[i].first < (*r)[i - 1].second)
+				return fail(c, HCM_ERR_INVALID, "placements overlap in the %s buffer ([%llu,%llu) and [%llu,%llu))", r == &vr ? "vertex" : "index",
+				            (unsigned long long)(*r)[i - 1].first, (unsigned long long)(*r)[i - 1].second, (unsigned long long)(*r)[i].first,
+				            (unsigned long long)(*r)[i].second);
+	}
+	if (n > c->placement_cap) {
+		if (c->d_placements) {
+			c->stats.device_bytes -= (size_t)c->placement_cap * sizeof(hcm_mesh_placement);
+			cudaFree(c->d_placements);
+		}
+		c->d_placements = nullptr, c->placement_cap = 0;
+		const uint32_t cap = std::max(4096u, n + n / 4);
+		CU(dev_alloc(c, &c->d_placements, cap));
+		c->placement_cap = cap;
+	}
+	cudaStream_t st = c->stream;
+	CU(cudaMemcpyAsync(c->d_placements, placements, (size_t)n * sizeof(hcm_mesh_placement), cudaMemcpyHostToDevice, st));
+	CU(cudaEventRecord(c->ev[EV_S0], st));
+	launch_scatter(c->d_placements, n, c->d_mesh_out, reinterpret_cast<const unsigned long long *>(c->d_vtx), c->d_idx, dev_vertex_base, dev_index_base,
+	               c->grid * 8, st);
+	CU(cudaGetLastError());
+	CU(cudaEventRecord(c->ev[EV_S1], st));
+	CU(cudaStreamSynchronize(st)); // `placements` may be pageable; the caller may hand the buffers to its renderer when this returns
+	c->stats.kernel_launches += 1;
+	c->stats.h2d_bytes += (uint64_t)n * sizeof(hcm_mesh_placement);
+	c->ev_sink = true;
 	return HCM_OK;
 }
 
@@ -1316,7 +1489,8 @@ int hcm_upload_and_mesh(hcm_ctx *c, uint32_t n_chunks, const int16_t *pos, const
 			return fail(c, HCM_ERR_NOT_RESIDENT, "task (%d,%d,%d) touches the window border: a neighbour cannot be resident", tp[0], tp[1], tp[2]);
 		tin[i] = TaskIn{(int16_t)cx, (int16_t)cy, (int16_t)cz, 0};
 	}
-	c->batch_pending = false, c->batch_done = false; // an unfetched earlier batch is dropped, like a second hcm_mesh_batch
+	c->batch_pending = false, c->batch_done = false, c->counts_valid = false; // an unfetched earlier batch is dropped, like a second hcm_mesh_batch
+	std::vector<uint32_t> sub_mesh_end; // per fetched sub-batch: end of its descriptor range
 
 	std::vector<uint32_t> perm(n_tasks), bucket_start; // perm[k] = caller's index of the k-th task in sub-batch order
 	uint32_t submitted = 0, n_sub = 0, fetched = 0;
@@ -1362,6 +1536,7 @@ int hcm_upload_and_mesh(hcm_ctx *c, uint32_t n_chunks, const int16_t *pos, const
 				       (cur.idx - prev.idx) * 2 + sizeof(BatchHeads);
 			}
 			prev = cur;
+			sub_mesh_end.push_back(overflow ? 0u : cur.meshes);
 			++fetched;
 		}
 		return HCM_OK;
@@ -1383,7 +1558,7 @@ int hcm_upload_and_mesh(hcm_ctx *c, uint32_t n_chunks, const int16_t *pos, const
 		std::vector<int32_t> &cb = c->cell_block;
 		cb.assign(c->n_cells, -1);
 		for (size_t i = 0; i < entries.size(); ++i)
-			cb[cell(c, entries[i].cx, entries[i].cy, entries[i].cz)] = (int32_t)(i / c->upload_block);
+			cb[cell(c, entries[i].cx, entries[i].cy, entries[i].cz)] = (int32_t)c->layout.of((uint32_t)i);
 		std::vector<int32_t> tmp(c->n_cells);
 		const size_t sx = 1, sz = (size_t)wx, sy = (size_t)wx * wz;
 		auto pass = [&](const std::vector<int32_t> &a, std::vector<int32_t> &b, size_t stride, int extent, int which) {
@@ -1455,7 +1630,7 @@ int hcm_upload_and_mesh(hcm_ctx *c, uint32_t n_chunks, const int16_t *pos, const
 		}
 		return fetch_completed(false);
 	};
-	if (int rc = upload_impl(c, n_chunks, pos, blocks, heights, &hooks)) {
+	if (int rc = upload_impl(c, n_chunks, pos, blocks, heights, nullptr, &hooks)) {
 		cudaStreamSynchronize(st), cudaStreamSynchronize(fs);
 		return rc;
 	}
@@ -1478,6 +1653,11 @@ int hcm_upload_and_mesh(hcm_ctx *c, uint32_t n_chunks, const int16_t *pos, const
 	}
 	for (uint32_t k = 0; k < n_tasks; ++k)
 		c->h_task_out[perm[k]] = c->h_task_stage[k];
+	// the kernel numbered each sub-batch's tasks from 0 in bucket order: hcm_mesh_desc::task is the caller's index
+	for (uint32_t sb = 0, m0 = 0; sb < n_sub; m0 = sub_mesh_end[sb], ++sb)
+		for (uint32_t m = m0; m < sub_mesh_end[sb]; ++m)
+			c->h_mesh_out[m].task = perm[sub_range[sb].first + c->h_mesh_out[m].task];
+	c->counts_valid = true, c->sink_meshes = prev.meshes; // hcm_mesh_emit_into may follow: the arenas hold the whole call's meshes
 	c->stats.d2h_bytes += d2h;
 	out->n_tasks = n_tasks, out->n_meshes = prev.meshes, out->n_vertices = prev.vtx, out->n_indices = prev.idx;
 	out->tasks = c->h_task_out, out->meshes = c->h_mesh_out, out->vertices = c->h_vtx, out->indices = c->h_idx;
@@ -1499,6 +1679,8 @@ int hcm_get_stats(hcm_ctx *c, hcm_stats *out) {
 	}
 	if (c->ev_fetch)
 		CU(cudaEventElapsedTime(&c->stats.fetch_copy_ms, c->ev[EV_F0], c->ev[EV_F1]));
+	if (c->ev_sink)
+		CU(cudaEventElapsedTime(&c->stats.sink_ms, c->ev[EV_S0], c->ev[EV_S1]));
 	*out = c->stats;
 	return HCM_OK;
 }

@@ -1944,8 +1944,50 @@ __global__ void __launch_bounds__(kThreads, 1) mesh_kernel(const __grid_constant
 }
 
 // ================================================================================================================
+// device-side sink: every placed mesh is copied from the batch arenas to the range the caller allocated for
+// it in its own vertex / index buffer -- what MeshHandle's two staging buffers and vkCmdCopyBuffer do in the reference
+// (client/include/client/mesh/MeshHandle.hpp:75-87, MeshCluster.hpp:76-118).  One CTA per mesh (grid-stride), 16-byte copies
+// where source and destination allow it: arena offsets are multiples of 4 vertices / 6 indices, the caller's offsets are
+// whatever its allocator returned (alignment sizeof(Vertex) = 8 and sizeof(Index) = 2, MeshCluster.hpp:44-55).
+// ================================================================================================================
+__global__ void __launch_bounds__(256) scatter_kernel(const hcm_mesh_placement *__restrict__ placements, u32 n, const hcm_mesh_desc *__restrict__ meshes,
+                                                      const u64 *__restrict__ vtx, const uint16_t *__restrict__ idx, u64 *__restrict__ vdst,
+                                                      uint16_t *__restrict__ idst) {
+	for (u32 i = blockIdx.x; i < n; i += gridDim.x) {
+		const hcm_mesh_placement pl = placements[i];
+		const u64 voff = meshes[pl.mesh].vertex_offset, ioff = meshes[pl.mesh].index_offset;
+		const u32 nv = meshes[pl.mesh].vertex_count, ni = meshes[pl.mesh].index_count;
+		const u64 *vs = vtx + voff;
+		u64 *vd = vdst + pl.vertex_offset;
+		if ((((size_t)vs | (size_t)vd) & 15) == 0) { // nv is a multiple of 4
+			const uint4 *s4 = reinterpret_cast<const uint4 *>(vs);
+			uint4 *d4 = reinterpret_cast<uint4 *>(vd);
+			for (u32 k = threadIdx.x; k < nv / 2; k += blockDim.x)
+				d4[k] = s4[k];
+		} else
+			for (u32 k = threadIdx.x; k < nv; k += blockDim.x)
+				vd[k] = vs[k];
+		const uint16_t *is = idx + ioff;
+		uint16_t *id = idst + pl.index_offset;
+		if ((((size_t)is | (size_t)id) & 3) == 0) { // ni is a multiple of 6
+			const u32 *s2 = reinterpret_cast<const u32 *>(is);
+			u32 *d2 = reinterpret_cast<u32 *>(id);
+			for (u32 k = threadIdx.x; k < ni / 2; k += blockDim.x)
+				d2[k] = s2[k];
+		} else
+			for (u32 k = threadIdx.x; k < ni; k += blockDim.x)
+				id[k] = is[k];
+	}
+}
+
+// ================================================================================================================
 // host-callable launchers (used by hcm_api.cu)
 // ================================================================================================================
+void launch_scatter(const hcm_mesh_placement *placements, u32 n, const hcm_mesh_desc *meshes, const u64 *vtx, const uint16_t *idx, void *vdst, void *idst,
+                    int grid, cudaStream_t st) {
+	if (n)
+		scatter_kernel<<<min((u32)grid, n), 256, 0, st>>>(placements, n, meshes, vtx, idx, (u64 *)vdst, (uint16_t *)idst);
+}
 void launch_derive(const DevWorld &w, const UploadEntry *entries, u32 n, const uint8_t *prop_index, const DevTables *tables, const int8_t *raw_heights,
                    cudaStream_t st) {
 	if (n)

@@ -58,16 +58,23 @@ assert BLOCK_EDIT_DTYPE.itemsize == 12 and SUNLIGHT_CHANGE_DTYPE.itemsize == 12
 class _Stats(ctypes.Structure):
     _fields_ = [("upload_copy_ms", ctypes.c_float), ("derive_ms", ctypes.c_float), ("classify_ms", ctypes.c_float), ("mesh_ms", ctypes.c_float),
                 ("fetch_copy_ms", ctypes.c_float), ("kernel_launches", ctypes.c_uint32), ("h2d_bytes", ctypes.c_uint64),
-                ("d2h_bytes", ctypes.c_uint64), ("device_bytes", ctypes.c_uint64)]
+                ("d2h_bytes", ctypes.c_uint64), ("device_bytes", ctypes.c_uint64), ("sink_ms", ctypes.c_float),
+                ("upload_unscanned_chunks", ctypes.c_uint32)]
+
+
+assert ctypes.sizeof(_Stats) == 56
 
 
 MESH_DESC_DTYPE = np.dtype([("task", np.uint32), ("transparent", np.uint32), ("vertex_offset", np.uint64), ("index_offset", np.uint64),
                             ("vertex_count", np.uint32), ("index_count", np.uint32), ("aabb_min", np.uint32, 3), ("aabb_max", np.uint32, 3)])
 TASK_RESULT_DTYPE = np.dtype([("first_mesh", np.uint32), ("n_meshes", np.uint32)])
 assert MESH_DESC_DTYPE.itemsize == 56
+MESH_PLACEMENT_DTYPE = np.dtype([("mesh", np.uint32), ("_pad", np.uint32), ("vertex_offset", np.uint64), ("index_offset", np.uint64)])
+assert MESH_PLACEMENT_DTYPE.itemsize == 24
+HINT_UNKNOWN, HINT_NOT_UNIFORM = -1, -2
 
 EXPORTS = ["hcm_registry_from_blob", "hcm_create", "hcm_destroy", "hcm_last_error", "hcm_status_string", "hcm_host_alloc", "hcm_host_free",
-           "hcm_upload_chunks", "hcm_remove_chunks", "hcm_rederive_chunks", "hcm_is_resident", "hcm_sync", "hcm_mesh_batch", "hcm_mesh_fetch", "hcm_mesh_wait",
+           "hcm_upload_chunks", "hcm_upload_chunks_hinted", "hcm_mesh_counts", "hcm_mesh_emit_into", "hcm_remove_chunks", "hcm_rederive_chunks", "hcm_is_resident", "hcm_sync", "hcm_mesh_batch", "hcm_mesh_fetch", "hcm_mesh_wait",
            "hcm_upload_and_mesh", "hcm_set_blocks", "hcm_get_stats", "hcm_stream", "hcm_debug_light"]
 
 _lib = None
@@ -100,6 +107,9 @@ def load_library():
         L.hcm_destroy.argtypes = [_vp]
         L.hcm_registry_from_blob.argtypes = [_vp, ctypes.c_size_t, ctypes.POINTER(_Registry)]
         L.hcm_upload_chunks.argtypes = [_vp, ctypes.c_uint32, _vp, _vp, _vp]
+        L.hcm_upload_chunks_hinted.argtypes = [_vp, ctypes.c_uint32, _vp, _vp, _vp, _vp]
+        L.hcm_mesh_counts.argtypes = [_vp, ctypes.POINTER(_BatchView)]
+        L.hcm_mesh_emit_into.argtypes = [_vp, ctypes.c_uint32, _vp, _vp, ctypes.c_uint64, _vp, ctypes.c_uint64]
         L.hcm_remove_chunks.argtypes = [_vp, ctypes.c_uint32, _vp]
         L.hcm_rederive_chunks.argtypes = [_vp, ctypes.c_uint32, _vp]
         L.hcm_is_resident.argtypes = [_vp, _vp]
@@ -200,6 +210,7 @@ class Mesher:
         if rc:
             raise HcmError(rc, (self.L.hcm_last_error(None) or b"").decode())
         self.ctx = ctx
+        self._keep = []
         self.origin = tuple(int(v) for v in origin)
         self.extent = tuple(int(v) for v in extent)
 
@@ -219,12 +230,19 @@ class Mesher:
             raise HcmError(rc, (self.L.hcm_last_error(self.ctx) or b"").decode())
 
     # ---- residency -------------------------------------------------------------------------------------------------
-    def upload(self, positions, blocks, heights) -> None:
+    def upload(self, positions, blocks, heights, uniform_hint=None) -> None:
+        """hcm_upload_chunks; with ``uniform_hint`` (int32 per chunk: a Block value, HINT_UNKNOWN or HINT_NOT_UNIFORM)
+        hcm_upload_chunks_hinted."""
         pos = np.ascontiguousarray(positions, dtype=np.int16).reshape(-1, 3)
         b = np.ascontiguousarray(blocks, dtype=np.uint16).reshape(len(pos), 32768)
         h = np.ascontiguousarray(heights, dtype=np.int8).reshape(len(pos), 1024)
-        self._keep = (pos, b, h)  # the C side reads them asynchronously until the next sync
-        self._check(self.L.hcm_upload_chunks(self.ctx, len(pos), _ptr(pos), _ptr(b), _ptr(h)))
+        # the C side reads the arrays asynchronously until the next sync / fetch: keep every one of them until then
+        self._keep.append((pos, b, h))
+        if uniform_hint is None:
+            self._check(self.L.hcm_upload_chunks(self.ctx, len(pos), _ptr(pos), _ptr(b), _ptr(h)))
+        else:
+            hint = np.ascontiguousarray(uniform_hint, dtype=np.int32).reshape(len(pos))
+            self._check(self.L.hcm_upload_chunks_hinted(self.ctx, len(pos), _ptr(pos), _ptr(b), _ptr(h), _ptr(hint)))
 
     def remove(self, positions) -> None:
         pos = np.ascontiguousarray(positions, dtype=np.int16).reshape(-1, 3)
@@ -266,6 +284,7 @@ class Mesher:
 
     def sync(self) -> None:
         self._check(self.L.hcm_sync(self.ctx))
+        self._keep.clear()
 
     # ---- meshing ---------------------------------------------------------------------------------------------------
     def mesh_async(self, positions) -> None:
@@ -275,6 +294,7 @@ class Mesher:
     def wait(self) -> dict:
         c = _BatchCounts()
         self._check(self.L.hcm_mesh_wait(self.ctx, ctypes.byref(c)))
+        self._keep.clear()
         return dict(n_tasks=c.n_tasks, n_meshes=c.n_meshes, n_vertices=c.n_vertices, n_indices=c.n_indices, n_worked=c.n_worked)
 
     @staticmethod
@@ -292,7 +312,24 @@ class Mesher:
     def fetch(self) -> BatchResult:
         v = _BatchView()
         self._check(self.L.hcm_mesh_fetch(self.ctx, ctypes.byref(v)))
+        self._keep.clear()
         return self._result(v)
+
+    # ---- device-side sink (hcm_mesh_counts + hcm_mesh_emit_into) ---------------------------------------------------
+    def counts(self) -> BatchResult:
+        """Tasks and mesh descriptors of the last batch; no vertex or index byte is copied (``vertices`` / ``indices`` are empty)."""
+        v = _BatchView()
+        self._check(self.L.hcm_mesh_counts(self.ctx, ctypes.byref(v)))
+        self._keep.clear()
+        r = self._result(v)
+        self.n_vertices, self.n_indices = int(v.n_vertices), int(v.n_indices)
+        return BatchResult(r.tasks, r.meshes, np.zeros(0, dtype=np.uint64), np.zeros(0, dtype=np.uint16))
+
+    def emit_into(self, placements, dev_vertex_ptr: int, vertex_capacity: int, dev_index_ptr: int, index_capacity: int) -> None:
+        """Copy the placed meshes into caller-owned DEVICE buffers (raw device pointers, capacities in vertices / indices)."""
+        pl = np.ascontiguousarray(placements, dtype=MESH_PLACEMENT_DTYPE)
+        self._check(self.L.hcm_mesh_emit_into(self.ctx, len(pl), _ptr(pl) if len(pl) else None, _vp(dev_vertex_ptr), int(vertex_capacity),
+                                              _vp(dev_index_ptr), int(index_capacity)))
 
     def upload_and_mesh(self, positions, blocks, heights, task_positions) -> BatchResult:
         """upload() + mesh_async() + fetch() with host->device copies, kernels and device->host copies overlapped

@@ -321,12 +321,13 @@ typedef struct hcm_stats {
 	float classify_ms;     /* classify kernel of the last hcm_mesh_batch */
 	float mesh_ms;         /* mesh kernel of the last hcm_mesh_batch */
 	float fetch_copy_ms;   /* device->host copies of the last hcm_mesh_fetch */
-	float sink_ms;         /* scatter kernel of the last hcm_mesh_emit_into */
 	uint32_t kernel_launches; /* kernels launched by this ctx since creation */
 	uint64_t h2d_bytes;    /* cumulative */
 	uint64_t d2h_bytes;    /* cumulative */
 	uint64_t device_bytes; /* device memory held by the ctx */
-} hcm_stats;
+	float sink_ms;         /* scatter kernel of the last hcm_mesh_emit_into */
+	uint32_t upload_unscanned_chunks; /* chunks of the last upload the copy engine took before a scan thread did (sent as they are) */
+} hcm_stats; /* 56 bytes */
 int hcm_get_stats(hcm_ctx *ctx, hcm_stats *out);
 
 void *hcm_stream(hcm_ctx *ctx); /* the ctx's cudaStream_t, for external event timing */
