@@ -121,6 +121,7 @@ struct hcm_ctx {
 	uint32_t edit_cap = 0, sun_cap = 0;
 	std::vector<hcm_sunlight_change> edit_sunlight;
 	std::vector<int16_t> edit_remesh;
+	std::vector<uint8_t> edit_remesh_flags;
 	bool use_batch_copy = true;
 	// pipeline granularity (env HCM_UPLOAD_BLOCK, HCM_MIN_SUB_BATCH: test knobs): chunks per pipeline stage (2048 = 128 MB of Block
 	// data); ready sets smaller than min_sub_batch wait for the next upload block
@@ -1211,10 +1212,10 @@ int hcm_set_blocks(hcm_ctx *c, uint32_t n, const hcm_block_edit *edits, hcm_edit
 	c->stats.d2h_bytes += (uint64_t)m * 4 + 4 + (uint64_t)n_changes * sizeof(hcm_sunlight_change);
 
 	// fan-out on the host: which chunks to derive again, which mesh tasks the reference pushes
-	std::vector<uint8_t> mark(c->n_cells, 0); // bit0: derive again, bit1: remesh
-	auto mark_remesh = [&](int x, int y, int z) {
+	std::vector<uint8_t> mark(c->n_cells, 0); // bit0: derive again, bit1: remesh pushed by a block edit, bit2: by a sunlight change
+	auto mark_remesh = [&](int x, int y, int z, uint8_t why) {
 		if (x >= 0 && y >= 0 && z >= 0 && x < c->w.wx && y < c->w.wy && z < c->w.wz)
-			mark[cell(c, x, y, z)] |= 2;
+			mark[cell(c, x, y, z)] |= why;
 		else
 			out->n_pending++;
 	};
@@ -1233,7 +1234,7 @@ int hcm_set_blocks(hcm_ctx *c, uint32_t n, const hcm_block_edit *edits, hcm_edit
 						continue;
 					const int rel[3] = {bp[0] - dx * HCM_CHUNK_SIZE, bp[1] - dy * HCM_CHUNK_SIZE, bp[2] - dz * HCM_CHUNK_SIZE};
 					if (chunk_should_remesh(rel)) // ChunkSetBlockTask.cpp:100-107
-						mark_remesh(cx + dx, cy + dy, cz + dz);
+						mark_remesh(cx + dx, cy + dy, cz + dz, 2);
 				}
 	}
 	for (const hcm_sunlight_change &s : c->edit_sunlight) {
@@ -1242,10 +1243,10 @@ int hcm_set_blocks(hcm_ctx *c, uint32_t n, const hcm_block_edit *edits, hcm_edit
 		for (int dy = -1; dy <= 1; ++dy) // ChunkSetSunlightTask.cpp:66-78: the test is against the chunk itself for every neighbour
 			for (int dz = -1; dz <= 1; ++dz)
 				for (int dx = -1; dx <= 1; ++dx)
-					mark_remesh(cx + dx, cy + dy, cz + dz);
+					mark_remesh(cx + dx, cy + dy, cz + dz, 4);
 	}
 	std::vector<int16_t> derive_pos;
-	c->edit_remesh.clear();
+	c->edit_remesh.clear(), c->edit_remesh_flags.clear();
 	for (int y = 0; y < c->w.wy; ++y)
 		for (int z = 0; z < c->w.wz; ++z)
 			for (int x = 0; x < c->w.wx; ++x) {
@@ -1255,11 +1256,12 @@ int hcm_set_blocks(hcm_ctx *c, uint32_t n, const hcm_block_edit *edits, hcm_edit
 				const int16_t p[3] = {(int16_t)(x + c->w.ox), (int16_t)(y + c->w.oy), (int16_t)(z + c->w.oz)};
 				if (f & 1)
 					derive_pos.insert(derive_pos.end(), p, p + 3);
-				if (f & 2) {
+				if (f & 6) {
 					const bool interior = x >= 1 && y >= 1 && z >= 1 && x <= c->w.wx - 2 && y <= c->w.wy - 2 && z <= c->w.wz - 2;
-					if (interior && c->nbr_count[cell(c, x, y, z)] == 27)
+					if (interior && c->nbr_count[cell(c, x, y, z)] == 27) {
 						c->edit_remesh.insert(c->edit_remesh.end(), p, p + 3);
-					else
+						c->edit_remesh_flags.push_back((uint8_t)(((f & 2) ? HCM_REMESH_BLOCK_EDIT : 0u) | ((f & 4) ? HCM_REMESH_SUNLIGHT : 0u)));
+					} else
 						out->n_pending++;
 				}
 			}
@@ -1267,7 +1269,7 @@ int hcm_set_blocks(hcm_ctx *c, uint32_t n, const hcm_block_edit *edits, hcm_edit
 		if (int rc = hcm_rederive_chunks(c, (uint32_t)(derive_pos.size() / 3), derive_pos.data()))
 			return rc;
 	out->n_sunlight = n_changes, out->sunlight = c->edit_sunlight.data();
-	out->n_remesh = (uint32_t)(c->edit_remesh.size() / 3), out->remesh_pos = c->edit_remesh.data();
+	out->n_remesh = (uint32_t)(c->edit_remesh.size() / 3), out->remesh_pos = c->edit_remesh.data(), out->remesh_flags = c->edit_remesh_flags.data();
 	return HCM_OK;
 }
 

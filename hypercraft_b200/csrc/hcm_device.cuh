@@ -6,6 +6,15 @@
 
 #include "../../include/hcm.h"
 
+// Kernel launch and dynamic shared memory go through two macros so that the CPU test tier (tests/cusim: an emulation of the
+// CUDA execution model that compiles these very sources with g++) can substitute its own; the CUDA build is what ships.
+#ifndef HCM_LAUNCH
+#define HCM_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#endif
+#ifndef HCM_DYNAMIC_SMEM
+#define HCM_DYNAMIC_SMEM(name) extern __shared__ __align__(128) uint8_t name[]
+#endif
+
 namespace hcm {
 
 // ---- launch geometry ------------------------------------------------------------------------------------------

@@ -25,6 +25,15 @@ constexpr u32 FULL = 0xffffffffu;
 // ================================================================================================================
 // small PTX helpers: mbarrier + TMA (cp.async.bulk.tensor)
 // ================================================================================================================
+#ifdef HCM_CUSIM // CPU test tier: the emulation's mbarrier / bulk-copy model (tests/cusim/cusim.cpp)
+using cusim::mbar_expect_tx;
+using cusim::mbar_init;
+using cusim::mbar_wait;
+using cusim::tma_load_1d;
+using cusim::tma_load_3d;
+__device__ __forceinline__ u32 lanemask_lt() { return (1u << cusim::self().lane) - 1u; }
+__device__ __forceinline__ void fence_proxy_async() {}
+#else
 __device__ __forceinline__ u32 smem_u32(const void *p) { return (u32)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(u64 *bar, u32 count) {
 	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
@@ -64,6 +73,9 @@ __device__ __forceinline__ u32 lanemask_lt() {
 	asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
 	return m;
 }
+// generic-proxy accesses to shared memory are ordered before the async-proxy (TMA) writes that follow
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+#endif
 __device__ __forceinline__ u32 warp_excl_scan(u32 v, int lane) {
 	u32 x = v;
 #pragma unroll
@@ -103,7 +115,7 @@ __device__ unsigned long long g_phase_cycles[64];
 // ================================================================================================================
 __global__ void __launch_bounds__(256, 3) derive_kernel(DevWorld w, const UploadEntry *__restrict__ entries, const uint8_t *__restrict__ prop_index,
                                                      const DevTables *__restrict__ tables, const int8_t *__restrict__ raw_heights) {
-	extern __shared__ __align__(128) uint8_t derive_smem[]; // the chunk's 64 KB of Block data, one TMA bulk copy
+	HCM_DYNAMIC_SMEM(derive_smem); // the chunk's 64 KB of Block data, one TMA bulk copy
 	__shared__ uint16_t s_pinfo[256];                       // pflags | light level << 8
 	__shared__ u32 s_idinfo[256];                           // by block id: row | pflags << 8 | level << 16, bit 31: the row depends on meta
 	__shared__ u32 s_and, s_or;
@@ -1248,7 +1260,7 @@ __global__ void flood_slots_kernel(uint4 *out) {
 	}
 	out[tid] = make_uint4(v[0] | (v[1] << 16), v[2] | (v[3] << 16), v[4] | (v[5] << 16), v[6] | (v[7] << 16));
 }
-void launch_flood_slots(uint4 *out, cudaStream_t st) { flood_slots_kernel<<<1, kThreads, 0, st>>>(out); }
+void launch_flood_slots(uint4 *out, cudaStream_t st) { HCM_LAUNCH(flood_slots_kernel, 1, kThreads, 0, st, out); }
 
 // The chunk's totals are known: claim its vertex, index and descriptor ranges.  One thread issues the three atomics back
 // to back and only then looks at the results, so their round trips to the L2 overlap (three lanes with one atomic each
@@ -1267,7 +1279,7 @@ __device__ __forceinline__ void claim_output(const MeshParams &p, Small &S, int 
 }
 
 __global__ void __launch_bounds__(kThreads, 1) mesh_kernel(const __grid_constant__ MeshMaps maps, const MeshParams p) {
-	extern __shared__ __align__(128) uint8_t smem[];
+	HCM_DYNAMIC_SMEM(smem);
 	uint8_t *vox = smem + SM_VOX;
 	uint8_t *light = smem + SM_LIGHT;
 	u32 *F = reinterpret_cast<u32 *>(smem + SM_F);
@@ -1293,7 +1305,7 @@ __global__ void __launch_bounds__(kThreads, 1) mesh_kernel(const __grid_constant
 
 	// the two TMA boxes with the flood inputs of a task (thread 0)
 	auto fetch_flood_inputs = [&](const TaskIn &t) {
-		asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // generic accesses to these bytes come first
+		fence_proxy_async(); // generic accesses to these bytes come first
 		mbar_expect_tx(&S.bar_flood, kFloodPassBytes + kFloodHeightBytes);
 		tma_load_3d(smem + SM_FPASS, &maps.pass, t.cx * 32 - 16, t.cz * 32 - 15, t.cy - 1, &S.bar_flood);
 		tma_load_3d(smem + SM_FHEIGHT, &maps.height, t.cx * 32 - 16, t.cz * 32 - 15, t.cy - 1, &S.bar_flood);
@@ -1336,7 +1348,7 @@ __global__ void __launch_bounds__(kThreads, 1) mesh_kernel(const __grid_constant
 		// (the flood's inputs -- pass words and sunlight heights of the 62 x 62 columns x 3 chunk layers around the task -- are
 		// two more boxes, already on their way: fetch_flood_inputs)
 		if (tid == 0) {
-			asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+			fence_proxy_async();
 			mbar_expect_tx(&S.bar, kVoxBytes);
 			tma_load_3d(vox, &maps.vox, ti.cx * 32, ti.cz * 32 - 2, ti.cy * 32 - 1, &S.bar); // stored column = x + kXMargin
 		}
@@ -1986,28 +1998,28 @@ __global__ void __launch_bounds__(256) scatter_kernel(const hcm_mesh_placement *
 void launch_scatter(const hcm_mesh_placement *placements, u32 n, const hcm_mesh_desc *meshes, const u64 *vtx, const uint16_t *idx, void *vdst, void *idst,
                     int grid, cudaStream_t st) {
 	if (n)
-		scatter_kernel<<<min((u32)grid, n), 256, 0, st>>>(placements, n, meshes, vtx, idx, (u64 *)vdst, (uint16_t *)idst);
+		HCM_LAUNCH(scatter_kernel, min((u32)grid, n), 256, 0, st, placements, n, meshes, vtx, idx, (u64 *)vdst, (uint16_t *)idst);
 }
 void launch_derive(const DevWorld &w, const UploadEntry *entries, u32 n, const uint8_t *prop_index, const DevTables *tables, const int8_t *raw_heights,
                    cudaStream_t st) {
 	if (n)
-		derive_kernel<<<n, 256, HCM_CHUNK_VOXELS * 2, st>>>(w, entries, prop_index, tables, raw_heights);
+		HCM_LAUNCH(derive_kernel, n, 256, HCM_CHUNK_VOXELS * 2, st, w, entries, prop_index, tables, raw_heights);
 }
 void launch_clear(const DevWorld &w, const UploadEntry *entries, u32 n, cudaStream_t st) {
 	if (n)
-		clear_kernel<<<n, 256, 0, st>>>(w, entries);
+		HCM_LAUNCH(clear_kernel, n, 256, 0, st, w, entries);
 }
 void launch_edit(const DevWorld &w, const hcm_block_edit *edits, u32 n, const uint2 *columns, u32 n_columns, u32 *result, const uint8_t *prop_index,
                  const DevTables *tables, int8_t *raw_heights, hcm_sunlight_change *changes, u32 *n_changes, u32 cap, cudaStream_t st) {
 	if (!n)
 		return;
-	edit_blocks_kernel<<<(n + 127) / 128, 128, 0, st>>>(w, edits, n, result);
-	sunlight_chain_kernel<<<(n_columns + 127) / 128, 128, 0, st>>>(w, edits, columns, n_columns, result, prop_index, tables, raw_heights, changes, n_changes, cap);
+	HCM_LAUNCH(edit_blocks_kernel, (n + 127) / 128, 128, 0, st, w, edits, n, result);
+	HCM_LAUNCH(sunlight_chain_kernel, (n_columns + 127) / 128, 128, 0, st, w, edits, columns, n_columns, result, prop_index, tables, raw_heights, changes, n_changes, cap);
 }
 void launch_classify(const DevWorld &w, const TaskIn *tasks, u32 n, u32 *worklist, BatchHeads *heads, hcm_task_result *task_out, int force_all,
                      cudaStream_t st) {
 	if (n)
-		classify_kernel<<<(n + 255) / 256, 256, 0, st>>>(w, tasks, n, worklist, heads, task_out, force_all);
+		HCM_LAUNCH(classify_kernel, (n + 255) / 256, 256, 0, st, w, tasks, n, worklist, heads, task_out, force_all);
 }
 #ifdef HCM_PHASE_TIMING
 extern "C" __attribute__((visibility("default"))) int hcm_debug_phase_cycles(unsigned long long *out, int reset) {
@@ -2026,6 +2038,6 @@ cudaError_t mesh_kernel_prepare() {
 	return cudaFuncSetAttribute(mesh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
 }
 int mesh_kernel_smem_bytes() { return kSmemBytes; }
-void launch_mesh(const MeshMaps &maps, const MeshParams &p, int grid, cudaStream_t st) { mesh_kernel<<<grid, kThreads, kSmemBytes, st>>>(maps, p); }
+void launch_mesh(const MeshMaps &maps, const MeshParams &p, int grid, cudaStream_t st) { HCM_LAUNCH(mesh_kernel, grid, kThreads, kSmemBytes, st, maps, p); }
 
 } // namespace hcm

@@ -163,23 +163,23 @@ public:
 	// MeshRequestQueue above.  high_priority = the `true` of Push<kMesh>(pos, true) that edits use.
 	// The chunk left the world (ChunkPool::Update evicts it, client/src/ChunkPool.cpp:9-33, and the task pool calls
 	// ChunkTaskData<kMesh>::OnUnload, ChunkMeshTask.inl:48): its device slot is freed, its pending request and its not yet
-	// uploaded copy are dropped.  Requests of its neighbours stay; like Pop() in the reference they fail (NOT_RESIDENT)
-	// unless the chunk comes back before they are flushed.
+	// uploaded copy are dropped.  Requests of its neighbours stay pending: like Pop() in the reference (ChunkMeshTask.cpp:29-31
+	// returns nullopt for that one task) Flush leaves them out of its round until the chunk has come back.
+	// Lock order as in Flush -- ctx first, then the bookkeeping -- and both held to the end: a Submit + Flush of a new object for
+	// `pos` cannot slip between the bookkeeping and hcm_remove_chunks (which would then delete the fresh device copy).
 	void Unload(const ChunkPos3 &pos) {
-		{
-			std::lock_guard<std::mutex> g(m_mutex);
-			m_resident.erase(pos);
-			m_queue.Drop(pos);
-			m_snapshot.erase(pos);
-			for (size_t i = 0; i < m_upload.size();) {
-				const auto p = m_upload[i]->GetPosition();
-				if (ChunkPos3{(int16_t)p.x, (int16_t)p.y, (int16_t)p.z} == pos)
-					m_upload.erase(m_upload.begin() + (std::ptrdiff_t)i);
-				else
-					++i;
-			}
-		}
 		std::lock_guard<std::mutex> ctx_lock(m_ctx_mutex);
+		std::lock_guard<std::mutex> g(m_mutex);
+		m_resident.erase(pos);
+		m_queue.Drop(pos);
+		m_snapshot.erase(pos);
+		for (size_t i = 0; i < m_upload.size();) {
+			const auto p = m_upload[i]->GetPosition();
+			if (ChunkPos3{(int16_t)p.x, (int16_t)p.y, (int16_t)p.z} == pos)
+				m_upload.erase(m_upload.begin() + (std::ptrdiff_t)i);
+			else
+				++i;
+		}
 		const int16_t p[3] = {pos.x, pos.y, pos.z};
 		check(hcm_remove_chunks(m_ctx, 1, p));
 	}
@@ -213,8 +213,10 @@ public:
 	// (client/src/ChunkSetBlockTask.cpp:78-129, ChunkFloodSunlightTask.cpp:41-57, ChunkSetSunlightTask.cpp:42-90) without
 	// re-uploading 64 KB per touched chunk.  The caller has already applied (or now applies) the same blocks to its own
 	// Chunk objects with Chunk::SetBlock; `on_sunlight(const SunlightChange&)` is where it calls Chunk::SetSunlightHeight,
-	// `on_remesh(const ChunkPos3&)` where it would Push<kMesh> -- typically Submit(the 27 chunks around that position, true);
-	// the callbacks run inside the ctx's critical section: Submit / MarkDirty are fine there, Flush / SetBlocks are not.
+	// `on_remesh(const ChunkPos3&, bool high_priority)` where it would Push<kMesh> -- typically Submit(the 27 chunks around that
+	// position, high_priority).  high_priority is the reference's: true for the fan-out of a changed block
+	// (ChunkSetBlockTask.cpp:119), false for positions that only a changed sunlight height reaches (ChunkSetSunlightTask.cpp:84).
+	// The callbacks run inside the ctx's critical section: Submit / MarkDirty are fine there, Flush / SetBlocks are not.
 	struct SetBlock {
 		ChunkPos3 chunk;
 		uint16_t index; // InnerIndex3: x + (y*32 + z)*32
@@ -239,7 +241,7 @@ public:
 			on_sunlight(SunlightChange{ChunkPos3{s.chunk[0], s.chunk[1], s.chunk[2]}, s.index, s.old_height, s.new_height});
 		}
 		for (uint32_t i = 0; i < r.n_remesh; ++i)
-			on_remesh(ChunkPos3{r.remesh_pos[3 * i], r.remesh_pos[3 * i + 1], r.remesh_pos[3 * i + 2]});
+			on_remesh(ChunkPos3{r.remesh_pos[3 * i], r.remesh_pos[3 * i + 1], r.remesh_pos[3 * i + 2]}, (r.remesh_flags[i] & HCM_REMESH_BLOCK_EDIT) != 0);
 		return r.n_changed_blocks;
 	}
 
@@ -287,6 +289,43 @@ public:
 					m_heights[i * HCM_CHUNK_COLUMNS + k] = (int8_t)upload[i]->GetSunlightHeight(k);
 			}
 		}
+		// Readiness per task, as ChunkTaskData<kMesh>::Pop tests it (ChunkMeshTask.cpp:18-34): a task one of whose 27 chunks is
+		// neither on the device nor part of this upload (its neighbour was Unloaded after the request) is left out of the round
+		// and stays pending; every other task runs.  One evicted chunk must not stall the world.
+		{
+			std::unordered_set<ChunkPos3, ChunkPos3Hash> coming;
+			for (const auto &c : upload) {
+				const auto p = c->GetPosition();
+				coming.insert(ChunkPos3{(int16_t)p.x, (int16_t)p.y, (int16_t)p.z});
+			}
+			std::vector<size_t> deferred;
+			for (size_t i = 0; i < tasks.size(); ++i) {
+				bool ready = true;
+				for (int dx = -1; dx <= 1 && ready; ++dx)
+					for (int dy = -1; dy <= 1 && ready; ++dy)
+						for (int dz = -1; dz <= 1 && ready; ++dz) {
+							const ChunkPos3 q{(int16_t)(tasks[i].x + dx), (int16_t)(tasks[i].y + dy), (int16_t)(tasks[i].z + dz)};
+							const int16_t qp[3] = {q.x, q.y, q.z};
+							ready = coming.count(q) || hcm_is_resident(m_ctx, qp);
+						}
+				if (!ready)
+					deferred.push_back(i);
+			}
+			if (!deferred.empty()) {
+				std::lock_guard<std::mutex> g(m_mutex);
+				for (size_t k = deferred.size(); k-- > 0;) {
+					const size_t i = deferred[k];
+					m_queue.Push(tasks[i], high[i]);
+					m_snapshot.emplace(tasks[i], std::move(snapshots[i])); // a newer snapshot, if one came in, wins
+					tasks.erase(tasks.begin() + (std::ptrdiff_t)i), high.erase(high.begin() + (std::ptrdiff_t)i);
+					snapshots.erase(snapshots.begin() + (std::ptrdiff_t)i);
+				}
+				if (tasks.empty()) { // nothing can run: the chunks waiting to go up wait with their tasks
+					m_upload.insert(m_upload.begin(), upload.begin(), upload.end());
+					return;
+				}
+			}
+		}
 		std::vector<int16_t> tp(tasks.size() * 3);
 		for (size_t i = 0; i < tasks.size(); ++i)
 			tp[3 * i] = tasks[i].x, tp[3 * i + 1] = tasks[i].y, tp[3 * i + 2] = tasks[i].z;
@@ -297,13 +336,30 @@ public:
 			// nothing was pushed: the round goes back to pending, behind the requests that arrived meanwhile
 			std::lock_guard<std::mutex> g(m_mutex);
 			m_upload.insert(m_upload.begin(), upload.begin(), upload.end());
-			for (size_t i = 0; i < tasks.size(); ++i) {
-				m_queue.Push(tasks[i], high[i]);
-				m_snapshot.emplace(tasks[i], std::move(snapshots[i])); // a newer snapshot, if one came in, wins
-			}
+			requeue(tasks, high, snapshots, 0);
 			throw Error(rc, hcm_last_error(m_ctx));
 		}
-		for (uint32_t t = 0; t < v.n_tasks; ++t) {
+		uint32_t t = 0;
+		try {
+			push_results(v, tasks, t, sink);
+		} catch (...) { // the sink threw at task t: that task and the ones behind it were not delivered -- they stay pending
+			std::lock_guard<std::mutex> g(m_mutex);
+			requeue(tasks, high, snapshots, t);
+			throw;
+		}
+	}
+
+	hcm_ctx *Context() { return m_ctx; }
+
+private:
+	void requeue(std::vector<ChunkPos3> &tasks, const std::vector<bool> &high, std::vector<std::array<std::shared_ptr<ChunkT>, 27>> &snapshots, size_t from) {
+		for (size_t i = from; i < tasks.size(); ++i) {
+			m_queue.Push(tasks[i], high[i]);
+			m_snapshot.emplace(tasks[i], std::move(snapshots[i])); // a newer snapshot, if one came in, wins
+		}
+	}
+	template <typename Sink> void push_results(const hcm_batch_view &v, const std::vector<ChunkPos3> &tasks, uint32_t &t, Sink &&sink) {
+		for (t = 0; t < v.n_tasks; ++t) {
 			std::vector<BlockMesh> meshes(v.tasks[t].n_meshes);
 			for (uint32_t k = 0; k < v.tasks[t].n_meshes; ++k) {
 				const hcm_mesh_desc &d = v.meshes[v.tasks[t].first_mesh + k];
@@ -317,10 +373,6 @@ public:
 			sink(tasks[t], std::move(meshes));
 		}
 	}
-
-	hcm_ctx *Context() { return m_ctx; }
-
-private:
 	void check(int rc) {
 		if (rc)
 			throw Error(rc, hcm_last_error(m_ctx));
@@ -427,19 +479,22 @@ public:
 			by_rank[owner_or_throw(e.chunk.x)].push_back(e);
 		uint32_t changed = 0;
 		std::vector<ChunkPos3> remesh;
-		std::unordered_set<ChunkPos3, ChunkPos3Hash> seen;
-		auto add = [&](const ChunkPos3 &p) {
-			if (seen.insert(p).second)
+		std::unordered_map<ChunkPos3, bool, ChunkPos3Hash> seen; // position -> high priority (sticky, as in MeshRequestQueue)
+		auto add = [&](const ChunkPos3 &p, bool high) {
+			auto ins = seen.emplace(p, high);
+			if (ins.second)
 				remesh.push_back(p);
+			else
+				ins.first->second = ins.first->second || high;
 		};
 		for (size_t r = 0; r < m_shards.size(); ++r) {
 			if (by_rank[r].empty())
 				continue;
-			auto add_foreign = [&](const ChunkPos3 &c, int dx, int dy, int dz) { // a fan-out position the owner's ctx cannot report
+			auto add_foreign = [&](const ChunkPos3 &c, int dx, int dy, int dz, bool high) { // a fan-out position the owner's ctx cannot report
 				const ChunkPos3 q{(int16_t)(c.x + dx), (int16_t)(c.y + dy), (int16_t)(c.z + dz)};
 				const int o = Owner(q.x);
 				if (o >= 0 && o != (int)r)
-					add(q);
+					add(q, high);
 			};
 			std::vector<ChunkPos3> touched;
 			for (const SetBlock &e : by_rank[r]) {
@@ -449,7 +504,7 @@ public:
 					for (int dy = -1; dy <= 1; ++dy)
 						for (int dz = -1; dz <= 1; ++dz)
 							if (ShouldRemesh(bx - dx * HCM_CHUNK_SIZE, by - dy * HCM_CHUNK_SIZE, bz - dz * HCM_CHUNK_SIZE))
-								add_foreign(e.chunk, dx, dy, dz);
+								add_foreign(e.chunk, dx, dy, dz, true);
 			}
 			changed += m_shards[r]->SetBlocks(
 			    by_rank[r],
@@ -458,17 +513,17 @@ public:
 				    for (int dx = -1; dx <= 1; dx += 2)
 					    for (int dy = -1; dy <= 1; ++dy)
 						    for (int dz = -1; dz <= 1; ++dz)
-							    add_foreign(s.chunk, dx, dy, dz);
+							    add_foreign(s.chunk, dx, dy, dz, false);
 				    on_sunlight(s);
 			    },
-			    [&](const ChunkPos3 &p) { add(p); });
+			    [&](const ChunkPos3 &p, bool high) { add(p, high); });
 			for (const ChunkPos3 &c : touched)
 				for (int h : Holders(c.x))
 					if (h != (int)r)
 						m_shards[h]->MarkDirty(c);
 		}
 		for (const ChunkPos3 &p : remesh)
-			on_remesh(p);
+			on_remesh(p, seen[p]);
 		return changed;
 	}
 

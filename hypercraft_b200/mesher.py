@@ -47,7 +47,7 @@ class _BatchCounts(ctypes.Structure):
 
 class _EditResult(ctypes.Structure):
     _fields_ = [("n_changed_blocks", ctypes.c_uint32), ("n_sunlight", ctypes.c_uint32), ("n_remesh", ctypes.c_uint32), ("n_pending", ctypes.c_uint32),
-                ("sunlight", _vp), ("remesh_pos", _vp)]
+                ("sunlight", _vp), ("remesh_pos", _vp), ("remesh_flags", _vp)]
 
 
 BLOCK_EDIT_DTYPE = np.dtype([("chunk", np.int16, 3), ("index", np.uint16), ("block", np.uint16), ("_pad", np.uint16)])
@@ -258,8 +258,9 @@ class Mesher:
 
     def set_blocks(self, edit_list) -> dict:
         """Block edits on the resident world (hcm_set_blocks).  ``edit_list`` = [((cx,cy,cz), index, block), ...] or a
-        BLOCK_EDIT_DTYPE array.  Returns n_changed_blocks, n_pending, ``sunlight`` (SUNLIGHT_CHANGE_DTYPE copies) and
-        ``remesh`` (int16[n,3]: the mesh tasks to submit)."""
+        BLOCK_EDIT_DTYPE array.  Returns n_changed_blocks, n_pending, ``sunlight`` (SUNLIGHT_CHANGE_DTYPE copies),
+        ``remesh`` (int16[n,3]: the mesh tasks to submit) and ``remesh_flags`` (u8[n]: 1 = pushed by a block edit -- high priority in
+        the reference --, 2 = pushed by a sunlight change)."""
         if isinstance(edit_list, np.ndarray) and edit_list.dtype == BLOCK_EDIT_DTYPE:
             e = np.ascontiguousarray(edit_list)
         else:
@@ -276,7 +277,7 @@ class Mesher:
             return np.frombuffer(buf, dtype=dtype, count=count).copy()
 
         return dict(n_changed_blocks=r.n_changed_blocks, n_pending=r.n_pending, sunlight=copy(r.sunlight, r.n_sunlight, SUNLIGHT_CHANGE_DTYPE),
-                    remesh=copy(r.remesh_pos, r.n_remesh * 3, np.int16).reshape(-1, 3))
+                    remesh=copy(r.remesh_pos, r.n_remesh * 3, np.int16).reshape(-1, 3), remesh_flags=copy(r.remesh_flags, r.n_remesh, np.uint8))
 
     def is_resident(self, pos) -> bool:
         p = np.ascontiguousarray(pos, dtype=np.int16)
@@ -300,7 +301,7 @@ class Mesher:
     @staticmethod
     def _result(v: _BatchView) -> BatchResult:
         def view(ptr, count, dtype):
-            if not count:
+            if not count or not ptr:  # hcm_mesh_counts returns totals without arrays
                 return np.zeros(0, dtype=dtype)
             nbytes = count * np.dtype(dtype).itemsize
             buf = (ctypes.c_uint8 * nbytes).from_address(ptr)

@@ -195,7 +195,8 @@ int hcm_is_resident(const hcm_ctx *ctx, const int16_t pos[3]); /* 1 / 0 */
  *      all 26 neighbours (ChunkSetSunlightTask.cpp:66-78 tests the column against the chunk itself for every i, which
  *      is always true).  Deduplicated; positions whose 27 chunks are not all resident are counted in n_pending instead.
  * The caller applies `sunlight` to its own Chunk objects (Chunk::SetSunlightHeight) and passes `remesh_pos` to
- * hcm_mesh_batch.  Pointers in the result belong to the ctx and stay valid until its next call.
+ * hcm_mesh_batch; `remesh_flags` tells the edit's own fan-out (high priority in the reference) from the positions only a
+ * changed sunlight height reaches (low priority).  Pointers in the result belong to the ctx and stay valid until its next call.
  * ---------------------------------------------------------------------------------------------------------- */
 typedef struct hcm_block_edit {
 	int16_t chunk[3]; /* ChunkPos3 */
@@ -218,7 +219,10 @@ typedef struct hcm_edit_result {
 	uint32_t n_pending;
 	const hcm_sunlight_change *sunlight; /* [n_sunlight], each (chunk, column) at most once */
 	const int16_t *remesh_pos;           /* [n_remesh x 3] */
+	const uint8_t *remesh_flags;         /* [n_remesh] HCM_REMESH_*: who pushes the task in the reference */
 } hcm_edit_result;
+#define HCM_REMESH_BLOCK_EDIT 1u /* Push<kMesh>(pos, high_priority = true), ChunkSetBlockTask.cpp:119 */
+#define HCM_REMESH_SUNLIGHT 2u   /* Push<kMesh>(pos, false), ChunkSetSunlightTask.cpp:84 */
 
 int hcm_set_blocks(hcm_ctx *ctx, uint32_t n, const hcm_block_edit *edits, hcm_edit_result *out);
 int hcm_sync(hcm_ctx *ctx);

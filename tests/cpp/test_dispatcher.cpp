@@ -139,7 +139,7 @@ int main(int argc, char **argv) {
 		int n_sun = 0, n_remesh = 0;
 		const uint32_t changed = disp.SetBlocks(
 		    edits, [&](const D::SunlightChange &s) { world[{s.chunk.x, s.chunk.y, s.chunk.z}]->heights[s.index] = s.new_height, ++n_sun; },
-		    [&](const hcm_host::ChunkPos3 &p) { disp.Submit(gather(p.x, p.y, p.z)), ++n_remesh; });
+		    [&](const hcm_host::ChunkPos3 &p, bool high) { disp.Submit(gather(p.x, p.y, p.z), high), ++n_remesh; });
 		disp.Flush(sink);
 		printf("device edits: %u blocks changed, %d sunlight heights changed, %d chunks remeshed\n", changed, n_sun, n_remesh);
 		if (!changed || !n_remesh)

@@ -24,6 +24,7 @@ std::vector<uint64_t> vertices;
 std::vector<uint16_t> indices;
 bool fail_next = false;
 std::vector<std::array<int, 3>> removed;
+std::set<std::array<int, 3>> resident; // what the device holds
 uint32_t tag(int x, int y, int z) { return (uint32_t)((x + 50) * 10000 + (y + 50) * 100 + (z + 50)); }
 } // namespace fake
 
@@ -36,10 +37,13 @@ int hcm_create(const hcm_registry *, const hcm_config *, hcm_ctx **out) { return
 void hcm_destroy(hcm_ctx *c) { delete c; }
 const char *hcm_last_error(const hcm_ctx *) { return "fake"; }
 int hcm_remove_chunks(hcm_ctx *, uint32_t n, const int16_t *pos) {
-	for (uint32_t i = 0; i < n; ++i)
+	for (uint32_t i = 0; i < n; ++i) {
 		fake::removed.push_back({pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]});
+		fake::resident.erase({pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]});
+	}
 	return HCM_OK;
 }
+int hcm_is_resident(const hcm_ctx *, const int16_t pos[3]) { return (int)fake::resident.count({pos[0], pos[1], pos[2]}); }
 int hcm_set_blocks(hcm_ctx *, uint32_t, const hcm_block_edit *, hcm_edit_result *out) { return *out = hcm_edit_result{}, HCM_OK; }
 // one mesh per task: 4 vertices whose first word is the task position's tag, 6 indices, aabb_min[0] = tag
 int hcm_upload_and_mesh(hcm_ctx *, uint32_t n_chunks, const int16_t *pos, const uint16_t *blocks, const int8_t *heights, uint32_t n_tasks,
@@ -54,9 +58,16 @@ int hcm_upload_and_mesh(hcm_ctx *, uint32_t n_chunks, const int16_t *pos, const 
 		if (blocks[(size_t)i * HCM_CHUNK_VOXELS] != (uint16_t)fake::tag(pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]) || heights[(size_t)i * HCM_CHUNK_COLUMNS] != (int8_t)pos[3 * i])
 			return HCM_ERR_INVALID;
 	}
+	for (const auto &u : c.uploaded)
+		fake::resident.insert(u);
 	fake::tasks.clear(), fake::meshes.clear(), fake::vertices.clear(), fake::indices.clear();
 	for (uint32_t t = 0; t < n_tasks; ++t) {
 		c.tasks.push_back({task_pos[3 * t], task_pos[3 * t + 1], task_pos[3 * t + 2]});
+		for (int dx = -1; dx <= 1; ++dx) // like the device: one missing neighbour fails the WHOLE call
+			for (int dy = -1; dy <= 1; ++dy)
+				for (int dz = -1; dz <= 1; ++dz)
+					if (!fake::resident.count({task_pos[3 * t] + dx, task_pos[3 * t + 1] + dy, task_pos[3 * t + 2] + dz}))
+						return HCM_ERR_NOT_RESIDENT;
 		const uint32_t g = fake::tag(task_pos[3 * t], task_pos[3 * t + 1], task_pos[3 * t + 2]);
 		hcm_mesh_desc d{};
 		d.task = t, d.transparent = t & 1, d.vertex_offset = fake::vertices.size(), d.index_offset = fake::indices.size(), d.vertex_count = 4, d.index_count = 6;
@@ -195,6 +206,48 @@ int main() {
 	disp.Flush(sink);
 	CHECK(sunk.size() == 1 && sunk[0] == (ChunkPos3{0, 0, 0}));
 	CHECK(fake::calls.back().uploaded.size() == 1 && fake::calls.back().uploaded[0] == (std::array<int, 3>{1, 0, 0}));
+
+	// round 5d: the neighbour stays away -- the task that reads it is left out of the round and stays pending (the reference's
+	// Pop returns nullopt for that one task, ChunkMeshTask.cpp:29-31), every other task runs; when the chunk is back, so is the task
+	sunk.clear();
+	disp.Submit(gather(0, 0, 0));
+	disp.Submit(gather(-1, 0, 0));
+	disp.Submit(gather(-1, -1, 0), true);
+	disp.Unload({1, 0, 0}); // read by task (0,0,0) only
+	{
+		const size_t calls_before = fake::calls.size();
+		disp.Flush(sink);
+		CHECK(fake::calls.size() == calls_before + 1 && fake::calls.back().tasks.size() == 2);
+		CHECK(sunk.size() == 2 && sunk[0] == (ChunkPos3{-1, -1, 0}) && sunk[1] == (ChunkPos3{-1, 0, 0}) && disp.Pending() == 1);
+		disp.Flush(sink); // still away: nothing to run, no call, no exception
+		CHECK(fake::calls.size() == calls_before + 1 && sunk.size() == 2 && disp.Pending() == 1);
+		disp.Submit(gather(1, 0, 0)); // the chunk is in the world again (its own task is requested, and it is uploaded)
+		disp.Flush(sink);
+		CHECK(sunk.size() == 4 && disp.Pending() == 0);
+		CHECK((sunk[2] == (ChunkPos3{0, 0, 0}) && sunk[3] == (ChunkPos3{1, 0, 0})));
+	}
+
+	// round 5e: the sink throws at the second task of three -- the first was delivered, the other two are pending again
+	sunk.clear();
+	disp.Submit(gather(0, 0, 0));
+	disp.Submit(gather(0, 0, 1));
+	disp.Submit(gather(0, 1, 0));
+	{
+		int n = 0;
+		bool threw2 = false;
+		try {
+			disp.Flush([&](const ChunkPos3 &p, std::vector<hcm_host::BlockMesh> &&m) {
+				if (++n == 2)
+					throw std::runtime_error("renderer gone");
+				sink(p, std::move(m));
+			});
+		} catch (const std::runtime_error &) {
+			threw2 = true;
+		}
+		CHECK(threw2 && sunk.size() == 1 && sunk[0] == (ChunkPos3{0, 0, 0}) && disp.Pending() == 2);
+		disp.Flush(sink);
+		CHECK(sunk.size() == 3 && sunk[1] == (ChunkPos3{0, 0, 1}) && sunk[2] == (ChunkPos3{0, 1, 0}) && disp.Pending() == 0);
+	}
 
 	// round 5c: a chunk object is replaced twice while a task that reads it is waiting -- one copy goes up, the latest
 	sunk.clear();

@@ -20,7 +20,9 @@ struct hcm_ctx {
 	std::vector<hcm_block_edit> edits;
 	std::vector<hcm_sunlight_change> sun;
 	std::vector<int16_t> remesh;
+	std::vector<uint8_t> remesh_flags;
 	std::vector<hcm_task_result> results;
+	std::set<P3> resident;
 	bool in_window(int x, int y, int z) const {
 		return x >= cfg.origin[0] && x < cfg.origin[0] + cfg.extent[0] && y >= cfg.origin[1] && y < cfg.origin[1] + cfg.extent[1] && z >= cfg.origin[2] &&
 		       z < cfg.origin[2] + cfg.extent[2];
@@ -40,13 +42,19 @@ int hcm_create(const hcm_registry *, const hcm_config *cfg, hcm_ctx **out) {
 }
 void hcm_destroy(hcm_ctx *) {} // kept for inspection
 const char *hcm_last_error(const hcm_ctx *) { return "fake"; }
-int hcm_remove_chunks(hcm_ctx *, uint32_t, const int16_t *) { return HCM_OK; }
+int hcm_remove_chunks(hcm_ctx *c, uint32_t n, const int16_t *pos) {
+	for (uint32_t i = 0; i < n; ++i)
+		c->resident.erase({pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]});
+	return HCM_OK;
+}
+int hcm_is_resident(const hcm_ctx *c, const int16_t pos[3]) { return (int)c->resident.count({pos[0], pos[1], pos[2]}); }
 int hcm_upload_and_mesh(hcm_ctx *c, uint32_t n_chunks, const int16_t *pos, const uint16_t *, const int8_t *, uint32_t n_tasks, const int16_t *tp,
                         hcm_batch_view *out) {
 	c->uploads.emplace_back(), c->tasks.emplace_back();
 	for (uint32_t i = 0; i < n_chunks; ++i) {
 		g_violations += !c->in_window(pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]);
 		c->uploads.back().push_back({pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]});
+		c->resident.insert({pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]});
 	}
 	for (uint32_t t = 0; t < n_tasks; ++t) {
 		g_violations += !c->in_window(tp[3 * t] - 1, tp[3 * t + 1] - 1, tp[3 * t + 2] - 1) || !c->in_window(tp[3 * t] + 1, tp[3 * t + 1] + 1, tp[3 * t + 2] + 1);
@@ -84,7 +92,8 @@ int hcm_set_blocks(hcm_ctx *c, uint32_t n, const hcm_block_edit *e, hcm_edit_res
 	for (const P3 &p : fan)
 		for (int k = 0; k < 3; ++k)
 			c->remesh.push_back((int16_t)p[k]);
-	*out = hcm_edit_result{n, (uint32_t)c->sun.size(), (uint32_t)fan.size(), 0, c->sun.data(), c->remesh.data()};
+	c->remesh_flags.assign(fan.size(), (uint8_t)(c->sun.empty() ? HCM_REMESH_BLOCK_EDIT : HCM_REMESH_BLOCK_EDIT | HCM_REMESH_SUNLIGHT));
+	*out = hcm_edit_result{n, (uint32_t)c->sun.size(), (uint32_t)fan.size(), 0, c->sun.data(), c->remesh.data(), c->remesh_flags.data()};
 	return HCM_OK;
 }
 }
@@ -176,7 +185,7 @@ int main() {
 	int n_sun = 0;
 	uint32_t changed = disp.SetBlocks(
 	    edits, [&](const D::SunlightChange &) { ++n_sun; },
-	    [&](const ChunkPos3 &p) {
+	    [&](const ChunkPos3 &p, bool) {
 		    asked.push_back(p);
 		    if (is_task(p))
 			    disp.Submit(gather(p.x, p.y, p.z), true);
@@ -207,7 +216,7 @@ int main() {
 	world.at({1, 0, 0})->blocks[edits[0].index] = 1;
 	disp.SetBlocks(
 	    edits, [&](const D::SunlightChange &s) { world.at({s.chunk.x, s.chunk.y, s.chunk.z})->heights[s.index] = s.new_height, ++n_sun; },
-	    [&](const ChunkPos3 &p) {
+	    [&](const ChunkPos3 &p, bool) {
 		    asked.push_back(p);
 		    if (is_task(p))
 			    disp.Submit(gather(p.x, p.y, p.z), true);
@@ -224,7 +233,7 @@ int main() {
 	world.at({0, 0, 0})->blocks[edits[0].index] = 1;
 	disp.SetBlocks(
 	    edits, [&](const D::SunlightChange &s) { world.at({s.chunk.x, s.chunk.y, s.chunk.z})->heights[s.index] = s.new_height; },
-	    [&](const ChunkPos3 &p) {
+	    [&](const ChunkPos3 &p, bool) {
 		    asked.push_back(p);
 		    if (is_task(p))
 			    disp.Submit(gather(p.x, p.y, p.z), true);

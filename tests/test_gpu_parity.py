@@ -170,19 +170,47 @@ def test_reference_terrain(have_ref, port):
 def test_cpp_host_mirror_dispatcher():
     """hypercraft_b200/host/hcm_host.hpp (the C++ side a HyperCraft build would compile in): Submit 27-chunk arrays,
     Flush into a PushChunkMesh-shaped sink, compare with the oracle -- see tests/cpp/test_dispatcher.cpp."""
-    import os
     import subprocess
 
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    exe = os.path.join(root, "tests", "cpp", "test_dispatcher")
-    src = exe + ".cpp"
-    lib = os.path.join(root, "hypercraft_b200", "csrc")
-    subprocess.run(["g++", "-std=c++20", "-O2", "-pthread", "-o", exe, src, f"-L{lib}", "-lhcm", "-ldl", f"-Wl,-rpath,{lib}"], check=True)
     import hcoracle
 
+    exe, root = _build_cpp("test_dispatcher")
     hcoracle.build(ref=False, port=True)
     r = subprocess.run([exe, os.path.join(root, "hypercraft_b200", "data", "registry.bin"), hcoracle.PORT_SO], capture_output=True, text=True)
     assert r.returncode == 0 and r.stdout.strip().splitlines()[-1].startswith("PASS"), r.stdout + r.stderr
+
+
+def _build_cpp(name):
+    """tests/cpp/<name>.cpp linked against the library under test (libhcm.so; the CPU emulation build under HCM_TEST_SIM)."""
+    import subprocess
+
+    from hypercraft_b200 import mesher as M
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "tests", "cpp", name)
+    libdir, libfile = os.path.split(M.LIB_PATH)
+    subprocess.run(["g++", "-std=c++20", "-O2", "-pthread", "-o", exe, exe + ".cpp", f"-L{libdir}", "-l" + libfile[3:-3], "-ldl", f"-Wl,-rpath,{libdir}"],
+                   check=True)
+    return exe, root
+
+
+def test_cpp_sharded_dispatcher_on_two_devices():
+    """hcm_host::ShardedMeshDispatcher::FlushParallel over two hcm_ctx on two devices (SURVEY 8e): world load and edits across the
+    cut, every pushed mesh against the oracle -- tests/cpp/test_sharded_gpu.cpp.  Skipped on a one-GPU box."""
+    import subprocess
+
+    import hcoracle
+
+    exe, root = _build_cpp("test_sharded_gpu")
+    hcoracle.build(ref=False, port=True)
+    env = dict(os.environ)
+    if os.environ.get("HCM_TEST_SIM"):
+        env["CUSIM_DEVICES"] = "2"
+    r = subprocess.run([exe, os.path.join(root, "hypercraft_b200", "data", "registry.bin"), hcoracle.PORT_SO], capture_output=True, text=True, env=env)
+    last = (r.stdout.strip().splitlines() or [""])[-1]
+    if r.returncode == 0 and last.startswith("SKIP"):
+        pytest.skip(last)
+    assert r.returncode == 0 and last.startswith("PASS"), r.stdout + r.stderr
 
 
 def _terrain_world(radius):
@@ -460,4 +488,199 @@ def test_set_blocks_on_device_matches_host_chain(port):
     with pytest.raises(M.HcmError) as e:
         m.set_blocks([((2, 2, 2), 0, 1)])
     assert e.value.status == -4
+    m.close()
+
+
+def _device_buffer(nbytes):
+    """(raw device pointer, read-back function, keep-alive) of a caller-owned device buffer: torch on the GPU box, plain host memory
+    under the CPU emulation (where "device memory" is host memory)."""
+    if os.environ.get("HCM_TEST_SIM"):
+        a = np.full(nbytes, 0xEE, dtype=np.uint8)
+        return a.ctypes.data, (lambda: a.copy()), a
+    import torch
+
+    t = torch.full((nbytes,), 0xEE, dtype=torch.uint8, device="cuda:0")
+    torch.cuda.synchronize()
+    return t.data_ptr(), (lambda: t.cpu().numpy()), t
+
+
+def test_whole_load_sphere_is_byte_identical_to_the_cpu_mesher(port):
+    """EVERY chunk of a load sphere (r = 8: 2 109 tasks, 3 071 resident chunks of the reference's terrain where oracle/_ref is
+    present) against the CPU mesher -- the unmodified reference there, else the port -- through the per-chunk digest of the serialised
+    meshes that bench.py's parity gate uses (mesh count, flags, AABBs, vertex bytes, index bytes).  Plain path and pipelined path."""
+    import hcoracle
+    from hypercraft_b200 import mesher as M, worldgen
+
+    meshed, resident = worldgen.load_radius_positions(8)
+    if hcoracle.have_ref():
+        ref = hcoracle.RefWorld()
+        ref.generate(resident)
+        blocks, heights = ref.get_chunks(resident)
+        _, want = ref.mesh_batch(meshed, per_chunk=True)
+    else:
+        blocks = np.zeros((len(resident), 32768), dtype=np.uint16)
+        heights = np.zeros((len(resident), 1024), dtype=np.int8)
+        chunks = {}
+        for i, p in enumerate(resident):
+            blocks[i], heights[i] = worldgen.synth_terrain_chunk(12314524, p)
+            chunks[tuple(int(c) for c in p)] = (blocks[i], heights[i])
+        _, want, _ = port.mesh_batch(chunks, meshed, threads=os.cpu_count() or 1)
+    m = M.Mesher(origin=(-9, -9, -9), extent=(19, 19, 19), max_chunks=len(resident), max_tasks=len(meshed))
+    m.upload(resident, blocks, heights)
+    got = hcoracle.digest_batch(m.mesh(meshed))
+    bad = np.nonzero((got != want).any(axis=1))[0]
+    assert len(bad) == 0, f"{len(bad)} of {len(meshed)} chunks differ, first: task {meshed[bad[0]]} got {got[bad[0]]} want {want[bad[0]]}"
+    assert int(want[:, 1].sum()) > 100000  # a real world, not a sphere of air
+    res = m.upload_and_mesh(resident, blocks, heights, meshed)
+    got = hcoracle.digest_batch(res)
+    assert (got == want).all(), "pipelined path differs"
+    # hcm_mesh_desc::task is the caller's task index on the pipelined path as well
+    for t in range(0, len(meshed), 13):
+        first, n = int(res.tasks[t]["first_mesh"]), int(res.tasks[t]["n_meshes"])
+        assert (res.meshes["task"][first:first + n] == t).all()
+    m.close()
+
+
+def test_hinted_upload_and_scan_balance(port, monkeypatch):
+    """hcm_upload_chunks_hinted: chunks the caller declares uniform are derived from the hint without their 64 KB being read (the
+    arrays passed for them hold garbage here), HCM_HINT_NOT_UNIFORM chunks go up unscanned, HCM_HINT_UNKNOWN ones are scanned; and a
+    large unhinted upload gives the same meshes whether the scan threads or the copy engine take the work items (HCM_UPLOAD_ADAPTIVE)."""
+    from hypercraft_b200 import mesher as M
+
+    allpos, blocks, heights, chunks, tasks = _small_world()
+    uniform = (blocks == blocks[:, :1]).all(axis=1)
+    assert uniform.sum() > 20 and (~uniform).sum() > 20
+    hint = np.where(uniform, blocks[:, 0].astype(np.int32), M.HINT_NOT_UNIFORM).astype(np.int32)
+    hint[::3] = np.where(uniform[::3], hint[::3], M.HINT_UNKNOWN)
+    poisoned = blocks.copy()
+    poisoned[uniform] = 0xBEEF  # must never be looked at
+    m = M.Mesher(origin=(-2, -2, -2), extent=(5, 5, 5))
+    m.upload(allpos, poisoned, heights, uniform_hint=hint)
+    res = m.mesh(tasks)
+    for t, p in enumerate(tasks):
+        got, want = res.serialise(t), port.mesh(chunks, p)
+        assert got.size == want.size and (got == want).all(), f"hinted upload: task {p}\n" + describe_diff(got, want)
+    with pytest.raises(M.HcmError) as e:
+        m.upload(allpos[:1], blocks[:1], heights[:1], uniform_hint=np.array([70000], dtype=np.int32))
+    assert e.value.status == -1
+    m.close()
+    # >= 256 chunks: the threaded path.  Same bytes with the balance on and off; `upload_unscanned_chunks` says who took what.
+    meshed, resident, wb, wh = _terrain_world(5)
+    kw = dict(origin=(-6, -6, -6), extent=(13, 13, 13), max_chunks=len(resident), max_tasks=len(meshed))
+    out = {}
+    for adaptive in ("0", "1"):
+        monkeypatch.setenv("HCM_UPLOAD_ADAPTIVE", adaptive)
+        monkeypatch.setenv("HCM_UPLOAD_BLOCK", "128")
+        monkeypatch.setenv("HCM_UPLOAD_FIRST_BLOCK", "64")
+        m = M.Mesher(**kw)
+        res = m.upload_and_mesh(resident, wb, wh, meshed)
+        out[adaptive] = [res.serialise(t).tobytes() for t in range(len(meshed))]
+        unscanned = m.stats()["upload_unscanned_chunks"]
+        assert unscanned == 0 if adaptive == "0" else unscanned <= len(resident)
+        m.close()
+    assert out["0"] == out["1"]
+
+
+def test_device_sink_emit_into(port):
+    """SURVEY 8f row 2, the CUDA half: hcm_mesh_counts -> the host allocates a range per mesh the way MeshCluster::try_alloc does
+    (client/include/client/mesh/MeshCluster.hpp:38-67; here: shuffled order, odd alignment padding) -> hcm_mesh_emit_into writes the
+    vertices and indices into caller-owned DEVICE buffers.  The bytes at every mesh's offsets equal the fetched (host) output, which
+    equals the oracle; bytes between the ranges are untouched; the error paths leave the buffers alone."""
+    from hypercraft_b200 import mesher as M
+
+    allpos, blocks, heights, chunks, tasks = _small_world()
+    m = M.Mesher(origin=(-2, -2, -2), extent=(5, 5, 5))
+    m.upload(allpos, blocks, heights)
+    m.mesh_async(tasks)
+    cnt = m.counts()
+    assert len(cnt.vertices) == 0 and len(cnt.indices) == 0 and len(cnt.tasks) == len(tasks)
+    md = cnt.meshes
+    assert int(md["vertex_count"].sum()) == m.n_vertices and int(md["index_count"].sum()) == m.n_indices and len(md) > 20
+    # allocator: meshes placed in a shuffled order, each range preceded by a gap of 1..5 vertices / 1..7 indices
+    rng = np.random.default_rng(17)
+    order = rng.permutation(len(md))
+    pl = np.zeros(len(md), dtype=M.MESH_PLACEMENT_DTYPE)
+    vpos, ipos = 3, 1
+    for k, mi in enumerate(order):
+        vpos += int(rng.integers(1, 6))
+        ipos += int(rng.integers(1, 8))
+        pl[k] = (mi, 0, vpos, ipos)
+        vpos += int(md["vertex_count"][mi])
+        ipos += int(md["index_count"][mi])
+    vcap, icap = vpos + 9, ipos + 5
+    vptr, vread, _vkeep = _device_buffer(vcap * 8)
+    iptr, iread, _ikeep = _device_buffer(icap * 2)
+    m.emit_into(pl, vptr, vcap, iptr, icap)
+    assert m.stats()["sink_ms"] >= 0.0
+    vbuf, ibuf = vread().view(np.uint64), iread().view(np.uint16)
+    host = m.fetch()  # the same batch through the host path
+    assert (host.meshes == md).all()
+    vmask, imask = np.zeros(vcap, dtype=bool), np.zeros(icap, dtype=bool)
+    for k, mi in enumerate(order):
+        d = md[mi]
+        vo, io, nv, ni = int(pl[k]["vertex_offset"]), int(pl[k]["index_offset"]), int(d["vertex_count"]), int(d["index_count"])
+        assert (vbuf[vo:vo + nv] == host.vertices[int(d["vertex_offset"]):int(d["vertex_offset"]) + nv]).all(), f"mesh {mi}: vertices"
+        assert (ibuf[io:io + ni] == host.indices[int(d["index_offset"]):int(d["index_offset"]) + ni]).all(), f"mesh {mi}: indices"
+        vmask[vo:vo + nv] = True
+        imask[io:io + ni] = True
+    assert (vbuf[~vmask] == np.uint64(0xEEEEEEEEEEEEEEEE)).all() and (ibuf[~imask] == 0xEEEE).all()  # nothing outside the ranges
+    for t, p in enumerate(tasks):  # and the host path is the oracle's
+        got, want = host.serialise(t), port.mesh(chunks, p)
+        assert got.size == want.size and (got == want).all()
+    # errors: a range beyond the capacity, overlapping ranges, an unknown mesh, no descriptors yet
+    bad = pl.copy()
+    bad[0]["vertex_offset"] = vcap - 1
+    with pytest.raises(M.HcmError) as e:
+        m.emit_into(bad, vptr, vcap, iptr, icap)
+    assert e.value.status == -1
+    bad = pl.copy()
+    bad[1]["index_offset"] = bad[0]["index_offset"] + 2
+    with pytest.raises(M.HcmError) as e:
+        m.emit_into(bad, vptr, vcap, iptr, icap)
+    assert e.value.status == -1
+    bad = pl.copy()
+    bad[2]["mesh"] = len(md)
+    with pytest.raises(M.HcmError) as e:
+        m.emit_into(bad, vptr, vcap, iptr, icap)
+    assert e.value.status == -1
+    assert (vread().view(np.uint64) == vbuf).all() and (iread().view(np.uint16) == ibuf).all()  # failed calls wrote nothing
+    m.mesh_async(tasks[:3])
+    with pytest.raises(M.HcmError) as e:
+        m.emit_into(pl[:1], vptr, vcap, iptr, icap)
+    assert e.value.status == -7
+    # after hcm_upload_and_mesh the arenas hold the whole call's meshes: emit_into works on them as well
+    res = m.upload_and_mesh(allpos[:0], blocks[:0], heights[:0], tasks)
+    pl2 = np.zeros(len(res.meshes), dtype=M.MESH_PLACEMENT_DTYPE)
+    pl2["mesh"] = np.arange(len(res.meshes))
+    pl2["vertex_offset"] = np.concatenate([[0], np.cumsum(res.meshes["vertex_count"])[:-1]])
+    pl2["index_offset"] = np.concatenate([[0], np.cumsum(res.meshes["index_count"])[:-1]])
+    m.emit_into(pl2, vptr, vcap, iptr, icap)
+    vb2 = vread().view(np.uint64)
+    for k in range(0, len(pl2), 5):
+        d = res.meshes[k]
+        vo, nv = int(pl2[k]["vertex_offset"]), int(d["vertex_count"])
+        assert (vb2[vo:vo + nv] == res.vertices[int(d["vertex_offset"]):int(d["vertex_offset"]) + nv]).all()
+    m.close()
+
+
+def test_set_blocks_reports_who_pushes_each_remesh():
+    """hcm_edit_result::remesh_flags: the fan-out of a changed block is the reference's high-priority push
+    (ChunkSetBlockTask.cpp:119), positions only a changed sunlight height reaches are its low-priority push
+    (ChunkSetSunlightTask.cpp:84)."""
+    from hypercraft_b200 import mesher as M, worldgen
+
+    allpos = np.array([[x, y, z] for x in range(-2, 3) for y in range(-2, 3) for z in range(-2, 3)], dtype=np.int16)
+    b = np.zeros((len(allpos), 32768), dtype=np.uint16)
+    h = np.zeros((len(allpos), 1024), dtype=np.int8)  # an empty, fully sunlit world
+    m = M.Mesher(origin=(-2, -2, -2), extent=(5, 5, 5))
+    m.upload(allpos, b, h)
+    # stone in the middle of chunk (0,0,0): only that chunk is within reach of the block, but the height change pushes all 27
+    r = m.set_blocks([((0, 0, 0), 16 + (16 * 32 + 16) * 32, 1)])
+    flags = {tuple(int(v) for v in p): int(f) for p, f in zip(r["remesh"], r["remesh_flags"])}
+    assert r["n_changed_blocks"] == 1 and len(r["sunlight"]) >= 1 and len(flags) == 27
+    assert flags[(0, 0, 0)] == 3 and all(f == 2 for p, f in flags.items() if p != (0, 0, 0))
+    # air back in, next to the -x face: (0,0,0) and (-1,0,0) are pushed by the block edit
+    r = m.set_blocks([((0, 0, 0), 16 + (16 * 32 + 16) * 32, 0), ((0, 0, 0), 0 + (16 * 32 + 16) * 32, 9)])  # glass passes light: no height change
+    flags = {tuple(int(v) for v in p): int(f) for p, f in zip(r["remesh"], r["remesh_flags"])}
+    assert flags[(0, 0, 0)] & 1 and flags[(-1, 0, 0)] & 1
     m.close()
