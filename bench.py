@@ -58,6 +58,9 @@ def parse_args():
     ap.add_argument("--no-secondary", action="store_true", help="skip secondary_configs (configs 3 and 5) at N = 1")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU work per step of the --impl reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU leg (parity gate and cpu_baseline): profiling runs only")
+    ap.add_argument("--dry-run-emulated", action="store_true",
+                    help="DEVELOPER DRY RUN, never a measurement: run this script's own logic against tests/cusim (the CPU emulation build of the "
+                         "library, test infrastructure) on a machine without a GPU; the line says \"emulated\": true and its numbers mean nothing")
     return ap.parse_args()
 
 
@@ -301,36 +304,62 @@ def run_reference(args, rank, world):
 
 
 class Dist:
-    """torch.distributed plumbing of the bench: barrier and small reductions only -- nothing of the data path."""
+    """torch.distributed plumbing of the bench: barrier and small reductions only -- nothing of the data path.
+    `emulated` (--dry-run-emulated): gloo and CPU tensors, so that the N > 1 logic can be exercised without GPUs."""
 
-    def __init__(self, world: int, local: int):
+    def __init__(self, world: int, local: int, emulated: bool = False):
         import torch
 
-        self.torch, self.world = torch, world
+        self.torch, self.world, self.emulated = torch, world, emulated
+        self.device = "cpu" if emulated else "cuda"
         if world > 1:
             import torch.distributed as dist
 
             self.dist = dist
-            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            if emulated:
+                dist.init_process_group("gloo")
+            else:
+                dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def sync(self):
+        if not self.emulated:
+            self.torch.cuda.synchronize()
 
     def barrier(self):
-        self.torch.cuda.synchronize()
+        self.sync()
         if self.world > 1:
             self.dist.barrier()
-        self.torch.cuda.synchronize()
+        self.sync()
 
     def reduce(self, values, op: str = "sum") -> list:
-        t = self.torch.tensor([float(v) for v in values], dtype=self.torch.float64, device="cuda")
+        t = self.torch.tensor([float(v) for v in values], dtype=self.torch.float64, device=self.device)
         if self.world > 1:
             self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX if op == "max" else self.dist.ReduceOp.SUM)
         return [float(x) for x in t.tolist()]
 
     def gather(self, value: float) -> list:
-        t = self.torch.zeros(self.world, dtype=self.torch.float64, device="cuda")
+        t = self.torch.zeros(self.world, dtype=self.torch.float64, device=self.device)
         t[int(os.environ.get("RANK", "0"))] = float(value)
         if self.world > 1:
             self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
         return [float(x) for x in t.tolist()]
+
+    def stream_timer(self, stream_ptr: int, local: int):
+        """(start, stop -> ms): CUDA events recorded on the ctx's own stream (torch.cuda.Event only sees streams torch knows, so the
+        ctx stream is wrapped as an ExternalStream); host clock in the emulated dry run."""
+        if self.emulated:
+            box = {}
+            return (lambda: box.__setitem__("t", time.perf_counter())), (lambda: (time.perf_counter() - box["t"]) * 1e3)
+        torch = self.torch
+        stream = torch.cuda.ExternalStream(stream_ptr, device=torch.device("cuda", local))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+        def stop():
+            e1.record(stream)
+            self.sync()
+            return e0.elapsed_time(e1)
+
+        return (lambda: e0.record(stream)), stop
 
     def close(self):
         if self.world > 1:
@@ -341,14 +370,12 @@ def measure(D: Dist, local: int, meshed, resident, pb, ph, origin, extent, steps
     """One workload on this rank's GPU: `steps` device-timed steps with the inputs resident in HBM, `steps` end-to-end steps from
     pinned host buffers, then the parity gate over every chunk of the last end-to-end result.  Times are max over ranks, counts are
     sums over ranks."""
-    import torch
-
     from hypercraft_b200 import mesher as M
 
     m = M.Mesher(origin=origin, extent=extent, device=local, max_chunks=len(resident), max_tasks=len(meshed))
     m.upload(resident, pb.array, ph.array)
     m.sync()
-    stream = torch.cuda.ExternalStream(m.stream_ptr(), device=torch.device("cuda", local))
+    t_start, t_stop = D.stream_timer(m.stream_ptr(), local)
 
     def step_resident():
         m.rederive()
@@ -361,17 +388,16 @@ def measure(D: Dist, local: int, meshed, resident, pb, ph, origin, extent, steps
     # ---- timed: K steps, device timed on the ctx stream, max over ranks --------------------------------------------
     D.barrier()
     launches0 = m.stats()["kernel_launches"]
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     mesh_ms, derive_ms, classify_ms = [], [], []
-    e0.record(stream)
+    t_start()
     for _ in range(steps):
         step_resident()
         s = m.stats()
         mesh_ms.append(s["mesh_ms"]), derive_ms.append(s["derive_ms"]), classify_ms.append(s["classify_ms"])
-    e1.record(stream)
+    elapsed_ms = t_stop()
     D.barrier()
     launches = m.stats()["kernel_launches"] - launches0
-    ms_per_step = D.reduce([e0.elapsed_time(e1)], "max")[0] / steps
+    ms_per_step = D.reduce([elapsed_ms], "max")[0] / steps
     tot_chunks, tot_quads, tot_launches, tot_worked = D.reduce([len(meshed), counts["n_vertices"] // 4, launches, counts["n_worked"]])
 
     # ---- end to end: host buffers in, host meshes out, every step ---------------------------------------------------
@@ -388,7 +414,7 @@ def measure(D: Dist, local: int, meshed, resident, pb, ph, origin, extent, steps
     t0 = time.perf_counter()
     for _ in range(steps):
         res = m.upload_and_mesh(resident, pb.array, ph.array, meshed)  # same three stages, overlapped
-    torch.cuda.synchronize()
+    D.sync()
     e2e_local = (time.perf_counter() - t0) * 1e3 / steps
     e2e_ms_step = D.reduce([e2e_local], "max")[0]
     s = m.stats()
@@ -494,10 +520,19 @@ def main():
 
     import torch
 
-    if not torch.cuda.is_available():
+    emulated = args.dry_run_emulated
+    if emulated:  # developer dry run of this script's logic on the CPU emulation build (tests/cusim): never a measurement
+        from hypercraft_b200 import mesher as M
+
+        sim_dir = os.path.join(ROOT, "tests", "cusim")
+        subprocess.run(["make", "-C", sim_dir], check=True, stdout=subprocess.DEVNULL)
+        M.LIB_PATH, M._lib = os.path.join(sim_dir, "_build", "libhcm_sim.so"), None
+        local = 0
+    elif not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the mesher has no CPU path (use --impl reference for the CPU baseline)")
-    torch.cuda.set_device(local)
-    D = Dist(world, local)
+    else:
+        torch.cuda.set_device(local)
+    D = Dist(world, local, emulated)
 
     from hypercraft_b200 import shard as sh
     from hypercraft_b200 import worldgen
@@ -518,7 +553,7 @@ def main():
                               "warmup": max(args.warmup, 3), "ms_per_step": c4["ms_per_step"], "higher_is_better": True, "scaling": "strong",
                               "vs_baseline": None, "dtype": "u8/u16 integer", "data": f"synthetic: DefaultTerrain(seed {SEED}) or repo terrain, see config4",
                               "config": {"workload": c4["workload"], "radius": radius}, "quads_per_s": c4["quads_per_s"],
-                              "e2e": c4["e2e"], "config4": c4, "parity": c4["parity"], "clocks": clocks}))
+                              "e2e": c4["e2e"], "config4": c4, "parity": c4["parity"], "clocks": clocks, **({"emulated": True} if emulated else {})}))
         D.close()
         return
 
@@ -592,6 +627,8 @@ def main():
             out["config4"] = config4
         if secondary is not None:
             out["secondary_configs"] = secondary
+        if emulated:
+            out = {"emulated": True, "note": "DRY RUN on the CPU emulation build (tests/cusim): exercises bench.py's logic, measures nothing", **out}
         print(json.dumps(out))
     D.close()
 

@@ -37,3 +37,41 @@ def test_upload_paths_under_a_busy_copy_engine():
     """CUSIM_EVENT_BUSY makes cudaEventQuery answer 'not ready' a few times first, so the uploading thread of a threaded upload waits
     for the scan threads instead of taking every work item itself: mixed scanned / unscanned blocks."""
     _run({"CUSIM_EVENT_BUSY": "40"}, "-k", "pipelined_world_load or hinted_upload")
+
+
+def _bench_dry_run(n_ranks, *args):
+    import json
+
+    cmd = [sys.executable]
+    if n_ranks > 1:
+        cmd += ["-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n_ranks}", "--master-addr", "127.0.0.1", "--master-port", "29533"]
+    cmd += [os.path.join(ROOT, "bench.py"), "--gpus", str(n_ranks), "--dry-run-emulated", "--steps", "1", "--warmup", "1", *args]
+    r = subprocess.run(cmd, capture_output=True, text=True, cwd=ROOT, timeout=900)
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    assert r.returncode == 0 and len(lines) == 1, r.stdout[-2000:] + r.stderr[-3000:]
+    return json.loads(lines[0])
+
+
+def test_bench_logic_dry_run_on_the_emulation():
+    """bench.py's own Python -- workload set-up, the three timed regions, per-chunk parity digests, roofline and CPU-baseline blocks --
+    exercised end to end at a tiny radius on the emulation (`--dry-run-emulated`: the line is flagged and its numbers mean nothing)."""
+    d = _bench_dry_run(1, "--radius", "3", "--no-secondary")
+    assert d["emulated"] is True and d["n_gpus"] == 1 and d["gpu_launches"] == 3
+    p = d["parity"]
+    assert p["chunks_meshed"] == p["byte_compared_chunks"] == d["config"]["chunks_meshed_per_gpu"] and p["byte_mismatches"] == 0 and p["count_mismatches"] == 0
+    rf = d["roofline"]
+    assert rf["units_per_launch"] == d["config"]["tasks_through_full_kernel_per_gpu"] and rf["derive_kernel"]["units_per_launch"] == d["config"]["chunks_resident_per_gpu"]
+    assert abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-12 and rf["step_frac"] > 0
+    assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0 and d["cpu_baseline"]["cores"] >= 1
+
+
+def test_bench_two_ranks_dry_run_on_the_emulation():
+    """--gpus 2 under torchrun (gloo in the dry run): every rank's chunks go through the parity gate (counts summed over the ranks) and
+    the config-4 block cuts ONE sphere into two x-slabs whose union is the whole task list."""
+    d = _bench_dry_run(2, "--radius", "3", "--config4-radius", "4")
+    assert d["emulated"] is True and d["n_gpus"] == 2 and d["cpu_baseline"] is None
+    p = d["parity"]
+    assert p["ranks"] == 2 and p["byte_compared_chunks"] == p["chunks_meshed"] == 2 * d["config"]["chunks_meshed_per_gpu"] and p["byte_mismatches"] == 0
+    c4 = d["config4"]
+    assert c4["scaling"] == "strong" and sum(c4["tasks_per_rank"]) == c4["chunks_meshed"] == c4["parity"]["byte_compared_chunks"]
+    assert c4["parity"]["byte_mismatches"] == 0 and len(c4["slab_x_bounds"]) == 2 and c4["slab_x_bounds"][0][1] == c4["slab_x_bounds"][1][0]
