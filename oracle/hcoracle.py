@@ -161,6 +161,67 @@ class RefWorld:
         return n, faces[:max(n, 0) * 24].copy(), tex, dyn.value
 
 
+class RefEditWorld:
+    """The reference's own block-edit chain: a reference World holding the caller's chunks, edits pushed as World::SetBlockBulk does,
+    the reference's ChunkTaskPool::Run run to quiescence on one thread (oracle/ref_shim.cpp: hcref_edit_*).  Pins hcm_set_blocks and
+    oracle/edit_oracle.py to compiled reference code (kSetBlock, kFloodSunlight, kSetSunlight and the kMesh tasks they push)."""
+
+    EDIT_DTYPE = np.dtype([("chunk", np.int16, 3), ("index", np.uint16), ("block", np.uint16), ("_pad", np.uint16)])
+
+    def __init__(self, load_radius: int = 4):
+        if not have_ref():
+            raise RuntimeError("oracle/_ref/libhcref.so missing: run `make -C oracle ref` where /root/reference exists")
+        L = ctypes.CDLL(REF_SO)
+        L.hcref_edit_create.restype = _vp
+        L.hcref_edit_apply.restype = ctypes.c_int64
+        L.hcref_edit_pushed_mesh.restype = ctypes.c_int64
+        self.L = L
+        self.w = _vp(L.hcref_edit_create(ctypes.c_int(load_radius)))
+
+    def __del__(self):
+        try:
+            self.L.hcref_edit_destroy(self.w)
+        except Exception:
+            pass
+
+    def set_chunk(self, pos, blocks, heights) -> None:
+        p = np.asarray(pos, dtype=np.int16)
+        b = np.ascontiguousarray(blocks, dtype=np.uint16).reshape(-1)
+        h = np.ascontiguousarray(heights, dtype=np.int8).reshape(-1)
+        if self.L.hcref_edit_set_chunk(self.w, _ptr(p), _ptr(b), _ptr(h)) != 0:
+            raise KeyError(f"{tuple(int(v) for v in p)} is outside the reference world's load sphere")
+
+    def get_chunk(self, pos):
+        p = np.asarray(pos, dtype=np.int16)
+        b = np.empty(32768, dtype=np.uint16)
+        h = np.empty(1024, dtype=np.int8)
+        if self.L.hcref_edit_get_chunk(self.w, _ptr(p), _ptr(b), _ptr(h)) != 0:
+            raise KeyError(tuple(int(x) for x in p))
+        return b, h
+
+    def apply(self, edit_list, with_meshes: bool = False):
+        """edit_list = [((cx,cy,cz), index, block), ...].  -> (pushed int16[n,3] in the order the mesh tasks ran, high u8[n],
+        n_still_queued, [serialised meshes per pushed task] or None)."""
+        e = np.zeros(len(edit_list), dtype=self.EDIT_DTYPE)
+        for i, (cpos, index, block) in enumerate(edit_list):
+            e[i]["chunk"], e[i]["index"], e[i]["block"] = cpos, index, block
+        cap = 4096
+        pos = np.zeros((cap, 3), dtype=np.int16)
+        high = np.zeros(cap, dtype=np.uint8)
+        still = ctypes.c_uint64(0)
+        n = self.L.hcref_edit_apply(self.w, _ptr(e), ctypes.c_uint64(len(e)), _ptr(pos), _ptr(high), ctypes.c_uint64(cap), ctypes.byref(still))
+        assert 0 <= n <= cap
+        meshes = None
+        if with_meshes:
+            meshes = []
+            for i in range(n):
+                size = self.L.hcref_edit_pushed_mesh(self.w, ctypes.c_uint64(i), None)
+                buf = np.zeros(size, dtype=np.uint8)
+                self.L.hcref_edit_pushed_mesh(self.w, ctypes.c_uint64(i), _ptr(buf))
+                meshes.append(buf)
+        return pos[:n].copy(), high[:n].copy(), int(still.value), meshes
+
+
 _port_lib = None
 
 

@@ -8,6 +8,10 @@
 //     header oracle/shadow/client/WorldRenderer.hpp,
 //   * calls the reference's own `DefaultTerrain::Generate` (client/src/DefaultTerrain.cpp:10-164)
 //     to produce benchmark inputs,
+//   * drives the reference's own block-edit chain -- ChunkTaskRunner<kSetBlock / kFloodSunlight / kSetSunlight / kMesh>::Run, popped
+//     and run by the reference's own ChunkTaskPool::Run on one thread (client/src/ChunkSetBlockTask.cpp,
+//     ChunkFloodSunlightTask.cpp, ChunkSetSunlightTask.cpp, ChunkTaskPool.cpp, ChunkPool.cpp, World.cpp, all unmodified) -- behind a
+//     ClientBase that does nothing (client/include/client/ClientBase.hpp:15-28: four pure virtuals), to pin hcm_set_blocks,
 //   * flattens the reference's block/texture registry (block/include/block/Block.hpp:41,
 //     texture/include/texture/BlockTexture.hpp) into the `hcm_registry` blob of include/hcm.h.
 //
@@ -17,6 +21,7 @@
 
 #include <client/BlockLightAlgo.hpp>
 #include <client/BlockMeshAlgo.hpp>
+#include <client/ClientBase.hpp>
 #include <client/DefaultTerrain.hpp>
 #include <client/World.hpp>
 #include <client/WorldRenderer.hpp>
@@ -534,5 +539,136 @@ int hcref_dynamic_mesh_eval(uint16_t block, const uint16_t *neighbours, hcm_mesh
 }
 
 int hcref_hardware_threads() { return (int)std::thread::hardware_concurrency(); }
+
+
+// ---------------------------------------------------------------- edit chain ---------------------------------------
+// A reference World whose chunk pool holds the caller's chunks, a ClientBase that does nothing, and the reference's own task pool
+// run to quiescence on the calling thread.  World declares `friend class LocalClient` (World.hpp:39): a class of that name --
+// the real one is not part of this build -- may attach itself as the world's client exactly like LocalClient::Create does.
+} // extern "C"
+namespace hc::client {
+class LocalClient final : public ClientBase {
+public:
+	static std::shared_ptr<LocalClient> Attach(const std::shared_ptr<World> &world) {
+		auto c = std::make_shared<LocalClient>();
+		c->m_world_ptr = world;
+		world->m_client_weak_ptr = c;
+		return c;
+	}
+	bool IsConnected() override { return true; }
+	void LoadChunks(std::span<const ChunkPos3>) override {}                                  // the harness fills the chunks itself
+	void SetChunkBlocks(ChunkPos3, std::span<const ChunkSetBlockEntry>) override {}        // server notification: nobody to tell
+	void SetChunkSunlights(ChunkPos3, std::span<const ChunkSetSunlightEntry>) override {}
+};
+} // namespace hc::client
+namespace {
+struct EditWorld {
+	std::shared_ptr<World> world;
+	std::shared_ptr<LocalClient> client;
+	std::shared_ptr<WorldRenderer> renderer;
+	std::vector<ChunkPos3> pushed;
+	std::vector<std::vector<hc::client::BlockMesh>> pushed_meshes;
+	std::unordered_map<PosKey, uint8_t, PosHash> high; // kMesh requests seen queued with high priority
+};
+} // namespace
+extern "C" {
+
+// load_radius: ChunkPool::Update creates (empty, not yet generated) Chunk objects for the reference's load sphere around the
+// origin (client/src/ChunkPool.cpp:9-33); hcref_edit_set_chunk fills the ones the caller wants to exist and marks them generated.
+void *hcref_edit_create(int load_radius) {
+	auto *w = new EditWorld{};
+	w->world = World::Create((ChunkPos1)load_radius, (ChunkPos1)(load_radius + 2));
+	w->renderer = WorldRenderer::Create(w->world);
+	w->renderer->push_log = &w->pushed, w->renderer->mesh_log = &w->pushed_meshes;
+	w->client = LocalClient::Attach(w->world);
+	w->world->Start();
+	return w;
+}
+void hcref_edit_destroy(void *wp) { delete (EditWorld *)wp; }
+int hcref_edit_set_chunk(void *wp, const int16_t pos[3], const uint16_t *blocks, const int8_t *heights) {
+	auto *w = (EditWorld *)wp;
+	auto chunk = w->world->GetChunkPool().FindRawChunk(ChunkPos3{pos[0], pos[1], pos[2]});
+	if (!chunk)
+		return -1; // outside the load sphere
+	memcpy((void *)&chunk->GetBlockRef(0u), blocks, 32768 * 2);
+	for (uint32_t i = 0; i < 1024; ++i)
+		chunk->SetSunlightHeight(i, heights[i]);
+	chunk->SetGeneratedFlag();
+	return 0;
+}
+int hcref_edit_get_chunk(void *wp, const int16_t pos[3], uint16_t *blocks, int8_t *heights) {
+	auto *w = (EditWorld *)wp;
+	auto chunk = w->world->GetChunkPool().FindChunk(ChunkPos3{pos[0], pos[1], pos[2]});
+	if (!chunk)
+		return -1;
+	memcpy(blocks, chunk->GetBlockData(), 32768 * 2);
+	for (uint32_t i = 0; i < 1024; ++i)
+		heights[i] = chunk->GetSunlightHeight(i);
+	return 0;
+}
+
+// World::SetBlockBulk's push (World.hpp:124-135: one Push<kSetBlock>(chunk, entries, kLocal) per chunk, in the caller's order) and
+// then ChunkTaskPool::Run (ChunkTaskPool.cpp:89-133) on this thread with the worker's producer limits (WorldWorker.cpp:19-22)
+// until nothing runs any more.  Tick tasks (kUpdateBlock: water spreading etc.) are never produced: no tick passes.
+// Returns the number of mesh tasks that ran (PushChunkMesh calls, in order); out_pos / out_high receive up to `cap` of them
+// (high = the request was seen queued with ChunkTaskPriority::kHigh), *n_still_queued the mesh requests that can never run
+// because one of their 27 chunks does not exist.
+int64_t hcref_edit_apply(void *wp, const hcm_block_edit *edits, uint64_t n, int16_t *out_pos, uint8_t *out_high, uint64_t cap, uint64_t *n_still_queued) {
+	auto *w = (EditWorld *)wp;
+	auto *pool = const_cast<ChunkTaskPool *>(&w->world->GetChunkTaskPool());
+	w->pushed.clear(), w->pushed_meshes.clear(), w->high.clear();
+	std::vector<ChunkPos3> order;
+	std::unordered_map<PosKey, std::vector<ChunkBlockEntry>, PosHash> by_chunk;
+	for (uint64_t i = 0; i < n; ++i) {
+		const PosKey k{edits[i].chunk[0], edits[i].chunk[1], edits[i].chunk[2]};
+		if (!by_chunk.count(k))
+			order.push_back(ChunkPos3{k.x, k.y, k.z});
+		block::Block b;
+		static_assert(sizeof(block::Block) == 2);
+		memcpy(&b, &edits[i].block, 2);
+		by_chunk[k].push_back(ChunkBlockEntry{.index = (InnerIndex3)edits[i].index, .block = b});
+	}
+	for (const ChunkPos3 &c : order)
+		pool->Push<ChunkTaskType::kSetBlock>(c, std::span<const ChunkBlockEntry>{by_chunk[PosKey{c.x, c.y, c.z}]}, ChunkUpdateType::kLocal);
+	ChunkTaskPoolProducerConfig cfg{};
+	cfg.max_high_priority_tasks = 64, cfg.max_tick_tasks = 0, cfg.max_tasks = 256;
+	ChunkTaskPoolToken token{pool, cfg};
+	auto note_priorities = [&]() {
+		ChunkTaskPoolLocked locked{pool};
+		for (auto it = locked.GetDataMap().begin(); it != locked.GetDataMap().end(); ++it) {
+			const auto &mesh = std::get<static_cast<std::size_t>(ChunkTaskType::kMesh)>(it->second);
+			if (mesh.IsQueued() && mesh.GetPriority() == ChunkTaskPriority::kHigh)
+				w->high[PosKey{it->first.x, it->first.y, it->first.z}] = 1;
+		}
+	};
+	int idle = 0;
+	for (int guard = 0; guard < 1000000 && idle < 6; ++guard) {
+		note_priorities();
+		const size_t pushes = w->pushed.size();
+		pool->Run(&token);
+		idle = (pool->GetRunningTaskCountApprox() == 0 && w->pushed.size() == pushes) ? idle + 1 : 0;
+	}
+	uint64_t still = 0;
+	{
+		ChunkTaskPoolLocked locked{pool};
+		for (auto it = locked.GetDataMap().begin(); it != locked.GetDataMap().end(); ++it)
+			still += std::get<static_cast<std::size_t>(ChunkTaskType::kMesh)>(it->second).IsQueued();
+	}
+	if (n_still_queued)
+		*n_still_queued = still;
+	for (uint64_t i = 0; i < w->pushed.size() && i < cap; ++i) {
+		const ChunkPos3 &p = w->pushed[i];
+		out_pos[3 * i] = p.x, out_pos[3 * i + 1] = p.y, out_pos[3 * i + 2] = p.z;
+		out_high[i] = w->high.count(PosKey{p.x, p.y, p.z}) ? 1 : 0;
+	}
+	return (int64_t)w->pushed.size();
+}
+// serialised meshes of the i-th mesh task hcref_edit_apply ran (size query with out == NULL)
+int64_t hcref_edit_pushed_mesh(void *wp, uint64_t i, uint8_t *out) {
+	auto *w = (EditWorld *)wp;
+	if (i >= w->pushed_meshes.size())
+		return -1;
+	return out ? (int64_t)serialise(w->pushed_meshes[i], out) : (int64_t)serialised_size(w->pushed_meshes[i]);
+}
 
 } // extern "C"

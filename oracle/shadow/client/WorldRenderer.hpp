@@ -30,11 +30,20 @@ public:
 		world_ptr->m_world_renderer_weak_ptr = ret;
 		return ret;
 	}
+	std::vector<ChunkPos3> *push_log{nullptr}; // when set: every pushed position, in order (the edit-chain harness of ref_shim.cpp)
+	std::vector<std::vector<BlockMesh>> *mesh_log{nullptr};
+
 	inline void PushChunkMesh(const ChunkPos3 &chunk_pos, std::vector<BlockMesh> &&meshes) {
 		captured_pos = chunk_pos;
+		if (push_log)
+			push_log->push_back(chunk_pos);
+		if (mesh_log)
+			mesh_log->push_back(meshes);
 		captured = std::move(meshes);
 		++push_count;
 	}
+	// World::update() (client/src/World.cpp:7-12) tells the renderer to drop the meshes of unloaded chunks: nothing to drop here
+	inline void EraseUnloadedMeshes() {}
 };
 
 } // namespace hc::client

@@ -312,7 +312,8 @@ def test_output_arena_grows_instead_of_truncating(port):
 def test_edit_driven_incremental_remesh(port):
     """Config 5: seeded single-block edits; after each, re-upload the edited chunk (blocks + recomputed sunlight column),
     remesh exactly the reference's fan-out set and compare every remeshed chunk with the oracle on the updated world."""
-    from hypercraft_b200 import edits, mesher as M, registry, worldgen
+    import edit_oracle as edits
+    from hypercraft_b200 import mesher as M, registry, worldgen
 
     reg = registry.load()
     vpass = reg.props["transparency"][reg.prop_index] == 2
@@ -433,7 +434,8 @@ def test_set_blocks_on_device_matches_host_chain(port):
     reference's kSetBlock / kFloodSunlight / kSetSunlight chain: changed-block count, every sunlight change, the mesh tasks
     pushed, and -- the state that matters -- the meshes of ALL interior chunks afterwards against the oracle on the
     host-edited world."""
-    from hypercraft_b200 import edits, mesher as M, registry, worldgen
+    import edit_oracle as edits
+    from hypercraft_b200 import mesher as M, registry, worldgen
 
     reg = registry.load()
     vpass = reg.props["transparency"][reg.prop_index] == 2
@@ -683,4 +685,31 @@ def test_set_blocks_reports_who_pushes_each_remesh():
     r = m.set_blocks([((0, 0, 0), 16 + (16 * 32 + 16) * 32, 0), ((0, 0, 0), 0 + (16 * 32 + 16) * 32, 9)])  # glass passes light: no height change
     flags = {tuple(int(v) for v in p): int(f) for p, f in zip(r["remesh"], r["remesh_flags"])}
     assert flags[(0, 0, 0)] & 1 and flags[(-1, 0, 0)] & 1
+    m.close()
+
+
+def test_set_blocks_matches_the_reference_edit_chain_golden():
+    """hcm_set_blocks + the mesh kernel against the UNMODIFIED reference's kSetBlock / kFloodSunlight / kSetSunlight / kMesh tasks
+    (tests/golden/edit_chain_golden.json, recorded from oracle/_ref by tests/golden/make_edit_golden.py): per batch the number of
+    changed blocks, every sunlight height change, the mesh tasks pushed and who pushed them (priority), and the SHA-256 of every
+    remeshed chunk's meshes against the digest of the reference's own mesher run after the reference's own edit."""
+    import edit_oracle
+    from hypercraft_b200 import mesher as M
+
+    golden = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "edit_chain_golden.json")))
+    allpos, chunks = edit_oracle.edit_test_world()
+    m = M.Mesher(origin=(-2, -2, -2), extent=(5, 5, 5))
+    m.upload(allpos, np.stack([chunks[tuple(int(c) for c in p)][0] for p in allpos]), np.stack([chunks[tuple(int(c) for c in p)][1] for p in allpos]))
+    for rec in golden["batches"]:
+        r = m.set_blocks([(tuple(c), i, b) for c, i, b in rec["edits"]])
+        assert r["n_changed_blocks"] == rec["n_changed_blocks"], rec["name"]
+        got_sun = sorted([[int(v) for v in s["chunk"]], int(s["index"]), int(s["old_height"]), int(s["new_height"])] for s in r["sunlight"])
+        assert got_sun == rec["sunlight"], rec["name"]
+        want = {tuple(int(v) for v in k.split(",")): e for k, e in rec["remesh"].items()}
+        got = {tuple(int(v) for v in p): int(f) for p, f in zip(r["remesh"], r["remesh_flags"])}
+        assert set(got) == set(want), rec["name"]
+        assert all(bool(got[p] & 1) == bool(want[p]["high"]) for p in want), rec["name"]
+        res = m.mesh(r["remesh"])
+        for t, p in enumerate(r["remesh"]):
+            assert hashlib.sha256(res.serialise(t).tobytes()).hexdigest() == want[tuple(int(v) for v in p)]["mesh_sha256"], (rec["name"], p)
     m.close()

