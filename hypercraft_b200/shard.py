@@ -116,18 +116,32 @@ def mirror_plan(touched_chunks, bounds) -> list[list[tuple[int, int, int]]]:
     return out
 
 
+def chunk_should_remesh(rel) -> bool:
+    """ChunkShouldRemesh (client/include/client/ChunkMeshTask.inl:9-15): a block at `rel` (relative to a chunk's origin) can change that
+    chunk's mesh iff its L1 distance to the box [-1,33]^3 is below 15 -- hcm_host::ShardedMeshDispatcher::ShouldRemesh in Python."""
+    dist = 0
+    for c in rel:
+        c = int(c)
+        dist += -1 - c if c < -1 else (c - 33 if c >= 33 else 0)
+    return dist < 15
+
+
+def remesh_offsets(block_pos) -> list[tuple[int, int, int]]:
+    """Chunk offsets whose mesh task the reference pushes after an edit at chunk-local `block_pos` (ChunkSetBlockTask.cpp:100-107)."""
+    return [(0, 0, 0)] + [(dx, dy, dz) for dx in (-1, 0, 1) for dy in (-1, 0, 1) for dz in (-1, 0, 1) if (dx, dy, dz) != (0, 0, 0)
+                          and chunk_should_remesh((block_pos[0] - 32 * dx, block_pos[1] - 32 * dy, block_pos[2] - 32 * dz))]
+
+
 def foreign_fanout(edit_list, sunlight_chunks, bounds, rank: int) -> set:
     """Remesh positions in OTHER ranks' slabs caused by `rank`'s edits.  Its hcm_set_blocks cannot report them -- one of their
     27 chunks lies outside its window, so the device counts them as pending -- hence they follow from the reference's rules on
     the host: per edit the neighbours passing ChunkShouldRemesh (ChunkSetBlockTask.cpp:100-107; every edit counts as a change,
     a superset by the no-op edits), per chunk with a changed sunlight height all 26 neighbours (ChunkSetSunlightTask.cpp:66-78).
     Same rule as hcm_host::ShardedMeshDispatcher::SetBlocks."""
-    from . import edits as _edits
-
     out = set()
     for cpos, index, _ in edit_list:
         bp = (int(index) & 31, int(index) >> 10, (int(index) >> 5) & 31)
-        for d in _edits.remesh_offsets(bp):
+        for d in remesh_offsets(bp):
             q = (int(cpos[0]) + d[0], int(cpos[1]) + d[1], int(cpos[2]) + d[2])
             if owner_rank(q, bounds) != rank:
                 out.add(q)
