@@ -95,14 +95,14 @@ class RefWorld:
                                     ctypes.c_int(threads or self.hardware_threads()))
 
     def set_chunk(self, pos, blocks: np.ndarray, heights: np.ndarray) -> None:
-        p = np.asarray(pos, dtype=np.int16)
+        p = np.ascontiguousarray(pos, dtype=np.int16)
         b = np.ascontiguousarray(blocks, dtype=np.uint16).reshape(-1)
         h = np.ascontiguousarray(heights, dtype=np.int8).reshape(-1)
         assert b.size == 32768 and h.size == 1024
         self.L.hcref_world_set_chunk(self.w, _ptr(p), _ptr(b), _ptr(h))
 
     def get_chunk(self, pos):
-        p = np.asarray(pos, dtype=np.int16)
+        p = np.ascontiguousarray(pos, dtype=np.int16)
         b = np.empty(32768, dtype=np.uint16)
         h = np.empty(1024, dtype=np.int8)
         if self.L.hcref_world_get_chunk(self.w, _ptr(p), _ptr(b), _ptr(h)) != 0:
@@ -122,7 +122,7 @@ class RefWorld:
 
     def mesh(self, pos) -> np.ndarray:
         """Unmodified ``ChunkTaskRunner<kMesh>::Run`` on one chunk; returns the serialised meshes."""
-        p = np.asarray(pos, dtype=np.int16)
+        p = np.ascontiguousarray(pos, dtype=np.int16)
         n = self.L.hcref_mesh(self.w, _ptr(p))
         if n < 0:
             raise KeyError("a neighbour chunk is missing")
@@ -146,7 +146,7 @@ class RefWorld:
         return {f[0]: getattr(st, f[0]) for f in Stats._fields_}, pc
 
     def light34(self, pos) -> np.ndarray:
-        p = np.asarray(pos, dtype=np.int16)
+        p = np.ascontiguousarray(pos, dtype=np.int16)
         out = np.zeros(34 * 34 * 34, dtype=np.uint8)
         if self.L.hcref_light34(self.w, _ptr(p), _ptr(out)) != 0:
             raise KeyError("a neighbour chunk is missing")
@@ -185,14 +185,14 @@ class RefEditWorld:
             pass
 
     def set_chunk(self, pos, blocks, heights) -> None:
-        p = np.asarray(pos, dtype=np.int16)
+        p = np.ascontiguousarray(pos, dtype=np.int16)
         b = np.ascontiguousarray(blocks, dtype=np.uint16).reshape(-1)
         h = np.ascontiguousarray(heights, dtype=np.int8).reshape(-1)
         if self.L.hcref_edit_set_chunk(self.w, _ptr(p), _ptr(b), _ptr(h)) != 0:
             raise KeyError(f"{tuple(int(v) for v in p)} is outside the reference world's load sphere")
 
     def get_chunk(self, pos):
-        p = np.asarray(pos, dtype=np.int16)
+        p = np.ascontiguousarray(pos, dtype=np.int16)
         b = np.empty(32768, dtype=np.uint16)
         h = np.empty(1024, dtype=np.int8)
         if self.L.hcref_edit_get_chunk(self.w, _ptr(p), _ptr(b), _ptr(h)) != 0:
@@ -220,6 +220,72 @@ class RefEditWorld:
                 self.L.hcref_edit_pushed_mesh(self.w, ctypes.c_uint64(i), _ptr(buf))
                 meshes.append(buf)
         return pos[:n].copy(), high[:n].copy(), int(still.value), meshes
+
+
+BIND_SO = os.path.join(HERE, "_ref", "libhcbind.so")
+
+
+def have_binding() -> bool:
+    return os.path.exists(BIND_SO)
+
+
+class BindingWorld:
+    """oracle/_ref/libhcbind.so: the UNMODIFIED reference client (task pool, chunk pool, world, edit tasks) with client/src/ChunkMeshTask.cpp
+    replaced by hypercraft_b200/host/reference_binding/ChunkMeshTask.cpp -- the drop-in mesh lane on top of the C ABI -- compiled
+    against the reference's own Chunk / ChunkTaskPool / WorldRenderer types (make -C oracle binding).  `hcm_library` is the build of
+    the C ABI the binding's hcm_* calls resolve to (libhcm.so on a GPU box; the CPU emulation build in the CPU test tier)."""
+
+    def __init__(self, hcm_library: str, origin, extent, load_radius: int, device: int = 0):
+        if not have_binding():
+            raise RuntimeError("oracle/_ref/libhcbind.so missing: run `make -C oracle binding` where /root/reference exists")
+        self._hcm = ctypes.CDLL(hcm_library, mode=ctypes.RTLD_GLOBAL)
+        L = ctypes.CDLL(BIND_SO)
+        L.hcref_edit_create.restype = _vp
+        L.hcref_edit_mesh.restype = ctypes.c_int64
+        L.hcref_edit_pushed_mesh.restype = ctypes.c_int64
+        self.L = L
+        o = np.ascontiguousarray(origin, dtype=np.int16)
+        e = np.ascontiguousarray(extent, dtype=np.uint16)
+        err = ctypes.create_string_buffer(512)
+        rc = L.hcref_binding_configure(ctypes.c_int(device), _ptr(o), _ptr(e), err, ctypes.c_uint64(512))
+        if rc:
+            raise RuntimeError(f"hcm_binding::Configure failed with status {rc}: {err.value.decode()}")
+        self.w = _vp(L.hcref_edit_create(ctypes.c_int(load_radius)))
+
+    def close(self):
+        if getattr(self, "w", None):
+            self.L.hcref_edit_destroy(self.w)
+            self.L.hcref_binding_shutdown()
+            self.w = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_chunk(self, pos, blocks, heights) -> None:
+        p = np.ascontiguousarray(pos, dtype=np.int16)
+        b = np.ascontiguousarray(blocks, dtype=np.uint16).reshape(-1)
+        h = np.ascontiguousarray(heights, dtype=np.int8).reshape(-1)
+        if self.L.hcref_edit_set_chunk(self.w, _ptr(p), _ptr(b), _ptr(h)) != 0:
+            raise KeyError(f"{tuple(int(v) for v in p)} is outside the reference world's load sphere")
+
+    def mesh(self, positions, high: bool = False):
+        """Push<kMesh> for every position, the reference's ChunkTaskPool::Run to quiescence.  -> {position: serialised meshes} of the
+        PushChunkMesh calls the (shadow) WorldRenderer received, and the number of calls."""
+        pos = np.ascontiguousarray(positions, dtype=np.int16).reshape(-1, 3)
+        cap = 4 * len(pos) + 64
+        out = np.zeros((cap, 3), dtype=np.int16)
+        n = self.L.hcref_edit_mesh(self.w, _ptr(pos), ctypes.c_uint64(len(pos)), ctypes.c_int(1 if high else 0), _ptr(out), ctypes.c_uint64(cap))
+        assert 0 <= n <= cap
+        got = {}
+        for i in range(n):
+            size = self.L.hcref_edit_pushed_mesh(self.w, ctypes.c_uint64(i), None)
+            buf = np.zeros(size, dtype=np.uint8)
+            self.L.hcref_edit_pushed_mesh(self.w, ctypes.c_uint64(i), _ptr(buf))
+            got[tuple(int(v) for v in out[i])] = buf
+        return got, int(n)
 
 
 _port_lib = None

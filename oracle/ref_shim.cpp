@@ -671,4 +671,50 @@ int64_t hcref_edit_pushed_mesh(void *wp, uint64_t i, uint8_t *out) {
 	return out ? (int64_t)serialise(w->pushed_meshes[i], out) : (int64_t)serialised_size(w->pushed_meshes[i]);
 }
 
+
+// Mesh tasks through the task pool: Push<kMesh>(pos, high) for every listed position (what ChunkGenerateTask.cpp:38 does after a
+// chunk is generated) and ChunkTaskPool::Run to quiescence.  In oracle/_ref/libhcref.so the tasks are run by the reference's own
+// ChunkTaskRunner<kMesh>::Run; in oracle/_ref/libhcbind.so (make binding) by hypercraft_b200/host/reference_binding/ChunkMeshTask.cpp,
+// the drop-in replacement of that translation unit -- same harness, same sink.  Results: hcref_edit_pushed_mesh.
+int64_t hcref_edit_mesh(void *wp, const int16_t *pos, uint64_t n, int high, int16_t *out_pos, uint64_t cap) {
+	auto *w = (EditWorld *)wp;
+	auto *pool = const_cast<ChunkTaskPool *>(&w->world->GetChunkTaskPool());
+	w->pushed.clear(), w->pushed_meshes.clear(), w->high.clear();
+	for (uint64_t i = 0; i < n; ++i)
+		pool->Push<ChunkTaskType::kMesh>(ChunkPos3{pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]}, high != 0);
+	ChunkTaskPoolProducerConfig cfg{};
+	cfg.max_high_priority_tasks = 64, cfg.max_tick_tasks = 0, cfg.max_tasks = 256;
+	ChunkTaskPoolToken token{pool, cfg};
+	int idle = 0;
+	for (int guard = 0; guard < 10000000 && idle < 6; ++guard) {
+		const size_t pushes = w->pushed.size();
+		pool->Run(&token);
+		idle = (pool->GetRunningTaskCountApprox() == 0 && w->pushed.size() == pushes) ? idle + 1 : 0;
+	}
+	for (uint64_t i = 0; i < w->pushed.size() && i < cap; ++i)
+		out_pos[3 * i] = w->pushed[i].x, out_pos[3 * i + 1] = w->pushed[i].y, out_pos[3 * i + 2] = w->pushed[i].z;
+	return (int64_t)w->pushed.size();
+}
+
+#ifdef HCREF_WITH_BINDING
+} // extern "C"
+#include "../hypercraft_b200/host/reference_binding/hcm_binding.hpp"
+extern "C" {
+// libhcbind.so only: create the process-wide dispatcher of the replacement mesh lane (hcm_binding::Configure) over the given chunk
+// window, with the registry exported from the reference tables above.  Returns 0, or the hcm_status of the failure.
+int hcref_binding_configure(int device, const int16_t origin[3], const uint16_t extent[3], char *err, uint64_t err_cap) {
+	std::vector<uint8_t> blob((size_t)hcref_registry_blob(nullptr, 0));
+	hcref_registry_blob(blob.data(), blob.size());
+	try {
+		hcm_binding::Configure(blob.data(), blob.size(), device, hcm_host::ChunkPos3{origin[0], origin[1], origin[2]}, {extent[0], extent[1], extent[2]});
+	} catch (const hcm_host::Error &e) {
+		if (err && err_cap)
+			snprintf(err, err_cap, "%s", e.what());
+		return e.status;
+	}
+	return 0;
+}
+void hcref_binding_shutdown() { hcm_binding::Shutdown(); }
+#endif
+
 } // extern "C"
