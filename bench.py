@@ -418,21 +418,113 @@ def measure(D: Dist, local: int, meshed, resident, pb, ph, origin, extent, steps
     e2e_local = (time.perf_counter() - t0) * 1e3 / steps
     e2e_ms_step = D.reduce([e2e_local], "max")[0]
     s = m.stats()
+    unscanned = int(s["upload_unscanned_chunks"])
     out = {"ms_per_step": ms_per_step, "value": tot_chunks / (ms_per_step / 1e3), "quads_per_s": tot_quads / (ms_per_step / 1e3),
            "total_chunks": tot_chunks, "total_quads": tot_quads, "total_launches": tot_launches, "total_worked": tot_worked,
            "counts": counts, "kernel_ms": {"derive": float(np.mean(derive_ms)), "classify": float(np.mean(classify_ms)), "mesh": float(np.mean(mesh_ms))},
            "e2e_ms_per_step": e2e_ms_step, "e2e_value": tot_chunks / (e2e_ms_step / 1e3), "e2e_serial_ms": e2e_serial_ms,
            "e2e_ms_per_rank": D.gather(e2e_local), "worked_per_rank": D.gather(counts["n_worked"]), "tasks_per_rank": D.gather(len(meshed)),
            "h2d_step": (s["h2d_bytes"] - h2d0) // steps, "d2h_step": (s["d2h_bytes"] - d2h0) // steps, "device_bytes": s["device_bytes"],
-           "parity": None, "cpu_stats": None}
+           "unscanned_last_upload": unscanned, "device_sink": None, "hinted": None, "parity": None, "cpu_stats": None}
     if check:
         parity, st = compare_all_chunks(res, arm, meshed, cpu_threads)
         bad = D.reduce([parity["chunks_meshed"], parity["byte_compared_chunks"], parity["count_mismatches"], parity["byte_mismatches"]])
         parity.update(chunks_meshed=int(bad[0]), byte_compared_chunks=int(bad[1]), count_mismatches=int(bad[2]), byte_mismatches=int(bad[3]),
                       ranks=D.world)
         out["parity"], out["cpu_stats"] = parity, st
+    # further end-to-end variants (they run new batches: `res` above is no longer valid from here on)
+    out["device_sink"] = device_sink_steps(D, m, local, meshed, resident, pb, ph, steps)
+    out["hinted"] = hinted_steps(D, m, meshed, resident, pb, ph, steps)
     m.close()
     return out
+
+
+def device_buffer(D: Dist, nbytes: int, local: int):
+    """A caller-owned device buffer (what a renderer's vertex / index buffer is): (raw pointer, keep-alive, read-back)."""
+    if D.emulated:
+        a = np.zeros(max(nbytes, 16), dtype=np.uint8)
+        return a.ctypes.data, a, (lambda: a)
+    t = D.torch.zeros(max(nbytes, 16), dtype=D.torch.uint8, device=f"cuda:{local}")
+    D.sync()
+    return t.data_ptr(), t, (lambda: t.cpu().numpy())
+
+
+def device_sink_steps(D: Dist, m, local: int, meshed, resident, pb, ph, steps: int) -> dict:
+    """SURVEY 8f row 2, the CUDA half of the zero-copy upload: the same world load as `e2e`, but the meshes stay on the device --
+    hcm_upload_chunks + hcm_mesh_batch + hcm_mesh_counts (descriptors only) -> the host gives every mesh a range of ONE vertex and ONE
+    index buffer the way MeshCluster::try_alloc does (client/include/client/mesh/MeshCluster.hpp:38-67: first fit in a virtual block,
+    alignment sizeof(Vertex) / sizeof(Index); here a bump allocator over a fresh cluster) -> hcm_mesh_emit_into.  No vertex or index
+    byte crosses the bus; the result is checked against the fetched (host) output of the same batch."""
+    from hypercraft_b200 import mesher as M
+
+    m.upload(resident, pb.array, ph.array)
+    m.mesh_async(meshed)
+    cnt = m.counts()
+    nv, ni = m.n_vertices, m.n_indices
+    vptr, vkeep, vread = device_buffer(D, nv * 8, local)
+    iptr, ikeep, iread = device_buffer(D, ni * 2, local)
+
+    def place(md):
+        pl = np.zeros(len(md), dtype=M.MESH_PLACEMENT_DTYPE)
+        pl["mesh"] = np.arange(len(md), dtype=np.uint32)
+        pl["vertex_offset"][1:] = np.cumsum(md["vertex_count"][:-1], dtype=np.uint64)
+        pl["index_offset"][1:] = np.cumsum(md["index_count"][:-1], dtype=np.uint64)
+        return pl
+
+    m.emit_into(place(cnt.meshes), vptr, nv, iptr, ni)
+    d2h0, h2d0 = m.stats()["d2h_bytes"], m.stats()["h2d_bytes"]
+    D.barrier()
+    t0 = time.perf_counter()
+    sink_ms = []
+    for _ in range(steps):
+        m.upload(resident, pb.array, ph.array)
+        m.mesh_async(meshed)
+        cnt = m.counts()
+        pl = place(cnt.meshes)
+        m.emit_into(pl, vptr, nv, iptr, ni)
+        sink_ms.append(m.stats()["sink_ms"])
+    D.sync()
+    local_ms = (time.perf_counter() - t0) * 1e3 / steps
+    ms = D.reduce([local_ms], "max")[0]
+    s = m.stats()
+    # the device buffers hold what the host path returns for the same batch
+    host = m.fetch()
+    vb, ib = vread().view(np.uint64), iread().view(np.uint16)
+    ok = len(host.meshes) == len(pl)
+    for k in np.linspace(0, max(len(pl) - 1, 0), num=min(len(pl), 512), dtype=np.int64) if len(pl) else []:
+        d = host.meshes[k]
+        vo, io = int(pl[k]["vertex_offset"]), int(pl[k]["index_offset"])
+        ok = ok and bool((vb[vo:vo + int(d["vertex_count"])] == host.vertices[int(d["vertex_offset"]):int(d["vertex_offset"]) + int(d["vertex_count"])]).all())
+        ok = ok and bool((ib[io:io + int(d["index_count"])] == host.indices[int(d["index_offset"]):int(d["index_offset"]) + int(d["index_count"])]).all())
+    total = D.reduce([len(meshed)])[0]
+    del vkeep, ikeep
+    return {"value": total / (ms / 1e3), "unit": "chunks/s", "ms_per_step": ms, "h2d_bytes_per_step": int((s["h2d_bytes"] - h2d0) // steps),
+            "d2h_bytes_per_step": int((s["d2h_bytes"] - d2h0) // steps), "d2h_vertex_index_bytes_per_step": 0, "scatter_kernel_ms": float(np.mean(sink_ms)),
+            "device_vertex_bytes": int(nv * 8), "device_index_bytes": int(ni * 2), "meshes_placed": int(len(pl)), "device_bytes_equal_host_path": bool(ok),
+            "call": "hcm_upload_chunks + hcm_mesh_batch + hcm_mesh_counts + host range allocation + hcm_mesh_emit_into (unpipelined)"}
+
+
+def hinted_steps(D: Dist, m, meshed, resident, pb, ph, steps: int) -> dict:
+    """NOT the headline (the hint is knowledge computed outside the timed region): the same world load with the per-chunk `uniform value`
+    hint a HyperCraft build can pass -- its generator knows when it filled a chunk with one block (client/src/ChunkGenerateTask.cpp:21-39)
+    -- so that neither the scan threads nor the copy engine touch the 64 KB of a uniform chunk.  Shows what the host-side scan costs."""
+    b = pb.array
+    uniform = (b[:, :64] == b[:, :1]).all(axis=1)
+    idx = np.nonzero(uniform)[0]
+    uniform[idx] = (b[idx] == b[idx, :1]).all(axis=1)
+    hint = np.where(uniform, b[:, 0].astype(np.int32), -2).astype(np.int32)  # HCM_HINT_NOT_UNIFORM for the rest
+    m.upload(resident, pb.array, ph.array, uniform_hint=hint)
+    m.mesh(meshed)
+    D.barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        m.upload(resident, pb.array, ph.array, uniform_hint=hint)
+        res = m.mesh(meshed)
+    D.sync()
+    ms = D.reduce([(time.perf_counter() - t0) * 1e3 / steps], "max")[0]
+    total = D.reduce([len(meshed)])[0]
+    return {"value": total / (ms / 1e3), "unit": "chunks/s", "ms_per_step": ms, "uniform_chunks_hinted": int(uniform.sum()), "vertices": int(len(res.vertices)),
+            "call": "hcm_upload_chunks_hinted + hcm_mesh_batch + hcm_mesh_fetch (unpipelined); compare with e2e.unpipelined_ms_per_step"}
 
 
 def config4_block(D: Dist, args, rank: int, world: int, local: int, threads: int) -> dict:
@@ -485,7 +577,9 @@ def config4_block(D: Dist, args, rank: int, world: int, local: int, threads: int
     return {"workload": workload_name(radius, True), "radius": radius, "scaling": "strong", "chunks_meshed": int(r["total_chunks"]),
             "value": r["value"], "unit": "chunks/s", "ms_per_step": r["ms_per_step"], "quads_per_s": r["quads_per_s"],
             "e2e": {"value": r["e2e_value"], "unit": "chunks/s", "ms_per_step": r["e2e_ms_per_step"], "ms_per_rank": r["e2e_ms_per_rank"],
-                    "h2d_bytes_per_step_rank0": int(r["h2d_step"]), "d2h_bytes_per_step_rank0": int(r["d2h_step"])},
+                    "h2d_bytes_per_step_rank0": int(r["h2d_step"]), "d2h_bytes_per_step_rank0": int(r["d2h_step"]),
+                    "chunks_sent_unscanned_last_step_rank0": r["unscanned_last_upload"]},
+            "e2e_device_sink": r["device_sink"],
             "kernel_ms_rank0": r["kernel_ms"], "slab_x_bounds": [[int(a), int(b)] for a, b in bounds],
             "tasks_per_rank": [int(v) for v in r["tasks_per_rank"]], "worked_chunks_per_rank": [int(v) for v in worked],
             "worked_imbalance_max_over_mean": float(max(worked) / max(np.mean(worked), 1.0)),
@@ -540,6 +634,15 @@ def main():
     radius = args.radius
     threads = max(1, (os.cpu_count() or 1) // world)
     os.environ.setdefault("HCM_HOST_THREADS", str(max(1, min(15, threads - 1))))  # upload scan threads of this rank's hcm_ctx
+    if world > 1:  # ranks share one host: each keeps to its own cores (the scan threads and the CPU arm inherit the mask)
+        try:
+            cores = sorted(os.sched_getaffinity(0))
+            per = max(1, len(cores) // world)
+            mine = cores[local * per:(local + 1) * per]
+            if mine:
+                os.sched_setaffinity(0, mine)
+        except (AttributeError, OSError):
+            pass
     check = not args.no_cpu_baseline
     sampler = ClockSampler(local)
     sampler.start()
@@ -616,7 +719,10 @@ def main():
             "quads_per_s": r["quads_per_s"], "quads_per_step": r["total_quads"], "vertices_per_step_per_gpu": int(counts["n_vertices"]),
             "e2e": {"value": r["e2e_value"], "unit": "chunks/s", "ms_per_step": r["e2e_ms_per_step"], "h2d_bytes_per_step": int(r["h2d_step"]),
                     "d2h_bytes_per_step": int(r["d2h_step"]), "call": "hcm_upload_and_mesh", "unpipelined_ms_per_step": r["e2e_serial_ms"],
-                    "ms_per_rank": r["e2e_ms_per_rank"]},
+                    "ms_per_rank": r["e2e_ms_per_rank"], "chunks_sent_unscanned_last_step": r["unscanned_last_upload"],
+                    "upload": "scan threads and copy engine share the work items: what the engine takes first crosses the bus unscanned "
+                              "(derive_kernel finds uniform chunks on the device as well)"},
+            "e2e_device_sink": r["device_sink"], "e2e_with_generator_hints": r["hinted"],
             "gpu_launches": int(r["total_launches"]),
             "kernel_ms": r["kernel_ms"],
             "roofline": roofline_block(len(meshed), int(counts["n_worked"]), len(resident), int(counts["n_vertices"]), int(counts["n_meshes"]),
