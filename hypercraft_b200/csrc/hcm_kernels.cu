@@ -781,6 +781,7 @@ __device__ __forceinline__ void flood_channel(const MeshParams &p, const ColInfo
 				const int c = ci.idx(k);
 				const u64 g = step > 0 ? rd[c] : 0ull;
 				u64 add = 0;
+				PHASE_COUNT(27, 1); // column evaluations
 				if (lv && step > 0) {
 					if (step > ci.lim(k))
 						live &= ~(1u << k);
@@ -800,6 +801,7 @@ __device__ __forceinline__ void flood_channel(const MeshParams &p, const ColInfo
 				}
 				const u64 ng = g | add;
 				if (add) {
+					PHASE_COUNT(25, 1); // ... that gained cells
 					changed = true, next_dirty |= 1u << k;
 					if (k < kInnerSlots) {
 #pragma unroll

@@ -28,7 +28,7 @@ def pytest_configure(config):
     if os.environ.get("HCM_TEST_SIM"):
         from hypercraft_b200 import mesher
 
-        mesher.LIB_PATH = build_sim()
+        mesher.LIB_PATH = os.environ.get("HCM_TEST_SIM_LIB") or build_sim()  # HCM_TEST_SIM_LIB: another build of the emulation (sanitizers)
         mesher._lib = None
 
 

@@ -83,6 +83,8 @@ cudaError_t cudaEventElapsedTime(float *, cudaEvent_t, cudaEvent_t);
 cudaError_t cudaGetDriverEntryPoint(const char *, void **, unsigned long long, cudaDriverEntryPointQueryResult *);
 }
 template <typename F> static inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAttribute, int) { return cudaSuccess; }
+template <typename T> static inline cudaError_t cudaMemcpyFromSymbol(void *dst, const T &symbol, size_t n) { return memcpy(dst, &symbol, n), cudaSuccess; }
+template <typename T> static inline cudaError_t cudaMemcpyToSymbol(T &symbol, const void *src, size_t n) { return memcpy(&symbol, src, n), cudaSuccess; }
 
 // ---- the fibre machine --------------------------------------------------------------------------------------------------
 namespace cusim {
