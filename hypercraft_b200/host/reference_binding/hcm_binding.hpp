@@ -20,7 +20,7 @@ void Shutdown();
 Dispatcher *Get(); // nullptr before Configure
 
 // The two places of the reference that change a chunk after it was generated -- ChunkTaskRunner<kSetBlock>::Run
-// (client/src/ChunkSetBlockTask.cpp:92) and ChunkTaskRunner<kSetSunlight>::Run (client/src/ChunkSetSunlightTask.cpp:60) -- call
+// (client/src/ChunkSetBlockTask.cpp:92) and ChunkTaskRunner<kSetSunlight>::Run (client/src/ChunkSetSunlightTask.cpp:58) -- call
 // this before their Push<kMesh>, unless they go through Dispatcher::SetBlocks, which edits on the device.
 inline void MarkDirty(const hc::ChunkPos3 &pos) {
 	if (Dispatcher *d = Get())
