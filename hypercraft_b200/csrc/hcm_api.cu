@@ -919,8 +919,11 @@ static int upload_impl(hcm_ctx *c, uint32_t n, const int16_t *pos, const uint16_
 				if (s == IT_DONE)
 					break;
 				if (s == IT_FREE && adaptive) {
-					if (!engine_idle)
+					if (!engine_idle) {
 						engine_idle = blk == 0 || cudaEventQuery(c->block_events[blk - 1]) == cudaSuccess;
+						if (!engine_idle)
+							(void)cudaGetLastError(); // "not ready" is an answer, not an error: it must not surface at the next cudaGetLastError()
+					}
 					uint8_t expect = IT_FREE;
 					if (engine_idle && item_state[it].compare_exchange_strong(expect, IT_BUSY, std::memory_order_acq_rel)) {
 						resolve_item(it, false);
@@ -1508,8 +1511,10 @@ int hcm_upload_and_mesh(hcm_ctx *c, uint32_t n_chunks, const int16_t *pos, const
 				CU(cudaEventSynchronize(c->sub_events[fetched]));
 			else {
 				cudaError_t q = cudaEventQuery(c->sub_events[fetched]);
-				if (q == cudaErrorNotReady)
+				if (q == cudaErrorNotReady) {
+					(void)cudaGetLastError(); // an answer, not an error
 					return HCM_OK;
+				}
 				CU(q);
 			}
 			const BatchHeads cur = c->h_heads_ring[fetched];
