@@ -520,7 +520,9 @@ def hinted_steps(D: Dist, m, meshed, resident, pb, ph, steps: int) -> dict:
     b = pb.array
     uniform = (b[:, :64] == b[:, :1]).all(axis=1)
     idx = np.nonzero(uniform)[0]
-    uniform[idx] = (b[idx] == b[idx, :1]).all(axis=1)
+    for i0 in range(0, len(idx), 1024):  # in slices: the candidates are two thirds of the world
+        sel = idx[i0:i0 + 1024]
+        uniform[sel] = (b[sel] == b[sel, :1]).all(axis=1)
     hint = np.where(uniform, b[:, 0].astype(np.int32), -2).astype(np.int32)  # HCM_HINT_NOT_UNIFORM for the rest
     m.upload(resident, pb.array, ph.array, uniform_hint=hint)
     m.mesh(meshed)
