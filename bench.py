@@ -601,6 +601,30 @@ def config4_block(D: Dist, args, rank: int, world: int, local: int, threads: int
             "parity": r["parity"], "setup_seconds": setup_s}
 
 
+def sharded_dispatcher_check(emulated: bool) -> dict:
+    """N > 1 only, rank 0: the C++ host mirror for several GPUs -- hcm_host::ShardedMeshDispatcher, one hcm_ctx per device over x-slabs,
+    FlushParallel with one host thread per GPU, edits across the cut -- run through the C ABI on devices 0 and 1 of this box and compared
+    mesh for mesh with the CPU oracle (tests/cpp/test_sharded_gpu.cpp).  A correctness check riding along with the scaling run, not a
+    measurement."""
+    import hcoracle
+    from hypercraft_b200 import mesher as M
+
+    t0 = time.time()
+    try:
+        exe = os.path.join(ROOT, "tests", "cpp", "test_sharded_gpu")
+        libdir, libfile = os.path.split(M.LIB_PATH)
+        subprocess.run(["g++", "-std=c++20", "-O2", "-pthread", "-o", exe, exe + ".cpp", f"-L{libdir}", "-l" + libfile[3:-3], "-ldl", f"-Wl,-rpath,{libdir}"],
+                       check=True, capture_output=True, timeout=300)
+        hcoracle.build(ref=False, port=True)
+        env = dict(os.environ, CUSIM_DEVICES="2") if emulated else dict(os.environ)
+        r = subprocess.run([exe, os.path.join(ROOT, "hypercraft_b200", "data", "registry.bin"), hcoracle.PORT_SO], capture_output=True, text=True, timeout=300, env=env)
+        lines = r.stdout.strip().splitlines()
+        return {"devices": 2, "returncode": r.returncode, "result": lines[-1] if lines else r.stderr[-300:], "detail": lines[:-1], "seconds": time.time() - t0,
+                "what": "tests/cpp/test_sharded_gpu.cpp: ShardedMeshDispatcher world load (FlushParallel) + edits across the cut on two devices, every mesh vs the oracle"}
+    except Exception as e:  # a check that cannot run must not take the scaling numbers down
+        return {"devices": 2, "error": f"{type(e).__name__}: {e}", "seconds": time.time() - t0}
+
+
 def secondary_configs(local: int, threads: int) -> dict:
     """BASELINE.json configs[2] (worst-case face density) and configs[4] (edit-driven remesh), small and bounded; each result is
     compared with the CPU arm chunk for chunk.  See tools/bench_configs.py."""
@@ -703,6 +727,8 @@ def main():
     if world == 1 and rank == 0 and not args.no_secondary and check:
         secondary = secondary_configs(local, threads)
 
+    D.barrier()  # the last collective: what follows is rank 0's alone
+    sharded_check = sharded_dispatcher_check(emulated) if world > 1 and rank == 0 else None  # after every collective: the other ranks are done
     if rank == 0:
         peaks = {}
         try:
@@ -742,6 +768,8 @@ def main():
         }
         if config4 is not None:
             out["config4"] = config4
+        if sharded_check is not None:
+            out["sharded_dispatcher"] = sharded_check
         if secondary is not None:
             out["secondary_configs"] = secondary
         if emulated:

@@ -75,3 +75,4 @@ def test_bench_two_ranks_dry_run_on_the_emulation():
     c4 = d["config4"]
     assert c4["scaling"] == "strong" and sum(c4["tasks_per_rank"]) == c4["chunks_meshed"] == c4["parity"]["byte_compared_chunks"]
     assert c4["parity"]["byte_mismatches"] == 0 and len(c4["slab_x_bounds"]) == 2 and c4["slab_x_bounds"][0][1] == c4["slab_x_bounds"][1][0]
+    assert d["sharded_dispatcher"]["returncode"] == 0 and d["sharded_dispatcher"]["result"].startswith("PASS"), d["sharded_dispatcher"]
