@@ -183,6 +183,8 @@ struct hcm_ctx {
 	int force_all = 0;
 
 	cudaEvent_t ev[10]{};
+	cudaEvent_t ev_peer = nullptr; // orders hcm_copy_chunks_from between two contexts' streams
+	uint64_t peers_tried = 0;      // bit d: direct access to device d has been asked for (hcm_copy_chunks_from)
 	bool ev_upload = false, ev_batch = false, ev_fetch = false, ev_sink = false;
 	hcm_stats stats{};
 	std::string err;
@@ -568,6 +570,8 @@ void hcm_destroy(hcm_ctx *c) {
 	for (auto &e : c->ev)
 		if (e)
 			cudaEventDestroy(e);
+	if (c->ev_peer)
+		cudaEventDestroy(c->ev_peer);
 	for (auto &e : c->block_events)
 		cudaEventDestroy(e);
 	for (auto &e : c->sub_events)
@@ -641,6 +645,7 @@ int hcm_create(const hcm_registry *registry, const hcm_config *cfg, hcm_ctx **ou
 	CUB(cudaStreamCreateWithFlags(&c->fetch_stream, cudaStreamNonBlocking));
 	for (int i = 0; i < EV_COUNT; ++i)
 		CUB(cudaEventCreate(&c->ev[i]));
+	CUB(cudaEventCreateWithFlags(&c->ev_peer, cudaEventDisableTiming));
 
 	DevWorld &w = c->w;
 	w.ox = cfg->origin[0], w.oy = cfg->origin[1], w.oz = cfg->origin[2];
@@ -1016,6 +1021,94 @@ int hcm_upload_chunks_hinted(hcm_ctx *c, uint32_t n, const int16_t *pos, const u
 			if (uniform_hint[i] > 0xffff || uniform_hint[i] < HCM_HINT_NOT_UNIFORM)
 				return fail(c, HCM_ERR_INVALID, "uniform_hint[%u] = %d is neither a Block value nor HCM_HINT_*", i, uniform_hint[i]);
 	return upload_impl(c, n, pos, blocks, heights, uniform_hint, nullptr);
+}
+
+int hcm_copy_chunks_from(hcm_ctx *c, hcm_ctx *src, uint32_t n, const int16_t *pos) {
+	if (!c || !src)
+		return HCM_ERR_INVALID;
+	if (n == 0)
+		return HCM_OK;
+	if (!pos)
+		return fail(c, HCM_ERR_INVALID, "null positions");
+	if (c == src)
+		return fail(c, HCM_ERR_INVALID, "source and destination are the same context");
+	if (n > c->max_chunks)
+		return fail(c, HCM_ERR_CAPACITY, "copy of %u chunks exceeds max_chunks %u", n, c->max_chunks);
+	std::vector<UploadEntry> entries(n);
+	std::vector<int32_t> src_slot(n), fresh;
+	auto roll_back = [&]() {
+		for (auto it = fresh.rbegin(); it != fresh.rend(); ++it) {
+			c->free_slots.push_back(c->slot_of[*it]);
+			c->slot_of[*it] = -1;
+			const int fx = *it % c->w.wx, fz = (*it / c->w.wx) % c->w.wz, fy = *it / (c->w.wx * c->w.wz);
+			bump_neighbours(c, fx, fy, fz, -1);
+		}
+	};
+	for (uint32_t i = 0; i < n; ++i) {
+		int sx, sy, sz, cx, cy, cz;
+		int rc = HCM_OK;
+		if (!in_window(src, pos + 3 * i, &sx, &sy, &sz) || src->slot_of[cell(src, sx, sy, sz)] < 0)
+			rc = fail(c, HCM_ERR_NOT_RESIDENT, "chunk (%d,%d,%d) is not resident in the source context", pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]);
+		else if (!in_window(c, pos + 3 * i, &cx, &cy, &cz))
+			rc = fail(c, HCM_ERR_OUT_OF_WINDOW, "chunk (%d,%d,%d) is outside the window", pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]);
+		int32_t slot = -1;
+		if (!rc) {
+			src_slot[i] = src->slot_of[cell(src, sx, sy, sz)];
+			slot = c->slot_of[cell(c, cx, cy, cz)];
+			if (slot < 0) {
+				if (c->free_slots.empty())
+					rc = fail(c, HCM_ERR_CAPACITY, "more than %u resident chunks", c->max_chunks);
+				else {
+					slot = c->free_slots.back();
+					c->free_slots.pop_back();
+					c->slot_of[cell(c, cx, cy, cz)] = slot;
+					fresh.push_back((int32_t)cell(c, cx, cy, cz));
+					bump_neighbours(c, cx, cy, cz, +1);
+				}
+			}
+		}
+		if (rc) {
+			roll_back();
+			return rc;
+		}
+		entries[i] = UploadEntry{slot, (int16_t)cx, (int16_t)cy, (int16_t)cz, 0, 0};
+	}
+	// direct access between the two GPUs (NVLink / NVSwitch) where the topology offers it; without it the driver stages the copy
+	if (src->device != c->device && src->device < 64 && !((c->peers_tried >> src->device) & 1)) {
+		c->peers_tried |= 1ull << src->device;
+		int can = 0;
+		CU(cudaSetDevice(c->device));
+		if (cudaDeviceCanAccessPeer(&can, c->device, src->device) == cudaSuccess && can)
+			if (cudaDeviceEnablePeerAccess(src->device, 0) != cudaSuccess)
+				(void)cudaGetLastError(); // already enabled by somebody else in this process: fine
+	}
+	// src's stream -> event -> dst's stream: the copies read what src had enqueued (edits, derives) before this call
+	CU(cudaSetDevice(src->device));
+	CU(cudaEventRecord(src->ev_peer, src->stream));
+	CU(cudaSetDevice(c->device));
+	cudaStream_t st = c->stream;
+	CU(cudaStreamWaitEvent(st, src->ev_peer, 0));
+	for (uint32_t i = 0; i < n;) { // one copy per run of chunks whose slots are consecutive on both sides
+		uint32_t j = i + 1;
+		while (j < n && entries[j].slot == entries[j - 1].slot + 1 && src_slot[j] == src_slot[j - 1] + 1)
+			++j;
+		CU(cudaMemcpyPeerAsync(c->d_raw + (size_t)entries[i].slot * HCM_CHUNK_VOXELS, c->device, src->d_raw + (size_t)src_slot[i] * HCM_CHUNK_VOXELS, src->device,
+		                       (size_t)(j - i) * HCM_CHUNK_VOXELS * 2, st));
+		CU(cudaMemcpyPeerAsync(c->d_rawh + (size_t)entries[i].slot * HCM_CHUNK_COLUMNS, c->device, src->d_rawh + (size_t)src_slot[i] * HCM_CHUNK_COLUMNS,
+		                       src->device, (size_t)(j - i) * HCM_CHUNK_COLUMNS, st));
+		i = j;
+	}
+	CU(cudaEventRecord(c->ev_peer, st)); // src must not overwrite the slots (a later edit) before they have been read
+	CU(cudaMemcpyAsync(c->d_entries, entries.data(), (size_t)n * sizeof(UploadEntry), cudaMemcpyHostToDevice, st)); // pageable: staged before return
+	launch_derive(c->w, c->d_entries, n, c->d_prop_index, c->d_tables, c->d_rawh, st);
+	CU(cudaGetLastError());
+	c->stats.kernel_launches += 1;
+	c->stats.p2p_bytes += (uint64_t)n * (HCM_CHUNK_VOXELS * 2 + HCM_CHUNK_COLUMNS);
+	c->stats.h2d_bytes += (uint64_t)n * sizeof(UploadEntry);
+	CU(cudaSetDevice(src->device));
+	CU(cudaStreamWaitEvent(src->stream, c->ev_peer, 0));
+	CU(cudaSetDevice(c->device));
+	return HCM_OK;
 }
 
 int hcm_remove_chunks(hcm_ctx *c, uint32_t n, const int16_t *pos) {

@@ -208,6 +208,47 @@ public:
 		return m_queue.Size();
 	}
 
+	// Halo replication: chunks that are resident on `src`'s GPU become resident here, device to device
+	// (hcm_copy_chunks_from: cudaMemcpyPeerAsync, NVLink between peer GPUs) -- the way a chunk the owner of a slab edited on its device
+	// (SetBlocks) reaches the neighbour that holds it as halo, without the 64 KB going through the host again.  The bookkeeping
+	// follows: this dispatcher now knows the chunk OBJECT `src` knows (the host edited that object in place, so it describes the
+	// device copy), and a copy of the position that was still waiting to go up from the host is dropped.
+	void CopyChunksFrom(MeshTaskDispatcher &src, const std::vector<ChunkPos3> &positions) {
+		if (positions.empty() || &src == this)
+			return;
+		// both contexts are busy for the duration of the call; lock in address order (two dispatchers may copy from each other)
+		std::mutex &first = this < &src ? m_ctx_mutex : src.m_ctx_mutex, &second = this < &src ? src.m_ctx_mutex : m_ctx_mutex;
+		std::lock_guard<std::mutex> l1(first), l2(second);
+		std::vector<int16_t> p(positions.size() * 3);
+		for (size_t i = 0; i < positions.size(); ++i)
+			p[3 * i] = positions[i].x, p[3 * i + 1] = positions[i].y, p[3 * i + 2] = positions[i].z;
+		check(hcm_copy_chunks_from(m_ctx, src.m_ctx, (uint32_t)positions.size(), p.data()));
+		std::unordered_map<ChunkPos3, const ChunkT *, ChunkPos3Hash> known;
+		{
+			std::lock_guard<std::mutex> g(src.m_mutex);
+			for (const ChunkPos3 &q : positions) {
+				auto it = src.m_resident.find(q);
+				if (it != src.m_resident.end())
+					known.emplace(q, it->second);
+			}
+		}
+		std::lock_guard<std::mutex> g(m_mutex);
+		for (const ChunkPos3 &q : positions) {
+			auto it = known.find(q);
+			if (it != known.end())
+				m_resident[q] = it->second;
+			else
+				m_resident.erase(q); // nobody knows which object this is: the next task that reads it uploads the host's copy
+			for (size_t i = 0; i < m_upload.size();) {
+				const auto up = m_upload[i]->GetPosition();
+				if (ChunkPos3{(int16_t)up.x, (int16_t)up.y, (int16_t)up.z} == q && (it == known.end() || m_upload[i].get() != it->second))
+					m_upload.erase(m_upload.begin() + (std::ptrdiff_t)i);
+				else
+					++i;
+			}
+		}
+	}
+
 	// ChunkSetBlockEntry deltas (common/include/common/Data.hpp:11-14) for chunks that are already on the device -- the
 	// work of ChunkTaskRunner<kSetBlock>::Run and of the kFloodSunlight / kSetSunlight chain it starts
 	// (client/src/ChunkSetBlockTask.cpp:78-129, ChunkFloodSunlightTask.cpp:41-57, ChunkSetSunlightTask.cpp:42-90) without
@@ -390,12 +431,14 @@ private:
 };
 
 // One MeshTaskDispatcher per GPU over x-slabs of the world: chunks are independent given their halo, so
-// the GPUs never exchange anything -- a task runs on the GPU whose slab [x_lo, x_hi) holds its position, and that GPU's
+// meshing needs no exchange between the GPUs -- a task runs on the GPU whose slab [x_lo, x_hi) holds its position, and that GPU's
 // window spans the planes x_lo - 1 .. x_hi, i.e. the boundary planes live on both neighbours.  The host's Chunk objects
-// are the authority: a chunk that changes is marked dirty on every GPU that can hold it and goes up again with the next
-// task that reads it.  Edits (SetBlocks) run on the owner of the edited chunk, whose column of the world is complete
+// are the authority: a chunk that changes on the host is marked dirty on every GPU that can hold it and goes up again with the
+// next task that reads it.  Edits (SetBlocks) run on the owner of the edited chunk, whose column of the world is complete
 // (the sunlight chain walks along y, the cut is along x); GPUs holding a touched chunk as halo do not run the chain, they
-// take the chunk as data.  hypercraft_b200/shard.py is the same bookkeeping for the Python benchmark.
+// take the chunk as data -- from the owner's GPU, device to device (the one exchange step of the path: hcm_copy_chunks_from,
+// cudaMemcpyPeerAsync over NVLink), or, with peer_halo = false, from the host.  hypercraft_b200/shard.py is the same bookkeeping
+// for the Python benchmark.
 template <typename ChunkT> class ShardedMeshDispatcher {
 public:
 	using Shard = MeshTaskDispatcher<ChunkT>;
@@ -404,9 +447,11 @@ public:
 		int16_t x_lo, x_hi; // tasks with x_lo <= x < x_hi
 	};
 	// world window: origin / extent in y and z are shared, x comes from the slabs (which must tile an x-range, in order)
+	// peer_halo: a chunk the owner edited on its device reaches the GPUs that hold it as halo device to device
+	// (MeshTaskDispatcher::CopyChunksFrom); false: those GPUs are told the chunk is dirty and take the host's copy with their next task.
 	ShardedMeshDispatcher(const void *registry_blob, size_t blob_size, const std::vector<Slab> &slabs, int16_t origin_y, int16_t origin_z,
-	                      uint16_t extent_y, uint16_t extent_z)
-	    : m_slabs(slabs) {
+	                      uint16_t extent_y, uint16_t extent_z, bool peer_halo = true)
+	    : m_slabs(slabs), m_peer_halo(peer_halo) {
 		if (slabs.empty())
 			throw Error(HCM_ERR_INVALID, "no slabs");
 		for (size_t r = 0; r < slabs.size(); ++r) {
@@ -517,10 +562,22 @@ public:
 				    on_sunlight(s);
 			    },
 			    [&](const ChunkPos3 &p, bool high) { add(p, high); });
+			std::vector<std::vector<ChunkPos3>> to_holder(m_shards.size());
+			std::unordered_set<ChunkPos3, ChunkPos3Hash> once;
 			for (const ChunkPos3 &c : touched)
-				for (int h : Holders(c.x))
-					if (h != (int)r)
+				if (once.insert(c).second)
+					for (int h : Holders(c.x))
+						if (h != (int)r)
+							to_holder[(size_t)h].push_back(c);
+			for (size_t h = 0; h < m_shards.size(); ++h) {
+				if (to_holder[h].empty())
+					continue;
+				if (m_peer_halo)
+					m_shards[h]->CopyChunksFrom(*m_shards[r], to_holder[h]); // ordered after the owner's edit kernels (same stream)
+				else
+					for (const ChunkPos3 &c : to_holder[h])
 						m_shards[h]->MarkDirty(c);
+			}
 		}
 		for (const ChunkPos3 &p : remesh)
 			on_remesh(p, seen[p]);
@@ -564,6 +621,7 @@ private:
 		return (size_t)r;
 	}
 	std::vector<Slab> m_slabs;
+	bool m_peer_halo;
 	std::vector<std::unique_ptr<Shard>> m_shards;
 };
 

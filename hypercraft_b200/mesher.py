@@ -59,10 +59,10 @@ class _Stats(ctypes.Structure):
     _fields_ = [("upload_copy_ms", ctypes.c_float), ("derive_ms", ctypes.c_float), ("classify_ms", ctypes.c_float), ("mesh_ms", ctypes.c_float),
                 ("fetch_copy_ms", ctypes.c_float), ("kernel_launches", ctypes.c_uint32), ("h2d_bytes", ctypes.c_uint64),
                 ("d2h_bytes", ctypes.c_uint64), ("device_bytes", ctypes.c_uint64), ("sink_ms", ctypes.c_float),
-                ("upload_unscanned_chunks", ctypes.c_uint32)]
+                ("upload_unscanned_chunks", ctypes.c_uint32), ("p2p_bytes", ctypes.c_uint64)]
 
 
-assert ctypes.sizeof(_Stats) == 56
+assert ctypes.sizeof(_Stats) == 64
 
 
 MESH_DESC_DTYPE = np.dtype([("task", np.uint32), ("transparent", np.uint32), ("vertex_offset", np.uint64), ("index_offset", np.uint64),
@@ -74,7 +74,7 @@ assert MESH_PLACEMENT_DTYPE.itemsize == 24
 HINT_UNKNOWN, HINT_NOT_UNIFORM = -1, -2
 
 EXPORTS = ["hcm_registry_from_blob", "hcm_create", "hcm_destroy", "hcm_last_error", "hcm_status_string", "hcm_host_alloc", "hcm_host_free",
-           "hcm_upload_chunks", "hcm_upload_chunks_hinted", "hcm_mesh_counts", "hcm_mesh_emit_into", "hcm_remove_chunks", "hcm_rederive_chunks", "hcm_is_resident", "hcm_sync", "hcm_mesh_batch", "hcm_mesh_fetch", "hcm_mesh_wait",
+           "hcm_upload_chunks", "hcm_upload_chunks_hinted", "hcm_mesh_counts", "hcm_mesh_emit_into", "hcm_copy_chunks_from", "hcm_remove_chunks", "hcm_rederive_chunks", "hcm_is_resident", "hcm_sync", "hcm_mesh_batch", "hcm_mesh_fetch", "hcm_mesh_wait",
            "hcm_upload_and_mesh", "hcm_set_blocks", "hcm_get_stats", "hcm_stream", "hcm_debug_light"]
 
 _lib = None
@@ -111,6 +111,7 @@ def load_library():
         L.hcm_mesh_counts.argtypes = [_vp, ctypes.POINTER(_BatchView)]
         L.hcm_mesh_emit_into.argtypes = [_vp, ctypes.c_uint32, _vp, _vp, ctypes.c_uint64, _vp, ctypes.c_uint64]
         L.hcm_remove_chunks.argtypes = [_vp, ctypes.c_uint32, _vp]
+        L.hcm_copy_chunks_from.argtypes = [_vp, _vp, ctypes.c_uint32, _vp]
         L.hcm_rederive_chunks.argtypes = [_vp, ctypes.c_uint32, _vp]
         L.hcm_is_resident.argtypes = [_vp, _vp]
         L.hcm_sync.argtypes = [_vp]
@@ -243,6 +244,11 @@ class Mesher:
         else:
             hint = np.ascontiguousarray(uniform_hint, dtype=np.int32).reshape(len(pos))
             self._check(self.L.hcm_upload_chunks_hinted(self.ctx, len(pos), _ptr(pos), _ptr(b), _ptr(h), _ptr(hint)))
+
+    def copy_chunks_from(self, src: "Mesher", positions) -> None:
+        """hcm_copy_chunks_from: chunks resident in ``src`` become resident here, device to device (halo replication between GPUs)."""
+        pos = np.ascontiguousarray(positions, dtype=np.int16).reshape(-1, 3)
+        self._check(self.L.hcm_copy_chunks_from(self.ctx, src.ctx, len(pos), _ptr(pos)))
 
     def remove(self, positions) -> None:
         pos = np.ascontiguousarray(positions, dtype=np.int16).reshape(-1, 3)

@@ -177,6 +177,16 @@ int hcm_remove_chunks(hcm_ctx *ctx, uint32_t n, const int16_t *pos /* n x 3 */);
  * hcm_rederive_chunks(ctx, 0, NULL) followed by hcm_mesh_batch. */
 int hcm_rederive_chunks(hcm_ctx *ctx, uint32_t n, const int16_t *pos /* n x 3 */);
 int hcm_is_resident(const hcm_ctx *ctx, const int16_t pos[3]); /* 1 / 0 */
+/* Halo replication between contexts ("if the pool is already device-resident, cudaMemcpyPeerAsync the boundary planes over
+ * NVLink"): the Block data and sunlight heights of the listed chunks go from `src`'s resident world to `dst`'s, device to device
+ * (cudaMemcpyPeerAsync: NVLink / NVSwitch between peer GPUs, a plain device copy when both contexts share a GPU), and are derived again
+ * on `dst`.  With the world cut into x-slabs (one ctx per GPU, each holding its slab dilated by a chunk) this is how a chunk the owner
+ * edited with hcm_set_blocks reaches the neighbours that hold it as halo -- no host round trip, no second PCIe crossing.
+ * Every position must be resident in `src` (HCM_ERR_NOT_RESIDENT) and inside `dst`'s window (HCM_ERR_OUT_OF_WINDOW); positions must be
+ * distinct.  Asynchronous like hcm_upload_chunks: the copies are ordered after everything enqueued on `src` before the call, later
+ * work on `src` is ordered after them, later calls on `dst` see the chunks.  Both contexts must belong to the calling process; the
+ * caller serialises calls on BOTH for the duration of this one. */
+int hcm_copy_chunks_from(hcm_ctx *dst, hcm_ctx *src, uint32_t n, const int16_t *pos /* n x 3 */);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Block edits on the device-resident world: what the reference does in three task types,
@@ -331,7 +341,8 @@ typedef struct hcm_stats {
 	uint64_t device_bytes; /* device memory held by the ctx */
 	float sink_ms;         /* scatter kernel of the last hcm_mesh_emit_into */
 	uint32_t upload_unscanned_chunks; /* chunks of the last upload the copy engine took before a scan thread did (sent as they are) */
-} hcm_stats; /* 56 bytes */
+	uint64_t p2p_bytes;    /* cumulative: bytes received device to device through hcm_copy_chunks_from */
+} hcm_stats; /* 64 bytes */
 int hcm_get_stats(hcm_ctx *ctx, hcm_stats *out);
 
 void *hcm_stream(hcm_ctx *ctx); /* the ctx's cudaStream_t, for external event timing */

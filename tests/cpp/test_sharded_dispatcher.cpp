@@ -23,6 +23,7 @@ struct hcm_ctx {
 	std::vector<uint8_t> remesh_flags;
 	std::vector<hcm_task_result> results;
 	std::set<P3> resident;
+	std::vector<std::pair<const hcm_ctx *, std::vector<P3>>> peer_copies; // hcm_copy_chunks_from calls received: (source, positions)
 	bool in_window(int x, int y, int z) const {
 		return x >= cfg.origin[0] && x < cfg.origin[0] + cfg.extent[0] && y >= cfg.origin[1] && y < cfg.origin[1] + cfg.extent[1] && z >= cfg.origin[2] &&
 		       z < cfg.origin[2] + cfg.extent[2];
@@ -48,6 +49,16 @@ int hcm_remove_chunks(hcm_ctx *c, uint32_t n, const int16_t *pos) {
 	return HCM_OK;
 }
 int hcm_is_resident(const hcm_ctx *c, const int16_t pos[3]) { return (int)c->resident.count({pos[0], pos[1], pos[2]}); }
+int hcm_copy_chunks_from(hcm_ctx *dst, hcm_ctx *src, uint32_t n, const int16_t *pos) {
+	dst->peer_copies.emplace_back(src, std::vector<P3>{});
+	for (uint32_t i = 0; i < n; ++i) {
+		const P3 p{pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]};
+		g_violations += !dst->in_window(p[0], p[1], p[2]) || !src->resident.count(p);
+		dst->peer_copies.back().second.push_back(p);
+		dst->resident.insert(p);
+	}
+	return HCM_OK;
+}
 int hcm_upload_and_mesh(hcm_ctx *c, uint32_t n_chunks, const int16_t *pos, const uint16_t *, const int8_t *, uint32_t n_tasks, const int16_t *tp,
                         hcm_batch_view *out) {
 	c->uploads.emplace_back(), c->tasks.emplace_back();
@@ -147,8 +158,12 @@ int main() {
 		threw = true;
 	}
 	CHECK(threw);
+	for (const bool peer : {true, false}) { // halo replication device to device (the default), and through the host
 	g_ctx.clear();
-	D disp(blob, sizeof blob, {{0, -3, 0}, {1, 0, 3}}, -2, -2, 5, 5);
+	g_violations = 0;
+	for (auto &kv : world) // fresh chunk objects: nothing is resident anywhere
+		kv.second = std::make_shared<Chunk>(Chunk{{kv.first[0], kv.first[1], kv.first[2]}});
+	D disp(blob, sizeof blob, {{0, -3, 0}, {1, 0, 3}}, -2, -2, 5, 5, peer);
 	CHECK(disp.Ranks() == 2 && g_ctx.size() == 2);
 	CHECK(g_ctx[0]->cfg.device == 0 && g_ctx[0]->cfg.origin[0] == -4 && g_ctx[0]->cfg.extent[0] == 5); // planes -4 .. 0
 	CHECK(g_ctx[1]->cfg.device == 1 && g_ctx[1]->cfg.origin[0] == -1 && g_ctx[1]->cfg.extent[0] == 5); // planes -1 .. 3
@@ -203,7 +218,11 @@ int main() {
 	disp.Flush(sink);
 	CHECK(g_violations == 0 && g_ctx[0]->tasks.size() == 2 && g_ctx[1]->tasks.size() == 2);
 	CHECK(g_ctx[0]->uploads[1].empty());                                                    // the owner edited on the device
-	CHECK(g_ctx[1]->uploads[1].size() == 1 && g_ctx[1]->uploads[1][0] == (P3{-1, 0, 0}));  // the halo holder takes the chunk again
+	if (peer) { // the halo holder received the chunk from the owner's GPU, nothing came from the host
+		CHECK(g_ctx[1]->uploads[1].empty() && g_ctx[1]->peer_copies.size() == 1 && g_ctx[1]->peer_copies[0].first == g_ctx[0] &&
+		      (g_ctx[1]->peer_copies[0].second == std::vector<P3>{P3{-1, 0, 0}}) && g_ctx[0]->peer_copies.empty());
+	} else
+		CHECK(g_ctx[1]->uploads[1].size() == 1 && g_ctx[1]->uploads[1][0] == (P3{-1, 0, 0}) && g_ctx[1]->peer_copies.empty()); // ... takes the chunk again
 	CHECK(has(g_ctx[1]->tasks[1], {0, 0, 0}) && has(g_ctx[0]->tasks[1], {-1, 0, 0}));
 	for (int r = 0; r < 2; ++r)
 		for (const P3 &t : g_ctx[r]->tasks[1])
@@ -240,7 +259,12 @@ int main() {
 	    });
 	CHECK(asked.size() == 27 && asked_has({-1, 1, -1}) && asked_has({1, -1, 1}));
 	disp.Flush(sink);
-	CHECK(g_ctx[0]->tasks.size() == 3 && g_ctx[0]->tasks[2].size() == 9 && g_ctx[0]->uploads[2].size() == 1 && g_ctx[0]->uploads[2][0] == (P3{0, 0, 0}));
+	CHECK(g_ctx[0]->tasks.size() == 3 && g_ctx[0]->tasks[2].size() == 9);
+	if (peer)
+		CHECK(g_ctx[0]->uploads[2].empty() && g_ctx[0]->peer_copies.size() == 1 && g_ctx[0]->peer_copies[0].first == g_ctx[1] &&
+		      (g_ctx[0]->peer_copies[0].second == std::vector<P3>{P3{0, 0, 0}}));
+	else
+		CHECK(g_ctx[0]->uploads[2].size() == 1 && g_ctx[0]->uploads[2][0] == (P3{0, 0, 0}));
 	CHECK(g_ctx[1]->tasks.size() == 4 && g_ctx[1]->tasks[3].size() == 18 && g_ctx[1]->uploads[3].empty() && sunk.size() == 27 && g_violations == 0);
 
 	// both GPUs' rounds on their own host threads: the sink is called concurrently, every task exactly once
@@ -260,6 +284,7 @@ int main() {
 		CHECK(pushed == 54 && wrong_rank == 0 && seen.size() == 54 && disp.Pending() == 0 && g_violations == 0);
 		CHECK(g_ctx[0]->tasks.back().size() == 27 && g_ctx[1]->tasks.back().size() == 27 && g_ctx[0]->uploads.back().empty() && g_ctx[1]->uploads.back().empty());
 	}
+	} // peer / host halo
 
 	printf("%s\n", fails ? "FAIL" : "PASS");
 	return fails != 0;

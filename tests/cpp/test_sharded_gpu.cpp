@@ -148,7 +148,7 @@ int main(int argc, char **argv) {
 			for (int z = -1; z <= 1; ++z)
 				disp.Submit(gather(x, y, z));
 	disp.FlushParallel(sink);
-	int fails = 0;
+	int fails = 0, fails_early = 0;
 	if (pushed != 54 || std::set<std::array<int, 3>>(seen.begin(), seen.end()).size() != 54 || bad) {
 		printf("world load: %d pushed, %d mismatches\n", pushed.load(), bad.load());
 		++fails;
@@ -165,6 +165,9 @@ int main(int argc, char **argv) {
 	int n_sun = 0, n_remesh = 0, n_high = 0;
 	seen.clear();
 	pushed = 0;
+	hcm_stats before[2], after[2];
+	for (int r = 0; r < 2; ++r)
+		hcm_get_stats(disp.Rank(r).Context(), &before[r]);
 	const uint32_t changed = disp.SetBlocks(
 	    edits, [&](const D::SunlightChange &s) { world.at({s.chunk.x, s.chunk.y, s.chunk.z})->heights[s.index] = s.new_height, ++n_sun; },
 	    [&](const hcm_host::ChunkPos3 &p, bool high) {
@@ -172,6 +175,16 @@ int main(int argc, char **argv) {
 			    disp.Submit(gather(p.x, p.y, p.z), high), ++n_remesh, n_high += high;
 	    });
 	disp.FlushParallel(sink);
+	for (int r = 0; r < 2; ++r)
+		hcm_get_stats(disp.Rank(r).Context(), &after[r]);
+	// the touched chunks reached the other GPU device to device (hcm_copy_chunks_from), not through the host: each GPU received whole
+	// chunks from its neighbour and far less than one chunk's 64 KB from the host during the round
+	const uint64_t p2p[2] = {after[0].p2p_bytes - before[0].p2p_bytes, after[1].p2p_bytes - before[1].p2p_bytes};
+	const uint64_t h2d[2] = {after[0].h2d_bytes - before[0].h2d_bytes, after[1].h2d_bytes - before[1].h2d_bytes};
+	printf("halo replication: GPU 0 received %llu B from GPU 1 and %llu B from the host, GPU 1 %llu B from GPU 0 and %llu B from the host\n",
+	       (unsigned long long)p2p[0], (unsigned long long)h2d[0], (unsigned long long)p2p[1], (unsigned long long)h2d[1]);
+	if (p2p[0] < 66560 || p2p[1] < 66560 || h2d[0] > 32768 || h2d[1] > 32768)
+		++fails_early;
 	printf("edits across the cut: %u blocks changed, %d sunlight heights, %d remesh tasks (%d high priority), %d pushed\n", changed, n_sun, n_remesh, n_high,
 	       pushed.load());
 	bool both_sides = false, left = false, right = false;
@@ -180,6 +193,7 @@ int main(int argc, char **argv) {
 	both_sides = left && right;
 	if (!changed || !n_sun || pushed != n_remesh || !both_sides || !n_high || bad)
 		++fails;
+	fails += fails_early;
 	printf("%s: %zu vertices, %d mismatches\n", fails ? "FAIL" : "PASS", verts.load(), bad.load());
 	return fails ? 1 : 0;
 }

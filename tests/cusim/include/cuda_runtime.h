@@ -68,6 +68,9 @@ cudaError_t cudaMemcpy(void *, const void *, size_t, cudaMemcpyKind);
 cudaError_t cudaMemcpyAsync(void *, const void *, size_t, cudaMemcpyKind, cudaStream_t);
 cudaError_t cudaMemcpyBatchAsync(void **dsts, void **srcs, size_t *sizes, size_t count, cudaMemcpyAttributes *attrs, size_t *attr_idx, size_t n_attrs,
                                  size_t *fail_idx, cudaStream_t);
+cudaError_t cudaDeviceCanAccessPeer(int *can, int device, int peer);
+cudaError_t cudaDeviceEnablePeerAccess(int peer, unsigned flags);
+cudaError_t cudaMemcpyPeerAsync(void *dst, int dst_device, const void *src, int src_device, size_t, cudaStream_t);
 cudaError_t cudaMemsetAsync(void *, int, size_t, cudaStream_t);
 cudaError_t cudaStreamCreateWithFlags(cudaStream_t *, unsigned);
 cudaError_t cudaStreamDestroy(cudaStream_t);

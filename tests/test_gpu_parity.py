@@ -713,3 +713,50 @@ def test_set_blocks_matches_the_reference_edit_chain_golden():
         for t, p in enumerate(r["remesh"]):
             assert hashlib.sha256(res.serialise(t).tobytes()).hexdigest() == want[tuple(int(v) for v in p)]["mesh_sha256"], (rec["name"], p)
     m.close()
+
+
+def test_halo_replication_between_contexts(port):
+    """hcm_copy_chunks_from (boundary planes from GPU to GPU when the pool is device resident): chunks resident in one context
+    become resident in another, device to device, and mesh there like uploaded ones; after hcm_set_blocks on the owner the touched
+    chunks are replicated and the holder's meshes follow the edit.  Two contexts on device 0 here (cudaMemcpyPeerAsync between two
+    GPUs is the same call; tests/cpp/test_sharded_gpu.cpp covers two devices)."""
+    import edit_oracle
+    from hypercraft_b200 import mesher as M, registry
+
+    reg = registry.load()
+    vpass = reg.props["transparency"][reg.prop_index] == 2
+    allpos, chunks = edit_oracle.edit_test_world(31)
+    owner = M.Mesher(origin=(-2, -2, -2), extent=(5, 5, 5))
+    owner.upload(allpos, np.stack([chunks[tuple(int(c) for c in p)][0] for p in allpos]), np.stack([chunks[tuple(int(c) for c in p)][1] for p in allpos]))
+    holder = M.Mesher(origin=(-1, -2, -2), extent=(4, 5, 5))  # sees the planes x = -1 .. 2
+    mine = allpos[allpos[:, 0] >= -1]
+    h2d0 = holder.stats()["h2d_bytes"]
+    holder.copy_chunks_from(owner, mine)
+    tasks = np.array([[x, y, z] for x in (0, 1) for y in (-1, 0, 1) for z in (-1, 0, 1)], dtype=np.int16)
+
+    def check(what):
+        res = holder.mesh(tasks)
+        for t, p in enumerate(tasks):
+            got, want = res.serialise(t), port.mesh(chunks, p)
+            assert got.size == want.size and (got == want).all(), f"{what}: task {p}\n" + describe_diff(got, want)
+
+    check("replicated world")
+    s = holder.stats()
+    assert s["p2p_bytes"] == len(mine) * (65536 + 1024) and s["h2d_bytes"] - h2d0 < 65536  # whole chunks from the peer, bookkeeping from the host
+    # an edit on the owner: a shaft in chunk (0,0,0) next to the holder's first task plane, a lamp, stone on top of (1,1,0)
+    batch = [((0, 0, 0), 3 + (y * 32 + 7) * 32, 0) for y in range(32)] + [((0, 0, 0), 4 + (2 * 32 + 7) * 32, 24), ((1, 1, 0), 9 + (31 * 32 + 9) * 32, 1)]
+    r = owner.set_blocks(batch)
+    n, sun, _ = edit_oracle.apply_block_edits(chunks, batch, vpass)
+    assert r["n_changed_blocks"] == n and len(r["sunlight"]) == len(sun)
+    touched = {tuple(c) for c, _, _ in batch} | {tuple(int(v) for v in s_["chunk"]) for s_ in r["sunlight"]}
+    holder.copy_chunks_from(owner, np.array(sorted(t for t in touched if t[0] >= -1), dtype=np.int16))
+    check("after the owner's edit")
+    # errors: not resident in the source, outside the destination's window; nothing changes
+    with pytest.raises(M.HcmError) as e:
+        owner.copy_chunks_from(holder, np.array([[-2, 0, 0]], dtype=np.int16))  # the holder never had x = -2
+    assert e.value.status == -4
+    with pytest.raises(M.HcmError) as e:
+        holder.copy_chunks_from(owner, np.array([[-2, 0, 0]], dtype=np.int16))
+    assert e.value.status == -5
+    check("after the failed calls")
+    owner.close(), holder.close()
