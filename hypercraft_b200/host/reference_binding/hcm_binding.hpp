@@ -27,4 +27,11 @@ inline void MarkDirty(const hc::ChunkPos3 &pos) {
 		d->MarkDirty(hcm_host::ChunkPos3{pos.x, pos.y, pos.z});
 }
 
+// ChunkPool::Update erases the chunks beyond the unload radius (client/src/ChunkPool.cpp:17-23): the same loop calls this, so that the
+// device slot is freed and the chunk's pending request and not yet uploaded copy are dropped (ChunkTaskData<kMesh>::OnUnload).
+inline void Unload(const hc::ChunkPos3 &pos) {
+	if (Dispatcher *d = Get())
+		d->Unload(hcm_host::ChunkPos3{pos.x, pos.y, pos.z});
+}
+
 } // namespace hcm_binding
