@@ -173,6 +173,7 @@ public:
 		m_resident.erase(pos);
 		m_queue.Drop(pos);
 		m_snapshot.erase(pos);
+		m_check_readiness = true; // a pending task may now lack one of its 27 chunks
 		for (size_t i = 0; i < m_upload.size();) {
 			const auto p = m_upload[i]->GetPosition();
 			if (ChunkPos3{(int16_t)p.x, (int16_t)p.y, (int16_t)p.z} == pos)
@@ -297,8 +298,10 @@ public:
 		std::vector<bool> high;
 		std::vector<std::shared_ptr<ChunkT>> upload;
 		std::vector<std::array<std::shared_ptr<ChunkT>, 27>> snapshots; // read-only inputs, held until the sink has run
+		bool check_readiness;
 		{
 			std::lock_guard<std::mutex> g(m_mutex);
+			check_readiness = m_check_readiness;
 			tasks = m_queue.Pop(max_tasks, &high);
 			if (tasks.empty())
 				return;
@@ -332,8 +335,10 @@ public:
 		}
 		// Readiness per task, as ChunkTaskData<kMesh>::Pop tests it (ChunkMeshTask.cpp:18-34): a task one of whose 27 chunks is
 		// neither on the device nor part of this upload (its neighbour was Unloaded after the request) is left out of the round
-		// and stays pending; every other task runs.  One evicted chunk must not stall the world.
-		{
+		// and stays pending; every other task runs.  One evicted chunk must not stall the world.  Submit names all 27 chunks of a
+		// task and queues the ones the device lacks, so only an Unload can open such a gap: the test (27 look-ups per task) runs only
+		// after one, and until no pending task waits for a chunk any more.
+		if (check_readiness) {
 			std::unordered_set<ChunkPos3, ChunkPos3Hash> coming;
 			for (const auto &c : upload) {
 				const auto p = c->GetPosition();
@@ -352,7 +357,11 @@ public:
 				if (!ready)
 					deferred.push_back(i);
 			}
-			if (!deferred.empty()) {
+			if (deferred.empty()) {
+				std::lock_guard<std::mutex> g(m_mutex);
+				if (m_queue.Size() == 0)
+					m_check_readiness = false; // every pending task was looked at and is ready
+			} else {
 				std::lock_guard<std::mutex> g(m_mutex);
 				for (size_t k = deferred.size(); k-- > 0;) {
 					const size_t i = deferred[k];
@@ -424,6 +433,7 @@ private:
 	std::unordered_map<ChunkPos3, const ChunkT *, ChunkPos3Hash> m_resident;
 	std::vector<std::shared_ptr<ChunkT>> m_upload;
 	MeshRequestQueue m_queue;
+	bool m_check_readiness{false}; // an Unload happened: Flush tests its tasks' 27 chunks until nothing pending waits for one
 	std::unordered_map<ChunkPos3, std::array<std::shared_ptr<ChunkT>, 27>, ChunkPos3Hash> m_snapshot; // held until the task is flushed
 	std::vector<int16_t> m_pos;
 	std::vector<uint16_t> m_blocks;
