@@ -184,6 +184,12 @@ struct hcm_ctx {
 
 	cudaEvent_t ev[10]{};
 	cudaEvent_t ev_peer = nullptr; // orders hcm_copy_chunks_from between two contexts' streams
+	// task lists go up from two pinned buffers in turn, so that hcm_mesh_batch never waits for the stream (a pageable source makes
+	// cudaMemcpyAsync wait for the previous batch's kernels) and batches can be enqueued back to back
+	TaskIn *h_task_ring[2] = {nullptr, nullptr};
+	cudaEvent_t task_ring_ev[2] = {nullptr, nullptr};
+	bool task_ring_used[2] = {false, false};
+	int task_ring_next = 0;
 	uint64_t peers_tried = 0;      // bit d: direct access to device d has been asked for (hcm_copy_chunks_from)
 	bool ev_upload = false, ev_batch = false, ev_fetch = false, ev_sink = false;
 	hcm_stats stats{};
@@ -563,7 +569,10 @@ void hcm_destroy(hcm_ctx *c) {
 	for (void *p : dev)
 		if (p)
 			cudaFree(p);
-	void *host[] = {c->h_heads, c->h_task_out, c->h_mesh_out, c->h_vtx, c->h_idx, c->h_heads_ring, c->h_task_stage};
+	void *host[] = {c->h_heads, c->h_task_out, c->h_mesh_out, c->h_vtx, c->h_idx, c->h_heads_ring, c->h_task_stage, c->h_task_ring[0], c->h_task_ring[1]};
+	for (auto &e : c->task_ring_ev)
+		if (e)
+			cudaEventDestroy(e);
 	for (void *p : host)
 		if (p)
 			cudaFreeHost(p);
@@ -714,6 +723,10 @@ int hcm_create(const hcm_registry *registry, const hcm_config *cfg, hcm_ctx **ou
 	CUB(dev_alloc(c, &c->d_heads, 1));
 	CUB(dev_alloc(c, &c->d_task_out, c->max_tasks));
 	CUB(cudaHostAlloc((void **)&c->h_heads, sizeof(BatchHeads), cudaHostAllocDefault));
+	for (int i = 0; i < 2; ++i) {
+		CUB(cudaHostAlloc((void **)&c->h_task_ring[i], (size_t)c->max_tasks * sizeof(TaskIn), cudaHostAllocDefault));
+		CUB(cudaEventCreateWithFlags(&c->task_ring_ev[i], cudaEventDisableTiming));
+	}
 	const uint64_t v0 = cfg->vertex_capacity ? cfg->vertex_capacity : std::max<uint64_t>(4ull << 20, (uint64_t)c->max_tasks * 512);
 	if (int rc = alloc_arenas(c, v0, 2 * c->max_tasks + 64))
 		return bail(rc);
@@ -1406,8 +1419,16 @@ static int submit(hcm_ctx *c, uint32_t n, const int16_t *pos, int force_all) {
 	c->batch_n = n;
 	c->batch_pending = true, c->batch_done = false, c->counts_valid = false;
 	c->force_all = force_all;
-	if (n)
-		CU(cudaMemcpyAsync(c->d_tasks, c->tasks.data(), n * sizeof(TaskIn), cudaMemcpyHostToDevice, c->stream));
+	if (n) {
+		const int b = c->task_ring_next;
+		c->task_ring_next ^= 1;
+		if (c->task_ring_used[b])
+			CU(cudaEventSynchronize(c->task_ring_ev[b])); // the copy of two batches ago has left this buffer
+		memcpy(c->h_task_ring[b], c->tasks.data(), (size_t)n * sizeof(TaskIn));
+		CU(cudaMemcpyAsync(c->d_tasks, c->h_task_ring[b], (size_t)n * sizeof(TaskIn), cudaMemcpyHostToDevice, c->stream));
+		CU(cudaEventRecord(c->task_ring_ev[b], c->stream));
+		c->task_ring_used[b] = true;
+	}
 	c->stats.h2d_bytes += (uint64_t)n * sizeof(TaskIn);
 	return launch_batch(c);
 }
