@@ -45,6 +45,53 @@ H_BYTES = 34 ** 3 * 3  # blocks (2 B) + light (1 B) on [-1,32]^3: SURVEY.md sect
 DERIVE_READ, DERIVE_WRITE_FIXED, DERIVE_WRITE_PER_LEVEL = 65536 + 1024, 32768 + 4096 + 1024, 4096
 
 
+class Watchdog:
+    """A bench line must come out even if an optional block (device sink, hinted upload, config 4, secondary configs) hangs or a rank
+    dies inside a collective: every stage arms a deadline; when one passes, rank 0 prints the line from what is complete (`line_fn`,
+    set once the headline numbers exist) with the stage named under "watchdog", and every rank leaves.  Without a headline the exit
+    code is 3 -- a failed run, not a hung box."""
+
+    def __init__(self, rank: int):
+        self.rank, self.stage, self.deadline, self.line_fn, self.lock, self.printed = rank, "start", None, None, threading.Lock(), False
+        threading.Thread(target=self._run, daemon=True).start()
+
+    def arm(self, stage: str, seconds: float):
+        self.stage, self.deadline = stage, time.time() + seconds
+
+    def emit(self, line: dict):
+        with self.lock:
+            if not self.printed:
+                self.printed = True
+                print(json.dumps(line), flush=True)
+
+    def _run(self):
+        while True:
+            time.sleep(1.0)
+            if self.deadline is not None and time.time() > self.deadline:
+                msg = f"stage '{self.stage}' exceeded its time budget; the line holds what was complete"
+                sys.stderr.write(f"bench.py[rank {self.rank}]: watchdog: {msg}\n")
+                sys.stderr.flush()
+                if self.line_fn is not None:
+                    if self.rank == 0:
+                        try:
+                            self.emit({**self.line_fn(), "watchdog": msg})
+                        except Exception as e:  # never hang in the handler
+                            sys.stderr.write(f"bench.py: watchdog could not build the line: {e}\n")
+                            os._exit(3)
+                    os._exit(0)
+                os._exit(3)
+
+
+def guarded(what: str, fn, *a, **kw):
+    """Optional blocks never take the headline down: an exception becomes {"error": ...}."""
+    try:
+        return fn(*a, **kw)
+    except BaseException as e:  # noqa: BLE001 -- incl. SystemExit from a failed native call wrapper
+        if isinstance(e, KeyboardInterrupt):
+            raise
+        return {"error": f"{what}: {type(e).__name__}: {e}"[:600]}
+
+
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -366,10 +413,11 @@ class Dist:
             self.dist.destroy_process_group()
 
 
-def measure(D: Dist, local: int, meshed, resident, pb, ph, origin, extent, steps: int, warmup: int, arm, cpu_threads: int, check: bool) -> dict:
+def measure(D: Dist, local: int, meshed, resident, pb, ph, origin, extent, steps: int, warmup: int, arm, cpu_threads: int, check: bool,
+            on_core=None) -> dict:
     """One workload on this rank's GPU: `steps` device-timed steps with the inputs resident in HBM, `steps` end-to-end steps from
     pinned host buffers, then the parity gate over every chunk of the last end-to-end result.  Times are max over ranks, counts are
-    sums over ranks."""
+    sums over ranks.  `on_core(out)` is called once those numbers exist, before the optional end-to-end variants run."""
     from hypercraft_b200 import mesher as M
 
     m = M.Mesher(origin=origin, extent=extent, device=local, max_chunks=len(resident), max_tasks=len(meshed))
@@ -405,6 +453,7 @@ def measure(D: Dist, local: int, meshed, resident, pb, ph, origin, extent, steps
     warm = {"derive": float(np.mean(derive_ms)), "classify": float(np.mean(classify_ms)), "mesh": float(np.mean(mesh_ms))}
     mesh_ms, derive_ms, classify_ms = [s["mesh_ms"]], [s["derive_ms"]], [s["classify_ms"]]
     launches = s["kernel_launches"] - launches0
+    variants = m.tune_info()  # the A/B rounds ran in the warm-up steps; the timed steps used what they selected
     ms_per_step = D.reduce([elapsed_ms], "max")[0] / steps
     tot_chunks, tot_quads, tot_launches, tot_worked = D.reduce([len(meshed), counts["n_vertices"] // 4, launches, counts["n_worked"]])
 
@@ -434,17 +483,32 @@ def measure(D: Dist, local: int, meshed, resident, pb, ph, origin, extent, steps
            "e2e_ms_per_step": e2e_ms_step, "e2e_value": tot_chunks / (e2e_ms_step / 1e3), "e2e_serial_ms": e2e_serial_ms,
            "e2e_ms_per_rank": D.gather(e2e_local), "worked_per_rank": D.gather(counts["n_worked"]), "tasks_per_rank": D.gather(len(meshed)),
            "h2d_step": (s["h2d_bytes"] - h2d0) // steps, "d2h_step": (s["d2h_bytes"] - d2h0) // steps, "device_bytes": s["device_bytes"],
-           "unscanned_last_upload": unscanned, "device_sink": None, "hinted": None, "parity": None, "cpu_stats": None}
+           "unscanned_last_upload": unscanned, "device_sink": None, "hinted": None, "parity": None, "cpu_stats": None, "variants": variants}
     if check:
         parity, st = compare_all_chunks(res, arm, meshed, cpu_threads)
         bad = D.reduce([parity["chunks_meshed"], parity["byte_compared_chunks"], parity["count_mismatches"], parity["byte_mismatches"]])
         parity.update(chunks_meshed=int(bad[0]), byte_compared_chunks=int(bad[1]), count_mismatches=int(bad[2]), byte_mismatches=int(bad[3]),
                       ranks=D.world)
         out["parity"], out["cpu_stats"] = parity, st
-    # further end-to-end variants (they run new batches: `res` above is no longer valid from here on)
-    out["device_sink"] = device_sink_steps(D, m, local, meshed, resident, pb, ph, steps)
-    out["hinted"] = hinted_steps(D, m, meshed, resident, pb, ph, steps)
-    m.close()
+    if on_core is not None:
+        on_core(out)
+    # further end-to-end variants (they run new batches: `res` above is no longer valid from here on).  No collective inside them: a
+    # rank that fails in one must not leave the others waiting; their local times are combined afterwards, in one reduction.
+    sink = guarded("device sink", device_sink_steps, D, m, local, meshed, resident, pb, ph, steps)
+    hinted = guarded("hinted upload", hinted_steps, D, m, meshed, resident, pb, ph, steps)
+    fixed = guarded("fixed upload", fixed_upload_steps, D, m, meshed, resident, pb, ph, steps)
+    legs = [sink, hinted, fixed]
+    red = D.reduce([leg.get("local_ms", 0.0) if "error" not in leg else 0.0 for leg in legs], "max")
+    bad = D.reduce([1.0 if "error" in leg else 0.0 for leg in legs])
+    for leg, ms_, nbad in zip(legs, red, bad):
+        if "error" not in leg:
+            leg.pop("local_ms", None)
+            if nbad:
+                leg["error"] = f"failed on {int(nbad)} other rank(s)"
+            else:
+                leg["ms_per_step"], leg["value"], leg["unit"] = ms_, tot_chunks / (ms_ / 1e3), "chunks/s"
+    out["device_sink"], out["hinted"], out["fixed_upload"] = sink, hinted, fixed
+    guarded("close", m.close)
     return out
 
 
@@ -482,7 +546,7 @@ def device_sink_steps(D: Dist, m, local: int, meshed, resident, pb, ph, steps: i
 
     m.emit_into(place(cnt.meshes), vptr, nv, iptr, ni)
     d2h0, h2d0 = m.stats()["d2h_bytes"], m.stats()["h2d_bytes"]
-    D.barrier()
+    D.sync()
     t0 = time.perf_counter()
     sink_ms = []
     for _ in range(steps):
@@ -494,7 +558,6 @@ def device_sink_steps(D: Dist, m, local: int, meshed, resident, pb, ph, steps: i
         sink_ms.append(m.stats()["sink_ms"])
     D.sync()
     local_ms = (time.perf_counter() - t0) * 1e3 / steps
-    ms = D.reduce([local_ms], "max")[0]
     s = m.stats()
     # the device buffers hold what the host path returns for the same batch
     host = m.fetch()
@@ -505,9 +568,8 @@ def device_sink_steps(D: Dist, m, local: int, meshed, resident, pb, ph, steps: i
         vo, io = int(pl[k]["vertex_offset"]), int(pl[k]["index_offset"])
         ok = ok and bool((vb[vo:vo + int(d["vertex_count"])] == host.vertices[int(d["vertex_offset"]):int(d["vertex_offset"]) + int(d["vertex_count"])]).all())
         ok = ok and bool((ib[io:io + int(d["index_count"])] == host.indices[int(d["index_offset"]):int(d["index_offset"]) + int(d["index_count"])]).all())
-    total = D.reduce([len(meshed)])[0]
     del vkeep, ikeep
-    return {"value": total / (ms / 1e3), "unit": "chunks/s", "ms_per_step": ms, "h2d_bytes_per_step": int((s["h2d_bytes"] - h2d0) // steps),
+    return {"local_ms": local_ms, "h2d_bytes_per_step": int((s["h2d_bytes"] - h2d0) // steps),
             "d2h_bytes_per_step": int((s["d2h_bytes"] - d2h0) // steps), "d2h_vertex_index_bytes_per_step": 0, "scatter_kernel_ms": float(np.mean(sink_ms)),
             "device_vertex_bytes": int(nv * 8), "device_index_bytes": int(ni * 2), "meshes_placed": int(len(pl)), "device_bytes_equal_host_path": bool(ok),
             "call": "hcm_upload_chunks + hcm_mesh_batch + hcm_mesh_counts + host range allocation + hcm_mesh_emit_into (unpipelined)"}
@@ -526,16 +588,31 @@ def hinted_steps(D: Dist, m, meshed, resident, pb, ph, steps: int) -> dict:
     hint = np.where(uniform, b[:, 0].astype(np.int32), -2).astype(np.int32)  # HCM_HINT_NOT_UNIFORM for the rest
     m.upload(resident, pb.array, ph.array, uniform_hint=hint)
     m.mesh(meshed)
-    D.barrier()
+    D.sync()
     t0 = time.perf_counter()
     for _ in range(steps):
         m.upload(resident, pb.array, ph.array, uniform_hint=hint)
         res = m.mesh(meshed)
     D.sync()
-    ms = D.reduce([(time.perf_counter() - t0) * 1e3 / steps], "max")[0]
-    total = D.reduce([len(meshed)])[0]
-    return {"value": total / (ms / 1e3), "unit": "chunks/s", "ms_per_step": ms, "uniform_chunks_hinted": int(uniform.sum()), "vertices": int(len(res.vertices)),
+    return {"local_ms": (time.perf_counter() - t0) * 1e3 / steps, "uniform_chunks_hinted": int(uniform.sum()), "vertices": int(len(res.vertices)),
             "call": "hcm_upload_chunks_hinted + hcm_mesh_batch + hcm_mesh_fetch (unpipelined); compare with e2e.unpipelined_ms_per_step"}
+
+
+def fixed_upload_steps(D: Dist, m, meshed, resident, pb, ph, steps: int) -> dict:
+    """A/B of the upload balance, for information: the same hcm_upload_and_mesh steps as `e2e` with the round-1 upload (every chunk waits
+    for its scan, HCM_UPLOAD_ADAPTIVE=0 behaviour) selected through hcm_set_option.  `e2e` stays the library's default mode."""
+    m.set_option("upload_adaptive", 0)
+    try:
+        m.upload_and_mesh(resident, pb.array, ph.array, meshed)
+        D.sync()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            m.upload_and_mesh(resident, pb.array, ph.array, meshed)
+        D.sync()
+        ms = (time.perf_counter() - t0) * 1e3 / steps
+    finally:
+        m.set_option("upload_adaptive", 1)
+    return {"local_ms": ms, "call": "hcm_upload_and_mesh with every chunk scanned by the host first (round-1 upload mode)"}
 
 
 def config4_block(D: Dist, args, rank: int, world: int, local: int, threads: int) -> dict:
@@ -681,10 +758,13 @@ def main():
     check = not args.no_cpu_baseline
     sampler = ClockSampler(local)
     sampler.start()
+    wd = Watchdog(rank)
 
     if args.strong:  # config 4 as the headline
         args.config4_radius = radius
+        wd.arm("config4 as the headline", 2400)
         c4 = config4_block(D, args, rank, world, local, threads)
+        wd.deadline = None
         clocks = sampler.stop()
         if rank == 0:
             print(json.dumps({"metric": "chunks meshed/sec", "value": c4["value"], "unit": "chunks/s", "n_gpus": world, "steps": args.steps,
@@ -697,6 +777,7 @@ def main():
 
     centre = (3 * radius * rank, 0, 0)
     t_setup = time.time()
+    wd.arm("set-up (terrain generation)", 900)
     meshed, resident = worldgen.load_radius_positions(radius)
     c = np.asarray(centre, dtype=np.int16)
     meshed, resident = (meshed + c).astype(np.int16), (resident + c).astype(np.int16)
@@ -706,42 +787,25 @@ def main():
     ext = 2 * radius + 3
     origin, extent = (centre[0] - radius - 1, -radius - 1, -radius - 1), (ext, ext, ext)
     setup_s = time.time() - t_setup
-    r = measure(D, local, meshed, resident, pb, ph, origin, extent, args.steps, args.warmup, arm, threads, check)
-    clocks = sampler.stop()  # sampled from the first warm-up step to the last end-to-end step
-    pb.free(), ph.free()
 
-    cpu_baseline = None
-    if rank == 0 and world == 1 and check:  # the CPU baseline is reported at N = 1 only; the same call was the parity gate's checker
-        st = r["cpu_stats"]
-        cpu_baseline = {"value": st["chunks"] / st["seconds"], "unit": "chunks/s", "cores": threads, "kind": getattr(arm, "kind", "reference"),
-                        "quads_per_s": st["vertices"] / 4 / st["seconds"], "cpu_model": cpu_model(),
-                        "sample": f"{len(meshed)} of {len(meshed)} chunks (the whole r={radius} task list, {st['seconds']:.1f} s), "
-                                  + getattr(arm, "what", "unmodified ChunkTaskRunner<kMesh>::Run, one runner per thread")}
-        cpu_baseline["reference_pool_threads"] = pool_baseline(arm, meshed[:: max(1, len(meshed) // 8192)], threads)
-    del arm
-
-    config4 = None
-    if world > 1 and args.config4_radius > 0:
-        config4 = config4_block(D, args, rank, world, local, threads)
-    secondary = None
-    if world == 1 and rank == 0 and not args.no_secondary and check:
-        secondary = secondary_configs(local, threads)
-
-    D.barrier()  # the last collective: what follows is rank 0's alone
-    sharded_check = sharded_dispatcher_check(emulated) if world > 1 and rank == 0 else None  # after every collective: the other ranks are done
-    if rank == 0:
-        peaks = {}
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak_gbs, peak_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json)") if "hbm_gbs" in peaks else (6650.0, "fallback (B200_PROFILING.md)")
+    traffic = None
+    if radius == 20:  # the committed ncu launch list is of this workload; other radii have no measured traffic figure
         try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_summary.json")))
         except Exception:
             pass
-        peak_gbs, peak_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json)") if "hbm_gbs" in peaks else (6650.0, "fallback (B200_PROFILING.md)")
-        traffic = None
-        if radius == 20:  # the committed ncu launch list is of this workload; other radii have no measured traffic figure
-            try:
-                traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_summary.json")))
-            except Exception:
-                pass
+
+    # everything the line is built from; optional blocks fill their slots as they complete (the watchdog prints what is there)
+    S = {"r": None, "clocks": None, "cpu_baseline": None, "config4": None, "sharded": None, "secondary": None}
+
+    def build_line() -> dict:
+        r = S["r"]
         counts = r["counts"]
         out = {
             "metric": "chunks meshed/sec", "value": r["value"], "unit": "chunks/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -759,23 +823,62 @@ def main():
                     "ms_per_rank": r["e2e_ms_per_rank"], "chunks_sent_unscanned_last_step": r["unscanned_last_upload"],
                     "upload": "scan threads and copy engine share the work items: what the engine takes first crosses the bus unscanned "
                               "(derive_kernel finds uniform chunks on the device as well)"},
-            "e2e_device_sink": r["device_sink"], "e2e_with_generator_hints": r["hinted"],
+            "e2e_device_sink": r.get("device_sink"), "e2e_with_generator_hints": r.get("hinted"), "e2e_round1_upload_mode": r.get("fixed_upload"),
             "gpu_launches": int(r["total_launches"]),
-            "kernel_ms": r["kernel_ms"],
+            "kernel_ms": r["kernel_ms"], "kernel_variants": r.get("variants"),
             "roofline": roofline_block(len(meshed), int(counts["n_worked"]), len(resident), int(counts["n_vertices"]), int(counts["n_meshes"]),
                                        r["kernel_ms"], r["ms_per_step"], peak_gbs, peak_src, traffic),
-            "cpu_baseline": cpu_baseline, "parity": r["parity"], "clocks": clocks,
+            "cpu_baseline": S["cpu_baseline"], "parity": r["parity"], "clocks": S["clocks"],
         }
-        if config4 is not None:
-            out["config4"] = config4
-        if sharded_check is not None:
-            out["sharded_dispatcher"] = sharded_check
-        if secondary is not None:
-            out["secondary_configs"] = secondary
+        if S["config4"] is not None:
+            out["config4"] = S["config4"]
+        if S["sharded"] is not None:
+            out["sharded_dispatcher"] = S["sharded"]
+        if S["secondary"] is not None:
+            out["secondary_configs"] = S["secondary"]
         if emulated:
             out = {"emulated": True, "note": "DRY RUN on the CPU emulation build (tests/cusim): exercises bench.py's logic, measures nothing", **out}
-        print(json.dumps(out))
-    D.close()
+        return out
+
+    def core_done(core: dict):
+        # headline numbers (value, e2e, parity) exist: from here on a line is printed whatever happens to the optional blocks
+        S["r"] = core
+        S["clocks"] = sampler.stop()  # sampled from the first warm-up step to the last end-to-end step
+        if rank == 0 and world == 1 and check and core["cpu_stats"]:  # the CPU baseline is reported at N = 1 only; the same call was the parity gate's checker
+            st = core["cpu_stats"]
+            S["cpu_baseline"] = {"value": st["chunks"] / st["seconds"], "unit": "chunks/s", "cores": threads, "kind": getattr(arm, "kind", "reference"),
+                                 "quads_per_s": st["vertices"] / 4 / st["seconds"], "cpu_model": cpu_model(),
+                                 "sample": f"{len(meshed)} of {len(meshed)} chunks (the whole r={radius} task list, {st['seconds']:.1f} s), "
+                                           + getattr(arm, "what", "unmodified ChunkTaskRunner<kMesh>::Run, one runner per thread")}
+        wd.line_fn = build_line
+        wd.arm("optional end-to-end variants (device sink, hinted upload, round-1 upload mode)", 420)
+
+    wd.arm("headline measurement (device-timed steps, end-to-end steps, parity gate)", 1200)
+    r = measure(D, local, meshed, resident, pb, ph, origin, extent, args.steps, args.warmup, arm, threads, check, on_core=core_done)
+    S["r"] = r
+    pb.free(), ph.free()
+
+    if S["cpu_baseline"] is not None:
+        wd.arm("cpu_baseline at the reference client's worker count", 300)
+        S["cpu_baseline"]["reference_pool_threads"] = guarded("pool baseline", pool_baseline, arm, meshed[:: max(1, len(meshed) // 8192)], threads)
+    del arm
+
+    if world > 1 and args.config4_radius > 0:
+        wd.arm("config4 (one r = %d sphere in x-slabs)" % args.config4_radius, 1200)
+        S["config4"] = config4_block(D, args, rank, world, local, threads)
+    if world == 1 and rank == 0 and not args.no_secondary and check:
+        wd.arm("secondary_configs (configs 3 and 5)", 600)
+        S["secondary"] = secondary_configs(local, threads)
+
+    wd.arm("last barrier", 300)
+    D.barrier()  # the last collective: what follows is rank 0's alone
+    if world > 1 and rank == 0:  # after every collective: the other ranks are done
+        wd.arm("sharded dispatcher check", 700)
+        S["sharded"] = sharded_dispatcher_check(emulated)
+    wd.deadline = None
+    if rank == 0:
+        wd.emit(build_line())
+    guarded("close", D.close)
 
 
 if __name__ == "__main__":

@@ -7,6 +7,7 @@
 #include <mutex>
 #include <thread>
 #include <cstdarg>
+#include <cstddef>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -22,7 +23,12 @@
 
 namespace hcm {
 void launch_derive(const DevWorld &w, const UploadEntry *entries, uint32_t n, const uint8_t *prop_index, const DevTables *tables,
-                   const int8_t *raw_heights, cudaStream_t st);
+                   const int8_t *raw_heights, int variant, cudaStream_t st);
+void launch_derive_digest(const DevWorld &w, const UploadEntry *entries, uint32_t n, const int8_t *raw_heights, const unsigned long long *expect,
+                          unsigned long long *out, uint32_t *mismatches, cudaStream_t st);
+void launch_mesh_digest(const hcm_task_result *task_out, const hcm_mesh_desc *meshes, const unsigned long long *vtx, const uint16_t *idx, uint32_t n,
+                        uint32_t mesh_cap, unsigned long long vtx_cap, unsigned long long idx_cap, const unsigned long long *expect, unsigned long long *out,
+                        uint32_t *mismatches, cudaStream_t st);
 void launch_clear(const DevWorld &w, const UploadEntry *entries, uint32_t n, cudaStream_t st);
 void launch_flood_slots(uint4 *out, cudaStream_t st);
 void launch_edit(const DevWorld &w, const hcm_block_edit *edits, uint32_t n, const uint2 *columns, uint32_t n_columns, uint32_t *result, const uint8_t *prop_index,
@@ -31,7 +37,7 @@ void launch_classify(const DevWorld &w, const TaskIn *tasks, uint32_t n, uint32_
                      cudaStream_t st);
 cudaError_t mesh_kernel_prepare();
 int mesh_kernel_smem_bytes();
-void launch_mesh(const MeshMaps &maps, const MeshParams &p, int grid, cudaStream_t st);
+void launch_mesh(const MeshMaps &maps, const MeshParams &p, int grid, int variant, cudaStream_t st);
 void launch_scatter(const hcm_mesh_placement *placements, uint32_t n, const hcm_mesh_desc *meshes, const unsigned long long *vtx, const uint16_t *idx, void *vdst,
                     void *idst, int grid, cudaStream_t st);
 } // namespace hcm
@@ -100,7 +106,28 @@ struct BlockLayout {
 	uint32_t hi(uint32_t b) const { return std::min(n, first + b * size); }
 };
 
+// Qualification of a kernel variant on the device (hcm.h, "Kernel variants")
+struct KernelTune {
+	int forced = -1; // 0 | 1: environment / hcm_set_option; -1: the A/B rounds decide
+	uint32_t selected = 0, state = HCM_TUNE_PENDING, rounds = 0, mismatches = 0;
+	float best_base = 0.f, best_var = 0.f;
+	bool in_flight = false; // an A/B round is in the stream; its verdict is read at the next host synchronisation
+	bool invalid = false;   // ... and must be discarded (the batch overflowed its arenas)
+};
+struct TuneHost { // pinned
+	uint32_t mismatch[2]; // derive, mesh
+	BatchHeads heads_variant, heads_base; // allocation heads after each form's run of a mesh round (an overflowed run proves nothing)
+};
+
 struct hcm_ctx {
+	bool tune = true; // env HCM_TUNE
+	bool tune_fault = false; // test knob: corrupt the variant's hash of unit 0 before the comparison (the rejection path)
+	uint32_t tune_min_chunks = 2048, tune_min_tasks = 2048, tune_rounds = 2;
+	KernelTune tune_derive, tune_mesh;
+	unsigned long long *d_digest[2] = {nullptr, nullptr}; // per chunk / per task hashes of the two forms' output
+	uint32_t *d_tune_mismatch = nullptr;                   // [2]
+	TuneHost *h_tune = nullptr;
+	bool batch_ab = false; // the last mesh batch was an A/B round (which events bracket its classify kernel)
 	BlockLayout layout{0, 1, 1}; // of the upload in progress (hcm_upload_and_mesh buckets its tasks by stage)
 	int device = 0;
 	cudaStream_t stream = nullptr;
@@ -182,7 +209,7 @@ struct hcm_ctx {
 	bool batch_pending = false, batch_done = false;
 	int force_all = 0;
 
-	cudaEvent_t ev[10]{};
+	cudaEvent_t ev[20]{};
 	cudaEvent_t ev_peer = nullptr; // orders hcm_copy_chunks_from between two contexts' streams
 	// task lists go up from two pinned buffers in turn, so that hcm_mesh_batch never waits for the stream (a pageable source makes
 	// cudaMemcpyAsync wait for the previous batch's kernels) and batches can be enqueued back to back
@@ -198,8 +225,14 @@ struct hcm_ctx {
 
 namespace {
 
-enum { EV_UP0, EV_UP1, EV_UP2, EV_B0, EV_B1, EV_B2, EV_F0, EV_F1, EV_S0, EV_S1, EV_COUNT };
-static_assert(EV_COUNT <= 10, "hcm_ctx::ev");
+enum { EV_UP0, EV_UP1, EV_UP2, EV_B0, EV_B1, EV_B2, EV_F0, EV_F1, EV_S0, EV_S1,
+       EV_TD0, EV_TD1, // the variant's run of a derive A/B round (the baseline's run is bracketed by the round's own two events)
+       EV_TD2, EV_TD3,
+       EV_TM0, EV_TM1, // the variant's run of a mesh A/B round: TM0 also ends the classify kernel there; the baseline's run is EV_B1 .. EV_B2
+       EV_TB0, EV_TB1,         // ... and the baseline's run of that round (EV_B1 / EV_B2 may be re-recorded by a later batch before the verdict is read)
+       EV_TD_DONE, EV_TM_DONE, // the round's verdict has reached the pinned TuneHost
+       EV_COUNT };
+static_assert(EV_COUNT <= 20, "hcm_ctx::ev");
 
 int fail(hcm_ctx *c, int status, const char *fmt, ...) {
 	char buf[512];
@@ -468,16 +501,138 @@ template <typename T> int host_reserve_keep(hcm_ctx *c, T **p, uint64_t *cap, ui
 	return HCM_OK;
 }
 
+// ---- kernel variants: A/B rounds on the device (hcm.h, "Kernel variants") -------------------------------------------------
+void tune_decide(KernelTune &t, float base_ms, float var_ms, uint32_t mismatches, uint32_t want_rounds) {
+	t.in_flight = false;
+	if (t.invalid || t.forced >= 0 || t.state != HCM_TUNE_PENDING)
+		return;
+	t.best_base = t.rounds ? std::min(t.best_base, base_ms) : base_ms;
+	t.best_var = t.rounds ? std::min(t.best_var, var_ms) : var_ms;
+	++t.rounds, t.mismatches += mismatches;
+	if (mismatches)
+		t.state = HCM_TUNE_VARIANT_REJECTED, t.selected = 0; // once is enough: this device does not reproduce the baseline's bytes with it
+	else if (t.rounds >= want_rounds) {
+		const bool faster = t.best_var < 0.98f * t.best_base;
+		t.state = faster ? HCM_TUNE_VARIANT_ADOPTED : HCM_TUNE_BASELINE_KEPT, t.selected = faster ? 1u : 0u;
+	}
+}
+
+// read the verdict of every round that has completed (never waits)
+int tune_harvest(hcm_ctx *c) {
+	for (int k = 0; k < 2; ++k) {
+		KernelTune &t = k == 0 ? c->tune_derive : c->tune_mesh;
+		if (!t.in_flight)
+			continue;
+		const cudaError_t q = cudaEventQuery(c->ev[k == 0 ? EV_TD_DONE : EV_TM_DONE]);
+		if (q == cudaErrorNotReady) {
+			(void)cudaGetLastError(); // an answer, not an error
+			continue;
+		}
+		CU(q);
+		float base = 0.f, var = 0.f;
+		if (k == 0) {
+			CU(cudaEventElapsedTime(&var, c->ev[EV_TD0], c->ev[EV_TD1]));
+			CU(cudaEventElapsedTime(&base, c->ev[EV_TD2], c->ev[EV_TD3]));
+		} else {
+			CU(cudaEventElapsedTime(&var, c->ev[EV_TM0], c->ev[EV_TM1]));
+			CU(cudaEventElapsedTime(&base, c->ev[EV_TB0], c->ev[EV_TB1]));
+			if (c->h_tune->heads_variant.overflow || c->h_tune->heads_base.overflow)
+				t.invalid = true;
+		}
+		tune_decide(t, base, var, c->h_tune->mismatch[k], c->tune_rounds);
+	}
+	return HCM_OK;
+}
+
+bool tune_wants_round(const hcm_ctx *c, const KernelTune &t, uint32_t units, uint32_t min_units) {
+	return c->tune && t.forced < 0 && t.state == HCM_TUNE_PENDING && !t.in_flight && units >= min_units;
+}
+
+// derive_kernel over `n` entries on `st`.  rec_begin / rec_end: EV_UP1 right before / EV_UP2 right after the launch hcm_stats reports.
+int derive_launch(hcm_ctx *c, const UploadEntry *entries, uint32_t n, cudaStream_t st, bool rec_begin, bool rec_end) {
+	KernelTune &t = c->tune_derive;
+	if (t.in_flight)
+		if (int rc = tune_harvest(c))
+			return rc;
+	if (n && tune_wants_round(c, t, n, c->tune_min_chunks)) {
+		// A/B round: the variant first, the baseline last -- whatever the verdict, the world holds the baseline's bytes
+		CU(cudaMemsetAsync(c->d_tune_mismatch, 0, sizeof(uint32_t), st));
+		CU(cudaEventRecord(c->ev[EV_TD0], st));
+		launch_derive(c->w, entries, n, c->d_prop_index, c->d_tables, c->d_rawh, 1, st);
+		CU(cudaEventRecord(c->ev[EV_TD1], st));
+		launch_derive_digest(c->w, entries, n, c->d_rawh, nullptr, c->d_digest[0], c->d_tune_mismatch, st);
+		if (c->tune_fault)
+			CU(cudaMemsetAsync(c->d_digest[0], 0xa5, sizeof(unsigned long long), st));
+		if (rec_begin)
+			CU(cudaEventRecord(c->ev[EV_UP1], st));
+		CU(cudaEventRecord(c->ev[EV_TD2], st));
+		launch_derive(c->w, entries, n, c->d_prop_index, c->d_tables, c->d_rawh, 0, st);
+		CU(cudaEventRecord(c->ev[EV_TD3], st));
+		if (rec_end)
+			CU(cudaEventRecord(c->ev[EV_UP2], st));
+		launch_derive_digest(c->w, entries, n, c->d_rawh, c->d_digest[0], c->d_digest[1], c->d_tune_mismatch, st);
+		CU(cudaGetLastError());
+		CU(cudaMemcpyAsync(&c->h_tune->mismatch[0], c->d_tune_mismatch, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+		CU(cudaEventRecord(c->ev[EV_TD_DONE], st));
+		t.in_flight = true, t.invalid = false;
+		c->stats.kernel_launches += 4;
+		return HCM_OK;
+	}
+	if (rec_begin)
+		CU(cudaEventRecord(c->ev[EV_UP1], st));
+	launch_derive(c->w, entries, n, c->d_prop_index, c->d_tables, c->d_rawh, (int)t.selected, st);
+	CU(cudaGetLastError());
+	if (rec_end)
+		CU(cudaEventRecord(c->ev[EV_UP2], st));
+	c->stats.kernel_launches += 1;
+	return HCM_OK;
+}
+
 int launch_batch(hcm_ctx *c) {
 	cudaStream_t st = c->stream;
+	KernelTune &t = c->tune_mesh;
+	if (t.in_flight)
+		if (int rc = tune_harvest(c))
+			return rc;
 	CU(cudaEventRecord(c->ev[EV_B0], st));
 	CU(cudaMemsetAsync(c->d_heads, 0, sizeof(BatchHeads), st));
 	launch_classify(c->w, c->d_tasks, c->batch_n, c->d_worklist, c->d_heads, c->d_task_out, c->force_all, st);
+	c->batch_ab = !c->force_all && !c->d_debug_light && tune_wants_round(c, t, c->batch_n, c->tune_min_tasks);
+	if (c->batch_ab) {
+		// A/B round over the same work list: the variant first; then the allocation heads and the cursor start over (the work list and
+		// its count stay) and the baseline writes the batch's result
+		static_assert(offsetof(BatchHeads, n_work) == 24 && offsetof(BatchHeads, cursor) == 28, "BatchHeads layout");
+		CU(cudaMemsetAsync(c->d_tune_mismatch + 1, 0, sizeof(uint32_t), st));
+		CU(cudaEventRecord(c->ev[EV_TM0], st));
+		launch_mesh(c->maps, mesh_params(c, 0), c->grid, 1, st);
+		CU(cudaEventRecord(c->ev[EV_TM1], st));
+		launch_mesh_digest(c->d_task_out, c->d_mesh_out, reinterpret_cast<const unsigned long long *>(c->d_vtx), c->d_idx, c->batch_n, c->mesh_cap, c->vtx_cap,
+		                   c->idx_cap, nullptr, c->d_digest[0], c->d_tune_mismatch + 1, st);
+		if (c->tune_fault)
+			CU(cudaMemsetAsync(c->d_digest[0], 0xa5, sizeof(unsigned long long), st));
+		CU(cudaMemcpyAsync(&c->h_tune->heads_variant, c->d_heads, sizeof(BatchHeads), cudaMemcpyDeviceToHost, st));
+		CU(cudaMemsetAsync(c->d_heads, 0, offsetof(BatchHeads, n_work), st));
+		CU(cudaMemsetAsync(&c->d_heads->cursor, 0, sizeof(unsigned int), st));
+	}
 	CU(cudaEventRecord(c->ev[EV_B1], st));
-	launch_mesh(c->maps, mesh_params(c, 0), c->grid, st);
+	if (c->batch_ab)
+		CU(cudaEventRecord(c->ev[EV_TB0], st));
+	launch_mesh(c->maps, mesh_params(c, 0), c->grid, c->batch_ab ? 0 : (int)t.selected, st);
 	CU(cudaGetLastError());
 	CU(cudaEventRecord(c->ev[EV_B2], st));
+	if (c->batch_ab)
+		CU(cudaEventRecord(c->ev[EV_TB1], st));
 	c->stats.kernel_launches += 2;
+	if (c->batch_ab) {
+		launch_mesh_digest(c->d_task_out, c->d_mesh_out, reinterpret_cast<const unsigned long long *>(c->d_vtx), c->d_idx, c->batch_n, c->mesh_cap, c->vtx_cap,
+		                   c->idx_cap, c->d_digest[0], c->d_digest[1], c->d_tune_mismatch + 1, st);
+		CU(cudaGetLastError());
+		CU(cudaMemcpyAsync(&c->h_tune->heads_base, c->d_heads, sizeof(BatchHeads), cudaMemcpyDeviceToHost, st));
+		CU(cudaMemcpyAsync(&c->h_tune->mismatch[1], c->d_tune_mismatch + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+		CU(cudaEventRecord(c->ev[EV_TM_DONE], st));
+		t.in_flight = true, t.invalid = false;
+		c->stats.kernel_launches += 3;
+	}
 	c->ev_batch = true;
 	return HCM_OK;
 }
@@ -492,6 +647,8 @@ int wait_batch(hcm_ctx *c) {
 		CU(cudaStreamSynchronize(c->stream));
 		CU(cudaMemcpy(c->h_heads, c->d_heads, sizeof(BatchHeads), cudaMemcpyDeviceToHost));
 		c->stats.d2h_bytes += sizeof(BatchHeads);
+		if (int rc = tune_harvest(c)) // the stream is idle: every round in it has a verdict (an overflowed one is discarded)
+			return rc;
 		if (!c->h_heads->overflow) {
 			c->batch_pending = false, c->batch_done = true;
 			return HCM_OK;
@@ -565,11 +722,11 @@ void hcm_destroy(hcm_ctx *c) {
 	if (c->stream)
 		cudaStreamSynchronize(c->stream);
 	void *dev[] = {c->w.prop8, c->w.pass, c->w.torch, c->w.height, c->w.cflags, c->w.slot, c->d_tables, c->d_prop_index, c->d_meshes, c->d_mesh_info, c->d_raw,
-	               c->d_rawh, c->d_entries, c->d_all_entries, c->d_tasks, c->d_worklist, c->d_heads, c->d_task_out, c->d_mesh_out, c->d_vtx, c->d_idx, c->d_dyn, c->d_flood_slots, c->d_debug_light, c->d_edits, c->d_edit_columns, c->d_edit_result, c->d_sun_changes, c->d_placements};
+	               c->d_rawh, c->d_entries, c->d_all_entries, c->d_tasks, c->d_worklist, c->d_heads, c->d_task_out, c->d_mesh_out, c->d_vtx, c->d_idx, c->d_dyn, c->d_flood_slots, c->d_debug_light, c->d_edits, c->d_edit_columns, c->d_edit_result, c->d_sun_changes, c->d_placements, c->d_digest[0], c->d_digest[1], c->d_tune_mismatch};
 	for (void *p : dev)
 		if (p)
 			cudaFree(p);
-	void *host[] = {c->h_heads, c->h_task_out, c->h_mesh_out, c->h_vtx, c->h_idx, c->h_heads_ring, c->h_task_stage, c->h_task_ring[0], c->h_task_ring[1]};
+	void *host[] = {c->h_heads, c->h_task_out, c->h_mesh_out, c->h_vtx, c->h_idx, c->h_heads_ring, c->h_task_stage, c->h_task_ring[0], c->h_task_ring[1], c->h_tune};
 	for (auto &e : c->task_ring_ev)
 		if (e)
 			cudaEventDestroy(e);
@@ -634,6 +791,16 @@ int hcm_create(const hcm_registry *registry, const hcm_config *cfg, hcm_ctx **ou
 	c->first_block = std::min(c->first_block, c->upload_block);
 	if (const char *ad = getenv("HCM_UPLOAD_ADAPTIVE"))
 		c->adaptive_upload = atoi(ad) != 0;
+	if (const char *tu = getenv("HCM_TUNE"))
+		c->tune = atoi(tu) != 0;
+	if (const char *dv = getenv("HCM_DERIVE_VARIANT"))
+		c->tune_derive.forced = atoi(dv) != 0, c->tune_derive.selected = (uint32_t)c->tune_derive.forced;
+	if (const char *mv = getenv("HCM_MESH_VARIANT"))
+		c->tune_mesh.forced = atoi(mv) != 0, c->tune_mesh.selected = (uint32_t)c->tune_mesh.forced;
+	if (const char *tc = getenv("HCM_TUNE_MIN_CHUNKS"))
+		c->tune_min_chunks = (uint32_t)std::max(1, atoi(tc));
+	if (const char *tt = getenv("HCM_TUNE_MIN_TASKS"))
+		c->tune_min_tasks = (uint32_t)std::max(1, atoi(tt));
 	DevTables tables;
 	std::vector<DevMeshInfo> minfo;
 	if (int rc = build_tables(c, registry, tables, minfo))
@@ -723,6 +890,11 @@ int hcm_create(const hcm_registry *registry, const hcm_config *cfg, hcm_ctx **ou
 	CUB(dev_alloc(c, &c->d_heads, 1));
 	CUB(dev_alloc(c, &c->d_task_out, c->max_tasks));
 	CUB(cudaHostAlloc((void **)&c->h_heads, sizeof(BatchHeads), cudaHostAllocDefault));
+	CUB(cudaHostAlloc((void **)&c->h_tune, sizeof(TuneHost), cudaHostAllocDefault));
+	memset(c->h_tune, 0, sizeof(TuneHost));
+	for (int i = 0; i < 2; ++i)
+		CUB(dev_alloc(c, &c->d_digest[i], (size_t)std::max(c->max_chunks, c->max_tasks)));
+	CUB(dev_alloc(c, &c->d_tune_mismatch, 2));
 	for (int i = 0; i < 2; ++i) {
 		CUB(cudaHostAlloc((void **)&c->h_task_ring[i], (size_t)c->max_tasks * sizeof(TaskIn), cudaHostAllocDefault));
 		CUB(cudaEventCreateWithFlags(&c->task_ring_ev[i], cudaEventDisableTiming));
@@ -999,13 +1171,8 @@ static int upload_impl(hcm_ctx *c, uint32_t n, const int16_t *pos, const uint16_
 		CU(cudaMemcpyAsync(c->d_entries + lo, ent + lo, (size_t)(hi - lo) * sizeof(UploadEntry), cudaMemcpyHostToDevice, cs)); // pageable: staged before return
 		CU(cudaEventRecord(c->block_events[blk], cs));
 		CU(cudaStreamWaitEvent(st, c->block_events[blk], 0));
-		if (blk == 0)
-			CU(cudaEventRecord(c->ev[EV_UP1], st));
-		launch_derive(c->w, c->d_entries + lo, hi - lo, c->d_prop_index, c->d_tables, c->d_rawh, st);
-		CU(cudaGetLastError());
-		c->stats.kernel_launches += 1;
-		if (blk + 1 == n_blocks)
-			CU(cudaEventRecord(c->ev[EV_UP2], st));
+		if (int rc = derive_launch(c, c->d_entries + lo, hi - lo, st, blk == 0, blk + 1 == n_blocks))
+			return rc;
 		if (hooks && hooks->block_enqueued)
 			if (int rc = hooks->block_enqueued(blk, n_blocks))
 				return rc;
@@ -1113,9 +1280,8 @@ int hcm_copy_chunks_from(hcm_ctx *c, hcm_ctx *src, uint32_t n, const int16_t *po
 	}
 	CU(cudaEventRecord(c->ev_peer, st)); // src must not overwrite the slots (a later edit) before they have been read
 	CU(cudaMemcpyAsync(c->d_entries, entries.data(), (size_t)n * sizeof(UploadEntry), cudaMemcpyHostToDevice, st)); // pageable: staged before return
-	launch_derive(c->w, c->d_entries, n, c->d_prop_index, c->d_tables, c->d_rawh, st);
-	CU(cudaGetLastError());
-	c->stats.kernel_launches += 1;
+	if (int rc = derive_launch(c, c->d_entries, n, st, false, false))
+		return rc;
 	c->stats.p2p_bytes += (uint64_t)n * (HCM_CHUNK_VOXELS * 2 + HCM_CHUNK_COLUMNS);
 	c->stats.h2d_bytes += (uint64_t)n * sizeof(UploadEntry);
 	CU(cudaSetDevice(src->device));
@@ -1182,11 +1348,8 @@ int hcm_rederive_chunks(hcm_ctx *c, uint32_t n, const int16_t *pos) {
 		if (!c->n_all_entries)
 			return HCM_OK;
 		CU(cudaEventRecord(c->ev[EV_UP0], st0));
-		CU(cudaEventRecord(c->ev[EV_UP1], st0));
-		launch_derive(c->w, c->d_all_entries, c->n_all_entries, c->d_prop_index, c->d_tables, c->d_rawh, st0);
-		CU(cudaGetLastError());
-		CU(cudaEventRecord(c->ev[EV_UP2], st0));
-		c->stats.kernel_launches += 1;
+		if (int rc = derive_launch(c, c->d_all_entries, c->n_all_entries, st0, true, true))
+			return rc;
 		c->ev_upload = true;
 		return HCM_OK;
 	} else {
@@ -1206,11 +1369,8 @@ int hcm_rederive_chunks(hcm_ctx *c, uint32_t n, const int16_t *pos) {
 	CU(cudaEventRecord(c->ev[EV_UP0], st));
 	CU(cudaMemcpyAsync(c->d_entries, entries.data(), entries.size() * sizeof(UploadEntry), cudaMemcpyHostToDevice, st));
 	c->stats.h2d_bytes += entries.size() * sizeof(UploadEntry);
-	CU(cudaEventRecord(c->ev[EV_UP1], st));
-	launch_derive(c->w, c->d_entries, (uint32_t)entries.size(), c->d_prop_index, c->d_tables, c->d_rawh, st);
-	CU(cudaGetLastError());
-	CU(cudaEventRecord(c->ev[EV_UP2], st));
-	c->stats.kernel_launches += 1;
+	if (int rc = derive_launch(c, c->d_entries, (uint32_t)entries.size(), st, true, true))
+		return rc;
 	c->ev_upload = true;
 	return HCM_OK;
 }
@@ -1387,7 +1547,7 @@ int hcm_sync(hcm_ctx *c) {
 		return HCM_ERR_INVALID;
 	CU(cudaSetDevice(c->device));
 	CU(cudaStreamSynchronize(c->stream));
-	return HCM_OK;
+	return tune_harvest(c);
 }
 
 static int submit(hcm_ctx *c, uint32_t n, const int16_t *pos, int force_all) {
@@ -1740,7 +1900,7 @@ int hcm_upload_and_mesh(hcm_ctx *c, uint32_t n_chunks, const int16_t *pos, const
 			const uint32_t t0 = submitted, t1 = ready;
 			CU(cudaMemsetAsync(&c->d_heads->n_work, 0, 2 * sizeof(unsigned int), st)); // n_work and cursor; the allocation heads keep counting
 			launch_classify(c->w, c->d_tasks + t0, t1 - t0, c->d_worklist, c->d_heads, c->d_task_out + t0, 0, st);
-			launch_mesh(c->maps, mesh_params(c, t0), c->grid, st);
+			launch_mesh(c->maps, mesh_params(c, t0), c->grid, (int)c->tune_mesh.selected, st);
 			CU(cudaGetLastError());
 			CU(cudaMemcpyAsync(c->h_heads_ring + n_sub, c->d_heads, sizeof(BatchHeads), cudaMemcpyDeviceToHost, st));
 			CU(cudaEventRecord(c->sub_events[n_sub], st));
@@ -1795,7 +1955,7 @@ int hcm_get_stats(hcm_ctx *c, hcm_stats *out) {
 		CU(cudaEventElapsedTime(&c->stats.derive_ms, c->ev[EV_UP1], c->ev[EV_UP2]));
 	}
 	if (c->ev_batch) {
-		CU(cudaEventElapsedTime(&c->stats.classify_ms, c->ev[EV_B0], c->ev[EV_B1]));
+		CU(cudaEventElapsedTime(&c->stats.classify_ms, c->ev[EV_B0], c->ev[c->batch_ab ? EV_TM0 : EV_B1]));
 		CU(cudaEventElapsedTime(&c->stats.mesh_ms, c->ev[EV_B1], c->ev[EV_B2]));
 	}
 	if (c->ev_fetch)
@@ -1807,6 +1967,56 @@ int hcm_get_stats(hcm_ctx *c, hcm_stats *out) {
 }
 
 void *hcm_stream(hcm_ctx *c) { return c ? (void *)c->stream : nullptr; }
+
+int hcm_get_tune_info(hcm_ctx *c, hcm_tune_info *out) {
+	if (!c || !out)
+		return HCM_ERR_INVALID;
+	CU(cudaSetDevice(c->device));
+	CU(cudaStreamSynchronize(c->stream));
+	if (int rc = tune_harvest(c))
+		return rc;
+	auto fill = [&](const KernelTune &t, hcm_kernel_tune &o) {
+		o.selected = t.selected, o.rounds = t.rounds, o.mismatches = t.mismatches, o.baseline_ms = t.best_base, o.variant_ms = t.best_var;
+		o.state = t.forced >= 0 ? (uint32_t)HCM_TUNE_FORCED : ((!c->tune && t.state == HCM_TUNE_PENDING) ? (uint32_t)HCM_TUNE_OFF : t.state);
+	};
+	fill(c->tune_derive, out->derive), fill(c->tune_mesh, out->mesh);
+	return HCM_OK;
+}
+
+int hcm_set_option(hcm_ctx *c, const char *name, int64_t value) {
+	if (!c || !name)
+		return HCM_ERR_INVALID;
+	auto force = [&](KernelTune &t) -> int {
+		if (value < -1 || value > 1)
+			return fail(c, HCM_ERR_INVALID, "%s = %lld: 0 (baseline), 1 (variant) or -1 (qualification decides)", name, (long long)value);
+		t.forced = (int)value;
+		if (value >= 0)
+			t.selected = (uint32_t)value;
+		else if (t.state != HCM_TUNE_VARIANT_ADOPTED)
+			t.selected = 0;
+		return HCM_OK;
+	};
+	const std::string n(name);
+	if (n == "upload_adaptive")
+		c->adaptive_upload = value != 0;
+	else if (n == "tune")
+		c->tune = value != 0;
+	else if (n == "tune_fault")
+		c->tune_fault = value != 0;
+	else if (n == "derive_variant")
+		return force(c->tune_derive);
+	else if (n == "mesh_variant")
+		return force(c->tune_mesh);
+	else if (n == "tune_min_chunks" && value >= 1)
+		c->tune_min_chunks = (uint32_t)std::min<int64_t>(value, 0x7fffffff);
+	else if (n == "tune_min_tasks" && value >= 1)
+		c->tune_min_tasks = (uint32_t)std::min<int64_t>(value, 0x7fffffff);
+	else if (n == "tune_rounds" && value >= 1 && value <= 16)
+		c->tune_rounds = (uint32_t)value;
+	else
+		return fail(c, HCM_ERR_INVALID, "hcm_set_option: unknown name or value out of range (%s = %lld)", name, (long long)value);
+	return HCM_OK;
+}
 
 int hcm_debug_light(hcm_ctx *c, const int16_t pos[3], uint8_t *out) {
 	if (!c || !pos || !out)

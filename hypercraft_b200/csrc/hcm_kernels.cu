@@ -113,24 +113,46 @@ __device__ unsigned long long g_phase_cycles[64];
 // ================================================================================================================
 // derive kernel: one CTA per uploaded chunk, 256 threads; thread t owns columns x4..x4+3 of row z
 // ================================================================================================================
+// kVariant 0 (baseline): the chunk's 64 KB arrive as ONE bulk copy; nothing is computed before the last byte has landed.
+// kVariant 1: FOUR 16 KB bulk copies (eight y-layers each) on four mbarriers.  The uniform test runs quarter by quarter and
+// a chunk that is not uniform leaves it at the first quarter that says so: its per-voxel lookups then run under the copies of the
+// later quarters, each waited for when the walk reaches its first layer.  The sunlight-height load (1 KB of HBM, a full DRAM
+// round trip that the baseline takes between the copy's completion and the block-wide vote) is issued before the first wait.
+// Same arithmetic, same bytes written; which one a context launches is decided on the device (hcm.h, "Kernel variants").
+constexpr int kDeriveQuarterBytes = HCM_CHUNK_VOXELS * 2 / 4; // 16384: y-layers 8q .. 8q+7
+template <int kVariant>
 __global__ void __launch_bounds__(256, 3) derive_kernel(DevWorld w, const UploadEntry *__restrict__ entries, const uint8_t *__restrict__ prop_index,
                                                      const DevTables *__restrict__ tables, const int8_t *__restrict__ raw_heights) {
 	HCM_DYNAMIC_SMEM(derive_smem); // the chunk's 64 KB of Block data, one TMA bulk copy
 	__shared__ uint16_t s_pinfo[256];                       // pflags | light level << 8
 	__shared__ u32 s_idinfo[256];                           // by block id: row | pflags << 8 | level << 16, bit 31: the row depends on meta
 	__shared__ u32 s_and, s_or;
-	__shared__ __align__(8) u64 s_bar;
+	__shared__ __align__(8) u64 s_bars[kVariant == 0 ? 1 : 4];
+	u64 &s_bar = s_bars[0];
 	const int tid = threadIdx.x;
 	const UploadEntry e = entries[blockIdx.x];
 	const bool host_uniform = e.flags & UE_UNIFORM;
 	if (tid == 0) {
 		mbar_init(&s_bar, 1);
+		if (kVariant == 1)
+			for (int q = 1; q < 4; ++q)
+				mbar_init(&s_bars[kVariant == 1 ? q : 0], 1);
 		s_and = 0xffffffffu, s_or = 0;
 	}
 	if (tid == 0 && !host_uniform) { // the copy first, the tables while it is in flight
-		mbar_expect_tx(&s_bar, HCM_CHUNK_VOXELS * 2);
-		tma_load_1d(derive_smem, w.raw + (size_t)e.slot * HCM_CHUNK_VOXELS, HCM_CHUNK_VOXELS * 2, &s_bar);
+		if (kVariant == 0) {
+			mbar_expect_tx(&s_bar, HCM_CHUNK_VOXELS * 2);
+			tma_load_1d(derive_smem, w.raw + (size_t)e.slot * HCM_CHUNK_VOXELS, HCM_CHUNK_VOXELS * 2, &s_bar);
+		} else
+			for (int q = 0; q < 4; ++q) {
+				mbar_expect_tx(&s_bars[kVariant == 1 ? q : 0], kDeriveQuarterBytes);
+				tma_load_1d(derive_smem + q * kDeriveQuarterBytes, w.raw + (size_t)e.slot * HCM_CHUNK_VOXELS + q * (kDeriveQuarterBytes / 2), kDeriveQuarterBytes,
+				            &s_bars[kVariant == 1 ? q : 0]);
+			}
 	}
+	char4 hv = make_char4(0, 0, 0, 0); // variant: the chunk's sunlight heights, requested before anything is waited for
+	if (kVariant == 1)
+		hv = *reinterpret_cast<const char4 *>(raw_heights + (size_t)e.slot * HCM_CHUNK_COLUMNS + (tid >> 3) * 32 + ((tid & 7) << 2));
 	s_pinfo[tid] = (uint16_t)(tables->pflags[tid] | ((tables->pmisc[tid] >> 4) << 8));
 	s_idinfo[tid] = reinterpret_cast<const u32 *>(prop_index + 65536)[tid];
 	__syncthreads();
@@ -155,7 +177,7 @@ __global__ void __launch_bounds__(256, 3) derive_kernel(DevWorld w, const Upload
 #pragma unroll 8
 		for (int y = 0; y < 32; ++y)
 			*reinterpret_cast<uint2 *>(rw + x4 + (y * 32 + z) * 32) = make_uint2(pat, pat);
-	} else {
+	} else if (kVariant == 0) {
 		mbar_wait(&s_bar, 0);
 		d0 = sraw[0], pat = d0 | (d0 << 16);
 		u32 acc_and = 0xffffffffu, acc_or = 0; // uniform <=> AND == OR == pattern
@@ -165,8 +187,33 @@ __global__ void __launch_bounds__(256, 3) derive_kernel(DevWorld w, const Upload
 			acc_and &= r.x & r.y, acc_or |= r.x | r.y;
 		}
 		same = acc_and == pat && acc_or == pat;
+	} else {
+		// quarter by quarter; the CTA leaves at the first quarter in which some thread saw a second value (the vote is block-wide,
+		// so every thread takes the same way out) -- the later quarters are then waited for by the walk below
+		mbar_wait(&s_bars[0], 0);
+		d0 = sraw[0], pat = d0 | (d0 << 16);
+		u32 acc_and = 0xffffffffu, acc_or = 0;
+		same = true;
+#pragma unroll 1
+		for (int q = 0; q < 4; ++q) {
+			if (q)
+				mbar_wait(&s_bars[kVariant == 1 ? q : 0], 0);
+#pragma unroll
+			for (int y = 8 * q; y < 8 * q + 8; ++y) {
+				const uint2 r = *reinterpret_cast<const uint2 *>(sraw + x4 + (y * 32 + z) * 32);
+				acc_and &= r.x & r.y, acc_or |= r.x | r.y;
+			}
+			same = acc_and == pat && acc_or == pat;
+			if (q < 3 && __syncthreads_or(!same)) {
+				same = false;
+				break;
+			}
+		}
 	}
-	*reinterpret_cast<char4 *>(w.height + col) = *reinterpret_cast<const char4 *>(raw_heights + (size_t)e.slot * HCM_CHUNK_COLUMNS + z * 32 + x4);
+	if (kVariant == 0)
+		*reinterpret_cast<char4 *>(w.height + col) = *reinterpret_cast<const char4 *>(raw_heights + (size_t)e.slot * HCM_CHUNK_COLUMNS + z * 32 + x4);
+	else
+		*reinterpret_cast<char4 *>(w.height + col) = hv;
 	if (__syncthreads_and(same)) {
 		const u32 pr = __ldg(prop_index + d0);
 		const u32 info = s_pinfo[pr], fl = info & 0xffu, lvl = info >> 8;
@@ -208,6 +255,8 @@ __global__ void __launch_bounds__(256, 3) derive_kernel(DevWorld w, const Upload
 	u32 f_and = 0xffffffffu, f_or = 0; // info words accumulated over the thread's voxels: flags in bits 8..15, light level from bit 16
 #pragma unroll 8
 	for (int y = 0; y < 32; ++y) {
+		if (kVariant == 1 && (y & 7) == 0 && y) // the quarter this layer opens (already there if the uniform test got that far)
+			mbar_wait(&s_bars[kVariant == 1 ? (y >> 3) : 0], 0);
 		const uint2 r = *reinterpret_cast<const uint2 *>(sraw + x4 + (y * 32 + z) * 32);
 		const u32 d[4] = {r.x & 0xffffu, r.x >> 16, r.y & 0xffffu, r.y >> 16};
 		u32 info[4];
@@ -893,6 +942,12 @@ __device__ __forceinline__ u32 pack_geo(u32 u, u32 v, u32 w, u32 h, bool tr, u32
 //     bare recurrence: it only leaves (u, v, width, height) per quad, in emission order;
 //  3. lane = quad: fetch the key of the quad's first cell, split into the opaque / transparent streams (ranks by
 //     ballot) and finish the records.  Records overwrite the mask's (already read) key slots in emission order.
+// kVariant 1 re-schedules the height test of pass 2 (hcm.h, "Kernel variants"): the row directly below a run is tested on its own
+// (most runs end there), after that FOUR rows per round -- their ED words come from four independent shuffles and the four unions
+// from four independent reductions, so a round of four rows waits for one shuffle and one reduction instead of four of each.  A run
+// that has died stays dead (alive == 0 passes every later test as 0), and rows past 31 never match a lane, so the extra rows of
+// the last round change nothing: the quads and the consumed sets are the baseline's.
+template <int kVariant>
 __device__ void merge_mask(Small &S, const u32 *F, u64 *keys, u32 *geo, int m, int g0, int lane) {
 	const u32 lt = (1u << lane) - 1u;
 	const u32 Frow = F[m * kFS + lane];
@@ -965,18 +1020,52 @@ __device__ void merge_mask(Small &S, const u32 *F, u64 *keys, u32 *geo, int m, i
 		const bool start = (startmask >> lane) & 1;
 		const u32 rm = start ? ((low - 1u) & ~lt) : 0u; // cells of the run that starts here
 		u32 height = 1, alive = rm;
-		for (int r = u + 1;; ++r) { // ED[31] == 0 ends every run
+		if (kVariant == 0) {
+			for (int r = u + 1;; ++r) { // ED[31] == 0 ends every run
 #ifdef HCM_PHASE_TIMING
-			++hsteps_;
+				++hsteps_;
 #endif
-			const u32 e = __shfl_sync(FULL, ED, (r - 1) & 31);
-			alive = (e & alive) == alive ? alive : 0u;
-			const u32 un = __reduce_or_sync(FULL, alive);
-			if (!un)
-				break;
-			height += alive != 0;
-			if (lane == r)
-				C |= un;
+				const u32 e = __shfl_sync(FULL, ED, (r - 1) & 31);
+				alive = (e & alive) == alive ? alive : 0u;
+				const u32 un = __reduce_or_sync(FULL, alive);
+				if (!un)
+					break;
+				height += alive != 0;
+				if (lane == r)
+					C |= un;
+			}
+		} else {
+			int r = u + 1; // the row whose cells the next test may consume; ED[31] == 0 ends every run at r = 32
+			u32 un;
+			{
+#ifdef HCM_PHASE_TIMING
+				++hsteps_;
+#endif
+				const u32 e = __shfl_sync(FULL, ED, (r - 1) & 31);
+				alive = (e & alive) == alive ? alive : 0u;
+				un = __reduce_or_sync(FULL, alive);
+				height += alive != 0;
+				if (lane == r)
+					C |= un;
+				++r;
+			}
+			while (un) {
+#ifdef HCM_PHASE_TIMING
+				hsteps_ += 4;
+#endif
+				const u32 e0 = __shfl_sync(FULL, ED, (r - 1) & 31), e1 = __shfl_sync(FULL, ED, r & 31);
+				const u32 e2 = __shfl_sync(FULL, ED, (r + 1) & 31), e3 = __shfl_sync(FULL, ED, (r + 2) & 31);
+				const u32 a0 = (e0 & alive) == alive ? alive : 0u;
+				const u32 a1 = (e1 & a0) == a0 ? a0 : 0u;
+				const u32 a2 = (e2 & a1) == a1 ? a1 : 0u;
+				const u32 a3 = (e3 & a2) == a2 ? a2 : 0u;
+				const u32 un0 = __reduce_or_sync(FULL, a0), un1 = __reduce_or_sync(FULL, a1);
+				const u32 un2 = __reduce_or_sync(FULL, a2), un3 = __reduce_or_sync(FULL, a3);
+				height += (a0 != 0) + (a1 != 0) + (a2 != 0) + (a3 != 0);
+				const int d = lane - r; // rows r .. r+3 lose what the runs still alive there cover
+				C |= d == 0 ? un0 : (d == 1 ? un1 : (d == 2 ? un2 : (d == 3 ? un3 : 0u)));
+				alive = a3, un = un3, r += 4;
+			}
 		}
 		if (start)
 			geo[base + nq + __popc(startmask & lt)] = (u32)u | ((u32)lane << 5) | ((u32)(__popc(rm) - 1) << 10) | ((height - 1) << 15);
@@ -1280,6 +1369,7 @@ __device__ __forceinline__ void claim_output(const MeshParams &p, Small &S, int 
 	}
 }
 
+template <int kVariant>
 __global__ void __launch_bounds__(kThreads, 1) mesh_kernel(const __grid_constant__ MeshMaps maps, const MeshParams p) {
 	HCM_DYNAMIC_SMEM(smem);
 	uint8_t *vox = smem + SM_VOX;
@@ -1818,7 +1908,7 @@ __global__ void __launch_bounds__(kThreads, 1) mesh_kernel(const __grid_constant
 							const long long tm0_ = clock64();
 							const u32 nr_ = __popc(__ballot_sync(FULL, F[m * kFS + lane] != 0));
 #endif
-							merge_mask(S, F, keys, geo, m, g0, lane);
+							merge_mask<kVariant>(S, F, keys, geo, m, g0, lane);
 #ifdef HCM_PHASE_TIMING
 							if (lane == 0) {
 								const unsigned long long d_ = (unsigned long long)(clock64() - tm0_);
@@ -1995,6 +2085,128 @@ __global__ void __launch_bounds__(256) scatter_kernel(const hcm_mesh_placement *
 }
 
 // ================================================================================================================
+// on-device qualification of the kernel variants (hcm.h, "Kernel variants"): position-salted hashes of what a launch wrote.
+// The sum of mix64(value ^ salt(position)) does not depend on the order in which threads add their terms, and the mesh hash
+// does not depend on where in the arenas a task's meshes were placed (the allocation order differs from run to run).
+// ================================================================================================================
+__device__ __forceinline__ u64 mix64(u64 x) {
+	x ^= x >> 33, x *= 0xff51afd7ed558ccdull;
+	x ^= x >> 33, x *= 0xc4ceb9fe1a85ec53ull;
+	return x ^ (x >> 33);
+}
+__device__ __forceinline__ u64 warp_sum64(u64 h) {
+#pragma unroll
+	for (int d = 16; d; d >>= 1)
+		h += __shfl_sync(FULL, h, (int)((threadIdx.x & 31) ^ d));
+	return h;
+}
+
+// one CTA per upload entry, the derive kernel's own thread mapping: everything derive_kernel writes for the chunk
+__global__ void __launch_bounds__(256) derive_digest_kernel(DevWorld w, const UploadEntry *__restrict__ entries, const int8_t *__restrict__ raw_heights,
+                                                            const u64 *__restrict__ expect, u64 *__restrict__ out, u32 *__restrict__ mismatches) {
+	__shared__ u64 s_sum;
+	const int tid = threadIdx.x;
+	const UploadEntry e = entries[blockIdx.x];
+	if (tid == 0)
+		s_sum = 0;
+	__syncthreads();
+	const int z = tid >> 3, x4 = (tid & 7) << 2;
+	const size_t gx = (size_t)e.cx * 32 + x4, gz = (size_t)e.cz * 32 + z;
+	const uint8_t *prow = w.prop8 + (((size_t)e.cy * 32) * w.Z + gz) * w.XP + gx + kXMargin;
+	const size_t pstride = (size_t)w.Z * w.XP;
+	const size_t col = ((size_t)e.cy * w.Z + gz) * w.X + gx;
+	const size_t plane = (size_t)w.wy * w.Z * w.X;
+	u64 h = 0;
+	u32 salt = (u32)tid << 8;
+	for (int y = 0; y < 32; ++y)
+		h += mix64(*reinterpret_cast<const u32 *>(prow + y * pstride) ^ ((u64)(salt + y) << 32));
+	const uint4 pw = *reinterpret_cast<const uint4 *>(w.pass + col);
+	h += mix64(pw.x ^ ((u64)(salt + 32) << 32)) + mix64(pw.y ^ ((u64)(salt + 33) << 32)) + mix64(pw.z ^ ((u64)(salt + 34) << 32)) + mix64(pw.w ^ ((u64)(salt + 35) << 32));
+	for (int l = 0; l < w.n_levels; ++l) {
+		const uint4 tw = *reinterpret_cast<const uint4 *>(w.torch + l * plane + col);
+		h += mix64(tw.x ^ ((u64)(salt + 40 + 4 * l) << 32)) + mix64(tw.y ^ ((u64)(salt + 41 + 4 * l) << 32)) + mix64(tw.z ^ ((u64)(salt + 42 + 4 * l) << 32)) +
+		     mix64(tw.w ^ ((u64)(salt + 43 + 4 * l) << 32));
+	}
+	h += mix64(*reinterpret_cast<const u32 *>(w.height + col) ^ ((u64)(salt + 60) << 32));
+	// the raw slot as well: a host-uniform entry has it written by the derive kernel (first and last 16 bytes per thread row suffice
+	// to see a wrong fill value; the full 64 KB are the upload's, not the kernel's, for every other entry)
+	if (e.flags & UE_UNIFORM) {
+		const uint16_t *raw = w.raw + (size_t)e.slot * HCM_CHUNK_VOXELS;
+		for (int y = 0; y < 32; ++y) {
+			const uint2 r = *reinterpret_cast<const uint2 *>(raw + x4 + (y * 32 + z) * 32);
+			h += mix64(((u64)r.y << 32 | r.x) ^ (u64)(salt + 64 + y));
+		}
+	}
+	if (tid == 0) {
+		const size_t ci = ((size_t)e.cy * w.wz + e.cz) * w.wx + e.cx;
+		h += mix64(w.cflags[ci] ^ (0x5151ull << 32)) + mix64((u32)w.slot[ci] ^ (0x5252ull << 32));
+	}
+	(void)raw_heights;
+	h = warp_sum64(h);
+	if ((tid & 31) == 0)
+		atomicAdd(reinterpret_cast<unsigned long long *>(&s_sum), (unsigned long long)h);
+	__syncthreads();
+	if (tid == 0) {
+		out[blockIdx.x] = s_sum;
+		if (expect && expect[blockIdx.x] != s_sum)
+			atomicAdd(mismatches, 1u);
+	}
+}
+
+// one warp per task: mesh count, then per mesh (in the task's order) flags, counts, AABB, vertex bytes, index bytes -- not the offsets
+__global__ void __launch_bounds__(256) mesh_digest_kernel(const hcm_task_result *__restrict__ task_out, const hcm_mesh_desc *__restrict__ meshes,
+                                                          const u64 *__restrict__ vtx, const uint16_t *__restrict__ idx, u32 n, u32 mesh_cap,
+                                                          unsigned long long vtx_cap, unsigned long long idx_cap, const u64 *__restrict__ expect,
+                                                          u64 *__restrict__ out, u32 *__restrict__ mismatches) {
+	const u32 t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	const int lane = threadIdx.x & 31;
+	if (t >= n)
+		return;
+	const hcm_task_result tr = task_out[t];
+	u64 h = lane == 0 ? mix64((u64)tr.n_meshes + 0x9e3779b97f4a7c15ull) : 0ull;
+	bool bad = tr.n_meshes > 2u * kMaxSplits || (u64)tr.first_mesh + tr.n_meshes > mesh_cap; // a descriptor range no kernel of this library writes
+	for (u32 k = 0; k < tr.n_meshes && !bad; ++k) {
+		const hcm_mesh_desc d = meshes[tr.first_mesh + k];
+		if (d.vertex_count > HCM_MESH_MAX_VERTICES || d.vertex_offset + d.vertex_count > vtx_cap || d.index_offset + d.index_count > idx_cap ||
+		    d.index_count > 6u * (HCM_MESH_MAX_VERTICES / 4)) {
+			bad = true;
+			break;
+		}
+		if (lane == 0) {
+			h += mix64(((u64)k << 40) ^ ((u64)d.transparent << 32) ^ d.vertex_count) + mix64(((u64)k << 40) ^ (1ull << 36) ^ d.index_count) +
+			     mix64(((u64)k << 40) ^ (2ull << 36) ^ d.task);
+			for (int c = 0; c < 3; ++c)
+				h += mix64(((u64)k << 40) ^ ((u64)(3 + c) << 36) ^ d.aabb_min[c]) + mix64(((u64)k << 40) ^ ((u64)(6 + c) << 36) ^ d.aabb_max[c]);
+		}
+		const u64 *v = vtx + d.vertex_offset;
+		for (u32 i = lane; i < d.vertex_count; i += 32)
+			h += mix64(v[i] ^ mix64(((u64)k << 32) | i));
+		const uint16_t *ix = idx + d.index_offset;
+		for (u32 i = lane; i < d.index_count; i += 32)
+			h += mix64((u64)ix[i] ^ mix64(((u64)(k + 64) << 32) | i));
+	}
+	h = warp_sum64(h);
+	if (bad)
+		h = ~0ull; // and it will not equal the other run's hash unless that one is broken in the same way: counted below
+	if (lane == 0) {
+		out[t] = h;
+		if (expect && (expect[t] != h || bad))
+			atomicAdd(mismatches, 1u);
+	}
+}
+
+void launch_derive_digest(const DevWorld &w, const UploadEntry *entries, u32 n, const int8_t *raw_heights, const u64 *expect, u64 *out, u32 *mismatches,
+                          cudaStream_t st) {
+	if (n)
+		HCM_LAUNCH(derive_digest_kernel, n, 256, 0, st, w, entries, raw_heights, expect, out, mismatches);
+}
+void launch_mesh_digest(const hcm_task_result *task_out, const hcm_mesh_desc *meshes, const u64 *vtx, const uint16_t *idx, u32 n, u32 mesh_cap,
+                        unsigned long long vtx_cap, unsigned long long idx_cap, const u64 *expect, u64 *out, u32 *mismatches, cudaStream_t st) {
+	if (n)
+		HCM_LAUNCH(mesh_digest_kernel, (n + 7) / 8, 256, 0, st, task_out, meshes, vtx, idx, n, mesh_cap, vtx_cap, idx_cap, expect, out, mismatches);
+}
+
+// ================================================================================================================
 // host-callable launchers (used by hcm_api.cu)
 // ================================================================================================================
 void launch_scatter(const hcm_mesh_placement *placements, u32 n, const hcm_mesh_desc *meshes, const u64 *vtx, const uint16_t *idx, void *vdst, void *idst,
@@ -2003,9 +2215,13 @@ void launch_scatter(const hcm_mesh_placement *placements, u32 n, const hcm_mesh_
 		HCM_LAUNCH(scatter_kernel, min((u32)grid, n), 256, 0, st, placements, n, meshes, vtx, idx, (u64 *)vdst, (uint16_t *)idst);
 }
 void launch_derive(const DevWorld &w, const UploadEntry *entries, u32 n, const uint8_t *prop_index, const DevTables *tables, const int8_t *raw_heights,
-                   cudaStream_t st) {
-	if (n)
-		HCM_LAUNCH(derive_kernel, n, 256, HCM_CHUNK_VOXELS * 2, st, w, entries, prop_index, tables, raw_heights);
+                   int variant, cudaStream_t st) {
+	if (!n)
+		return;
+	if (variant == 0)
+		HCM_LAUNCH(derive_kernel<0>, n, 256, HCM_CHUNK_VOXELS * 2, st, w, entries, prop_index, tables, raw_heights);
+	else
+		HCM_LAUNCH(derive_kernel<1>, n, 256, HCM_CHUNK_VOXELS * 2, st, w, entries, prop_index, tables, raw_heights);
 }
 void launch_clear(const DevWorld &w, const UploadEntry *entries, u32 n, cudaStream_t st) {
 	if (n)
@@ -2034,12 +2250,21 @@ extern "C" __attribute__((visibility("default"))) int hcm_debug_phase_cycles(uns
 }
 #endif
 cudaError_t mesh_kernel_prepare() {
-	cudaError_t e = cudaFuncSetAttribute(derive_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HCM_CHUNK_VOXELS * 2);
-	if (e != cudaSuccess)
-		return e;
-	return cudaFuncSetAttribute(mesh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+	cudaError_t e = cudaFuncSetAttribute(derive_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, HCM_CHUNK_VOXELS * 2);
+	if (e == cudaSuccess)
+		e = cudaFuncSetAttribute(derive_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, HCM_CHUNK_VOXELS * 2);
+	if (e == cudaSuccess)
+		e = cudaFuncSetAttribute(mesh_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+	if (e == cudaSuccess)
+		e = cudaFuncSetAttribute(mesh_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+	return e;
 }
 int mesh_kernel_smem_bytes() { return kSmemBytes; }
-void launch_mesh(const MeshMaps &maps, const MeshParams &p, int grid, cudaStream_t st) { HCM_LAUNCH(mesh_kernel, grid, kThreads, kSmemBytes, st, maps, p); }
+void launch_mesh(const MeshMaps &maps, const MeshParams &p, int grid, int variant, cudaStream_t st) {
+	if (variant == 0)
+		HCM_LAUNCH(mesh_kernel<0>, grid, kThreads, kSmemBytes, st, maps, p);
+	else
+		HCM_LAUNCH(mesh_kernel<1>, grid, kThreads, kSmemBytes, st, maps, p);
+}
 
 } // namespace hcm

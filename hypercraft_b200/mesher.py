@@ -65,6 +65,19 @@ class _Stats(ctypes.Structure):
 assert ctypes.sizeof(_Stats) == 64
 
 
+class _KernelTune(ctypes.Structure):
+    _fields_ = [("selected", ctypes.c_uint32), ("state", ctypes.c_uint32), ("rounds", ctypes.c_uint32), ("mismatches", ctypes.c_uint32),
+                ("baseline_ms", ctypes.c_float), ("variant_ms", ctypes.c_float)]
+
+
+class _TuneInfo(ctypes.Structure):
+    _fields_ = [("derive", _KernelTune), ("mesh", _KernelTune)]
+
+
+assert ctypes.sizeof(_TuneInfo) == 48
+TUNE_STATES = ["pending", "variant adopted", "baseline kept", "variant rejected (bytes differ)", "forced", "off"]
+
+
 MESH_DESC_DTYPE = np.dtype([("task", np.uint32), ("transparent", np.uint32), ("vertex_offset", np.uint64), ("index_offset", np.uint64),
                             ("vertex_count", np.uint32), ("index_count", np.uint32), ("aabb_min", np.uint32, 3), ("aabb_max", np.uint32, 3)])
 TASK_RESULT_DTYPE = np.dtype([("first_mesh", np.uint32), ("n_meshes", np.uint32)])
@@ -75,7 +88,7 @@ HINT_UNKNOWN, HINT_NOT_UNIFORM = -1, -2
 
 EXPORTS = ["hcm_registry_from_blob", "hcm_create", "hcm_destroy", "hcm_last_error", "hcm_status_string", "hcm_host_alloc", "hcm_host_free",
            "hcm_upload_chunks", "hcm_upload_chunks_hinted", "hcm_mesh_counts", "hcm_mesh_emit_into", "hcm_copy_chunks_from", "hcm_remove_chunks", "hcm_rederive_chunks", "hcm_is_resident", "hcm_sync", "hcm_mesh_batch", "hcm_mesh_fetch", "hcm_mesh_wait",
-           "hcm_upload_and_mesh", "hcm_set_blocks", "hcm_get_stats", "hcm_stream", "hcm_debug_light"]
+           "hcm_upload_and_mesh", "hcm_set_blocks", "hcm_get_stats", "hcm_stream", "hcm_debug_light", "hcm_get_tune_info", "hcm_set_option"]
 
 _lib = None
 
@@ -122,6 +135,8 @@ def load_library():
         L.hcm_set_blocks.argtypes = [_vp, ctypes.c_uint32, _vp, ctypes.POINTER(_EditResult)]
         L.hcm_get_stats.argtypes = [_vp, ctypes.POINTER(_Stats)]
         L.hcm_debug_light.argtypes = [_vp, _vp, _vp]
+        L.hcm_get_tune_info.argtypes = [_vp, ctypes.POINTER(_TuneInfo)]
+        L.hcm_set_option.argtypes = [_vp, ctypes.c_char_p, ctypes.c_int64]
         _lib = L
     return _lib
 
@@ -358,6 +373,20 @@ class Mesher:
         s = _Stats()
         self._check(self.L.hcm_get_stats(self.ctx, ctypes.byref(s)))
         return {f[0]: getattr(s, f[0]) for f in _Stats._fields_}
+
+    def tune_info(self) -> dict:
+        """hcm_get_tune_info: which form of derive_kernel / mesh_kernel this context launches and what the A/B rounds measured."""
+        t = _TuneInfo()
+        self._check(self.L.hcm_get_tune_info(self.ctx, ctypes.byref(t)))
+        out = {}
+        for name in ("derive", "mesh"):
+            k = getattr(t, name)
+            out[name] = {"selected": "variant" if k.selected else "baseline", "state": TUNE_STATES[k.state] if k.state < len(TUNE_STATES) else str(k.state),
+                         "rounds": int(k.rounds), "mismatches": int(k.mismatches), "baseline_ms": float(k.baseline_ms), "variant_ms": float(k.variant_ms)}
+        return out
+
+    def set_option(self, name: str, value: int) -> None:
+        self._check(self.L.hcm_set_option(self.ctx, name.encode(), int(value)))
 
     def stream_ptr(self) -> int:
         return int(self.L.hcm_stream(self.ctx) or 0)

@@ -38,6 +38,7 @@ struct alignas(4) char4 { signed char x, y, z, w; };
 struct dim3 { unsigned x = 1, y = 1, z = 1; dim3() = default; dim3(unsigned a, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {} };
 static inline uint2 make_uint2(unsigned x, unsigned y) { return uint2{x, y}; }
 static inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) { return uint4{x, y, z, w}; }
+static inline char4 make_char4(signed char x, signed char y, signed char z, signed char w) { return char4{x, y, z, w}; }
 
 // ---- runtime API subset -----------------------------------------------------------------------------------------------
 typedef int cudaError_t;

@@ -13,8 +13,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def _run(extra_env, *pytest_args):
     env = dict(os.environ, HCM_TEST_SIM="1", **extra_env)
-    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_parity.py"), "-m", "gpu", "-x", "-q", "-p", "no:cacheprovider",
-                        *pytest_args], capture_output=True, text=True, env=env, cwd=ROOT)
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_parity.py"), os.path.join(ROOT, "tests", "test_zz_kernel_variants.py"),
+                        "-m", "gpu", "-x", "-q", "-p", "no:cacheprovider", *pytest_args], capture_output=True, text=True, env=env, cwd=ROOT)
     tail = "\n".join((r.stdout + r.stderr).splitlines()[-25:])
     assert r.returncode == 0, tail
     return tail
@@ -30,7 +30,17 @@ def test_gpu_parity_suite_under_cpu_emulation():
 def test_kernels_under_the_reversed_schedule():
     """The emulation runs one warp at a time, lowest first; CUSIM_REVERSE visits warps and lanes highest first.  A missing barrier
     between a producer and a consumer warp gives stale data under one of the two orders."""
-    _run({"CUSIM_REVERSE": "1"}, "-k", "mesh_matches_oracle or light_stage or set_blocks_on_device or device_sink")
+    _run({"CUSIM_REVERSE": "1"}, "-n", "4", "-k", "mesh_matches_oracle or light_stage or set_blocks_on_device or device_sink or forced_variants or ab_rounds")
+
+
+def test_whole_suite_with_the_variant_kernels_forced():
+    """HCM_DERIVE_VARIANT=1 HCM_MESH_VARIANT=1: every context of the parity suite launches the variant forms of derive_kernel and
+    mesh_kernel (include/hcm.h, "Kernel variants") -- the same oracle bytes and reference digests must come out."""
+    tail = _run({"HCM_DERIVE_VARIANT": "1", "HCM_MESH_VARIANT": "1"}, "-n", "4", "--deselect",
+                "tests/test_zz_kernel_variants.py::test_ab_rounds_decide_and_never_change_a_byte", "--deselect",
+                "tests/test_zz_kernel_variants.py::test_a_differing_hash_rejects_the_variant_for_good", "--deselect",
+                "tests/test_zz_kernel_variants.py::test_tuning_can_be_switched_off")
+    assert " passed" in tail and "failed" not in tail
 
 
 def test_upload_paths_under_a_busy_copy_engine():
