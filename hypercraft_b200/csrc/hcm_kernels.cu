@@ -29,6 +29,7 @@ constexpr u32 FULL = 0xffffffffu;
 using cusim::mbar_expect_tx;
 using cusim::mbar_init;
 using cusim::mbar_wait;
+__device__ __forceinline__ bool mbar_wait_bounded(u64 *bar, u32 phase) { return mbar_wait(bar, phase), true; }
 using cusim::tma_load_1d;
 using cusim::tma_load_3d;
 __device__ __forceinline__ u32 lanemask_lt() { return (1u << cusim::self().lane) - 1u; }
@@ -53,6 +54,33 @@ __device__ __forceinline__ void mbar_wait(u64 *bar, u32 phase) {
 	             "}" ::"r"(smem_u32(bar)),
 	             "r"(phase)
 	             : "memory");
+}
+// The same wait with a way out: the variant form of a kernel (hcm.h, "Kernel variants") must never be able to hang the context that
+// is trying it out.  After ~0.25 s without the phase completing the wait gives up; the caller then works on whatever the buffer
+// holds, the A/B round's hashes differ and the variant is rejected -- the baseline form re-writes the data in the same round.
+__device__ __forceinline__ bool mbar_wait_bounded(u64 *bar, u32 phase) {
+	u32 done = 0;
+	unsigned long long t0 = 0;
+	for (u32 polls = 0;; ++polls) {
+		asm volatile("{\n"
+		             ".reg .pred p;\n"
+		             "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+		             "selp.u32 %0, 1, 0, p;\n"
+		             "}"
+		             : "=r"(done)
+		             : "r"(smem_u32(bar)), "r"(phase)
+		             : "memory");
+		if (done)
+			return true;
+		if ((polls & 63u) == 63u) {
+			unsigned long long now;
+			asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+			if (t0 == 0)
+				t0 = now;
+			else if (now - t0 > 250000000ull)
+				return false;
+		}
+	}
 }
 __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, int c0, int c1, int c2, u64 *bar) {
 	asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
@@ -190,14 +218,14 @@ __global__ void __launch_bounds__(256, 3) derive_kernel(DevWorld w, const Upload
 	} else {
 		// quarter by quarter; the CTA leaves at the first quarter in which some thread saw a second value (the vote is block-wide,
 		// so every thread takes the same way out) -- the later quarters are then waited for by the walk below
-		mbar_wait(&s_bars[0], 0);
+		mbar_wait_bounded(&s_bars[0], 0);
 		d0 = sraw[0], pat = d0 | (d0 << 16);
 		u32 acc_and = 0xffffffffu, acc_or = 0;
 		same = true;
 #pragma unroll 1
 		for (int q = 0; q < 4; ++q) {
 			if (q)
-				mbar_wait(&s_bars[kVariant == 1 ? q : 0], 0);
+				mbar_wait_bounded(&s_bars[kVariant == 1 ? q : 0], 0);
 #pragma unroll
 			for (int y = 8 * q; y < 8 * q + 8; ++y) {
 				const uint2 r = *reinterpret_cast<const uint2 *>(sraw + x4 + (y * 32 + z) * 32);
@@ -256,7 +284,7 @@ __global__ void __launch_bounds__(256, 3) derive_kernel(DevWorld w, const Upload
 #pragma unroll 8
 	for (int y = 0; y < 32; ++y) {
 		if (kVariant == 1 && (y & 7) == 0 && y) // the quarter this layer opens (already there if the uniform test got that far)
-			mbar_wait(&s_bars[kVariant == 1 ? (y >> 3) : 0], 0);
+			mbar_wait_bounded(&s_bars[kVariant == 1 ? (y >> 3) : 0], 0);
 		const uint2 r = *reinterpret_cast<const uint2 *>(sraw + x4 + (y * 32 + z) * 32);
 		const u32 d[4] = {r.x & 0xffffu, r.x >> 16, r.y & 0xffffu, r.y >> 16};
 		u32 info[4];
