@@ -506,8 +506,8 @@ void tune_decide(KernelTune &t, float base_ms, float var_ms, uint32_t mismatches
 	t.in_flight = false;
 	if (t.invalid || t.forced >= 0 || t.state != HCM_TUNE_PENDING)
 		return;
-	t.best_base = t.rounds ? std::min(t.best_base, base_ms) : base_ms;
-	t.best_var = t.rounds ? std::min(t.best_var, var_ms) : var_ms;
+	// rounds differ in size (an upload block, a whole re-derive): the two forms are compared on the SUMS over the same rounds
+	t.best_base += base_ms, t.best_var += var_ms;
 	++t.rounds, t.mismatches += mismatches;
 	if (mismatches)
 		t.state = HCM_TUNE_VARIANT_REJECTED, t.selected = 0; // once is enough: this device does not reproduce the baseline's bytes with it

@@ -355,8 +355,8 @@ void *hcm_stream(hcm_ctx *ctx); /* the ctx's cudaStream_t, for external event ti
  * `tune_min_chunks` chunks, a mesh batch of at least `tune_min_tasks` tasks) run BOTH forms on the same input, the variant
  * first, the baseline last (so that the call's result is the baseline's whatever happens), hash what each wrote -- per chunk
  * the derived property bytes, light planes, heights and flags; per task the mesh descriptors, vertex bytes and index bytes --
- * and time both with CUDA events.  After `tune_rounds` such calls the variant is adopted iff every hash matched and it was
- * at least 2 % faster; a single differing hash rejects it for the life of the context.  Nothing here involves the host CPU
+ * and time both with CUDA events.  After `tune_rounds` such calls the variant is adopted iff every hash matched and its time,
+ * summed over the rounds, was at least 2 % below the baseline's; a single differing hash rejects it for the life of the context.  Nothing here involves the host CPU
  * in the computation: both forms are sm_100a kernels of this library, and a rejected variant is simply never launched again.
  * Environment at hcm_create: HCM_TUNE=0 (baselines only), HCM_DERIVE_VARIANT / HCM_MESH_VARIANT = 0 | 1 (forced). */
 enum {
@@ -372,7 +372,7 @@ typedef struct hcm_kernel_tune {
 	uint32_t state;       /* HCM_TUNE_* */
 	uint32_t rounds;      /* A/B rounds completed */
 	uint32_t mismatches;  /* units (chunks / tasks) whose hashes differed, all rounds */
-	float baseline_ms;    /* best over the rounds */
+	float baseline_ms;    /* summed over the rounds (the rounds may differ in size; both forms ran on the same inputs) */
 	float variant_ms;
 } hcm_kernel_tune; /* 24 bytes */
 typedef struct hcm_tune_info {
