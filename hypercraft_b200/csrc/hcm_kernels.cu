@@ -1027,7 +1027,7 @@ __device__ void merge_mask(Small &S, const u32 *F, u64 *keys, u32 *geo, int m, i
 	}
 #ifdef HCM_PHASE_TIMING
 	const long long tms1_ = clock64();
-	u32 iters_ = 0, hsteps_ = 0;
+	u32 iters_ = 0, hsteps_ = 0, hrounds_ = 0;
 #endif
 	u32 C = 0, nq = 0;
 	const u32 right = ~((2u << lane) - 1u); // columns right of this lane
@@ -1051,7 +1051,7 @@ __device__ void merge_mask(Small &S, const u32 *F, u64 *keys, u32 *geo, int m, i
 		if (kVariant == 0) {
 			for (int r = u + 1;; ++r) { // ED[31] == 0 ends every run
 #ifdef HCM_PHASE_TIMING
-				++hsteps_;
+				++hsteps_, ++hrounds_;
 #endif
 				const u32 e = __shfl_sync(FULL, ED, (r - 1) & 31);
 				alive = (e & alive) == alive ? alive : 0u;
@@ -1067,7 +1067,7 @@ __device__ void merge_mask(Small &S, const u32 *F, u64 *keys, u32 *geo, int m, i
 			u32 un;
 			{
 #ifdef HCM_PHASE_TIMING
-				++hsteps_;
+				++hsteps_, ++hrounds_;
 #endif
 				const u32 e = __shfl_sync(FULL, ED, (r - 1) & 31);
 				alive = (e & alive) == alive ? alive : 0u;
@@ -1079,7 +1079,7 @@ __device__ void merge_mask(Small &S, const u32 *F, u64 *keys, u32 *geo, int m, i
 			}
 			while (un) {
 #ifdef HCM_PHASE_TIMING
-				hsteps_ += 4;
+				hsteps_ += 4, ++hrounds_;
 #endif
 				const u32 e0 = __shfl_sync(FULL, ED, (r - 1) & 31), e1 = __shfl_sync(FULL, ED, r & 31);
 				const u32 e2 = __shfl_sync(FULL, ED, (r + 1) & 31), e3 = __shfl_sync(FULL, ED, (r + 2) & 31);
@@ -1129,7 +1129,8 @@ __device__ void merge_mask(Small &S, const u32 *F, u64 *keys, u32 *geo, int m, i
 		PHASE_COUNT(37, tms1_ - tms0_);       // set-up loop cycles
 		PHASE_COUNT(38, tms2_ - tms1_);       // main loop cycles
 		PHASE_COUNT(39, iters_);              // main loop iterations
-		PHASE_COUNT(55, hsteps_);             // height steps
+		PHASE_COUNT(55, hsteps_);             // height steps (rows tested)
+		PHASE_COUNT(57, hrounds_);            // ... in this many dependent shuffle -> reduction round trips
 		PHASE_COUNT(56, clock64() - tms2_);   // record pass cycles
 	}
 #endif

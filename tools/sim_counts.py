@@ -16,6 +16,9 @@ ref = hcoracle.RefWorld(); ref.generate(resident)
 b, h = ref.get_chunks(resident)
 ext = 2 * R + 3
 m = M.Mesher(origin=(-R - 1,) * 3, extent=(ext,) * 3, max_chunks=len(resident), max_tasks=len(meshed))
+m.set_option("tune", 0)  # no A/B rounds here: one form per run
+if os.environ.get("V"):  # V=1: the variant forms (include/hcm.h, "Kernel variants")
+    m.set_option("derive_variant", int(os.environ["V"])), m.set_option("mesh_variant", int(os.environ["V"]))
 m.upload(resident, b, h)
 L = M.load_library()
 out = (ctypes.c_ulonglong * 64)()
@@ -25,7 +28,7 @@ L.hcm_debug_phase_cycles(out, 0)
 n = c["n_worked"]
 print(f"r={R}: {len(meshed)} tasks, {n} worked, {c['n_vertices'] // 4} quads")
 print(f"  flood: {out[28]/n:.2f} steps/task, {out[27]/n:.0f} column evaluations/task ({out[27]/max(out[28],1):.0f} per step), {out[25]/n:.0f} of them gained cells ({100*out[25]/max(out[27],1):.1f} %)")
-print(f"  warp merges: {out[20]/n:.1f} masks/task, {out[22]/n:.0f} rows/task, {out[39]/n:.0f} row iterations/task, {out[55]/max(out[39],1):.2f} height steps/iteration; tiny-mask warps {out[36]/n:.2f}/task; quads {out[23]/n:.0f}/task")
+print(f"  warp merges: {out[20]/n:.1f} masks/task, {out[22]/n:.0f} rows/task, {out[39]/n:.0f} row iterations/task, {out[55]/max(out[39],1):.2f} height steps/iteration in {out[57]/max(out[39],1):.2f} dependent round trips; tiny-mask warps {out[36]/n:.2f}/task; quads {out[23]/n:.0f}/task")
 for i in range(64):
-    if out[i] and i not in (20, 22, 23, 25, 27, 28, 36, 39, 55):
+    if out[i] and i not in (20, 22, 23, 25, 27, 28, 36, 39, 55, 57):
         print(f"  counter {i}: {out[i]/n:.1f}/task")
