@@ -35,6 +35,8 @@ void launch_edit(const DevWorld &w, const hcm_block_edit *edits, uint32_t n, con
                  const DevTables *tables, int8_t *raw_heights, hcm_sunlight_change *changes, uint32_t *n_changes, uint32_t cap, cudaStream_t st);
 void launch_classify(const DevWorld &w, const TaskIn *tasks, uint32_t n, uint32_t *worklist, BatchHeads *heads, hcm_task_result *task_out, int force_all,
                      cudaStream_t st);
+int derive_variant_count();
+int mesh_variant_count();
 cudaError_t mesh_kernel_prepare();
 int mesh_kernel_smem_bytes();
 void launch_mesh(const MeshMaps &maps, const MeshParams &p, int grid, int variant, cudaStream_t st);
@@ -106,17 +108,20 @@ struct BlockLayout {
 	uint32_t hi(uint32_t b) const { return std::min(n, first + b * size); }
 };
 
-// Qualification of a kernel variant on the device (hcm.h, "Kernel variants")
+// Qualification of the kernel variants on the device (hcm.h, "Kernel variants")
 struct KernelTune {
-	int forced = -1; // 0 | 1: environment / hcm_set_option; -1: the A/B rounds decide
-	uint32_t selected = 0, state = HCM_TUNE_PENDING, rounds = 0, mismatches = 0;
-	float best_base = 0.f, best_var = 0.f;
-	bool in_flight = false; // an A/B round is in the stream; its verdict is read at the next host synchronisation
-	bool invalid = false;   // ... and must be discarded (the batch overflowed its arenas)
+	int forced = -1; // 0 .. n: environment / hcm_set_option; -1: the A/B rounds decide
+	uint32_t n_variants = 0;
+	uint32_t selected = 0, state = HCM_TUNE_PENDING, rounds = 0;
+	uint32_t mismatches[HCM_MAX_VARIANTS] = {0, 0, 0};
+	float sum_base = 0.f, sum_var[HCM_MAX_VARIANTS] = {0.f, 0.f, 0.f};
+	bool in_flight = false; // an A/B round is in the stream; its verdict is read at the next launch or host synchronisation
+	bool invalid = false;   // ... and must be discarded
 };
+constexpr int kTuneRuns = HCM_MAX_VARIANTS + 2; // baseline, the variants, baseline again
 struct TuneHost { // pinned
-	uint32_t mismatch[2]; // derive, mesh
-	BatchHeads heads_variant, heads_base; // allocation heads after each form's run of a mesh round (an overflowed run proves nothing)
+	uint32_t mismatch[2][HCM_MAX_VARIANTS]; // [derive, mesh][variant - 1]
+	BatchHeads heads[kTuneRuns];             // allocation heads after each run of a mesh round (an overflowed run proves nothing)
 };
 
 struct hcm_ctx {
@@ -209,7 +214,8 @@ struct hcm_ctx {
 	bool batch_pending = false, batch_done = false;
 	int force_all = 0;
 
-	cudaEvent_t ev[20]{};
+	cudaEvent_t ev[12]{};
+	cudaEvent_t ev_tune[2][2 * kTuneRuns + 1]{}; // [derive, mesh]: begin / end of every run of an A/B round, then "verdict on the host"
 	cudaEvent_t ev_peer = nullptr; // orders hcm_copy_chunks_from between two contexts' streams
 	// task lists go up from two pinned buffers in turn, so that hcm_mesh_batch never waits for the stream (a pageable source makes
 	// cudaMemcpyAsync wait for the previous batch's kernels) and batches can be enqueued back to back
@@ -226,13 +232,10 @@ struct hcm_ctx {
 namespace {
 
 enum { EV_UP0, EV_UP1, EV_UP2, EV_B0, EV_B1, EV_B2, EV_F0, EV_F1, EV_S0, EV_S1,
-       EV_TD0, EV_TD1, // the variant's run of a derive A/B round (the baseline's run is bracketed by the round's own two events)
-       EV_TD2, EV_TD3,
-       EV_TM0, EV_TM1, // the variant's run of a mesh A/B round: TM0 also ends the classify kernel there; the baseline's run is EV_B1 .. EV_B2
-       EV_TB0, EV_TB1,         // ... and the baseline's run of that round (EV_B1 / EV_B2 may be re-recorded by a later batch before the verdict is read)
-       EV_TD_DONE, EV_TM_DONE, // the round's verdict has reached the pinned TuneHost
+       EV_BC, // end of the classify kernel in a mesh A/B round (EV_B1 .. EV_B2 bracket the round's last baseline run there)
        EV_COUNT };
-static_assert(EV_COUNT <= 20, "hcm_ctx::ev");
+static_assert(EV_COUNT <= 12, "hcm_ctx::ev");
+constexpr int kTuneDone = 2 * kTuneRuns;
 
 int fail(hcm_ctx *c, int status, const char *fmt, ...) {
 	char buf[512];
@@ -502,19 +505,30 @@ template <typename T> int host_reserve_keep(hcm_ctx *c, T **p, uint64_t *cap, ui
 }
 
 // ---- kernel variants: A/B rounds on the device (hcm.h, "Kernel variants") -------------------------------------------------
-void tune_decide(KernelTune &t, float base_ms, float var_ms, uint32_t mismatches, uint32_t want_rounds) {
+// Run r of a round: 0 = baseline, 1 .. n = variant r, n + 1 = baseline again (the call's result).
+void tune_decide(KernelTune &t, const float *run_ms, const uint32_t *mismatch, uint32_t want_rounds) {
 	t.in_flight = false;
 	if (t.invalid || t.forced >= 0 || t.state != HCM_TUNE_PENDING)
 		return;
-	// rounds differ in size (an upload block, a whole re-derive): the two forms are compared on the SUMS over the same rounds
-	t.best_base += base_ms, t.best_var += var_ms;
-	++t.rounds, t.mismatches += mismatches;
-	if (mismatches)
-		t.state = HCM_TUNE_VARIANT_REJECTED, t.selected = 0; // once is enough: this device does not reproduce the baseline's bytes with it
-	else if (t.rounds >= want_rounds) {
-		const bool faster = t.best_var < 0.98f * t.best_base;
-		t.state = faster ? HCM_TUNE_VARIANT_ADOPTED : HCM_TUNE_BASELINE_KEPT, t.selected = faster ? 1u : 0u;
+	const uint32_t n = t.n_variants;
+	// rounds differ in size (an upload block, a whole re-derive): the forms are compared on the SUMS over the same rounds
+	t.sum_base += 0.5f * (run_ms[0] + run_ms[n + 1]);
+	for (uint32_t v = 0; v < n; ++v)
+		t.sum_var[v] += run_ms[v + 1], t.mismatches[v] += mismatch[v];
+	if (++t.rounds < want_rounds)
+		return;
+	uint32_t best = 0;
+	bool any_bad = false;
+	for (uint32_t v = 0; v < n; ++v) {
+		if (t.mismatches[v]) {
+			any_bad = true; // this device does not reproduce the baseline's bytes with it: never launched again
+			continue;
+		}
+		if (t.sum_var[v] < 0.98f * t.sum_base && (!best || t.sum_var[v] < t.sum_var[best - 1]))
+			best = v + 1;
 	}
+	t.selected = best;
+	t.state = best ? HCM_TUNE_VARIANT_ADOPTED : (any_bad ? HCM_TUNE_VARIANT_REJECTED : HCM_TUNE_BASELINE_KEPT);
 }
 
 // read the verdict of every round that has completed (never waits)
@@ -523,29 +537,25 @@ int tune_harvest(hcm_ctx *c) {
 		KernelTune &t = k == 0 ? c->tune_derive : c->tune_mesh;
 		if (!t.in_flight)
 			continue;
-		const cudaError_t q = cudaEventQuery(c->ev[k == 0 ? EV_TD_DONE : EV_TM_DONE]);
+		const cudaError_t q = cudaEventQuery(c->ev_tune[k][kTuneDone]);
 		if (q == cudaErrorNotReady) {
 			(void)cudaGetLastError(); // an answer, not an error
 			continue;
 		}
 		CU(q);
-		float base = 0.f, var = 0.f;
-		if (k == 0) {
-			CU(cudaEventElapsedTime(&var, c->ev[EV_TD0], c->ev[EV_TD1]));
-			CU(cudaEventElapsedTime(&base, c->ev[EV_TD2], c->ev[EV_TD3]));
-		} else {
-			CU(cudaEventElapsedTime(&var, c->ev[EV_TM0], c->ev[EV_TM1]));
-			CU(cudaEventElapsedTime(&base, c->ev[EV_TB0], c->ev[EV_TB1]));
-			if (c->h_tune->heads_variant.overflow || c->h_tune->heads_base.overflow)
+		float ms[kTuneRuns] = {};
+		for (uint32_t r = 0; r < t.n_variants + 2; ++r) {
+			CU(cudaEventElapsedTime(&ms[r], c->ev_tune[k][2 * r], c->ev_tune[k][2 * r + 1]));
+			if (k == 1 && c->h_tune->heads[r].overflow)
 				t.invalid = true;
 		}
-		tune_decide(t, base, var, c->h_tune->mismatch[k], c->tune_rounds);
+		tune_decide(t, ms, c->h_tune->mismatch[k], c->tune_rounds);
 	}
 	return HCM_OK;
 }
 
 bool tune_wants_round(const hcm_ctx *c, const KernelTune &t, uint32_t units, uint32_t min_units) {
-	return c->tune && t.forced < 0 && t.state == HCM_TUNE_PENDING && !t.in_flight && units >= min_units;
+	return c->tune && t.n_variants && t.forced < 0 && t.state == HCM_TUNE_PENDING && !t.in_flight && units >= min_units;
 }
 
 // derive_kernel over `n` entries on `st`.  rec_begin / rec_end: EV_UP1 right before / EV_UP2 right after the launch hcm_stats reports.
@@ -555,27 +565,31 @@ int derive_launch(hcm_ctx *c, const UploadEntry *entries, uint32_t n, cudaStream
 		if (int rc = tune_harvest(c))
 			return rc;
 	if (n && tune_wants_round(c, t, n, c->tune_min_chunks)) {
-		// A/B round: the variant first, the baseline last -- whatever the verdict, the world holds the baseline's bytes
-		CU(cudaMemsetAsync(c->d_tune_mismatch, 0, sizeof(uint32_t), st));
-		CU(cudaEventRecord(c->ev[EV_TD0], st));
-		launch_derive(c->w, entries, n, c->d_prop_index, c->d_tables, c->d_rawh, 1, st);
-		CU(cudaEventRecord(c->ev[EV_TD1], st));
-		launch_derive_digest(c->w, entries, n, c->d_rawh, nullptr, c->d_digest[0], c->d_tune_mismatch, st);
-		if (c->tune_fault)
-			CU(cudaMemsetAsync(c->d_digest[0], 0xa5, sizeof(unsigned long long), st));
-		if (rec_begin)
-			CU(cudaEventRecord(c->ev[EV_UP1], st));
-		CU(cudaEventRecord(c->ev[EV_TD2], st));
-		launch_derive(c->w, entries, n, c->d_prop_index, c->d_tables, c->d_rawh, 0, st);
-		CU(cudaEventRecord(c->ev[EV_TD3], st));
-		if (rec_end)
-			CU(cudaEventRecord(c->ev[EV_UP2], st));
-		launch_derive_digest(c->w, entries, n, c->d_rawh, c->d_digest[0], c->d_digest[1], c->d_tune_mismatch, st);
+		// A/B round: baseline, every variant, baseline -- whatever the verdict, the world holds the baseline's bytes
+		cudaEvent_t *ev = c->ev_tune[0];
+		const uint32_t last = t.n_variants + 1;
+		CU(cudaMemsetAsync(c->d_tune_mismatch, 0, HCM_MAX_VARIANTS * sizeof(uint32_t), st));
+		for (uint32_t r = 0; r <= last; ++r) {
+			const int form = (r == 0 || r == last) ? 0 : (int)r;
+			if (r == last && rec_begin)
+				CU(cudaEventRecord(c->ev[EV_UP1], st));
+			CU(cudaEventRecord(ev[2 * r], st));
+			launch_derive(c->w, entries, n, c->d_prop_index, c->d_tables, c->d_rawh, form, st);
+			CU(cudaEventRecord(ev[2 * r + 1], st));
+			if (r == last && rec_end)
+				CU(cudaEventRecord(c->ev[EV_UP2], st));
+			if (r == 0) {
+				launch_derive_digest(c->w, entries, n, c->d_rawh, nullptr, c->d_digest[0], c->d_tune_mismatch, st);
+				if (c->tune_fault)
+					CU(cudaMemsetAsync(c->d_digest[0], 0xa5, sizeof(unsigned long long), st));
+			} else if (r < last)
+				launch_derive_digest(c->w, entries, n, c->d_rawh, c->d_digest[0], c->d_digest[1], c->d_tune_mismatch + (r - 1), st);
+		}
 		CU(cudaGetLastError());
-		CU(cudaMemcpyAsync(&c->h_tune->mismatch[0], c->d_tune_mismatch, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-		CU(cudaEventRecord(c->ev[EV_TD_DONE], st));
+		CU(cudaMemcpyAsync(c->h_tune->mismatch[0], c->d_tune_mismatch, HCM_MAX_VARIANTS * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+		CU(cudaEventRecord(ev[kTuneDone], st));
 		t.in_flight = true, t.invalid = false;
-		c->stats.kernel_launches += 4;
+		c->stats.kernel_launches += 2 * t.n_variants + 3;
 		return HCM_OK;
 	}
 	if (rec_begin)
@@ -599,39 +613,45 @@ int launch_batch(hcm_ctx *c) {
 	launch_classify(c->w, c->d_tasks, c->batch_n, c->d_worklist, c->d_heads, c->d_task_out, c->force_all, st);
 	c->batch_ab = !c->force_all && !c->d_debug_light && tune_wants_round(c, t, c->batch_n, c->tune_min_tasks);
 	if (c->batch_ab) {
-		// A/B round over the same work list: the variant first; then the allocation heads and the cursor start over (the work list and
-		// its count stay) and the baseline writes the batch's result
+		// A/B round over the same work list: baseline, every variant, baseline.  Between two runs the allocation heads and the cursor
+		// start over (the work list and its count stay); the last run writes the batch's result
 		static_assert(offsetof(BatchHeads, n_work) == 24 && offsetof(BatchHeads, cursor) == 28, "BatchHeads layout");
-		CU(cudaMemsetAsync(c->d_tune_mismatch + 1, 0, sizeof(uint32_t), st));
-		CU(cudaEventRecord(c->ev[EV_TM0], st));
-		launch_mesh(c->maps, mesh_params(c, 0), c->grid, 1, st);
-		CU(cudaEventRecord(c->ev[EV_TM1], st));
-		launch_mesh_digest(c->d_task_out, c->d_mesh_out, reinterpret_cast<const unsigned long long *>(c->d_vtx), c->d_idx, c->batch_n, c->mesh_cap, c->vtx_cap,
-		                   c->idx_cap, nullptr, c->d_digest[0], c->d_tune_mismatch + 1, st);
-		if (c->tune_fault)
-			CU(cudaMemsetAsync(c->d_digest[0], 0xa5, sizeof(unsigned long long), st));
-		CU(cudaMemcpyAsync(&c->h_tune->heads_variant, c->d_heads, sizeof(BatchHeads), cudaMemcpyDeviceToHost, st));
-		CU(cudaMemsetAsync(c->d_heads, 0, offsetof(BatchHeads, n_work), st));
-		CU(cudaMemsetAsync(&c->d_heads->cursor, 0, sizeof(unsigned int), st));
+		cudaEvent_t *ev = c->ev_tune[1];
+		const uint32_t last = t.n_variants + 1;
+		const unsigned long long *vtx = reinterpret_cast<const unsigned long long *>(c->d_vtx);
+		CU(cudaEventRecord(c->ev[EV_BC], st));
+		CU(cudaMemsetAsync(c->d_tune_mismatch + HCM_MAX_VARIANTS, 0, HCM_MAX_VARIANTS * sizeof(uint32_t), st));
+		for (uint32_t r = 0; r < last; ++r) {
+			CU(cudaEventRecord(ev[2 * r], st));
+			launch_mesh(c->maps, mesh_params(c, 0), c->grid, (int)r, st);
+			CU(cudaEventRecord(ev[2 * r + 1], st));
+			if (r == 0) {
+				launch_mesh_digest(c->d_task_out, c->d_mesh_out, vtx, c->d_idx, c->batch_n, c->mesh_cap, c->vtx_cap, c->idx_cap, nullptr, c->d_digest[0],
+				                   c->d_tune_mismatch, st);
+				if (c->tune_fault)
+					CU(cudaMemsetAsync(c->d_digest[0], 0xa5, sizeof(unsigned long long), st));
+			} else
+				launch_mesh_digest(c->d_task_out, c->d_mesh_out, vtx, c->d_idx, c->batch_n, c->mesh_cap, c->vtx_cap, c->idx_cap, c->d_digest[0], c->d_digest[1],
+				                   c->d_tune_mismatch + HCM_MAX_VARIANTS + (r - 1), st);
+			CU(cudaMemcpyAsync(&c->h_tune->heads[r], c->d_heads, sizeof(BatchHeads), cudaMemcpyDeviceToHost, st));
+			CU(cudaMemsetAsync(c->d_heads, 0, offsetof(BatchHeads, n_work), st));
+			CU(cudaMemsetAsync(&c->d_heads->cursor, 0, sizeof(unsigned int), st));
+		}
+		CU(cudaEventRecord(ev[2 * last], st));
 	}
 	CU(cudaEventRecord(c->ev[EV_B1], st));
-	if (c->batch_ab)
-		CU(cudaEventRecord(c->ev[EV_TB0], st));
 	launch_mesh(c->maps, mesh_params(c, 0), c->grid, c->batch_ab ? 0 : (int)t.selected, st);
 	CU(cudaGetLastError());
 	CU(cudaEventRecord(c->ev[EV_B2], st));
-	if (c->batch_ab)
-		CU(cudaEventRecord(c->ev[EV_TB1], st));
 	c->stats.kernel_launches += 2;
 	if (c->batch_ab) {
-		launch_mesh_digest(c->d_task_out, c->d_mesh_out, reinterpret_cast<const unsigned long long *>(c->d_vtx), c->d_idx, c->batch_n, c->mesh_cap, c->vtx_cap,
-		                   c->idx_cap, c->d_digest[0], c->d_digest[1], c->d_tune_mismatch + 1, st);
-		CU(cudaGetLastError());
-		CU(cudaMemcpyAsync(&c->h_tune->heads_base, c->d_heads, sizeof(BatchHeads), cudaMemcpyDeviceToHost, st));
-		CU(cudaMemcpyAsync(&c->h_tune->mismatch[1], c->d_tune_mismatch + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-		CU(cudaEventRecord(c->ev[EV_TM_DONE], st));
+		const uint32_t last = t.n_variants + 1;
+		CU(cudaEventRecord(c->ev_tune[1][2 * last + 1], st));
+		CU(cudaMemcpyAsync(&c->h_tune->heads[last], c->d_heads, sizeof(BatchHeads), cudaMemcpyDeviceToHost, st));
+		CU(cudaMemcpyAsync(c->h_tune->mismatch[1], c->d_tune_mismatch + HCM_MAX_VARIANTS, HCM_MAX_VARIANTS * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+		CU(cudaEventRecord(c->ev_tune[1][kTuneDone], st));
 		t.in_flight = true, t.invalid = false;
-		c->stats.kernel_launches += 3;
+		c->stats.kernel_launches += 2 * t.n_variants + 2;
 	}
 	c->ev_batch = true;
 	return HCM_OK;
@@ -736,6 +756,10 @@ void hcm_destroy(hcm_ctx *c) {
 	for (auto &e : c->ev)
 		if (e)
 			cudaEventDestroy(e);
+	for (auto &row : c->ev_tune)
+		for (auto &e : row)
+			if (e)
+				cudaEventDestroy(e);
 	if (c->ev_peer)
 		cudaEventDestroy(c->ev_peer);
 	for (auto &e : c->block_events)
@@ -793,10 +817,12 @@ int hcm_create(const hcm_registry *registry, const hcm_config *cfg, hcm_ctx **ou
 		c->adaptive_upload = atoi(ad) != 0;
 	if (const char *tu = getenv("HCM_TUNE"))
 		c->tune = atoi(tu) != 0;
+	c->tune_derive.n_variants = (uint32_t)std::min(derive_variant_count(), HCM_MAX_VARIANTS);
+	c->tune_mesh.n_variants = (uint32_t)std::min(mesh_variant_count(), HCM_MAX_VARIANTS);
 	if (const char *dv = getenv("HCM_DERIVE_VARIANT"))
-		c->tune_derive.forced = atoi(dv) != 0, c->tune_derive.selected = (uint32_t)c->tune_derive.forced;
+		c->tune_derive.forced = std::min(std::max(atoi(dv), 0), (int)c->tune_derive.n_variants), c->tune_derive.selected = (uint32_t)c->tune_derive.forced;
 	if (const char *mv = getenv("HCM_MESH_VARIANT"))
-		c->tune_mesh.forced = atoi(mv) != 0, c->tune_mesh.selected = (uint32_t)c->tune_mesh.forced;
+		c->tune_mesh.forced = std::min(std::max(atoi(mv), 0), (int)c->tune_mesh.n_variants), c->tune_mesh.selected = (uint32_t)c->tune_mesh.forced;
 	if (const char *tc = getenv("HCM_TUNE_MIN_CHUNKS"))
 		c->tune_min_chunks = (uint32_t)std::max(1, atoi(tc));
 	if (const char *tt = getenv("HCM_TUNE_MIN_TASKS"))
@@ -894,7 +920,10 @@ int hcm_create(const hcm_registry *registry, const hcm_config *cfg, hcm_ctx **ou
 	memset(c->h_tune, 0, sizeof(TuneHost));
 	for (int i = 0; i < 2; ++i)
 		CUB(dev_alloc(c, &c->d_digest[i], (size_t)std::max(c->max_chunks, c->max_tasks)));
-	CUB(dev_alloc(c, &c->d_tune_mismatch, 2));
+	CUB(dev_alloc(c, &c->d_tune_mismatch, 2 * HCM_MAX_VARIANTS));
+	for (auto &row : c->ev_tune)
+		for (auto &e : row)
+			CUB(cudaEventCreate(&e));
 	for (int i = 0; i < 2; ++i) {
 		CUB(cudaHostAlloc((void **)&c->h_task_ring[i], (size_t)c->max_tasks * sizeof(TaskIn), cudaHostAllocDefault));
 		CUB(cudaEventCreateWithFlags(&c->task_ring_ev[i], cudaEventDisableTiming));
@@ -1955,7 +1984,7 @@ int hcm_get_stats(hcm_ctx *c, hcm_stats *out) {
 		CU(cudaEventElapsedTime(&c->stats.derive_ms, c->ev[EV_UP1], c->ev[EV_UP2]));
 	}
 	if (c->ev_batch) {
-		CU(cudaEventElapsedTime(&c->stats.classify_ms, c->ev[EV_B0], c->ev[c->batch_ab ? EV_TM0 : EV_B1]));
+		CU(cudaEventElapsedTime(&c->stats.classify_ms, c->ev[EV_B0], c->ev[c->batch_ab ? EV_BC : EV_B1]));
 		CU(cudaEventElapsedTime(&c->stats.mesh_ms, c->ev[EV_B1], c->ev[EV_B2]));
 	}
 	if (c->ev_fetch)
@@ -1976,7 +2005,9 @@ int hcm_get_tune_info(hcm_ctx *c, hcm_tune_info *out) {
 	if (int rc = tune_harvest(c))
 		return rc;
 	auto fill = [&](const KernelTune &t, hcm_kernel_tune &o) {
-		o.selected = t.selected, o.rounds = t.rounds, o.mismatches = t.mismatches, o.baseline_ms = t.best_base, o.variant_ms = t.best_var;
+		o.selected = t.selected, o.rounds = t.rounds, o.n_variants = t.n_variants, o.baseline_ms = t.sum_base;
+		for (int v = 0; v < HCM_MAX_VARIANTS; ++v)
+			o.variant_ms[v] = t.sum_var[v], o.mismatches[v] = t.mismatches[v];
 		o.state = t.forced >= 0 ? (uint32_t)HCM_TUNE_FORCED : ((!c->tune && t.state == HCM_TUNE_PENDING) ? (uint32_t)HCM_TUNE_OFF : t.state);
 	};
 	fill(c->tune_derive, out->derive), fill(c->tune_mesh, out->mesh);
@@ -1987,8 +2018,8 @@ int hcm_set_option(hcm_ctx *c, const char *name, int64_t value) {
 	if (!c || !name)
 		return HCM_ERR_INVALID;
 	auto force = [&](KernelTune &t) -> int {
-		if (value < -1 || value > 1)
-			return fail(c, HCM_ERR_INVALID, "%s = %lld: 0 (baseline), 1 (variant) or -1 (qualification decides)", name, (long long)value);
+		if (value < -1 || value > (int64_t)t.n_variants)
+			return fail(c, HCM_ERR_INVALID, "%s = %lld: 0 (baseline), 1 .. %u (variant) or -1 (qualification decides)", name, (long long)value, t.n_variants);
 		t.forced = (int)value;
 		if (value >= 0)
 			t.selected = (uint32_t)value;

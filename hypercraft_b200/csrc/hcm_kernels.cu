@@ -141,24 +141,62 @@ __device__ unsigned long long g_phase_cycles[64];
 // ================================================================================================================
 // derive kernel: one CTA per uploaded chunk, 256 threads; thread t owns columns x4..x4+3 of row z
 // ================================================================================================================
-// kVariant 0 (baseline): the chunk's 64 KB arrive as ONE bulk copy; nothing is computed before the last byte has landed.
-// kVariant 1: FOUR 16 KB bulk copies (eight y-layers each) on four mbarriers.  The uniform test runs quarter by quarter and
-// a chunk that is not uniform leaves it at the first quarter that says so: its per-voxel lookups then run under the copies of the
-// later quarters, each waited for when the walk reaches its first layer.  The sunlight-height load (1 KB of HBM, a full DRAM
-// round trip that the baseline takes between the copy's completion and the block-wide vote) is issued before the first wait.
-// Same arithmetic, same bytes written; which one a context launches is decided on the device (hcm.h, "Kernel variants").
+// kForm 0 (baseline): the chunk's 64 KB arrive as ONE bulk copy; nothing is computed before the last byte has landed.
+// The variant forms re-schedule that (same arithmetic, same bytes written; which one a context launches is decided on the device:
+// hcm.h, "Kernel variants"):
+//   quarters (forms 1, 3): FOUR 16 KB bulk copies (eight y-layers each) on four mbarriers.  The uniform test runs quarter by quarter
+//     and a chunk that is not uniform leaves it at the first quarter that says so: its per-voxel lookups then run under the copies of
+//     the later quarters, each waited for when the walk reaches its first layer.
+//   hoist (forms 1, 2, 3): the sunlight-height load (1 KB of HBM, a full DRAM round trip that the baseline takes between the copy's
+//     completion and the block-wide vote) is issued before the first wait.
+//   L2 prefetch (forms 2, 3): the bytes in flight of the baseline are bounded by shared memory (3 CTAs x 64 KB per SM).  Thread 0
+//     also reads the entry of the CTA one wave of resident CTAs further down the grid and, once its own copy has landed, asks the
+//     L2 for that chunk's 64 KB + heights (cp.async.bulk.prefetch.L2): when that CTA starts, its copy is an L2 hit.
 constexpr int kDeriveQuarterBytes = HCM_CHUNK_VOXELS * 2 / 4; // 16384: y-layers 8q .. 8q+7
-template <int kVariant>
+constexpr int kDerivePrefetchDistance = 3 * 148;              // CTAs resident on a B200 at 3 per SM: one wave ahead
+constexpr int kDeriveForms = 4;
+#ifdef HCM_CUSIM
+__device__ __forceinline__ void prefetch_l2_bulk(const void *, u32) {}
+#else
+__device__ __forceinline__ void prefetch_l2_bulk(const void *src, u32 bytes) {
+	asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
+#endif
+// the entry one wave ahead, held by thread 0 (forms with the L2 prefetch only: the other forms carry nothing)
+template <bool kOn> struct DeriveAhead {};
+template <> struct DeriveAhead<true> {
+	int32_t slot = -1;
+	u32 flags = 0;
+	__device__ __forceinline__ void load(const UploadEntry *entries, int tid) {
+		if (tid == 0 && blockIdx.x + kDerivePrefetchDistance < gridDim.x) {
+			const UploadEntry a = entries[blockIdx.x + kDerivePrefetchDistance];
+			slot = a.slot, flags = a.flags;
+		}
+	}
+	__device__ __forceinline__ void issue(const DevWorld &w, const int8_t *raw_heights, int tid) const { // after the CTA's own copy has landed
+		if (tid == 0 && slot >= 0) {
+			if (!(flags & UE_UNIFORM))
+				prefetch_l2_bulk(w.raw + (size_t)slot * HCM_CHUNK_VOXELS, HCM_CHUNK_VOXELS * 2);
+			prefetch_l2_bulk(raw_heights + (size_t)slot * HCM_CHUNK_COLUMNS, HCM_CHUNK_COLUMNS);
+		}
+	}
+};
+template <int kForm>
 __global__ void __launch_bounds__(256, 3) derive_kernel(DevWorld w, const UploadEntry *__restrict__ entries, const uint8_t *__restrict__ prop_index,
                                                      const DevTables *__restrict__ tables, const int8_t *__restrict__ raw_heights) {
 	HCM_DYNAMIC_SMEM(derive_smem); // the chunk's 64 KB of Block data, one TMA bulk copy
 	__shared__ uint16_t s_pinfo[256];                       // pflags | light level << 8
 	__shared__ u32 s_idinfo[256];                           // by block id: row | pflags << 8 | level << 16, bit 31: the row depends on meta
 	__shared__ u32 s_and, s_or;
+	constexpr int kVariant = (kForm == 1 || kForm == 3) ? 1 : 0; // quarters
+	constexpr bool kHoist = kForm != 0, kPrefetch = kForm >= 2;
 	__shared__ __align__(8) u64 s_bars[kVariant == 0 ? 1 : 4];
 	u64 &s_bar = s_bars[0];
 	const int tid = threadIdx.x;
 	const UploadEntry e = entries[blockIdx.x];
+	DeriveAhead<kPrefetch> ahead;
+	if constexpr (kPrefetch)
+		ahead.load(entries, tid);
 	const bool host_uniform = e.flags & UE_UNIFORM;
 	if (tid == 0) {
 		mbar_init(&s_bar, 1);
@@ -178,8 +216,8 @@ __global__ void __launch_bounds__(256, 3) derive_kernel(DevWorld w, const Upload
 				            &s_bars[kVariant == 1 ? q : 0]);
 			}
 	}
-	char4 hv = make_char4(0, 0, 0, 0); // variant: the chunk's sunlight heights, requested before anything is waited for
-	if (kVariant == 1)
+	char4 hv = make_char4(0, 0, 0, 0); // hoist: the chunk's sunlight heights, requested before anything is waited for
+	if (kHoist)
 		hv = *reinterpret_cast<const char4 *>(raw_heights + (size_t)e.slot * HCM_CHUNK_COLUMNS + (tid >> 3) * 32 + ((tid & 7) << 2));
 	s_pinfo[tid] = (uint16_t)(tables->pflags[tid] | ((tables->pmisc[tid] >> 4) << 8));
 	s_idinfo[tid] = reinterpret_cast<const u32 *>(prop_index + 65536)[tid];
@@ -206,7 +244,12 @@ __global__ void __launch_bounds__(256, 3) derive_kernel(DevWorld w, const Upload
 		for (int y = 0; y < 32; ++y)
 			*reinterpret_cast<uint2 *>(rw + x4 + (y * 32 + z) * 32) = make_uint2(pat, pat);
 	} else if (kVariant == 0) {
-		mbar_wait(&s_bar, 0);
+		if constexpr (kForm == 0)
+			mbar_wait(&s_bar, 0);
+		else
+			mbar_wait_bounded(&s_bar, 0);
+		if constexpr (kPrefetch)
+			ahead.issue(w, raw_heights, tid);
 		d0 = sraw[0], pat = d0 | (d0 << 16);
 		u32 acc_and = 0xffffffffu, acc_or = 0; // uniform <=> AND == OR == pattern
 #pragma unroll
@@ -226,6 +269,9 @@ __global__ void __launch_bounds__(256, 3) derive_kernel(DevWorld w, const Upload
 		for (int q = 0; q < 4; ++q) {
 			if (q)
 				mbar_wait_bounded(&s_bars[kVariant == 1 ? q : 0], 0);
+			if constexpr (kPrefetch)
+				if (q == 3)
+					ahead.issue(w, raw_heights, tid); // the uniform test got to the last quarter: the whole copy has landed
 #pragma unroll
 			for (int y = 8 * q; y < 8 * q + 8; ++y) {
 				const uint2 r = *reinterpret_cast<const uint2 *>(sraw + x4 + (y * 32 + z) * 32);
@@ -238,10 +284,13 @@ __global__ void __launch_bounds__(256, 3) derive_kernel(DevWorld w, const Upload
 			}
 		}
 	}
-	if (kVariant == 0)
+	if (!kHoist)
 		*reinterpret_cast<char4 *>(w.height + col) = *reinterpret_cast<const char4 *>(raw_heights + (size_t)e.slot * HCM_CHUNK_COLUMNS + z * 32 + x4);
 	else
 		*reinterpret_cast<char4 *>(w.height + col) = hv;
+	if constexpr (kPrefetch)
+		if (host_uniform)
+			ahead.issue(w, raw_heights, tid); // nothing of its own to wait for
 	if (__syncthreads_and(same)) {
 		const u32 pr = __ldg(prop_index + d0);
 		const u32 info = s_pinfo[pr], fl = info & 0xffu, lvl = info >> 8;
@@ -283,8 +332,12 @@ __global__ void __launch_bounds__(256, 3) derive_kernel(DevWorld w, const Upload
 	u32 f_and = 0xffffffffu, f_or = 0; // info words accumulated over the thread's voxels: flags in bits 8..15, light level from bit 16
 #pragma unroll 8
 	for (int y = 0; y < 32; ++y) {
-		if (kVariant == 1 && (y & 7) == 0 && y) // the quarter this layer opens (already there if the uniform test got that far)
+		if (kVariant == 1 && (y & 7) == 0 && y) { // the quarter this layer opens (already there if the uniform test got that far)
 			mbar_wait_bounded(&s_bars[kVariant == 1 ? (y >> 3) : 0], 0);
+			if constexpr (kPrefetch)
+				if (y == 24)
+					ahead.issue(w, raw_heights, tid); // (a second request for the same lines, if the uniform test already made it, is answered by the L2)
+		}
 		const uint2 r = *reinterpret_cast<const uint2 *>(sraw + x4 + (y * 32 + z) * 32);
 		const u32 d[4] = {r.x & 0xffffu, r.x >> 16, r.y & 0xffffu, r.y >> 16};
 		u32 info[4];
@@ -2247,11 +2300,15 @@ void launch_derive(const DevWorld &w, const UploadEntry *entries, u32 n, const u
                    int variant, cudaStream_t st) {
 	if (!n)
 		return;
-	if (variant == 0)
-		HCM_LAUNCH(derive_kernel<0>, n, 256, HCM_CHUNK_VOXELS * 2, st, w, entries, prop_index, tables, raw_heights);
-	else
-		HCM_LAUNCH(derive_kernel<1>, n, 256, HCM_CHUNK_VOXELS * 2, st, w, entries, prop_index, tables, raw_heights);
+	switch (variant) {
+	case 1: HCM_LAUNCH(derive_kernel<1>, n, 256, HCM_CHUNK_VOXELS * 2, st, w, entries, prop_index, tables, raw_heights); break;
+	case 2: HCM_LAUNCH(derive_kernel<2>, n, 256, HCM_CHUNK_VOXELS * 2, st, w, entries, prop_index, tables, raw_heights); break;
+	case 3: HCM_LAUNCH(derive_kernel<3>, n, 256, HCM_CHUNK_VOXELS * 2, st, w, entries, prop_index, tables, raw_heights); break;
+	default: HCM_LAUNCH(derive_kernel<0>, n, 256, HCM_CHUNK_VOXELS * 2, st, w, entries, prop_index, tables, raw_heights); break;
+	}
 }
+int derive_variant_count() { return kDeriveForms - 1; }
+int mesh_variant_count() { return 1; }
 void launch_clear(const DevWorld &w, const UploadEntry *entries, u32 n, cudaStream_t st) {
 	if (n)
 		HCM_LAUNCH(clear_kernel, n, 256, 0, st, w, entries);
@@ -2282,6 +2339,10 @@ cudaError_t mesh_kernel_prepare() {
 	cudaError_t e = cudaFuncSetAttribute(derive_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, HCM_CHUNK_VOXELS * 2);
 	if (e == cudaSuccess)
 		e = cudaFuncSetAttribute(derive_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, HCM_CHUNK_VOXELS * 2);
+	if (e == cudaSuccess)
+		e = cudaFuncSetAttribute(derive_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, HCM_CHUNK_VOXELS * 2);
+	if (e == cudaSuccess)
+		e = cudaFuncSetAttribute(derive_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, HCM_CHUNK_VOXELS * 2);
 	if (e == cudaSuccess)
 		e = cudaFuncSetAttribute(mesh_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
 	if (e == cudaSuccess)

@@ -65,17 +65,22 @@ class _Stats(ctypes.Structure):
 assert ctypes.sizeof(_Stats) == 64
 
 
+MAX_VARIANTS = 3
+
+
 class _KernelTune(ctypes.Structure):
-    _fields_ = [("selected", ctypes.c_uint32), ("state", ctypes.c_uint32), ("rounds", ctypes.c_uint32), ("mismatches", ctypes.c_uint32),
-                ("baseline_ms", ctypes.c_float), ("variant_ms", ctypes.c_float)]
+    _fields_ = [("selected", ctypes.c_uint32), ("state", ctypes.c_uint32), ("rounds", ctypes.c_uint32), ("n_variants", ctypes.c_uint32),
+                ("baseline_ms", ctypes.c_float), ("variant_ms", ctypes.c_float * MAX_VARIANTS), ("mismatches", ctypes.c_uint32 * MAX_VARIANTS)]
 
 
 class _TuneInfo(ctypes.Structure):
     _fields_ = [("derive", _KernelTune), ("mesh", _KernelTune)]
 
 
-assert ctypes.sizeof(_TuneInfo) == 48
-TUNE_STATES = ["pending", "variant adopted", "baseline kept", "variant rejected (bytes differ)", "forced", "off"]
+assert ctypes.sizeof(_TuneInfo) == 88
+TUNE_STATES = ["pending", "variant adopted", "baseline kept", "baseline kept, a variant rejected (bytes differ)", "forced", "off"]
+VARIANT_NAMES = {"derive": ["baseline", "quarters + hoist", "hoist + L2 prefetch", "quarters + hoist + L2 prefetch"],
+                 "mesh": ["baseline", "merge height test four rows per round"]}
 
 
 MESH_DESC_DTYPE = np.dtype([("task", np.uint32), ("transparent", np.uint32), ("vertex_offset", np.uint64), ("index_offset", np.uint64),
@@ -381,8 +386,12 @@ class Mesher:
         out = {}
         for name in ("derive", "mesh"):
             k = getattr(t, name)
-            out[name] = {"selected": "variant" if k.selected else "baseline", "state": TUNE_STATES[k.state] if k.state < len(TUNE_STATES) else str(k.state),
-                         "rounds": int(k.rounds), "mismatches": int(k.mismatches), "baseline_ms": float(k.baseline_ms), "variant_ms": float(k.variant_ms)}
+            n = int(k.n_variants)
+            out[name] = {"selected": int(k.selected), "selected_name": VARIANT_NAMES[name][k.selected] if k.selected < len(VARIANT_NAMES[name]) else str(k.selected),
+                         "state": TUNE_STATES[k.state] if k.state < len(TUNE_STATES) else str(k.state), "rounds": int(k.rounds), "n_variants": n,
+                         "baseline_ms": float(k.baseline_ms), "variant_ms": [float(k.variant_ms[v]) for v in range(n)],
+                         "mismatches": [int(k.mismatches[v]) for v in range(n)],
+                         "variant_names": VARIANT_NAMES[name][1:n + 1], "times": "summed over the A/B rounds (CUDA events)"}
         return out
 
     def set_option(self, name: str, value: int) -> None:

@@ -350,38 +350,41 @@ void *hcm_stream(hcm_ctx *ctx); /* the ctx's cudaStream_t, for external event ti
 /* ------------------------------------------------------------------------------------------------------------
  * Kernel variants, qualified on the device that runs them
  * ------------------------------------------------------------------------------------------------------------
- * derive_kernel and mesh_kernel each exist in a baseline form and in a variant form that re-schedules the same arithmetic
+ * derive_kernel and mesh_kernel each exist in a baseline form and in variant forms that re-schedule the same arithmetic
  * (DESIGN.md section 3b).  A context starts on the baselines.  The first large calls (a re-derive / upload block of at least
- * `tune_min_chunks` chunks, a mesh batch of at least `tune_min_tasks` tasks) run BOTH forms on the same input, the variant
- * first, the baseline last (so that the call's result is the baseline's whatever happens), hash what each wrote -- per chunk
- * the derived property bytes, light planes, heights and flags; per task the mesh descriptors, vertex bytes and index bytes --
- * and time both with CUDA events.  After `tune_rounds` such calls the variant is adopted iff every hash matched and its time,
- * summed over the rounds, was at least 2 % below the baseline's; a single differing hash rejects it for the life of the context.  Nothing here involves the host CPU
- * in the computation: both forms are sm_100a kernels of this library, and a rejected variant is simply never launched again.
- * Environment at hcm_create: HCM_TUNE=0 (baselines only), HCM_DERIVE_VARIANT / HCM_MESH_VARIANT = 0 | 1 (forced). */
+ * `tune_min_chunks` chunks, a mesh batch of at least `tune_min_tasks` tasks) are A/B rounds: the baseline runs, then every
+ * variant, then the baseline again (so that the call's result is the baseline's whatever happens); a hash kernel digests what
+ * each run wrote -- per chunk the derived property bytes, light planes, heights and flags; per task the mesh descriptors,
+ * vertex bytes and index bytes -- the variants' hashes are compared with the baseline's on the device, and every run is timed
+ * with CUDA events.  After `tune_rounds` such calls the fastest variant whose every hash matched is adopted iff its time,
+ * summed over the rounds, was at least 2 % below the baseline's; a variant with a single differing hash is never launched
+ * again by this context.  Nothing here involves the host CPU in the computation: all forms are sm_100a kernels of this library.
+ * Environment at hcm_create: HCM_TUNE=0 (baselines only), HCM_DERIVE_VARIANT / HCM_MESH_VARIANT = 0 .. n (forced). */
 enum {
 	HCM_TUNE_PENDING = 0,          /* not enough large calls yet: the baseline runs */
-	HCM_TUNE_VARIANT_ADOPTED = 1,  /* identical bytes, faster: the variant runs from now on */
-	HCM_TUNE_BASELINE_KEPT = 2,    /* identical bytes, not faster */
-	HCM_TUNE_VARIANT_REJECTED = 3, /* the variant's output differed from the baseline's on this device */
+	HCM_TUNE_VARIANT_ADOPTED = 1,  /* identical bytes, faster: variant `selected` runs from now on */
+	HCM_TUNE_BASELINE_KEPT = 2,    /* no variant with identical bytes was faster */
+	HCM_TUNE_VARIANT_REJECTED = 3, /* baseline kept, and some variant's output differed from the baseline's on this device */
 	HCM_TUNE_FORCED = 4,           /* selected by environment / hcm_set_option */
 	HCM_TUNE_OFF = 5
 };
+#define HCM_MAX_VARIANTS 3
 typedef struct hcm_kernel_tune {
-	uint32_t selected;    /* 0 baseline, 1 variant: what the next launch uses */
+	uint32_t selected;    /* 0 baseline, k = variant k: what the next launch uses */
 	uint32_t state;       /* HCM_TUNE_* */
 	uint32_t rounds;      /* A/B rounds completed */
-	uint32_t mismatches;  /* units (chunks / tasks) whose hashes differed, all rounds */
-	float baseline_ms;    /* summed over the rounds (the rounds may differ in size; both forms ran on the same inputs) */
-	float variant_ms;
-} hcm_kernel_tune; /* 24 bytes */
+	uint32_t n_variants;  /* variant forms this kernel has (<= HCM_MAX_VARIANTS) */
+	float baseline_ms;    /* summed over the rounds (per round: the mean of the baseline's two runs); the rounds may differ in size */
+	float variant_ms[HCM_MAX_VARIANTS];       /* summed over the rounds, same inputs */
+	uint32_t mismatches[HCM_MAX_VARIANTS];    /* units (chunks / tasks) whose hashes differed, all rounds */
+} hcm_kernel_tune; /* 44 bytes */
 typedef struct hcm_tune_info {
 	hcm_kernel_tune derive, mesh;
-} hcm_tune_info; /* 48 bytes */
+} hcm_tune_info; /* 88 bytes */
 int hcm_get_tune_info(hcm_ctx *ctx, hcm_tune_info *out);
 
 /* Run-time knobs of a context (what the HCM_* environment variables set at hcm_create).  Names: "upload_adaptive" (0 | 1),
- * "tune" (0 | 1), "derive_variant" / "mesh_variant" (0 | 1: forced; -1: back to qualification), "tune_min_chunks",
+ * "tune" (0 | 1), "derive_variant" / "mesh_variant" (0 .. n: forced; -1: back to qualification), "tune_min_chunks",
  * "tune_min_tasks", "tune_rounds"; "tune_fault" (test knob: the next A/B rounds see one corrupted hash, which must reject the
  * variant).  HCM_ERR_INVALID for an unknown name or a value out of range. */
 int hcm_set_option(hcm_ctx *ctx, const char *name, int64_t value);
