@@ -440,3 +440,30 @@ def test_sharded_edit_round_equals_the_undivided_world(port, world):
             c = port.mesh(blind[r], t)
             stale += not (c.size == b.size and (c == b).all())
     assert mirrored > 0 and stale > 0  # the cuts were really crossed: without the mirror step some meshes come out stale
+
+
+def test_bench_watchdog_prints_the_line_and_leaves():
+    """bench.py's watchdog: when a stage outlives its budget, rank 0 prints the line built from what is complete (with the stage named under
+    "watchdog") and the process exits 0; without a headline yet it exits 3; other ranks print nothing."""
+    import json
+    import subprocess
+    import sys
+
+    prog = ("import sys, time; sys.path.insert(0, %r); import bench; wd = bench.Watchdog(int(sys.argv[1]));"
+            "wd.line_fn = (lambda: {'metric': 'chunks meshed/sec', 'value': 1.0}) if sys.argv[2] == 'headline' else None;"
+            "wd.arm('optional block', 0.5); time.sleep(30); print('not reached')") % ROOT
+    r = subprocess.run([sys.executable, "-c", prog, "0", "headline"], capture_output=True, text=True, timeout=60)
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert r.returncode == 0 and line["value"] == 1.0 and "optional block" in line["watchdog"] and "not reached" not in r.stdout
+    r = subprocess.run([sys.executable, "-c", prog, "0", "none"], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 3 and r.stdout.strip() == ""
+    r = subprocess.run([sys.executable, "-c", prog, "1", "headline"], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_bench_guarded_turns_exceptions_into_an_error_entry():
+    import bench
+
+    assert bench.guarded("x", lambda: {"ok": 1}) == {"ok": 1}
+    out = bench.guarded("device sink", lambda: 1 / 0)
+    assert "error" in out and "ZeroDivisionError" in out["error"] and out["error"].startswith("device sink")
