@@ -512,7 +512,7 @@ void tune_decide(KernelTune &t, const float *run_ms, const uint32_t *mismatch, u
 		return;
 	const uint32_t n = t.n_variants;
 	// rounds differ in size (an upload block, a whole re-derive): the forms are compared on the SUMS over the same rounds
-	t.sum_base += 0.5f * (run_ms[0] + run_ms[n + 1]);
+	t.sum_base += std::min(run_ms[0], run_ms[n + 1]); // the faster of the baseline's two runs: the first one of a small round is cache-cold
 	for (uint32_t v = 0; v < n; ++v)
 		t.sum_var[v] += run_ms[v + 1], t.mismatches[v] += mismatch[v];
 	if (++t.rounds < want_rounds)

@@ -374,7 +374,7 @@ typedef struct hcm_kernel_tune {
 	uint32_t state;       /* HCM_TUNE_* */
 	uint32_t rounds;      /* A/B rounds completed */
 	uint32_t n_variants;  /* variant forms this kernel has (<= HCM_MAX_VARIANTS) */
-	float baseline_ms;    /* summed over the rounds (per round: the mean of the baseline's two runs); the rounds may differ in size */
+	float baseline_ms;    /* summed over the rounds (per round: the faster of the baseline's two runs); the rounds may differ in size */
 	float variant_ms[HCM_MAX_VARIANTS];       /* summed over the rounds, same inputs */
 	uint32_t mismatches[HCM_MAX_VARIANTS];    /* units (chunks / tasks) whose hashes differed, all rounds */
 } hcm_kernel_tune; /* 44 bytes */
