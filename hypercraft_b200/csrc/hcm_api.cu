@@ -23,7 +23,7 @@
 
 namespace hcm {
 void launch_derive(const DevWorld &w, const UploadEntry *entries, uint32_t n, const uint8_t *prop_index, const DevTables *tables,
-                   const int8_t *raw_heights, int variant, cudaStream_t st);
+                   const int8_t *raw_heights, int variant, bool trial, cudaStream_t st);
 void launch_derive_digest(const DevWorld &w, const UploadEntry *entries, uint32_t n, const int8_t *raw_heights, const unsigned long long *expect,
                           unsigned long long *out, uint32_t *mismatches, cudaStream_t st);
 void launch_mesh_digest(const hcm_task_result *task_out, const hcm_mesh_desc *meshes, const unsigned long long *vtx, const uint16_t *idx, uint32_t n,
@@ -574,7 +574,7 @@ int derive_launch(hcm_ctx *c, const UploadEntry *entries, uint32_t n, cudaStream
 			if (r == last && rec_begin)
 				CU(cudaEventRecord(c->ev[EV_UP1], st));
 			CU(cudaEventRecord(ev[2 * r], st));
-			launch_derive(c->w, entries, n, c->d_prop_index, c->d_tables, c->d_rawh, form, st);
+			launch_derive(c->w, entries, n, c->d_prop_index, c->d_tables, c->d_rawh, form, true, st);
 			CU(cudaEventRecord(ev[2 * r + 1], st));
 			if (r == last && rec_end)
 				CU(cudaEventRecord(c->ev[EV_UP2], st));
@@ -594,7 +594,7 @@ int derive_launch(hcm_ctx *c, const UploadEntry *entries, uint32_t n, cudaStream
 	}
 	if (rec_begin)
 		CU(cudaEventRecord(c->ev[EV_UP1], st));
-	launch_derive(c->w, entries, n, c->d_prop_index, c->d_tables, c->d_rawh, (int)t.selected, st);
+	launch_derive(c->w, entries, n, c->d_prop_index, c->d_tables, c->d_rawh, (int)t.selected, false, st);
 	CU(cudaGetLastError());
 	if (rec_end)
 		CU(cudaEventRecord(c->ev[EV_UP2], st));

@@ -181,7 +181,11 @@ template <> struct DeriveAhead<true> {
 		}
 	}
 };
-template <int kForm>
+// kTrial: the launch is part of an A/B round.  Only there are the variant forms' waits bounded (a form being tried out must not be able
+// to hang the context: after a time-out the CTA stops waiting, its output differs, the form is rejected); a form that was adopted or
+// forced waits like the baseline does -- a bounded wait that gave up spuriously (a context switched out for a quarter of a second)
+// would corrupt data with nobody comparing.
+template <int kForm, bool kTrial = false>
 __global__ void __launch_bounds__(256, 3) derive_kernel(DevWorld w, const UploadEntry *__restrict__ entries, const uint8_t *__restrict__ prop_index,
                                                      const DevTables *__restrict__ tables, const int8_t *__restrict__ raw_heights) {
 	HCM_DYNAMIC_SMEM(derive_smem); // the chunk's 64 KB of Block data, one TMA bulk copy
@@ -194,6 +198,14 @@ __global__ void __launch_bounds__(256, 3) derive_kernel(DevWorld w, const Upload
 	u64 &s_bar = s_bars[0];
 	const int tid = threadIdx.x;
 	const UploadEntry e = entries[blockIdx.x];
+	bool gave_up = false; // kTrial only
+	auto wait_for = [&](u64 *bar) {
+		if constexpr (kTrial) {
+			if (!gave_up)
+				gave_up = !mbar_wait_bounded(bar, 0);
+		} else
+			mbar_wait(bar, 0);
+	};
 	DeriveAhead<kPrefetch> ahead;
 	if constexpr (kPrefetch)
 		ahead.load(entries, tid);
@@ -247,7 +259,7 @@ __global__ void __launch_bounds__(256, 3) derive_kernel(DevWorld w, const Upload
 		if constexpr (kForm == 0)
 			mbar_wait(&s_bar, 0);
 		else
-			mbar_wait_bounded(&s_bar, 0);
+			wait_for(&s_bar);
 		if constexpr (kPrefetch)
 			ahead.issue(w, raw_heights, tid);
 		d0 = sraw[0], pat = d0 | (d0 << 16);
@@ -261,14 +273,14 @@ __global__ void __launch_bounds__(256, 3) derive_kernel(DevWorld w, const Upload
 	} else {
 		// quarter by quarter; the CTA leaves at the first quarter in which some thread saw a second value (the vote is block-wide,
 		// so every thread takes the same way out) -- the later quarters are then waited for by the walk below
-		mbar_wait_bounded(&s_bars[0], 0);
+		wait_for(&s_bars[0]);
 		d0 = sraw[0], pat = d0 | (d0 << 16);
 		u32 acc_and = 0xffffffffu, acc_or = 0;
 		same = true;
 #pragma unroll 1
 		for (int q = 0; q < 4; ++q) {
 			if (q)
-				mbar_wait_bounded(&s_bars[kVariant == 1 ? q : 0], 0);
+				wait_for(&s_bars[kVariant == 1 ? q : 0]);
 			if constexpr (kPrefetch)
 				if (q == 3)
 					ahead.issue(w, raw_heights, tid); // the uniform test got to the last quarter: the whole copy has landed
@@ -333,7 +345,7 @@ __global__ void __launch_bounds__(256, 3) derive_kernel(DevWorld w, const Upload
 #pragma unroll 8
 	for (int y = 0; y < 32; ++y) {
 		if (kVariant == 1 && (y & 7) == 0 && y) { // the quarter this layer opens (already there if the uniform test got that far)
-			mbar_wait_bounded(&s_bars[kVariant == 1 ? (y >> 3) : 0], 0);
+			wait_for(&s_bars[kVariant == 1 ? (y >> 3) : 0]);
 			if constexpr (kPrefetch)
 				if (y == 24)
 					ahead.issue(w, raw_heights, tid); // (a second request for the same lines, if the uniform test already made it, is answered by the L2)
@@ -2297,15 +2309,29 @@ void launch_scatter(const hcm_mesh_placement *placements, u32 n, const hcm_mesh_
 		HCM_LAUNCH(scatter_kernel, min((u32)grid, n), 256, 0, st, placements, n, meshes, vtx, idx, (u64 *)vdst, (uint16_t *)idst);
 }
 void launch_derive(const DevWorld &w, const UploadEntry *entries, u32 n, const uint8_t *prop_index, const DevTables *tables, const int8_t *raw_heights,
-                   int variant, cudaStream_t st) {
+                   int variant, bool trial, cudaStream_t st) {
 	if (!n)
 		return;
-	switch (variant) {
-	case 1: HCM_LAUNCH(derive_kernel<1>, n, 256, HCM_CHUNK_VOXELS * 2, st, w, entries, prop_index, tables, raw_heights); break;
-	case 2: HCM_LAUNCH(derive_kernel<2>, n, 256, HCM_CHUNK_VOXELS * 2, st, w, entries, prop_index, tables, raw_heights); break;
-	case 3: HCM_LAUNCH(derive_kernel<3>, n, 256, HCM_CHUNK_VOXELS * 2, st, w, entries, prop_index, tables, raw_heights); break;
-	default: HCM_LAUNCH(derive_kernel<0>, n, 256, HCM_CHUNK_VOXELS * 2, st, w, entries, prop_index, tables, raw_heights); break;
+	// (the emulation's launch macro takes the kernel as ONE macro argument: no comma inside the template argument list)
+#define HCM_DERIVE_CASE(form, kernel) \
+	case form: HCM_LAUNCH(kernel, n, 256, HCM_CHUNK_VOXELS * 2, st, w, entries, prop_index, tables, raw_heights); break
+	if (trial) {
+		constexpr auto t1 = derive_kernel<1, true>, t2 = derive_kernel<2, true>, t3 = derive_kernel<3, true>;
+		switch (variant) {
+			HCM_DERIVE_CASE(1, t1);
+			HCM_DERIVE_CASE(2, t2);
+			HCM_DERIVE_CASE(3, t3);
+		default: HCM_LAUNCH(derive_kernel<0>, n, 256, HCM_CHUNK_VOXELS * 2, st, w, entries, prop_index, tables, raw_heights); break;
+		}
+	} else {
+		switch (variant) {
+			HCM_DERIVE_CASE(1, derive_kernel<1>);
+			HCM_DERIVE_CASE(2, derive_kernel<2>);
+			HCM_DERIVE_CASE(3, derive_kernel<3>);
+		default: HCM_LAUNCH(derive_kernel<0>, n, 256, HCM_CHUNK_VOXELS * 2, st, w, entries, prop_index, tables, raw_heights); break;
+		}
 	}
+#undef HCM_DERIVE_CASE
 }
 int derive_variant_count() { return kDeriveForms - 1; }
 int mesh_variant_count() { return 1; }
@@ -2343,6 +2369,12 @@ cudaError_t mesh_kernel_prepare() {
 		e = cudaFuncSetAttribute(derive_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, HCM_CHUNK_VOXELS * 2);
 	if (e == cudaSuccess)
 		e = cudaFuncSetAttribute(derive_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, HCM_CHUNK_VOXELS * 2);
+	if (e == cudaSuccess)
+		e = cudaFuncSetAttribute(derive_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, HCM_CHUNK_VOXELS * 2);
+	if (e == cudaSuccess)
+		e = cudaFuncSetAttribute(derive_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, HCM_CHUNK_VOXELS * 2);
+	if (e == cudaSuccess)
+		e = cudaFuncSetAttribute(derive_kernel<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, HCM_CHUNK_VOXELS * 2);
 	if (e == cudaSuccess)
 		e = cudaFuncSetAttribute(mesh_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
 	if (e == cudaSuccess)
