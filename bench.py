@@ -288,6 +288,67 @@ class PortArm:
         return self.port.mesh(self.chunks, tuple(int(c) for c in pos))
 
 
+def parse_cpulist(text: str) -> list:
+    """"0-15,32-47" -> [0..15, 32..47] (the format of sysfs cpulist files)."""
+    out = []
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        a, _, b = part.partition("-")
+        out.extend(range(int(a), int(b or a) + 1))
+    return out
+
+
+def split_cores_by_gpu(allowed: list, local_lists: list) -> list:
+    """Cores per rank for ranks sharing one host.  `local_lists[r]` = the cores on the NUMA node of rank r's GPU (sysfs
+    local_cpulist; None if unknown), `allowed` = this process' affinity mask.  Ranks whose GPUs hang off the same node share that node's
+    cores in rank order, so that a rank's scan threads, its pinned buffers (first touch) and its GPU's PCIe root sit on one socket; a rank
+    whose node is unknown, or whose share would be empty, falls back to an even split of the whole mask."""
+    world = len(local_lists)
+    allowed = sorted(allowed)
+    per = max(1, len(allowed) // world)
+    even = [allowed[r * per:(r + 1) * per] or allowed for r in range(world)]
+    out = []
+    for r, mine in enumerate(local_lists):
+        share = None
+        if mine:
+            node = [c for c in sorted(mine) if c in set(allowed)]
+            peers = [q for q in range(world) if local_lists[q] and sorted(local_lists[q]) == sorted(mine)]
+            k, n = peers.index(r), len(peers)
+            width = len(node) // n
+            share = node[k * width:(k + 1) * width] if width else None
+        out.append(share or even[r])
+    return out
+
+
+def pin_rank_to_cores(local: int, world: int, emulated: bool) -> dict:
+    """sched_setaffinity of this rank to its share of the host's cores (see split_cores_by_gpu); -> what was done, for the line."""
+    try:
+        allowed = sorted(os.sched_getaffinity(0))
+    except (AttributeError, OSError):
+        return {"cores": None, "how": "sched_getaffinity unavailable"}
+    lists = [None] * world
+    how = "even split of the affinity mask"
+    if not emulated:
+        try:
+            import torch
+
+            for r in range(world):
+                p = torch.cuda.get_device_properties(r)
+                path = f"/sys/bus/pci/devices/{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0/local_cpulist"
+                lists[r] = parse_cpulist(open(path).read()) or None
+            if all(lists):
+                how = "cores of the NUMA node of each rank's GPU (sysfs local_cpulist), shared among the ranks of that node"
+        except Exception:  # noqa: BLE001 -- no sysfs entry, fewer visible devices than ranks, older torch: even split
+            lists = [None] * world
+    mine = split_cores_by_gpu(allowed, lists)[local]
+    try:
+        os.sched_setaffinity(0, mine)
+    except OSError:
+        return {"cores": None, "how": "sched_setaffinity refused"}
+    return {"cores": mine, "how": how}
+
+
 def use_reference_build() -> bool:
     """oracle/_ref when it was compiled (it travels to the GPU box); HCM_BENCH_FORCE_PORT=1 selects the port (test knob)."""
     import hcoracle
@@ -746,15 +807,12 @@ def main():
     radius = args.radius
     threads = max(1, (os.cpu_count() or 1) // world)
     os.environ.setdefault("HCM_HOST_THREADS", str(max(1, min(15, threads - 1))))  # upload scan threads of this rank's hcm_ctx
+    affinity = None
     if world > 1:  # ranks share one host: each keeps to its own cores (the scan threads and the CPU arm inherit the mask)
-        try:
-            cores = sorted(os.sched_getaffinity(0))
-            per = max(1, len(cores) // world)
-            mine = cores[local * per:(local + 1) * per]
-            if mine:
-                os.sched_setaffinity(0, mine)
-        except (AttributeError, OSError):
-            pass
+        affinity = pin_rank_to_cores(local, world, emulated)
+        if affinity and affinity.get("cores"):
+            threads = max(1, len(affinity["cores"]))
+            os.environ["HCM_HOST_THREADS"] = str(max(1, min(15, threads - 1)))
     check = not args.no_cpu_baseline
     sampler = ClockSampler(local)
     sampler.start()
@@ -815,6 +873,7 @@ def main():
                        "chunks_meshed_per_gpu": int(len(meshed)), "chunks_resident_per_gpu": int(len(resident)),
                        "tasks_through_full_kernel_per_gpu": int(counts["n_worked"]),
                        "parallelism": f"{world} independent spheres (no collective)",
+                       "rank0_cpu_affinity": ({"n_cores": len(affinity["cores"]), "how": affinity["how"]} if affinity and affinity.get("cores") else None),
                        "l2": f"inputs ({r['device_bytes'] / 1e9:.1f} GB of device-resident world per GPU) larger than L2; no flush needed",
                        "setup_seconds": setup_s},
             "quads_per_s": r["quads_per_s"], "quads_per_step": r["total_quads"], "vertices_per_step_per_gpu": int(counts["n_vertices"]),

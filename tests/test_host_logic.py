@@ -467,3 +467,22 @@ def test_bench_guarded_turns_exceptions_into_an_error_entry():
     assert bench.guarded("x", lambda: {"ok": 1}) == {"ok": 1}
     out = bench.guarded("device sink", lambda: 1 / 0)
     assert "error" in out and "ZeroDivisionError" in out["error"] and out["error"].startswith("device sink")
+
+
+def test_bench_core_split_follows_the_gpus_numa_nodes():
+    """Ranks sharing a host: a rank gets cores of its GPU's NUMA node (shared in rank order among the ranks of that node), an even split
+    of the mask where the node is unknown; nobody ends up without a core."""
+    import bench
+
+    assert bench.parse_cpulist("0-3,8-9\n") == [0, 1, 2, 3, 8, 9] and bench.parse_cpulist("5") == [5]
+    allowed = list(range(32))
+    node0, node1 = list(range(0, 16)), list(range(16, 32))
+    got = bench.split_cores_by_gpu(allowed, [node0, node0, node0, node0, node1, node1, node1, node1])
+    assert got[0] == [0, 1, 2, 3] and got[3] == [12, 13, 14, 15] and got[4] == [16, 17, 18, 19] and got[7] == [28, 29, 30, 31]
+    assert sorted(c for g in got for c in g) == allowed
+    # unknown nodes: even split; a mask smaller than the node list is respected
+    assert bench.split_cores_by_gpu(allowed, [None] * 4) == [list(range(0, 8)), list(range(8, 16)), list(range(16, 24)), list(range(24, 32))]
+    got = bench.split_cores_by_gpu(list(range(8)), [node0, node1])
+    assert got[0] == list(range(8)) and got[1] == list(range(4, 8))  # node 1 has no allowed core: even split for that rank
+    # more ranks on a node than it has allowed cores: fall back, never an empty set
+    assert all(bench.split_cores_by_gpu([0, 1], [node0] * 4))
