@@ -129,7 +129,7 @@ struct hcm_ctx {
 	bool tune_fault = false; // test knob: corrupt the variant's hash of unit 0 before the comparison (the rejection path)
 	uint32_t tune_min_chunks = 2048, tune_min_tasks = 2048, tune_rounds = 2;
 	KernelTune tune_derive, tune_mesh;
-	unsigned long long *d_digest[2] = {nullptr, nullptr}; // per chunk / per task hashes of the two forms' output
+	unsigned long long *d_digest[2] = {nullptr, nullptr}; // per chunk / per task hashes of an A/B round: [0] the baseline's output, [1] the variant under comparison
 	uint32_t *d_tune_mismatch = nullptr;                   // [2]
 	TuneHost *h_tune = nullptr;
 	bool batch_ab = false; // the last mesh batch was an A/B round (which events bracket its classify kernel)
