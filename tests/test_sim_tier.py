@@ -49,6 +49,14 @@ def test_upload_paths_under_a_busy_copy_engine():
     _run({"CUSIM_EVENT_BUSY": "40"}, "-k", "pipelined_world_load or hinted_upload")
 
 
+def test_every_large_enough_call_as_an_ab_round():
+    """HCM_TUNE_MIN_CHUNKS=1 HCM_TUNE_MIN_TASKS=1: every derive launch and every mesh batch of a fresh context is an A/B round (baseline,
+    every variant, baseline, hashes compared) until the context has decided -- through uploads, pipelined world loads, edits, the device
+    sink, halo copies and re-derives.  Results must not change by a byte."""
+    _run({"HCM_TUNE_MIN_CHUNKS": "1", "HCM_TUNE_MIN_TASKS": "1"}, "-n", "4", "-k",
+         "mesh_matches_oracle or pipelined or set_blocks_on_device or device_sink or halo_replication or translation_invariance or forced_variants_on_a_terrain")
+
+
 def _bench_dry_run(n_ranks, *args):
     import json
 
