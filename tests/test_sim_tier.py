@@ -55,7 +55,7 @@ def test_every_large_enough_call_as_an_ab_round():
     every variant, baseline, hashes compared) until the context has decided -- through uploads, pipelined world loads, edits, the device
     sink, halo copies and re-derives.  Results must not change by a byte."""
     _run({"HCM_TUNE_MIN_CHUNKS": "1", "HCM_TUNE_MIN_TASKS": "1"}, "-n", "4", "-k",
-         "(mesh_matches_oracle and (mix or flow or checker)) or pipelined_upload_and_mesh_small or set_blocks_on_device or device_sink or halo_replication")
+         "(mesh_matches_oracle and (mix or flow or checker)) or pipelined_world_load or set_blocks_on_device or halo_replication or translation_invariance")
 
 
 def _bench_dry_run(n_ranks, *args):
