@@ -1092,11 +1092,71 @@ __device__ void merge_mask(Small &S, const u32 *F, u64 *keys, u32 *geo, int m, i
 	}
 #ifdef HCM_PHASE_TIMING
 	const long long tms1_ = clock64();
-	u32 iters_ = 0, hsteps_ = 0, hrounds_ = 0;
+	u32 iters_ = 0, hsteps_ = 0, hrounds_ = 0, hdeep_ = 0;
 #endif
 	u32 C = 0, nq = 0;
 	const u32 right = ~((2u << lane) - 1u); // columns right of this lane
 	u32 rr = rows;
+	if constexpr (kVariant == 2) {
+		// Two rows per iteration.  A row changes what a later row sees only through the cells its runs consume below it, and four rows
+		// out of five consume nothing (every run one row high: profiles/r02_emulation_event_counts.txt).  So row u and the next non-empty
+		// row u2 are scanned TOGETHER -- row words, run starts, run masks and the first height test of both, two independent chains in
+		// one instruction stream -- with u2 reading the consumed set as it stood before u.  That reading is right unless u2 = u + 1 and
+		// some run of u reaches into it (un1 != 0): then u2 is left for the next iteration, which sees the updated set.  (u2 > u + 1
+		// means row u + 1 holds no face, so no run of u can extend at all.)  Quads come out in the same order: u's, then u2's.
+		auto finish = [&](int u, u32 startmask, u32 rm, u32 alive, u32 un) { // first height test done: alive / un are its result
+			u32 height = 1 + (alive != 0);
+			int r = u + 1;
+			if (lane == r)
+				C |= un;
+			++r;
+			while (un) { // rare: some run is more than two rows high -- four rows per round, as in form 1
+				const u32 e0 = __shfl_sync(FULL, ED, (r - 1) & 31), e1 = __shfl_sync(FULL, ED, r & 31);
+				const u32 e2 = __shfl_sync(FULL, ED, (r + 1) & 31), e3 = __shfl_sync(FULL, ED, (r + 2) & 31);
+				const u32 a0 = (e0 & alive) == alive ? alive : 0u;
+				const u32 a1 = (e1 & a0) == a0 ? a0 : 0u;
+				const u32 a2 = (e2 & a1) == a1 ? a1 : 0u;
+				const u32 a3 = (e3 & a2) == a2 ? a2 : 0u;
+				const u32 un0 = __reduce_or_sync(FULL, a0), un1 = __reduce_or_sync(FULL, a1);
+				const u32 un2 = __reduce_or_sync(FULL, a2), un3 = __reduce_or_sync(FULL, a3);
+				height += (a0 != 0) + (a1 != 0) + (a2 != 0) + (a3 != 0);
+				const int d = lane - r;
+				C |= d == 0 ? un0 : (d == 1 ? un1 : (d == 2 ? un2 : (d == 3 ? un3 : 0u)));
+				alive = a3, un = un3, r += 4;
+			}
+			if (rm)
+				geo[base + nq + __popc(startmask & lt)] = (u32)u | ((u32)lane << 5) | ((u32)(__popc(rm) - 1) << 10) | ((height - 1) << 15);
+			nq += __popc(startmask);
+		};
+		while (rr) {
+			const int u = __ffs(rr) - 1;
+			rr &= rr - 1;
+			const int u2 = rr ? __ffs(rr) - 1 : 32; // the partner row (still in rr)
+			const u32 Fu = __shfl_sync(FULL, Frow, u), ELu = __shfl_sync(FULL, EL, u), Cu = __shfl_sync(FULL, C, u), e1 = __shfl_sync(FULL, ED, u);
+			const u32 Fv = __shfl_sync(FULL, Frow, u2 & 31), ELv = __shfl_sync(FULL, EL, u2 & 31), Cv = __shfl_sync(FULL, C, u2 & 31),
+			          e2 = __shfl_sync(FULL, ED, u2 & 31);
+			const u32 A = Fu & ~Cu, B = u2 < 32 ? (Fv & ~Cv) : 0u;
+			const u32 sm1 = A & ~((A << 1) & ELu), sm2 = B & ~((B << 1) & ELv);
+			const u32 nb1 = (sm1 | ~A) & right, nb2 = (sm2 | ~B) & right;
+			const u32 low1 = nb1 & (0u - nb1), low2 = nb2 & (0u - nb2);
+			const u32 rm1 = ((sm1 >> lane) & 1) ? ((low1 - 1u) & ~lt) : 0u, rm2 = ((sm2 >> lane) & 1) ? ((low2 - 1u) & ~lt) : 0u;
+			const u32 al1 = (e1 & rm1) == rm1 ? rm1 : 0u, al2 = (e2 & rm2) == rm2 ? rm2 : 0u;
+			const u32 un1 = __reduce_or_sync(FULL, al1), un2 = __reduce_or_sync(FULL, al2);
+#ifdef HCM_PHASE_TIMING
+			++iters_;
+#endif
+			if (A)
+				finish(u, sm1, rm1, al1, un1);
+			if (u2 < 32 && !(u2 == u + 1 && un1)) { // the partner's reading of the consumed set was right
+				rr &= rr - 1;
+				if (B)
+					finish(u2, sm2, rm2, al2, un2);
+#ifdef HCM_PHASE_TIMING
+				++hdeep_; // (form 2: rows that went through as partners)
+#endif
+			}
+		}
+	} else
 	while (rr) {
 		const int u = __ffs(rr) - 1;
 		rr &= rr - 1;
@@ -1142,6 +1202,10 @@ __device__ void merge_mask(Small &S, const u32 *F, u64 *keys, u32 *geo, int m, i
 					C |= un;
 				++r;
 			}
+#ifdef HCM_PHASE_TIMING
+			if (un)
+				++hdeep_; // some run of this row reaches into the next one
+#endif
 			while (un) {
 #ifdef HCM_PHASE_TIMING
 				hsteps_ += 4, ++hrounds_;
@@ -1196,6 +1260,7 @@ __device__ void merge_mask(Small &S, const u32 *F, u64 *keys, u32 *geo, int m, i
 		PHASE_COUNT(39, iters_);              // main loop iterations
 		PHASE_COUNT(55, hsteps_);             // height steps (rows tested)
 		PHASE_COUNT(57, hrounds_);            // ... in this many dependent shuffle -> reduction round trips
+		PHASE_COUNT(58, hdeep_);              // (variant form) row iterations with a run taller than one row
 		PHASE_COUNT(56, clock64() - tms2_);   // record pass cycles
 	}
 #endif
@@ -2334,7 +2399,7 @@ void launch_derive(const DevWorld &w, const UploadEntry *entries, u32 n, const u
 #undef HCM_DERIVE_CASE
 }
 int derive_variant_count() { return kDeriveForms - 1; }
-int mesh_variant_count() { return 1; }
+int mesh_variant_count() { return 2; }
 void launch_clear(const DevWorld &w, const UploadEntry *entries, u32 n, cudaStream_t st) {
 	if (n)
 		HCM_LAUNCH(clear_kernel, n, 256, 0, st, w, entries);
@@ -2379,14 +2444,18 @@ cudaError_t mesh_kernel_prepare() {
 		e = cudaFuncSetAttribute(mesh_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
 	if (e == cudaSuccess)
 		e = cudaFuncSetAttribute(mesh_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+	if (e == cudaSuccess)
+		e = cudaFuncSetAttribute(mesh_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
 	return e;
 }
 int mesh_kernel_smem_bytes() { return kSmemBytes; }
 void launch_mesh(const MeshMaps &maps, const MeshParams &p, int grid, int variant, cudaStream_t st) {
-	if (variant == 0)
-		HCM_LAUNCH(mesh_kernel<0>, grid, kThreads, kSmemBytes, st, maps, p);
-	else
+	if (variant == 1)
 		HCM_LAUNCH(mesh_kernel<1>, grid, kThreads, kSmemBytes, st, maps, p);
+	else if (variant == 2)
+		HCM_LAUNCH(mesh_kernel<2>, grid, kThreads, kSmemBytes, st, maps, p);
+	else
+		HCM_LAUNCH(mesh_kernel<0>, grid, kThreads, kSmemBytes, st, maps, p);
 }
 
 } // namespace hcm

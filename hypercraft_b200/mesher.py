@@ -80,7 +80,7 @@ class _TuneInfo(ctypes.Structure):
 assert ctypes.sizeof(_TuneInfo) == 88
 TUNE_STATES = ["pending", "variant adopted", "baseline kept", "baseline kept, a variant rejected (bytes differ)", "forced", "off"]
 VARIANT_NAMES = {"derive": ["baseline", "quarters + hoist", "hoist + L2 prefetch", "quarters + hoist + L2 prefetch"],
-                 "mesh": ["baseline", "merge height test four rows per round"]}
+                 "mesh": ["baseline", "merge height test four rows per round", "merge scan two rows per iteration"]}
 
 
 MESH_DESC_DTYPE = np.dtype([("task", np.uint32), ("transparent", np.uint32), ("vertex_offset", np.uint64), ("index_offset", np.uint64),

@@ -34,9 +34,9 @@ def test_kernels_under_the_reversed_schedule():
 
 
 def test_whole_suite_with_the_variant_kernels_forced():
-    """HCM_DERIVE_VARIANT=3 HCM_MESH_VARIANT=1: every context of the parity suite launches the variant forms of derive_kernel and
+    """HCM_DERIVE_VARIANT=3 HCM_MESH_VARIANT=2: every context of the parity suite launches the variant forms of derive_kernel and
     mesh_kernel (include/hcm.h, "Kernel variants") -- the same oracle bytes and reference digests must come out."""
-    tail = _run({"HCM_DERIVE_VARIANT": "3", "HCM_MESH_VARIANT": "1"}, "-n", "4", "--deselect",
+    tail = _run({"HCM_DERIVE_VARIANT": "3", "HCM_MESH_VARIANT": "2"}, "-n", "4", "--deselect",
                 "tests/test_zz_kernel_variants.py::test_ab_rounds_decide_and_never_change_a_byte", "--deselect",
                 "tests/test_zz_kernel_variants.py::test_a_differing_hash_rejects_the_variant_for_good", "--deselect",
                 "tests/test_zz_kernel_variants.py::test_tuning_can_be_switched_off", "-k",

@@ -20,15 +20,17 @@ KINDS = ["air", "stone", "checker", "transparent", "mix", "rawmeta", "caves", "f
 
 
 DERIVE_FORMS = [1, 2, 3]  # quarters + hoist, hoist + L2 prefetch, all three (hcm_kernels.cu: derive_kernel<kForm>)
+MESH_FORMS = [1, 2]       # merge height test four rows per round, merge scan two rows per iteration (merge_mask<kVariant>)
+FORMS = [(1, 1), (2, 2), (3, 1), (3, 2)]  # (derive, mesh) pairs run through the tests
 
 
-@pytest.fixture(scope="module", params=DERIVE_FORMS)
+@pytest.fixture(scope="module", params=FORMS, ids=lambda f: f"derive{f[0]}-mesh{f[1]}")
 def variant_mesher(request):
     from hypercraft_b200 import mesher as M
 
     m = M.Mesher(origin=(-2, -2, -2), extent=(5, 5, 5))
-    m.set_option("derive_variant", request.param)
-    m.set_option("mesh_variant", 1)
+    m.set_option("derive_variant", request.param[0])
+    m.set_option("mesh_variant", request.param[1])
     yield m
     m.close()
 
@@ -38,8 +40,8 @@ def variant_mesher(request):
 def test_forced_variants_match_oracle_and_reference_digests(variant_mesher, port, kind, seed):
     m = variant_mesher
     info = m.tune_info()
-    assert info["derive"]["state"] == info["mesh"]["state"] == "forced" and info["derive"]["selected"] in DERIVE_FORMS and info["mesh"]["selected"] == 1
-    assert info["derive"]["n_variants"] == 3 and info["mesh"]["n_variants"] == 1
+    assert info["derive"]["state"] == info["mesh"]["state"] == "forced" and info["derive"]["selected"] in DERIVE_FORMS and info["mesh"]["selected"] in MESH_FORMS
+    assert info["derive"]["n_variants"] == len(DERIVE_FORMS) and info["mesh"]["n_variants"] == len(MESH_FORMS)
     pos, blocks, heights, chunks = synth_world(kind, seed)
     m.upload(pos, blocks, heights)
     res = m.mesh(np.array([[0, 0, 0]], dtype=np.int16))
@@ -80,8 +82,8 @@ def sphere5(port):
     return _sphere(5, port)
 
 
-@pytest.mark.parametrize("form", DERIVE_FORMS)
-def test_forced_variants_on_a_terrain_sphere(sphere5, form):
+@pytest.mark.parametrize("form,mesh_form", FORMS[1:])
+def test_forced_variants_on_a_terrain_sphere(sphere5, form, mesh_form):
     """Every chunk of an r = 5 load sphere through the variant forms, plain path, re-derive path and pipelined path."""
     import hcoracle
     from hypercraft_b200 import mesher as M
@@ -89,7 +91,7 @@ def test_forced_variants_on_a_terrain_sphere(sphere5, form):
     meshed, resident, blocks, heights, want = sphere5
     m = M.Mesher(origin=(-6, -6, -6), extent=(13, 13, 13), max_chunks=len(resident), max_tasks=len(meshed))
     m.set_option("derive_variant", form)
-    m.set_option("mesh_variant", 1)
+    m.set_option("mesh_variant", mesh_form)
     m.upload(resident, blocks, heights)
     got = hcoracle.digest_batch(m.mesh(meshed))
     bad = np.nonzero((got != want).any(axis=1))[0]
