@@ -33,14 +33,16 @@ def test_kernels_under_the_reversed_schedule():
     _run({"CUSIM_REVERSE": "1"}, "-n", "4", "-k", "mesh_matches_oracle or light_stage or set_blocks_on_device or device_sink or forced_variants or ab_rounds")
 
 
-def test_whole_suite_with_the_variant_kernels_forced():
-    """HCM_DERIVE_VARIANT=3 HCM_MESH_VARIANT=2: every context of the parity suite launches the variant forms of derive_kernel and
-    mesh_kernel (include/hcm.h, "Kernel variants") -- the same oracle bytes and reference digests must come out."""
+def test_kernel_tests_with_the_variant_kernels_forced():
+    """HCM_DERIVE_VARIANT=3 HCM_MESH_VARIANT=2: every context of the parity suite's kernel tests launches variant forms of derive_kernel
+    and mesh_kernel (include/hcm.h, "Kernel variants") -- the same oracle bytes and reference digests must come out.  (The other forms
+    are forced test by test in tests/test_zz_kernel_variants.py, which the first test of this file runs on the emulation.)"""
     tail = _run({"HCM_DERIVE_VARIANT": "3", "HCM_MESH_VARIANT": "2"}, "-n", "4", "--deselect",
                 "tests/test_zz_kernel_variants.py::test_ab_rounds_decide_and_never_change_a_byte", "--deselect",
                 "tests/test_zz_kernel_variants.py::test_a_differing_hash_rejects_the_variant_for_good", "--deselect",
                 "tests/test_zz_kernel_variants.py::test_tuning_can_be_switched_off", "-k",
-                "not cpp_ and not structural_invariants and not forced_variants")  # (the forced-variant tests force them anyway; the C++ mirrors do not care)
+                "mesh_matches_oracle or light_stage or terrain_goldens or whole_load_sphere or pipelined_world_load or set_blocks_matches_the_reference "
+                "or mixed_neighbourhood or batch_of_many or output_arena_grows or edit_driven")  # the kernels' tests; host-only tests do not care
     assert " passed" in tail and "failed" not in tail
 
 
