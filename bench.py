@@ -21,6 +21,13 @@ Parity gate: EVERY chunk meshed in the last end-to-end step of EVERY rank is com
 a digest of its serialised meshes (mesh count, flags, AABBs, vertex bytes, index bytes); the mismatch count is summed over
 the ranks.  `parity.byte_compared_chunks == parity.chunks_meshed` is the bar.
 
+`kernel_variants`: derive_kernel and mesh_kernel ship in a baseline form and in re-scheduled variant forms; a context A/Bs them on its
+device during its first large calls (here: the warm-up steps) and runs what that selected in the timed steps (include/hcm.h, "Kernel
+variants").  The block reports the verdicts, the mismatch counts and every form's CUDA-event time.
+
+A watchdog guards every stage: if an optional block (device sink, hinted upload, round-1 upload mode, config 4, secondary configs, the
+sharded-dispatcher check) hangs or fails, the line is still printed from what is complete, with the stage named under "watchdog" / "error".
+
 Prints ONE JSON line on rank 0.
 """
 from __future__ import annotations
